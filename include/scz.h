@@ -1,0 +1,167 @@
+/*
+ * scz.h -- C ABI of libscz.so, the B200 (sm_100a) implementation of the
+ * dist-primitive hot path of LBruyne/Scalable-Collaborative-zkSNARK.
+ *
+ * The reference has no FFI: its hot path is generic Rust over arkworks types.
+ * Each entry point below names the reference function (file:line, relative to
+ * the reference tree) whose CPU work it replaces; INTEGRATION.md shows the
+ * `extern "C"` block and the thin Rust shim (`dist-primitive-gpu`) that keeps
+ * the reference's own signatures on top of these calls.
+ *
+ * Data layout (identical to arkworks' in-memory layout, so Rust slices are
+ * passed zero-copy):
+ *   Fr          32 B   4 x u64 little-endian limbs, Montgomery form, R = 2^256
+ *   Fq          48 B   6 x u64 little-endian limbs, Montgomery form, R = 2^384
+ *   G1 affine   96 B   x | y (Fq each); the point at infinity is x = y = 0
+ *                      (host entry points also take an optional byte mask that
+ *                      mirrors ark-ec Affine::infinity)
+ *   G1 Jacobian 144 B  X | Y | Z = ark-ec short_weierstrass::Projective;
+ *                      identity has Z = 0
+ *   triple      96 B   (Fr, Fr, Fr), one sumcheck round message
+ *
+ * Conventions: every function returns SCZ_OK (0) or a negative SCZ_ERR_*;
+ * scz_last_error(ctx) gives the text.  The caller owns all host buffers; the
+ * library never keeps a host pointer past return.  `_dev` entry points take
+ * DEVICE pointers (from scz_dev_alloc or any CUDA allocation on ctx's device)
+ * and run asynchronously on the ctx stream; the others take HOST pointers and
+ * return after the result is in host memory.  A ctx is not thread-safe; use one
+ * ctx per party / per host thread.  There is no CPU fallback anywhere: without
+ * a CUDA device scz_ctx_create fails with SCZ_ERR_CUDA.
+ */
+#ifndef SCZ_H
+#define SCZ_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SCZ_OK 0
+#define SCZ_ERR_BAD_ARG (-1)
+#define SCZ_ERR_LEN_MISMATCH (-2) /* ark-ec msm Err(min len) -> the reference unwrap()s: dmsm.rs:23 */
+#define SCZ_ERR_NOT_POW2 (-3)     /* dpoly_comm.rs:240,255 asserts */
+#define SCZ_ERR_LEVEL_OOB (-4)    /* dpoly_comm.rs:239,254 asserts */
+#define SCZ_ERR_CUDA (-5)
+#define SCZ_ERR_NET (-6)          /* MPCNetError (mpc-net/src/lib.rs:14-26) */
+#define SCZ_ERR_NOMEM (-7)
+
+#define SCZ_FR_BYTES 32
+#define SCZ_G1_AFFINE_BYTES 96
+#define SCZ_G1_JAC_BYTES 144
+#define SCZ_TRIPLE_BYTES 96
+
+typedef struct scz_ctx scz_ctx;
+typedef struct scz_pp scz_pp;   /* PackedSharingParams<Fr>, secret-sharing/src/pss.rs:17-33 */
+typedef struct scz_srs scz_srs; /* PolynomialCommitment<Bls12_381>, dpoly_comm.rs:30-34 (G1 part) */
+
+/* ---- network seam: MPCSerializeNet (dist-primitive/src/utils/serializing_net.rs) ------------
+ * All payloads are DEVICE buffers in device-native layout (no serialisation);
+ * `wire_bytes` is the size the reference would have put on the wire
+ * (ark-serialize compressed) and feeds the get_comm()-compatible counters.
+ * Return 0 on success.  A NULL vtable selects the built-in leader simulator
+ * (the reference's build without feature `comm`, serializing_net.rs:144-264). */
+typedef struct scz_net_vtable {
+    void *user;
+    /* worker_send_or_leader_receive_element (:11-39): every party contributes `bytes` from d_send;
+     * on the leader d_recv (n_parties * bytes, party-major) is filled. */
+    int32_t (*gather)(void *user, const void *d_send, void *d_recv, size_t bytes, size_t wire_bytes, void *stream);
+    /* worker_receive_or_leader_send_element (:76-96): leader's d_send holds n_parties * bytes; every party
+     * receives its slice in d_recv. */
+    int32_t (*scatter)(void *user, const void *d_send, void *d_recv, size_t bytes, size_t wire_bytes, void *stream);
+    /* the N hub rounds of hyperplonk/src/dhyperplonk.rs:271-294 as one exchange: every party sends the same
+     * `bytes` to all; d_recv (n_parties * bytes) is ordered by sender. */
+    int32_t (*all_gather)(void *user, const void *d_send, void *d_recv, size_t bytes, size_t wire_bytes, void *stream);
+    /* MPCNet::sync (mpc-net/src/lib.rs:275-286) */
+    int32_t (*sync)(void *user, void *stream);
+} scz_net_vtable;
+
+/* ---- context ---------------------------------------------------------------------------- */
+/* party_id / n_parties mirror MPCNet::party_id / n_parties (mpc-net/src/lib.rs:37-41); party 0 is the leader.
+ * net == NULL: leader simulator, party_id must be 0. */
+int32_t scz_ctx_create(int32_t device, uint32_t party_id, uint32_t n_parties, const scz_net_vtable *net,
+                       scz_ctx **out);
+void scz_ctx_destroy(scz_ctx *ctx);
+const char *scz_last_error(const scz_ctx *ctx);
+/* run on a caller-owned CUDA stream (cudaStream_t); NULL restores the ctx's own stream */
+int32_t scz_ctx_set_stream(scz_ctx *ctx, void *cuda_stream);
+int32_t scz_ctx_sync(scz_ctx *ctx);
+/* kernels launched so far by this ctx */
+uint64_t scz_ctx_launch_count(const scz_ctx *ctx);
+/* MPCNet::get_comm (mpc-net/src/lib.rs:59): (upload, download) in the reference's serialised bytes */
+int32_t scz_ctx_get_comm(const scz_ctx *ctx, uint64_t *upload, uint64_t *download);
+
+/* ---- device memory ---------------------------------------------------------------------- */
+int32_t scz_dev_alloc(scz_ctx *ctx, size_t bytes, void **d_ptr);
+int32_t scz_dev_free(scz_ctx *ctx, void *d_ptr);
+int32_t scz_h2d(scz_ctx *ctx, void *d_dst, const void *h_src, size_t bytes);
+int32_t scz_d2h(scz_ctx *ctx, void *h_dst, const void *d_src, size_t bytes);
+/* pinned host memory for callers that want full-rate PCIe copies */
+int32_t scz_host_alloc(scz_ctx *ctx, size_t bytes, void **h_ptr);
+int32_t scz_host_free(scz_ctx *ctx, void *h_ptr);
+/* fold an ark-ec `infinity` byte mask into the x = y = 0 encoding, in place on the device */
+int32_t scz_g1_apply_inf_mask_dev(scz_ctx *ctx, void *d_bases, const uint8_t *d_mask, size_t n);
+
+/* ---- element-wise kernels (unit-level parity with ark-ff / ark-ec) ------------------------ */
+/* op: 0 add, 1 sub, 2 mul (ark-ff Fp Add/Sub/Mul) */
+int32_t scz_fr_vec_op_dev(scz_ctx *ctx, int32_t op, const void *d_a, const void *d_b, void *d_out, size_t n);
+int32_t scz_fq_vec_op_dev(scz_ctx *ctx, int32_t op, const void *d_a, const void *d_b, void *d_out, size_t n);
+/* out[i] = a[i]^-1 (0 -> 0); Field::inverse */
+int32_t scz_fr_inv_dev(scz_ctx *ctx, const void *d_a, void *d_out, size_t n);
+/* Montgomery <-> canonical 32-byte little-endian integers (ark-ff into_bigint / from_bigint) */
+int32_t scz_fr_to_canonical_dev(scz_ctx *ctx, const void *d_a, void *d_out, size_t n);
+int32_t scz_fr_from_canonical_dev(scz_ctx *ctx, const void *d_a, void *d_out, size_t n);
+/* out[i] = acc[i] (Jacobian) + (negate[i] ? -p[i] : p[i]) (affine); Projective += Affine */
+int32_t scz_g1_add_affine_dev(scz_ctx *ctx, const void *d_acc_jac, const void *d_affine, const uint8_t *d_negate,
+                              void *d_out_jac, size_t n);
+/* op: 0 out = a + b, 1 out = 2a (b ignored); Projective Add / double_in_place */
+int32_t scz_g1_vec_op_dev(scz_ctx *ctx, int32_t op, const void *d_a_jac, const void *d_b_jac, void *d_out_jac,
+                          size_t n);
+/* out[i] = k[i] * p[i]; Projective * Fr */
+int32_t scz_g1_mul_fr_dev(scz_ctx *ctx, const void *d_jac, const void *d_k, void *d_out_jac, size_t n);
+/* Projective::into_affine / CurveGroup::normalize_batch: Jacobian -> packed affine (infinity -> 0,0) */
+int32_t scz_g1_to_affine_dev(scz_ctx *ctx, const void *d_jac, void *d_out_affine, size_t n);
+/* synthetic bases: out[i] = k[i] * G1 generator, packed affine (stands in for G1::rand, dpoly_comm.rs:214,229) */
+int32_t scz_g1_generator_mul_dev(scz_ctx *ctx, const void *d_k, void *d_out_affine, size_t n);
+
+/* ---- MSM: ark-ec VariableBaseMSM::msm, call sites dmsm.rs:23, dpoly_comm.rs:242,274,457 ----- */
+/* One launch sequence computes `batch` independent MSMs; out_jac holds batch Jacobian points. */
+int32_t scz_msm_g1_batched_dev(scz_ctx *ctx, const void *const *d_bases, const void *const *d_scalars,
+                               const size_t *lens, size_t batch, void *d_out_jac);
+/* host buffers; inf_mask may be NULL; bases_len != scalars_len -> SCZ_ERR_LEN_MISMATCH */
+int32_t scz_msm_g1(scz_ctx *ctx, const void *bases, const uint8_t *inf_mask, size_t bases_len, const void *scalars,
+                   size_t scalars_len, void *out_jac);
+/* window override for experiments: 0 = automatic */
+int32_t scz_msm_set_window(scz_ctx *ctx, uint32_t c);
+/* statistics of the last MSM launch sequence: total (point, window) pairs = bucket additions, buckets, windows */
+int32_t scz_msm_last_stats(const scz_ctx *ctx, uint64_t *bucket_adds, uint64_t *buckets, uint64_t *windows);
+
+/* ---- PSS: secret-sharing/src/pss.rs ------------------------------------------------------- */
+int32_t scz_pp_new(scz_ctx *ctx, size_t l, scz_pp **out);          /* PackedSharingParams::new, pss.rs:38-65 */
+void scz_pp_free(scz_pp *pp);
+int32_t scz_pp_info(const scz_pp *pp, size_t *t, size_t *l, size_t *n);
+/* kind: 0 = Fr (32 B), 1 = G1 Jacobian (144 B).  `batch` independent vectors, vector-major.
+ * pack_from_public (pss.rs:69-99): in batch x len_in (len_in <= 2l, zero padded) -> out batch x n
+ * pack_single      (pss.rs:103-113): in batch x 1 -> out batch x n
+ * unpack           (pss.rs:117-149): in batch x n -> out batch x l
+ * unpack2          (pss.rs:124-171): in batch x n -> out batch x l */
+int32_t scz_pss_pack_from_public_dev(scz_ctx *ctx, const scz_pp *pp, int32_t kind, const void *d_in, size_t len_in,
+                                     size_t batch, void *d_out);
+int32_t scz_pss_pack_single_dev(scz_ctx *ctx, const scz_pp *pp, int32_t kind, const void *d_in, size_t batch,
+                                void *d_out);
+int32_t scz_pss_unpack_dev(scz_ctx *ctx, const scz_pp *pp, int32_t kind, const void *d_in, size_t batch, void *d_out);
+int32_t scz_pss_unpack2_dev(scz_ctx *ctx, const scz_pp *pp, int32_t kind, const void *d_in, size_t batch,
+                            void *d_out);
+
+/* ---- d_msm: dist-primitive/src/dmsm.rs:9-43 ------------------------------------------------ */
+/* local MSMs -> gather -> leader: unpack2, sum, pack_from_public -> scatter.  out: batch Jacobian points
+ * (this party's packed shares of the batch results). */
+int32_t scz_d_msm_dev(scz_ctx *ctx, const scz_pp *pp, const void *const *d_bases, const void *const *d_scalars,
+                      const size_t *lens, size_t batch, void *d_out_jac);
+int32_t scz_d_msm(scz_ctx *ctx, const scz_pp *pp, const void *const *bases, const size_t *bases_lens,
+                  const void *const *scalars, const size_t *scalars_lens, size_t batch, void *out_jac);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

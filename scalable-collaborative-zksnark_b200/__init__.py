@@ -1,0 +1,16 @@
+"""scz-b200: the dist-primitive hot path of Scalable-Collaborative-zkSNARK on B200.
+
+Everything computes in libscz.so (hand-written sm_100a CUDA behind the C ABI of
+include/scz.h).  This package is the Python mirror of the reference's Rust
+interface for that path (PackedSharingParams, d_msm, ...); PyTorch is used only
+for device memory, streams and torch.distributed.  There is no CPU fallback:
+importing works anywhere (so the symbol table can be checked), but creating a
+Context without a CUDA device raises.
+"""
+from .binding import LIB_PATH, SczError, lib  # noqa: F401
+from .api import (  # noqa: F401
+    Context,
+    PackedSharingParams,
+    d_msm,
+    msm,
+)

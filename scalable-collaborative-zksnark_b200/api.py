@@ -1,0 +1,309 @@
+"""Python mirror of the reference's Rust interface for the hot path.
+
+Names, argument meaning and error behaviour follow the reference
+(`PackedSharingParams` secret-sharing/src/pss.rs:17-171, `d_msm`
+dist-primitive/src/dmsm.rs:9-43, ...).  Arrays use arkworks' in-memory layout:
+
+  Fr          (n, 4)  uint64   Montgomery limbs
+  G1 affine   (n, 12) uint64   x | y, infinity = all zero
+  G1 Jacobian (n, 18) uint64   X | Y | Z
+
+Every function accepts either numpy arrays (HOST path: the C ABI copies in and
+out, like a call from the Rust shim) or torch CUDA tensors of dtype int64 with the
+same shapes (DEVICE path: tables stay resident in HBM between calls).
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from .binding import NetVTable, SczError, lib
+
+FR_LIMBS, AFF_LIMBS, JAC_LIMBS = 4, 12, 18
+
+
+def _is_dev(x):
+    return isinstance(x, torch.Tensor)
+
+
+def _host(a, cols):
+    a = np.ascontiguousarray(a, dtype=np.uint64)
+    return a.reshape(-1, cols)
+
+
+def _dev(t, cols):
+    assert t.is_cuda and t.dtype == torch.int64 and t.is_contiguous(), "device operands: contiguous int64 CUDA tensors"
+    return t.reshape(-1, cols)
+
+
+def _ptr_array(ptrs):
+    return (C.c_void_p * len(ptrs))(*ptrs)
+
+
+class Context:
+    """One MPC party's handle (scz_ctx).  `net=None` selects the reference's leader
+    simulator (build without feature `comm`, serializing_net.rs:144-264)."""
+
+    def __init__(self, device=0, party_id=0, n_parties=8, net=None):
+        if not torch.cuda.is_available():
+            raise SczError(-5, "no CUDA device: scz-b200 has no CPU path")
+        self.L = lib()
+        self.device = torch.device("cuda", device)
+        self.net = net
+        self._vt = None
+        if net is not None:
+            self._vt = net.vtable()
+        h = C.c_void_p()
+        rc = self.L.scz_ctx_create(C.c_int32(device), C.c_uint32(party_id), C.c_uint32(n_parties),
+                                   C.byref(self._vt) if self._vt is not None else None, C.byref(h))
+        if rc != 0:
+            raise SczError(rc, "scz_ctx_create failed")
+        self.h = h
+        self.party_id, self.n_parties = party_id, n_parties
+        self.use_torch_stream()
+
+    def use_torch_stream(self):
+        """run on torch's current stream so torch.cuda.Event timing and tensors order with our kernels"""
+        with torch.cuda.device(self.device):
+            s = torch.cuda.current_stream().cuda_stream
+        self.check(self.L.scz_ctx_set_stream(self.h, C.c_void_p(s)))
+
+    def check(self, rc):
+        if rc != 0:
+            raise SczError(rc, self.L.scz_last_error(self.h).decode())
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.scz_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def sync(self):
+        self.check(self.L.scz_ctx_sync(self.h))
+
+    @property
+    def launches(self):
+        return int(self.L.scz_ctx_launch_count(self.h))
+
+    def get_comm(self):
+        """MPCNet::get_comm -> (upload, download) in the reference's serialised bytes"""
+        up, down = C.c_uint64(), C.c_uint64()
+        self.check(self.L.scz_ctx_get_comm(self.h, C.byref(up), C.byref(down)))
+        return up.value, down.value
+
+    # ---- device memory helpers (torch owns the allocations)
+    def to_device(self, a, cols):
+        a = _host(a, cols)
+        return torch.from_numpy(a.view(np.int64)).to(self.device, non_blocking=False).contiguous()
+
+    def empty(self, n, cols):
+        return torch.empty((n, cols), dtype=torch.int64, device=self.device)
+
+    @staticmethod
+    def to_host(t):
+        return t.detach().cpu().numpy().view(np.uint64)
+
+    # ---- unit-level element-wise ops (device tensors)
+    def fr_op(self, op, a, b):
+        a, b = _dev(a, 4), _dev(b, 4)
+        out = torch.empty_like(a)
+        self.check(self.L.scz_fr_vec_op_dev(self.h, {"add": 0, "sub": 1, "mul": 2}[op], C.c_void_p(a.data_ptr()),
+                                            C.c_void_p(b.data_ptr()), C.c_void_p(out.data_ptr()), C.c_size_t(len(a))))
+        return out
+
+    def fq_op(self, op, a, b):
+        a, b = _dev(a, 6), _dev(b, 6)
+        out = torch.empty_like(a)
+        self.check(self.L.scz_fq_vec_op_dev(self.h, {"add": 0, "sub": 1, "mul": 2}[op], C.c_void_p(a.data_ptr()),
+                                            C.c_void_p(b.data_ptr()), C.c_void_p(out.data_ptr()), C.c_size_t(len(a))))
+        return out
+
+    def _fr_unary(self, fn, a):
+        a = _dev(a, 4)
+        out = torch.empty_like(a)
+        self.check(fn(self.h, C.c_void_p(a.data_ptr()), C.c_void_p(out.data_ptr()), C.c_size_t(len(a))))
+        return out
+
+    def fr_inv(self, a): return self._fr_unary(self.L.scz_fr_inv_dev, a)
+    def fr_to_canonical(self, a): return self._fr_unary(self.L.scz_fr_to_canonical_dev, a)
+    def fr_from_canonical(self, a): return self._fr_unary(self.L.scz_fr_from_canonical_dev, a)
+
+    def g1_add_affine(self, acc_jac, aff, negate=None):
+        acc, aff = _dev(acc_jac, 18), _dev(aff, 12)
+        out = torch.empty_like(acc)
+        neg = C.c_void_p(negate.data_ptr()) if negate is not None else None
+        self.check(self.L.scz_g1_add_affine_dev(self.h, C.c_void_p(acc.data_ptr()), C.c_void_p(aff.data_ptr()), neg,
+                                                C.c_void_p(out.data_ptr()), C.c_size_t(len(acc))))
+        return out
+
+    def g1_add(self, a, b):
+        a, b = _dev(a, 18), _dev(b, 18)
+        out = torch.empty_like(a)
+        self.check(self.L.scz_g1_vec_op_dev(self.h, 0, C.c_void_p(a.data_ptr()), C.c_void_p(b.data_ptr()),
+                                            C.c_void_p(out.data_ptr()), C.c_size_t(len(a))))
+        return out
+
+    def g1_double(self, a):
+        a = _dev(a, 18)
+        out = torch.empty_like(a)
+        self.check(self.L.scz_g1_vec_op_dev(self.h, 1, C.c_void_p(a.data_ptr()), None, C.c_void_p(out.data_ptr()),
+                                            C.c_size_t(len(a))))
+        return out
+
+    def g1_mul(self, a, k):
+        a, k = _dev(a, 18), _dev(k, 4)
+        out = torch.empty_like(a)
+        self.check(self.L.scz_g1_mul_fr_dev(self.h, C.c_void_p(a.data_ptr()), C.c_void_p(k.data_ptr()),
+                                            C.c_void_p(out.data_ptr()), C.c_size_t(len(a))))
+        return out
+
+    def g1_to_affine(self, a):
+        a = _dev(a, 18)
+        out = self.empty(len(a), 12)
+        self.check(self.L.scz_g1_to_affine_dev(self.h, C.c_void_p(a.data_ptr()), C.c_void_p(out.data_ptr()),
+                                               C.c_size_t(len(a))))
+        return out
+
+    def g1_generator_mul(self, k):
+        """synthetic bases k[i]*G (stands in for G1::rand, dpoly_comm.rs:214,229)"""
+        k = _dev(k, 4)
+        out = self.empty(len(k), 12)
+        self.check(self.L.scz_g1_generator_mul_dev(self.h, C.c_void_p(k.data_ptr()), C.c_void_p(out.data_ptr()),
+                                                   C.c_size_t(len(k))))
+        return out
+
+    def msm_set_window(self, c):
+        self.check(self.L.scz_msm_set_window(self.h, C.c_uint32(c)))
+
+    def msm_last_stats(self):
+        a, b, w = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        self.check(self.L.scz_msm_last_stats(self.h, C.byref(a), C.byref(b), C.byref(w)))
+        return {"bucket_adds": a.value, "buckets": b.value, "windows": w.value}
+
+
+# ---------------------------------------------------------------------------- MSM
+def msm(ctx, bases, scalars, inf_mask=None):
+    """G1::msm(bases, scalars) (ark-ec VariableBaseMSM; dmsm.rs:23).  Raises SczError
+    (SCZ_ERR_LEN_MISMATCH) where the reference's `.unwrap()` would panic."""
+    if _is_dev(bases):
+        b, s = _dev(bases, 12), _dev(scalars, 4)
+        if len(b) != len(s):
+            raise SczError(-2, f"msm: {len(b)} bases vs {len(s)} scalars")
+        return msm_batched(ctx, [b], [s])
+    b, s = _host(bases, 12), _host(scalars, 4)
+    out = np.zeros((1, 18), dtype=np.uint64)
+    mask = None
+    if inf_mask is not None:
+        mask = np.ascontiguousarray(inf_mask, dtype=np.uint8)
+    ctx.check(ctx.L.scz_msm_g1(ctx.h, C.c_void_p(b.ctypes.data), C.c_void_p(mask.ctypes.data) if mask is not None else None,
+                               C.c_size_t(len(b)), C.c_void_p(s.ctypes.data), C.c_size_t(len(s)),
+                               C.c_void_p(out.ctypes.data)))
+    return out
+
+
+def msm_batched(ctx, bases_list, scalars_list):
+    """device path: one launch sequence for a batch of MSMs -> (batch, 18) Jacobian tensor"""
+    bs = [_dev(b, 12) for b in bases_list]
+    ss = [_dev(s, 4) for s in scalars_list]
+    for b, s in zip(bs, ss):
+        if len(b) != len(s):
+            raise SczError(-2, f"msm: {len(b)} bases vs {len(s)} scalars")
+    k = len(bs)
+    out = ctx.empty(k, 18)
+    lens = (C.c_size_t * k)(*[len(s) for s in ss])
+    ctx.check(ctx.L.scz_msm_g1_batched_dev(ctx.h, _ptr_array([b.data_ptr() for b in bs]),
+                                           _ptr_array([s.data_ptr() for s in ss]), lens, C.c_size_t(k),
+                                           C.c_void_p(out.data_ptr())))
+    return out
+
+
+# ---------------------------------------------------------------------------- PSS
+class PackedSharingParams:
+    """secret-sharing/src/pss.rs:17-171.  kind: 'fr' or 'g1' (Jacobian), like the
+    reference's `G: DomainCoeff<F>`.  Operands are (batch, len, limbs) or (len, limbs)."""
+
+    def __init__(self, ctx, l):
+        self.ctx = ctx
+        h = C.c_void_p()
+        ctx.check(ctx.L.scz_pp_new(ctx.h, C.c_size_t(l), C.byref(h)))
+        self.h = h
+        self.l, self.n, self.t = l, 8 * l, l - 1
+
+    def __del__(self):
+        try:
+            if self.h:
+                self.ctx.L.scz_pp_free(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    def _apply(self, which, x, kind, len_in, len_out):
+        ctx = self.ctx
+        cols = 4 if kind == "fr" else 18
+        host = not _is_dev(x)
+        xd = ctx.to_device(x, cols) if host else _dev(x, cols)
+        assert len(xd) % len_in == 0, f"operand length {len(xd)} is not a multiple of {len_in}"
+        batch = len(xd) // len_in
+        out = ctx.empty(batch * len_out, cols)
+        k = 0 if kind == "fr" else 1
+        a = (ctx.h, self.h, C.c_int32(k), C.c_void_p(xd.data_ptr()))
+        if which == "pack":
+            rc = ctx.L.scz_pss_pack_from_public_dev(*a, C.c_size_t(len_in), C.c_size_t(batch), C.c_void_p(out.data_ptr()))
+        elif which == "pack_single":
+            rc = ctx.L.scz_pss_pack_single_dev(*a, C.c_size_t(batch), C.c_void_p(out.data_ptr()))
+        elif which == "unpack":
+            rc = ctx.L.scz_pss_unpack_dev(*a, C.c_size_t(batch), C.c_void_p(out.data_ptr()))
+        else:
+            rc = ctx.L.scz_pss_unpack2_dev(*a, C.c_size_t(batch), C.c_void_p(out.data_ptr()))
+        ctx.check(rc)
+        out = out.reshape(batch, len_out, cols)
+        return ctx.to_host(out) if host else out
+
+    def pack_from_public(self, secrets, kind="fr", len_in=None):
+        return self._apply("pack", secrets, kind, len_in or self.l, self.n)
+
+    def pack_single(self, secret, kind="fr"):
+        return self._apply("pack_single", secret, kind, 1, self.n)
+
+    def unpack(self, shares, kind="fr"):
+        return self._apply("unpack", shares, kind, self.n, self.l)
+
+    def unpack2(self, shares, kind="fr"):
+        return self._apply("unpack2", shares, kind, self.n, self.l)
+
+
+# ---------------------------------------------------------------------------- d_msm
+def d_msm(ctx, pp, bases, scalars):
+    """dist-primitive/src/dmsm.rs:9-43: bases / scalars are lists (the batch) of arrays.
+    Returns this party's packed shares of the batch results, (batch, 18) Jacobian."""
+    if len(bases) != len(scalars):
+        raise AssertionError("assert_eq!(bases.len(), scalars.len())")   # dmsm.rs:16
+    k = len(bases)
+    if k and _is_dev(bases[0]):
+        bs = [_dev(b, 12) for b in bases]
+        ss = [_dev(s, 4) for s in scalars]
+        for b, s in zip(bs, ss):
+            if len(b) != len(s):
+                raise SczError(-2, f"d_msm: {len(b)} bases vs {len(s)} scalars")
+        out = ctx.empty(k, 18)
+        lens = (C.c_size_t * k)(*[len(s) for s in ss])
+        ctx.check(ctx.L.scz_d_msm_dev(ctx.h, pp.h, _ptr_array([b.data_ptr() for b in bs]),
+                                      _ptr_array([s.data_ptr() for s in ss]), lens, C.c_size_t(k),
+                                      C.c_void_p(out.data_ptr())))
+        return out
+    bs = [_host(b, 12) for b in bases]
+    ss = [_host(s, 4) for s in scalars]
+    out = np.zeros((k, 18), dtype=np.uint64)
+    bl = (C.c_size_t * k)(*[len(b) for b in bs])
+    sl = (C.c_size_t * k)(*[len(s) for s in ss])
+    ctx.check(ctx.L.scz_d_msm(ctx.h, pp.h, _ptr_array([b.ctypes.data for b in bs]), bl,
+                              _ptr_array([s.ctypes.data for s in ss]), sl, C.c_size_t(k), C.c_void_p(out.ctypes.data)))
+    return out
+
+
+__all__ = ["Context", "PackedSharingParams", "msm", "msm_batched", "d_msm", "NetVTable"]

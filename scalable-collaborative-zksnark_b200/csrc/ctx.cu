@@ -1,0 +1,205 @@
+// Context, device memory, and the two network back-ends.
+#include <stdarg.h>
+#include <string.h>
+
+#include "ctx.h"
+#include "net.h"
+
+namespace scz {
+
+int32_t Ctx::fail(int32_t code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    err = buf;
+    return code;
+}
+int32_t Ctx::cuda(cudaError_t e, const char *what) {
+    return fail(SCZ_ERR_CUDA, "CUDA error %d (%s) at %s", (int)e, cudaGetErrorString(e), what);
+}
+int32_t Ctx::pinned_reserve(size_t bytes) {
+    if (bytes <= pinned_cap) return SCZ_OK;
+    if (pinned) SCZ_CUDA(this, cudaFreeHost(pinned));
+    pinned = nullptr;
+    pinned_cap = 0;
+    size_t want = align_up(bytes, 1 << 16);
+    SCZ_CUDA(this, cudaMallocHost(&pinned, want));
+    pinned_cap = want;
+    return SCZ_OK;
+}
+
+// ------------------------------------------------------------------ leader simulator
+// serializing_net.rs:147-167: the leader "receives" n_parties clones of its own message
+int32_t LeaderSimNet::gather(Ctx *ctx, const void *d_send, void *d_recv, size_t bytes, size_t wire) {
+    download += wire * (n_parties - 1);
+    for (uint32_t j = 0; j < n_parties; j++)
+        SCZ_CUDA(ctx, cudaMemcpyAsync((char *)d_recv + (size_t)j * bytes, d_send, bytes, cudaMemcpyDeviceToDevice,
+                                      ctx->stream));
+    return SCZ_OK;
+}
+// serializing_net.rs:192-215: counts the N-1 outgoing messages, keeps element 0
+int32_t LeaderSimNet::scatter(Ctx *ctx, const void *d_send, void *d_recv, size_t bytes, size_t wire) {
+    upload += wire * (n_parties - 1);
+    SCZ_CUDA(ctx, cudaMemcpyAsync(d_recv, d_send, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+    return SCZ_OK;
+}
+// hyperplonk/src/dhyperplonk.rs:271-294 without `comm`: the own vector is used N times (:289-293)
+int32_t LeaderSimNet::all_gather(Ctx *ctx, const void *d_send, void *d_recv, size_t bytes, size_t wire) {
+    upload += wire * (n_parties - 1);
+    for (uint32_t j = 0; j < n_parties; j++)
+        SCZ_CUDA(ctx, cudaMemcpyAsync((char *)d_recv + (size_t)j * bytes, d_send, bytes, cudaMemcpyDeviceToDevice,
+                                      ctx->stream));
+    return SCZ_OK;
+}
+int32_t LeaderSimNet::sync(Ctx *) { return SCZ_OK; }
+
+// ------------------------------------------------------------------ host-supplied collectives
+int32_t CallbackNet::gather(Ctx *ctx, const void *d_send, void *d_recv, size_t bytes, size_t wire) {
+    if (is_leader()) download += wire * (n_parties - 1);
+    else upload += wire;
+    if (vt.gather(vt.user, d_send, d_recv, bytes, wire, ctx->stream) != 0) return ctx->fail(SCZ_ERR_NET, "net gather failed");
+    return SCZ_OK;
+}
+int32_t CallbackNet::scatter(Ctx *ctx, const void *d_send, void *d_recv, size_t bytes, size_t wire) {
+    if (is_leader()) upload += wire * (n_parties - 1);
+    else download += wire;
+    if (vt.scatter(vt.user, d_send, d_recv, bytes, wire, ctx->stream) != 0) return ctx->fail(SCZ_ERR_NET, "net scatter failed");
+    return SCZ_OK;
+}
+int32_t CallbackNet::all_gather(Ctx *ctx, const void *d_send, void *d_recv, size_t bytes, size_t wire) {
+    upload += wire * (n_parties - 1);
+    download += wire * (n_parties - 1);
+    if (vt.all_gather(vt.user, d_send, d_recv, bytes, wire, ctx->stream) != 0)
+        return ctx->fail(SCZ_ERR_NET, "net all_gather failed");
+    return SCZ_OK;
+}
+int32_t CallbackNet::sync(Ctx *ctx) {
+    if (vt.sync && vt.sync(vt.user, ctx->stream) != 0) return ctx->fail(SCZ_ERR_NET, "net sync failed");
+    return SCZ_OK;
+}
+
+}   // namespace scz
+
+using namespace scz;
+
+extern "C" {
+
+int32_t scz_ctx_create(int32_t device, uint32_t party_id, uint32_t n_parties, const scz_net_vtable *net, scz_ctx **out) {
+    if (!out || n_parties == 0 || party_id >= n_parties) return SCZ_ERR_BAD_ARG;
+    *out = nullptr;
+    if (!net && party_id != 0) return SCZ_ERR_BAD_ARG;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || device < 0 || device >= count) {
+        fprintf(stderr, "scz_ctx_create: no usable CUDA device %d (%s); libscz has no CPU path\n", device,
+                e == cudaSuccess ? "index out of range" : cudaGetErrorString(e));
+        return SCZ_ERR_CUDA;
+    }
+    scz_ctx *h = new scz_ctx();
+    Ctx *c = &h->c;
+    c->device = device;
+    if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete h;
+        return SCZ_ERR_CUDA;
+    }
+    c->own_stream = true;
+    cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
+    {   // keep freed temporaries cached in the pool instead of returning them to the driver
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            uint64_t thr = UINT64_MAX;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+        }
+    }
+    if (net) {
+        CallbackNet *n = new CallbackNet();
+        n->vt = *net;
+        c->net = n;
+    } else {
+        c->net = new LeaderSimNet();
+    }
+    c->net->n_parties = n_parties;
+    c->net->party_id = party_id;
+    *out = h;
+    return SCZ_OK;
+}
+void scz_ctx_destroy(scz_ctx *h) {
+    if (!h) return;
+    Ctx *c = &h->c;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    if (c->pinned) cudaFreeHost(c->pinned);
+    if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+    delete c->net;
+    delete h;
+}
+const char *scz_last_error(const scz_ctx *h) { return h ? h->c.err.c_str() : "null ctx"; }
+int32_t scz_ctx_set_stream(scz_ctx *h, void *s) {
+    if (!h) return SCZ_ERR_BAD_ARG;
+    Ctx *c = &h->c;
+    SCZ_CUDA(c, cudaSetDevice(c->device));
+    SCZ_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+    if (s) {
+        c->stream = (cudaStream_t)s;
+        c->own_stream = false;
+    } else {
+        SCZ_CUDA(c, cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        c->own_stream = true;
+    }
+    return SCZ_OK;
+}
+int32_t scz_ctx_sync(scz_ctx *h) {
+    if (!h) return SCZ_ERR_BAD_ARG;
+    SCZ_CUDA(&h->c, cudaStreamSynchronize(h->c.stream));
+    return SCZ_OK;
+}
+uint64_t scz_ctx_launch_count(const scz_ctx *h) { return h ? h->c.launches : 0; }
+int32_t scz_ctx_get_comm(const scz_ctx *h, uint64_t *up, uint64_t *down) {
+    if (!h) return SCZ_ERR_BAD_ARG;
+    if (up) *up = h->c.net->upload;
+    if (down) *down = h->c.net->download;
+    return SCZ_OK;
+}
+int32_t scz_dev_alloc(scz_ctx *h, size_t bytes, void **p) {
+    if (!h || !p) return SCZ_ERR_BAD_ARG;
+    SCZ_CUDA(&h->c, cudaSetDevice(h->c.device));
+    cudaError_t e = cudaMalloc(p, bytes ? bytes : 1);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return h->c.fail(SCZ_ERR_NOMEM, "cudaMalloc(%zu): %s", bytes, cudaGetErrorString(e));
+    }
+    return SCZ_OK;
+}
+int32_t scz_dev_free(scz_ctx *h, void *p) {
+    if (!h) return SCZ_ERR_BAD_ARG;
+    SCZ_CUDA(&h->c, cudaStreamSynchronize(h->c.stream));
+    SCZ_CUDA(&h->c, cudaFree(p));
+    return SCZ_OK;
+}
+int32_t scz_h2d(scz_ctx *h, void *d, const void *s, size_t bytes) {
+    if (!h) return SCZ_ERR_BAD_ARG;
+    SCZ_CUDA(&h->c, cudaMemcpyAsync(d, s, bytes, cudaMemcpyHostToDevice, h->c.stream));
+    SCZ_CUDA(&h->c, cudaStreamSynchronize(h->c.stream));
+    return SCZ_OK;
+}
+int32_t scz_d2h(scz_ctx *h, void *d, const void *s, size_t bytes) {
+    if (!h) return SCZ_ERR_BAD_ARG;
+    SCZ_CUDA(&h->c, cudaMemcpyAsync(d, s, bytes, cudaMemcpyDeviceToHost, h->c.stream));
+    SCZ_CUDA(&h->c, cudaStreamSynchronize(h->c.stream));
+    return SCZ_OK;
+}
+int32_t scz_host_alloc(scz_ctx *h, size_t bytes, void **p) {
+    if (!h || !p) return SCZ_ERR_BAD_ARG;
+    SCZ_CUDA(&h->c, cudaMallocHost(p, bytes ? bytes : 1));
+    return SCZ_OK;
+}
+int32_t scz_host_free(scz_ctx *h, void *p) {
+    if (!h) return SCZ_ERR_BAD_ARG;
+    SCZ_CUDA(&h->c, cudaFreeHost(p));
+    return SCZ_OK;
+}
+
+}   // extern "C"

@@ -1,0 +1,84 @@
+// Library-internal context: device, stream, grow-only workspace arena, error text.
+// One scz_ctx per MPC party (the reference spawns one task per party,
+// mpc-net/src/multi.rs:345-348); calls on a ctx are serialised by the caller.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+
+#include "../../include/scz.h"
+
+namespace scz {
+
+struct Net;
+
+struct Ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int sm_count = 148;
+    std::string err;
+    // pinned host staging for small results
+    char *pinned = nullptr;
+    size_t pinned_cap = 0;
+    Net *net = nullptr;
+    uint64_t launches = 0;   // kernels launched by this ctx (bench.py reports it as gpu_launches)
+    uint32_t msm_window_override = 0;
+    uint64_t msm_bucket_adds = 0, msm_buckets = 0, msm_windows = 0;   // statistics of the last MSM sequence
+
+    int32_t fail(int32_t code, const char *fmt, ...);
+    int32_t cuda(cudaError_t e, const char *what);
+    int32_t pinned_reserve(size_t bytes);
+};
+
+// Stream-ordered temporary from the device's CUDA memory pool (cudaMallocAsync): freed in
+// stream order when the object dies, so kernels already queued keep their memory and
+// steady-state calls never hit the allocator's slow path (release threshold = unlimited).
+struct DevTmp {
+    Ctx *c;
+    void *p = nullptr;
+    explicit DevTmp(Ctx *ctx) : c(ctx) {}
+    DevTmp(const DevTmp &) = delete;
+    DevTmp &operator=(const DevTmp &) = delete;
+    int32_t alloc(size_t bytes) {
+        cudaError_t e = cudaMallocAsync(&p, bytes ? bytes : 256, c->stream);
+        if (e != cudaSuccess) {
+            p = nullptr;
+            cudaGetLastError();
+            return c->fail(SCZ_ERR_NOMEM, "cudaMallocAsync(%zu): %s", bytes, cudaGetErrorString(e));
+        }
+        return SCZ_OK;
+    }
+    template <class T> T *as() const { return reinterpret_cast<T *>(p); }
+    ~DevTmp() {
+        if (p) cudaFreeAsync(p, c->stream);
+    }
+};
+
+#define SCZ_CUDA(ctx, expr)                                   \
+    do {                                                      \
+        cudaError_t e__ = (expr);                             \
+        if (e__ != cudaSuccess) return (ctx)->cuda(e__, #expr); \
+    } while (0)
+#define SCZ_TRY(expr)                  \
+    do {                               \
+        int32_t rc__ = (expr);         \
+        if (rc__ != SCZ_OK) return rc__; \
+    } while (0)
+#define SCZ_LAUNCH_CHECK(ctx)                                         \
+    do {                                                              \
+        (ctx)->launches++;                                            \
+        cudaError_t e__ = cudaGetLastError();                         \
+        if (e__ != cudaSuccess) return (ctx)->cuda(e__, "kernel launch"); \
+    } while (0)
+
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+static inline uint32_t ceil_div_u32(size_t a, size_t b) { return (uint32_t)((a + b - 1) / b); }
+
+}   // namespace scz
+
+struct scz_ctx {
+    scz::Ctx c;
+};

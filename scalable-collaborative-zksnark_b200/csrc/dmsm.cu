@@ -1,0 +1,103 @@
+// d_msm: dist-primitive/src/dmsm.rs:9-43.
+//   c_shares[k] = G::msm(bases[k], scalars[k])                       (:19-24)  -> one batched Pippenger sequence
+//   leader_compute_element(c_shares, f)                              (:29-40)
+//     f: transpose; per k: unpack2 -> sum of the l secrets -> [sum; l] -> pack_from_public; transpose
+// The gather / scatter payloads stay on the device in Jacobian form (144 B per
+// point); the byte counters use the reference's wire size, Vec<G1> compressed =
+// 8 + 48 * batch (ark-serialize, serializing_net.rs:17).
+#include <vector>
+
+#include "g1.cuh"
+#include "msm.h"
+#include "net.h"
+#include "pss.h"
+
+namespace scz {
+
+// sec[k*l + i] <- sum_i sec[k*l + i] for every i   (dmsm.rs:34-35)
+__global__ void k_g1_sum_replicate(void *sec, uint32_t l, uint32_t batch) {
+    uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= batch) return;
+    G1X acc = G1X::inf();
+    for (uint32_t i = 0; i < l; i++) acc = g1x_add(acc, g1x_from_jac(g1j_load(sec, (size_t)k * l + i)));
+    G1Jac r = g1x_to_jac(acc);
+    for (uint32_t i = 0; i < l; i++) g1j_store(sec, (size_t)k * l + i, r);
+}
+
+int32_t d_msm_dev(Ctx *ctx, const scz_pp *pp, const void *const *d_bases, const void *const *d_scalars,
+                  const size_t *lens, size_t batch, void *d_out) {
+    if (!pp) return ctx->fail(SCZ_ERR_BAD_ARG, "d_msm: null pp");
+    if (batch == 0) return SCZ_OK;
+    Net *net = ctx->net;
+    const size_t N = net->n_parties, PT = SCZ_G1_JAC_BYTES;
+    if (N != pp->n) return ctx->fail(SCZ_ERR_BAD_ARG, "d_msm: %zu parties but pp.n = %zu", N, pp->n);
+    DevTmp c_shares(ctx), recv(ctx), sec(ctx), send(ctx);
+    SCZ_TRY(c_shares.alloc(batch * PT));
+    SCZ_TRY(msm_g1_batched(ctx, d_bases, d_scalars, lens, batch, c_shares.p));
+    const size_t wire = 8 + 48 * batch;
+    if (net->is_leader()) {
+        SCZ_TRY(recv.alloc(N * batch * PT));
+        SCZ_TRY(sec.alloc(batch * pp->l * PT));
+        SCZ_TRY(send.alloc(N * batch * PT));
+    }
+    SCZ_TRY(net->gather(ctx, c_shares.p, recv.p, batch * PT, wire));
+    if (net->is_leader()) {
+        // recv is party-major [j][k]: vector k is the stride-`batch` column
+        SCZ_TRY(pss_apply(ctx, pp, PSS_UNPACK2, 1, recv.p, pp->n, 1, batch, batch, sec.p, pp->l, 1));
+        k_g1_sum_replicate<<<ceil_div_u32(batch, 32), 32, 0, ctx->stream>>>(sec.p, (uint32_t)pp->l, (uint32_t)batch);
+        SCZ_LAUNCH_CHECK(ctx);
+        SCZ_TRY(pss_apply(ctx, pp, PSS_PACK, 1, sec.p, pp->l, pp->l, 1, batch, send.p, 1, batch));
+    }
+    SCZ_TRY(net->scatter(ctx, send.p, d_out, batch * PT, wire));
+    return SCZ_OK;
+}
+
+}   // namespace scz
+
+using namespace scz;
+
+extern "C" {
+
+int32_t scz_d_msm_dev(scz_ctx *h, const scz_pp *pp, const void *const *d_bases, const void *const *d_scalars,
+                      const size_t *lens, size_t batch, void *d_out) {
+    if (!h) return SCZ_ERR_BAD_ARG;
+    if (batch && (!d_bases || !d_scalars || !lens || !d_out)) return h->c.fail(SCZ_ERR_BAD_ARG, "d_msm: null argument");
+    return d_msm_dev(&h->c, pp, d_bases, d_scalars, lens, batch, d_out);
+}
+
+int32_t scz_d_msm(scz_ctx *h, const scz_pp *pp, const void *const *bases, const size_t *bases_lens,
+                  const void *const *scalars, const size_t *scalars_lens, size_t batch, void *out_jac) {
+    if (!h) return SCZ_ERR_BAD_ARG;
+    Ctx *c = &h->c;
+    if (batch && (!bases || !scalars || !bases_lens || !scalars_lens || !out_jac))
+        return c->fail(SCZ_ERR_BAD_ARG, "d_msm: null argument");
+    size_t tot = 0;
+    for (size_t k = 0; k < batch; k++) {
+        if (bases_lens[k] != scalars_lens[k])   // G::msm(..).unwrap() panics in the reference (dmsm.rs:23)
+            return c->fail(SCZ_ERR_LEN_MISMATCH, "d_msm: entry %zu has %zu bases vs %zu scalars", k, bases_lens[k],
+                           scalars_lens[k]);
+        tot += bases_lens[k];
+    }
+    DevTmp d_b(c), d_s(c), d_o(c);
+    SCZ_TRY(d_b.alloc(tot * SCZ_G1_AFFINE_BYTES));
+    SCZ_TRY(d_s.alloc(tot * SCZ_FR_BYTES));
+    SCZ_TRY(d_o.alloc(batch * SCZ_G1_JAC_BYTES));
+    std::vector<const void *> bp(batch), sp(batch);
+    size_t off = 0;
+    for (size_t k = 0; k < batch; k++) {
+        size_t n = bases_lens[k];
+        bp[k] = d_b.as<char>() + off * SCZ_G1_AFFINE_BYTES;
+        sp[k] = d_s.as<char>() + off * SCZ_FR_BYTES;
+        if (n) {
+            SCZ_CUDA(c, cudaMemcpyAsync((void *)bp[k], bases[k], n * SCZ_G1_AFFINE_BYTES, cudaMemcpyHostToDevice, c->stream));
+            SCZ_CUDA(c, cudaMemcpyAsync((void *)sp[k], scalars[k], n * SCZ_FR_BYTES, cudaMemcpyHostToDevice, c->stream));
+        }
+        off += n;
+    }
+    SCZ_TRY(d_msm_dev(c, pp, bp.data(), sp.data(), bases_lens, batch, d_o.p));
+    SCZ_CUDA(c, cudaMemcpyAsync(out_jac, d_o.p, batch * SCZ_G1_JAC_BYTES, cudaMemcpyDeviceToHost, c->stream));
+    SCZ_CUDA(c, cudaStreamSynchronize(c->stream));
+    return SCZ_OK;
+}
+
+}   // extern "C"

@@ -1,0 +1,452 @@
+// Prime-field arithmetic for BLS12-381 Fr (8 x u32) and Fq (12 x u32) on sm_100a.
+//
+// Elements live in HBM exactly as arkworks keeps them in host memory
+// (ark-ff 0.4.2 Fp<MontBackend>: little-endian u64 limbs, Montgomery form,
+// R = 2^256 / 2^384), so a `&[Fr]` / coordinate array from the reference's Rust
+// side is consumed zero-copy.  Inside a thread an element is N 32-bit limbs in
+// registers.
+//
+// The multiplier is a CIOS Montgomery product on split even/odd accumulator
+// columns: every (mad.lo.cc, madc.hi.cc) pair lands on an aligned register pair
+// so ptxas emits one IMAD.WIDE.U32(.X) per 32x32 partial product and the carry
+// chains never need a separate propagate pass.  The kernels on this path are
+// bound by that integer pipe, not by HBM.
+//
+// Every carry-chain primitive has a host emulation behind `#ifndef
+// __CUDA_ARCH__` so tests/emu can check the limb logic on the CPU box that has
+// no GPU; the product library only ever runs the device side.
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define SCZ_HD __host__ __device__ __forceinline__
+#define SCZ_D __device__ __forceinline__
+#else
+#define SCZ_HD inline
+#define SCZ_D inline
+#endif
+
+namespace scz {
+
+// carry flag: lives in CC.CF on the device, in this struct on the host
+struct CF {
+    uint32_t v;
+};
+
+SCZ_HD uint32_t add_cc(CF &c, uint32_t a, uint32_t b) {
+#ifdef __CUDA_ARCH__
+    uint32_t r;
+    asm volatile("add.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+    return r;
+#else
+    uint64_t t = (uint64_t)a + b;
+    c.v = (uint32_t)(t >> 32);
+    return (uint32_t)t;
+#endif
+}
+SCZ_HD uint32_t addc_cc(CF &c, uint32_t a, uint32_t b) {
+#ifdef __CUDA_ARCH__
+    uint32_t r;
+    asm volatile("addc.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+    return r;
+#else
+    uint64_t t = (uint64_t)a + b + c.v;
+    c.v = (uint32_t)(t >> 32);
+    return (uint32_t)t;
+#endif
+}
+SCZ_HD uint32_t addc(CF &c, uint32_t a, uint32_t b) {
+#ifdef __CUDA_ARCH__
+    uint32_t r;
+    asm volatile("addc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+    return r;
+#else
+    return a + b + c.v;
+#endif
+}
+SCZ_HD uint32_t sub_cc(CF &c, uint32_t a, uint32_t b) {
+#ifdef __CUDA_ARCH__
+    uint32_t r;
+    asm volatile("sub.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+    return r;
+#else
+    uint64_t t = (uint64_t)a - b;
+    c.v = (uint32_t)(t >> 63);   // borrow
+    return (uint32_t)t;
+#endif
+}
+SCZ_HD uint32_t subc_cc(CF &c, uint32_t a, uint32_t b) {
+#ifdef __CUDA_ARCH__
+    uint32_t r;
+    asm volatile("subc.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+    return r;
+#else
+    uint64_t t = (uint64_t)a - b - c.v;
+    c.v = (uint32_t)(t >> 63);
+    return (uint32_t)t;
+#endif
+}
+// 0 - borrow  -> 0xffffffff when the chain borrowed, else 0
+SCZ_HD uint32_t borrow_mask(CF &c) {
+#ifdef __CUDA_ARCH__
+    uint32_t r;
+    asm volatile("subc.u32 %0, 0, 0;" : "=r"(r));
+    return r;
+#else
+    return 0u - c.v;
+#endif
+}
+SCZ_HD uint32_t mul_lo(uint32_t a, uint32_t b) { return a * b; }
+SCZ_HD uint32_t mul_hi(uint32_t a, uint32_t b) {
+#ifdef __CUDA_ARCH__
+    return __umulhi(a, b);
+#else
+    return (uint32_t)(((uint64_t)a * b) >> 32);
+#endif
+}
+SCZ_HD uint32_t mad_lo_cc(CF &c, uint32_t a, uint32_t b, uint32_t d) {
+#ifdef __CUDA_ARCH__
+    uint32_t r;
+    asm volatile("mad.lo.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(d));
+    return r;
+#else
+    uint64_t t = (uint64_t)(uint32_t)(a * b) + d;
+    c.v = (uint32_t)(t >> 32);
+    return (uint32_t)t;
+#endif
+}
+SCZ_HD uint32_t madc_lo_cc(CF &c, uint32_t a, uint32_t b, uint32_t d) {
+#ifdef __CUDA_ARCH__
+    uint32_t r;
+    asm volatile("madc.lo.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(d));
+    return r;
+#else
+    uint64_t t = (uint64_t)(uint32_t)(a * b) + d + c.v;
+    c.v = (uint32_t)(t >> 32);
+    return (uint32_t)t;
+#endif
+}
+SCZ_HD uint32_t madc_hi_cc(CF &c, uint32_t a, uint32_t b, uint32_t d) {
+#ifdef __CUDA_ARCH__
+    uint32_t r;
+    asm volatile("madc.hi.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(d));
+    return r;
+#else
+    uint64_t t = (((uint64_t)a * b) >> 32) + d + c.v;
+    c.v = (uint32_t)(t >> 32);
+    return (uint32_t)t;
+#endif
+}
+SCZ_HD uint32_t madc_hi(CF &c, uint32_t a, uint32_t b, uint32_t d) {
+#ifdef __CUDA_ARCH__
+    uint32_t r;
+    asm volatile("madc.hi.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(d));
+    return r;
+#else
+    return (uint32_t)(((uint64_t)a * b) >> 32) + d + c.v;
+#endif
+}
+
+// ---------------------------------------------------------------- field parameters
+// BLS12-381 scalar field r (ark-bls12-381 0.4.0 Fr), 8 x u32 little endian
+struct FrP {
+    static constexpr int N = 8;
+    static constexpr uint32_t INV = 0xffffffffu;   // -r^{-1} mod 2^32
+    SCZ_HD static constexpr uint32_t mod(int i) {
+        constexpr uint32_t M[8] = {0x00000001u, 0xffffffffu, 0xfffe5bfeu, 0x53bda402u,
+                                   0x09a1d805u, 0x3339d808u, 0x299d7d48u, 0x73eda753u};
+        return M[i];
+    }
+    SCZ_HD static constexpr uint32_t one(int i) {   // R mod r
+        constexpr uint32_t M[8] = {0xfffffffeu, 0x00000001u, 0x00034802u, 0x5884b7fau,
+                                   0xecbc4ff5u, 0x998c4fefu, 0xacc5056fu, 0x1824b159u};
+        return M[i];
+    }
+    SCZ_HD static constexpr uint32_t r2(int i) {    // R^2 mod r
+        constexpr uint32_t M[8] = {0xf3f29c6du, 0xc999e990u, 0x87925c23u, 0x2b6cedcbu,
+                                   0x7254398fu, 0x05d31496u, 0x9f59ff11u, 0x0748d9d9u};
+        return M[i];
+    }
+};
+// BLS12-381 base field p, 12 x u32
+struct FqP {
+    static constexpr int N = 12;
+    static constexpr uint32_t INV = 0xfffcfffdu;   // -p^{-1} mod 2^32
+    SCZ_HD static constexpr uint32_t mod(int i) {
+        constexpr uint32_t M[12] = {0xffffaaabu, 0xb9feffffu, 0xb153ffffu, 0x1eabfffeu, 0xf6b0f624u, 0x6730d2a0u,
+                                    0xf38512bfu, 0x64774b84u, 0x434bacd7u, 0x4b1ba7b6u, 0x397fe69au, 0x1a0111eau};
+        return M[i];
+    }
+    SCZ_HD static constexpr uint32_t one(int i) {   // R mod p
+        constexpr uint32_t M[12] = {0x0002fffdu, 0x76090000u, 0xc40c0002u, 0xebf4000bu, 0x53c758bau, 0x5f489857u,
+                                    0x70525745u, 0x77ce5853u, 0xa256ec6du, 0x5c071a97u, 0xfa80e493u, 0x15f65ec3u};
+        return M[i];
+    }
+    SCZ_HD static constexpr uint32_t r2(int i) {    // R^2 mod p
+        constexpr uint32_t M[12] = {0x1c341746u, 0xf4df1f34u, 0x09d104f1u, 0x0a76e6a6u, 0x4c95b6d5u, 0x8de5476cu,
+                                    0x939d83c0u, 0x67eb88a9u, 0xb519952du, 0x9a793e85u, 0x92cae3aau, 0x11988fe5u};
+        return M[i];
+    }
+};
+
+// ---------------------------------------------------------------- element type
+template <class P>
+struct Fp {
+    static constexpr int N = P::N;
+    uint32_t l[N];
+
+    SCZ_HD static Fp zero() {
+        Fp r;
+#pragma unroll
+        for (int i = 0; i < N; i++) r.l[i] = 0;
+        return r;
+    }
+    SCZ_HD static Fp one() {
+        Fp r;
+#pragma unroll
+        for (int i = 0; i < N; i++) r.l[i] = P::one(i);
+        return r;
+    }
+    SCZ_HD static Fp rsquared() {
+        Fp r;
+#pragma unroll
+        for (int i = 0; i < N; i++) r.l[i] = P::r2(i);
+        return r;
+    }
+    SCZ_HD bool is_zero() const {
+        uint32_t acc = 0;
+#pragma unroll
+        for (int i = 0; i < N; i++) acc |= l[i];
+        return acc == 0;
+    }
+    SCZ_HD bool operator==(const Fp &o) const {
+        uint32_t acc = 0;
+#pragma unroll
+        for (int i = 0; i < N; i++) acc |= l[i] ^ o.l[i];
+        return acc == 0;
+    }
+    SCZ_HD bool operator!=(const Fp &o) const { return !(*this == o); }
+};
+
+// r = a - p if a >= p  (a < 2p)
+template <class P>
+SCZ_HD void fp_final_sub(Fp<P> &a) {
+    constexpr int N = P::N;
+    CF c{0};
+    uint32_t t[N];
+    t[0] = sub_cc(c, a.l[0], P::mod(0));
+#pragma unroll
+    for (int i = 1; i < N; i++) t[i] = subc_cc(c, a.l[i], P::mod(i));
+    uint32_t borrow = borrow_mask(c);   // all-ones when a < p
+#pragma unroll
+    for (int i = 0; i < N; i++) a.l[i] = borrow ? a.l[i] : t[i];
+}
+
+template <class P>
+SCZ_HD Fp<P> fp_add(const Fp<P> &a, const Fp<P> &b) {
+    constexpr int N = P::N;
+    Fp<P> r;
+    CF c{0};
+    r.l[0] = add_cc(c, a.l[0], b.l[0]);
+#pragma unroll
+    for (int i = 1; i < N - 1; i++) r.l[i] = addc_cc(c, a.l[i], b.l[i]);
+    r.l[N - 1] = addc(c, a.l[N - 1], b.l[N - 1]);   // p < 2^(32N-1): no carry out
+    fp_final_sub(r);
+    return r;
+}
+template <class P>
+SCZ_HD Fp<P> fp_sub(const Fp<P> &a, const Fp<P> &b) {
+    constexpr int N = P::N;
+    Fp<P> r;
+    CF c{0};
+    r.l[0] = sub_cc(c, a.l[0], b.l[0]);
+#pragma unroll
+    for (int i = 1; i < N; i++) r.l[i] = subc_cc(c, a.l[i], b.l[i]);
+    uint32_t m = borrow_mask(c);
+    r.l[0] = add_cc(c, r.l[0], P::mod(0) & m);
+#pragma unroll
+    for (int i = 1; i < N - 1; i++) r.l[i] = addc_cc(c, r.l[i], P::mod(i) & m);
+    r.l[N - 1] = addc(c, r.l[N - 1], P::mod(N - 1) & m);
+    return r;
+}
+template <class P>
+SCZ_HD Fp<P> fp_neg(const Fp<P> &a) {
+    return fp_sub(Fp<P>::zero(), a);
+}
+template <class P>
+SCZ_HD Fp<P> fp_dbl(const Fp<P> &a) {
+    return fp_add(a, a);
+}
+
+// ---------------------------------------------------------------- Montgomery product
+namespace detail {
+template <int N>
+SCZ_HD void mul_n(uint32_t *acc, const uint32_t *a, uint32_t bi) {
+#pragma unroll
+    for (int j = 0; j < N; j += 2) {
+        acc[j] = mul_lo(a[j], bi);
+        acc[j + 1] = mul_hi(a[j], bi);
+    }
+}
+// acc[j],acc[j+1] += a[j]*bi over even j; leaves the carry out in CF
+template <int N>
+SCZ_HD void cmad_n(CF &c, uint32_t *acc, const uint32_t *a, uint32_t bi) {
+    acc[0] = mad_lo_cc(c, a[0], bi, acc[0]);
+    acc[1] = madc_hi_cc(c, a[0], bi, acc[1]);
+#pragma unroll
+    for (int j = 2; j < N; j += 2) {
+        acc[j] = madc_lo_cc(c, a[j], bi, acc[j]);
+        acc[j + 1] = madc_hi_cc(c, a[j], bi, acc[j + 1]);
+    }
+}
+// odd[j],odd[j+1] = a[j]*bi + odd[j+2],odd[j+3] + carry-in   (shift right by two limbs while accumulating)
+template <int N>
+SCZ_HD void madc_n_rshift(CF &c, uint32_t *odd, const uint32_t *a, uint32_t bi) {
+#pragma unroll
+    for (int j = 0; j < N - 2; j += 2) {
+        odd[j] = madc_lo_cc(c, a[j], bi, odd[j + 2]);
+        odd[j + 1] = madc_hi_cc(c, a[j], bi, odd[j + 3]);
+    }
+    odd[N - 2] = madc_lo_cc(c, a[N - 2], bi, 0);
+    odd[N - 1] = madc_hi(c, a[N - 2], bi, 0);
+}
+// same as cmad_n but the multiplicand is the (compile-time) modulus, offset `off` in {0,1}
+template <class P, int off>
+SCZ_HD void cmad_mod(CF &c, uint32_t *acc, uint32_t mi) {
+    constexpr int N = P::N;
+    acc[0] = mad_lo_cc(c, P::mod(off), mi, acc[0]);
+    acc[1] = madc_hi_cc(c, P::mod(off), mi, acc[1]);
+#pragma unroll
+    for (int j = 2; j < N; j += 2) {
+        acc[j] = madc_lo_cc(c, P::mod(j + off), mi, acc[j]);
+        acc[j + 1] = madc_hi_cc(c, P::mod(j + off), mi, acc[j + 1]);
+    }
+}
+template <class P>
+SCZ_HD void mad_n_redc(uint32_t *even, uint32_t *odd, const uint32_t *a, uint32_t bi, bool first) {
+    constexpr int N = P::N;
+    CF c{0};
+    if (first) {
+        mul_n<N>(odd, a + 1, bi);
+        mul_n<N>(even, a, bi);
+    } else {
+        even[0] = add_cc(c, even[0], odd[1]);
+        madc_n_rshift<N>(c, odd, a + 1, bi);
+        cmad_n<N>(c, even, a, bi);
+        odd[N - 1] = addc(c, odd[N - 1], 0);
+    }
+    uint32_t mi = even[0] * P::INV;
+    cmad_mod<P, 1>(c, odd, mi);
+    cmad_mod<P, 0>(c, even, mi);
+    odd[N - 1] = addc(c, odd[N - 1], 0);
+}
+}   // namespace detail
+
+template <class P>
+SCZ_HD Fp<P> fp_mul(const Fp<P> &a, const Fp<P> &b) {
+    constexpr int N = P::N;
+    uint32_t even[N], odd[N];
+#pragma unroll
+    for (int i = 0; i < N; i += 2) {
+        detail::mad_n_redc<P>(even, odd, a.l, b.l[i], i == 0);
+        detail::mad_n_redc<P>(odd, even, a.l, b.l[i + 1], false);
+    }
+    Fp<P> r;
+    CF c{0};
+    r.l[0] = add_cc(c, even[0], odd[1]);
+#pragma unroll
+    for (int i = 1; i < N - 1; i++) r.l[i] = addc_cc(c, even[i], odd[i + 1]);
+    r.l[N - 1] = addc(c, even[N - 1], 0);
+    fp_final_sub(r);
+    return r;
+}
+template <class P>
+SCZ_HD Fp<P> fp_sqr(const Fp<P> &a) {
+    return fp_mul(a, a);
+}
+// Montgomery form -> canonical integer (ark-ff into_bigint)
+template <class P>
+SCZ_HD Fp<P> fp_to_canon(const Fp<P> &a) {
+    Fp<P> one = Fp<P>::zero();
+    one.l[0] = 1;
+    return fp_mul(a, one);
+}
+template <class P>
+SCZ_HD Fp<P> fp_from_canon(const Fp<P> &a) {
+    return fp_mul(a, Fp<P>::rsquared());
+}
+// a^e for a public exponent given as canonical 32-bit limbs (square-and-multiply, MSB first)
+template <class P, int EL>
+SCZ_HD Fp<P> fp_pow(const Fp<P> &a, const uint32_t (&e)[EL]) {
+    Fp<P> acc = Fp<P>::one();
+    for (int i = EL * 32 - 1; i >= 0; i--) {
+        acc = fp_sqr(acc);
+        if ((e[i >> 5] >> (i & 31)) & 1) acc = fp_mul(acc, a);
+    }
+    return acc;
+}
+// Fermat inverse a^(p-2); 0 -> 0
+template <class P>
+SCZ_HD Fp<P> fp_inv(const Fp<P> &a) {
+    constexpr int N = P::N;
+    uint32_t e[N];
+    uint32_t borrow = 2;   // e = p - 2 with borrow propagation (r ends in ...00000001)
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+        uint32_t m = P::mod(i);
+        e[i] = m - borrow;
+        borrow = m < borrow ? 1u : 0u;
+    }
+    Fp<P> acc = Fp<P>::one();
+    for (int i = N * 32 - 1; i >= 0; i--) {
+        acc = fp_sqr(acc);
+        if ((e[i >> 5] >> (i & 31)) & 1) acc = fp_mul(acc, a);
+    }
+    return acc;
+}
+
+using Fr = Fp<FrP>;
+using Fq = Fp<FqP>;
+
+// ---------------------------------------------------------------- HBM access (128-bit loads/stores)
+#if defined(__CUDACC__)
+template <class P>
+SCZ_D Fp<P> fp_load(const void *base, size_t idx) {
+    constexpr int N = P::N;
+    const uint4 *p = reinterpret_cast<const uint4 *>(reinterpret_cast<const char *>(base) + idx * (N * 4));
+    Fp<P> r;
+#pragma unroll
+    for (int i = 0; i < N / 4; i++) {
+        uint4 v = __ldg(p + i);
+        r.l[4 * i] = v.x;
+        r.l[4 * i + 1] = v.y;
+        r.l[4 * i + 2] = v.z;
+        r.l[4 * i + 3] = v.w;
+    }
+    return r;
+}
+template <class P>
+SCZ_D Fp<P> fp_load_rw(const void *base, size_t idx) {   // plain (coherent) load for buffers written in-kernel
+    constexpr int N = P::N;
+    const uint4 *p = reinterpret_cast<const uint4 *>(reinterpret_cast<const char *>(base) + idx * (N * 4));
+    Fp<P> r;
+#pragma unroll
+    for (int i = 0; i < N / 4; i++) {
+        uint4 v = p[i];
+        r.l[4 * i] = v.x;
+        r.l[4 * i + 1] = v.y;
+        r.l[4 * i + 2] = v.z;
+        r.l[4 * i + 3] = v.w;
+    }
+    return r;
+}
+template <class P>
+SCZ_D void fp_store(void *base, size_t idx, const Fp<P> &a) {
+    constexpr int N = P::N;
+    uint4 *p = reinterpret_cast<uint4 *>(reinterpret_cast<char *>(base) + idx * (N * 4));
+#pragma unroll
+    for (int i = 0; i < N / 4; i++) p[i] = make_uint4(a.l[4 * i], a.l[4 * i + 1], a.l[4 * i + 2], a.l[4 * i + 3]);
+}
+#endif
+
+}   // namespace scz

@@ -1,0 +1,227 @@
+// BLS12-381 G1 group law for the MSM / PSS kernels (sm_100a).
+//
+// Bases arrive as packed affine (x | y), 96 B per point, Montgomery coordinates
+// (the reference's `G::Affine`, dist-primitive/src/dmsm.rs:10, with the
+// `infinity` flag folded into the otherwise impossible encoding x = y = 0).
+// Accumulators are extended Jacobian "XYZZ" (X, Y, ZZ, ZZZ) with x = X/ZZ,
+// y = Y/ZZZ, ZZ^3 = ZZZ^2: a mixed add costs 8M + 2S, and no inversion is
+// ever needed on the device.  Results leave as Jacobian (X, Y, Z), the layout
+// of ark-ec's `Projective` (what `d_msm` returns, dmsm.rs:15).
+//
+// Every exceptional case is handled (identity operands, P + P, P + (-P)): the
+// reference's own d_msm test feeds 256 copies of one point with all-one scalars
+// (dmsm.rs:97-104), which drives every addition of a bucket through them.
+#pragma once
+#include "field.cuh"
+
+namespace scz {
+
+struct G1Affine {   // 96 B in HBM
+    Fq x, y;
+    SCZ_HD bool is_inf() const { return x.is_zero() && y.is_zero(); }
+};
+struct G1Jac {      // 144 B in HBM, ark-ec Projective
+    Fq x, y, z;
+};
+struct G1X {        // XYZZ
+    Fq x, y, zz, zzz;
+    SCZ_HD bool is_inf() const { return zz.is_zero(); }
+    SCZ_HD static G1X inf() {
+        G1X r;
+        r.x = Fq::zero();
+        r.y = Fq::zero();
+        r.zz = Fq::zero();
+        r.zzz = Fq::zero();
+        return r;
+    }
+};
+
+SCZ_HD G1X g1x_from_affine(const G1Affine &p) {
+    if (p.is_inf()) return G1X::inf();
+    G1X r;
+    r.x = p.x;
+    r.y = p.y;
+    r.zz = Fq::one();
+    r.zzz = Fq::one();
+    return r;
+}
+SCZ_HD G1X g1x_from_jac(const G1Jac &p) {
+    if (p.z.is_zero()) return G1X::inf();
+    G1X r;
+    r.x = p.x;
+    r.y = p.y;
+    r.zz = fp_sqr(p.z);
+    r.zzz = fp_mul(r.zz, p.z);
+    return r;
+}
+// (X, Y, ZZ, ZZZ) -> Jacobian with Z = ZZZ: x = X*ZZ^2 / ZZZ^2 (ZZ^3 = ZZZ^2), y = Y*ZZZ^2 / ZZZ^3
+SCZ_HD G1Jac g1x_to_jac(const G1X &p) {
+    G1Jac r;
+    if (p.is_inf()) {   // ark-ec's identity: (1, 1, 0)
+        r.x = Fq::one();
+        r.y = Fq::one();
+        r.z = Fq::zero();
+        return r;
+    }
+    Fq zz2 = fp_sqr(p.zz);
+    Fq zzz2 = fp_sqr(p.zzz);
+    r.x = fp_mul(p.x, zz2);
+    r.y = fp_mul(p.y, zzz2);
+    r.z = p.zzz;
+    return r;
+}
+SCZ_HD G1X g1x_neg(const G1X &p) {
+    G1X r = p;
+    r.y = fp_neg(p.y);
+    return r;
+}
+// dbl-2008-s-1 (a = 0)
+SCZ_HD G1X g1x_double(const G1X &p) {
+    if (p.is_inf()) return p;
+    Fq u = fp_dbl(p.y);
+    Fq v = fp_sqr(u);
+    Fq w = fp_mul(u, v);
+    Fq s = fp_mul(p.x, v);
+    Fq xx = fp_sqr(p.x);
+    Fq m = fp_add(fp_dbl(xx), xx);
+    G1X r;
+    r.x = fp_sub(fp_sub(fp_sqr(m), s), s);
+    r.y = fp_sub(fp_mul(m, fp_sub(s, r.x)), fp_mul(w, p.y));
+    r.zz = fp_mul(v, p.zz);
+    r.zzz = fp_mul(w, p.zzz);
+    return r;
+}
+// mdbl-2008-s-1: double an affine point
+SCZ_HD G1X g1x_double_affine(const Fq &x, const Fq &y) {
+    Fq u = fp_dbl(y);
+    Fq v = fp_sqr(u);
+    Fq w = fp_mul(u, v);
+    Fq s = fp_mul(x, v);
+    Fq xx = fp_sqr(x);
+    Fq m = fp_add(fp_dbl(xx), xx);
+    G1X r;
+    r.x = fp_sub(fp_sub(fp_sqr(m), s), s);
+    r.y = fp_sub(fp_mul(m, fp_sub(s, r.x)), fp_mul(w, y));
+    r.zz = v;
+    r.zzz = w;
+    return r;
+}
+// madd-2008-s: acc += (x2, y2) affine, not infinity
+SCZ_HD void g1x_add_affine(G1X &acc, const Fq &x2, const Fq &y2) {
+    if (acc.is_inf()) {
+        acc.x = x2;
+        acc.y = y2;
+        acc.zz = Fq::one();
+        acc.zzz = Fq::one();
+        return;
+    }
+    Fq u2 = fp_mul(x2, acc.zz);
+    Fq s2 = fp_mul(y2, acc.zzz);
+    Fq p = fp_sub(u2, acc.x);
+    Fq r = fp_sub(s2, acc.y);
+    if (p.is_zero()) {
+        if (r.is_zero()) acc = g1x_double_affine(x2, y2);
+        else acc = G1X::inf();
+        return;
+    }
+    Fq pp = fp_sqr(p);
+    Fq ppp = fp_mul(p, pp);
+    Fq q = fp_mul(acc.x, pp);
+    Fq x3 = fp_sub(fp_sub(fp_sub(fp_sqr(r), ppp), q), q);
+    Fq y3 = fp_sub(fp_mul(r, fp_sub(q, x3)), fp_mul(acc.y, ppp));
+    acc.x = x3;
+    acc.y = y3;
+    acc.zz = fp_mul(acc.zz, pp);
+    acc.zzz = fp_mul(acc.zzz, ppp);
+}
+SCZ_HD void g1x_add_affine(G1X &acc, const G1Affine &p, bool negate) {
+    if (p.is_inf()) return;
+    Fq y = negate ? fp_neg(p.y) : p.y;
+    g1x_add_affine(acc, p.x, y);
+}
+// add-2008-s
+SCZ_HD G1X g1x_add(const G1X &a, const G1X &b) {
+    if (a.is_inf()) return b;
+    if (b.is_inf()) return a;
+    Fq u1 = fp_mul(a.x, b.zz);
+    Fq u2 = fp_mul(b.x, a.zz);
+    Fq s1 = fp_mul(a.y, b.zzz);
+    Fq s2 = fp_mul(b.y, a.zzz);
+    Fq p = fp_sub(u2, u1);
+    Fq r = fp_sub(s2, s1);
+    if (p.is_zero()) {
+        if (r.is_zero()) return g1x_double(a);
+        return G1X::inf();
+    }
+    Fq pp = fp_sqr(p);
+    Fq ppp = fp_mul(p, pp);
+    Fq q = fp_mul(u1, pp);
+    G1X o;
+    o.x = fp_sub(fp_sub(fp_sub(fp_sqr(r), ppp), q), q);
+    o.y = fp_sub(fp_mul(r, fp_sub(q, o.x)), fp_mul(s1, ppp));
+    o.zz = fp_mul(fp_mul(a.zz, b.zz), pp);
+    o.zzz = fp_mul(fp_mul(a.zzz, b.zzz), ppp);
+    return o;
+}
+// k * P, k = canonical little-endian 32-bit limbs (double-and-add, MSB first)
+template <int KL>
+SCZ_HD G1X g1x_mul_bits(const G1X &p, const uint32_t (&k)[KL]) {
+    G1X acc = G1X::inf();
+    for (int i = KL * 32 - 1; i >= 0; i--) {
+        acc = g1x_double(acc);
+        if ((k[i >> 5] >> (i & 31)) & 1) acc = g1x_add(acc, p);
+    }
+    return acc;
+}
+// k in Montgomery form
+SCZ_HD G1X g1x_mul_fr(const G1X &p, const Fr &k) {
+    Fr c = fp_to_canon(k);
+    return g1x_mul_bits(p, c.l);
+}
+
+#if defined(__CUDACC__)
+SCZ_D G1Affine g1a_load(const void *base, size_t idx) {
+    G1Affine p;
+    const char *b = reinterpret_cast<const char *>(base) + idx * 96;
+    p.x = fp_load<FqP>(b, 0);
+    p.y = fp_load<FqP>(b, 1);
+    return p;
+}
+SCZ_D void g1a_store(void *base, size_t idx, const G1Affine &p) {
+    char *b = reinterpret_cast<char *>(base) + idx * 96;
+    fp_store<FqP>(b, 0, p.x);
+    fp_store<FqP>(b, 1, p.y);
+}
+SCZ_D G1Jac g1j_load(const void *base, size_t idx) {
+    G1Jac p;
+    const char *b = reinterpret_cast<const char *>(base) + idx * 144;
+    p.x = fp_load_rw<FqP>(b, 0);
+    p.y = fp_load_rw<FqP>(b, 1);
+    p.z = fp_load_rw<FqP>(b, 2);
+    return p;
+}
+SCZ_D void g1j_store(void *base, size_t idx, const G1Jac &p) {
+    char *b = reinterpret_cast<char *>(base) + idx * 144;
+    fp_store<FqP>(b, 0, p.x);
+    fp_store<FqP>(b, 1, p.y);
+    fp_store<FqP>(b, 2, p.z);
+}
+SCZ_D G1X g1x_load(const void *base, size_t idx) {
+    G1X p;
+    const char *b = reinterpret_cast<const char *>(base) + idx * 192;
+    p.x = fp_load_rw<FqP>(b, 0);
+    p.y = fp_load_rw<FqP>(b, 1);
+    p.zz = fp_load_rw<FqP>(b, 2);
+    p.zzz = fp_load_rw<FqP>(b, 3);
+    return p;
+}
+SCZ_D void g1x_store(void *base, size_t idx, const G1X &p) {
+    char *b = reinterpret_cast<char *>(base) + idx * 192;
+    fp_store<FqP>(b, 0, p.x);
+    fp_store<FqP>(b, 1, p.y);
+    fp_store<FqP>(b, 2, p.zz);
+    fp_store<FqP>(b, 3, p.zzz);
+}
+#endif
+
+}   // namespace scz

@@ -1,0 +1,32 @@
+// Batched Pippenger MSM over BLS12-381 G1 (internal interface).
+#pragma once
+#include <stddef.h>
+#include <stdint.h>
+#include "ctx.h"
+
+namespace scz {
+
+// one MSM of a batch ("segment"); lives in device memory, read by every kernel of the pipeline
+struct MsmSeg {
+    const void *bases;     // packed affine, 96 B per point
+    const void *scalars;   // Fr Montgomery, 32 B per scalar
+    uint32_t len;
+    uint32_t point_base;   // prefix sum of len over the batch
+    uint32_t c;            // window bits
+    uint32_t W;            // windows = ceil(256 / c)
+    uint32_t nb;           // buckets per window = 2^(c-1)
+    uint32_t bucket_base;  // first global bucket of this segment (window w starts at bucket_base + w*nb)
+    uint32_t window_base;  // first global window of this segment
+    uint32_t pad_;
+};
+
+struct MsmStats {
+    uint64_t bucket_adds = 0, buckets = 0, windows = 0;
+};
+
+// d_out: batch Jacobian points (144 B each).  Asynchronous on ctx->stream.
+int32_t msm_g1_batched(Ctx *ctx, const void *const *d_bases, const void *const *d_scalars, const size_t *lens,
+                       size_t batch, void *d_out_jac);
+uint32_t msm_pick_window(size_t len);
+
+}   // namespace scz

@@ -1,0 +1,48 @@
+// The collective call-site layer of the reference, on device buffers.
+//
+// Mirrors MPCSerializeNet (dist-primitive/src/utils/serializing_net.rs):
+//   comm build  (:8-142)   -> CallbackNet: the host supplies gather / scatter /
+//                             all_gather over device memory (bench.py and the
+//                             tests plug torch.distributed + NCCL in here);
+//   no-comm build (:144-264) -> LeaderSimNet: a single party that sees N clones
+//                             of its own message and keeps element 0 of a scatter.
+// Byte counters reproduce MPCNet::get_comm in the reference's serialised sizes.
+#pragma once
+#include <stdint.h>
+#include "ctx.h"
+
+namespace scz {
+
+struct Net {
+    uint32_t n_parties = 1, party_id = 0;
+    uint64_t upload = 0, download = 0;
+    bool is_leader() const { return party_id == 0; }
+    virtual ~Net() {}
+    // d_recv: n_parties * bytes on the leader (ignored elsewhere)
+    virtual int32_t gather(Ctx *ctx, const void *d_send, void *d_recv, size_t bytes, size_t wire) = 0;
+    // d_send: n_parties * bytes on the leader; d_recv: bytes on everyone
+    virtual int32_t scatter(Ctx *ctx, const void *d_send, void *d_recv, size_t bytes, size_t wire) = 0;
+    virtual int32_t all_gather(Ctx *ctx, const void *d_send, void *d_recv, size_t bytes, size_t wire) = 0;
+    virtual int32_t sync(Ctx *ctx) = 0;
+    // true when non-leaders receive real data on scatter (false in the leader simulator: there are none)
+    virtual bool real() const = 0;
+};
+
+struct LeaderSimNet : Net {
+    int32_t gather(Ctx *ctx, const void *d_send, void *d_recv, size_t bytes, size_t wire) override;
+    int32_t scatter(Ctx *ctx, const void *d_send, void *d_recv, size_t bytes, size_t wire) override;
+    int32_t all_gather(Ctx *ctx, const void *d_send, void *d_recv, size_t bytes, size_t wire) override;
+    int32_t sync(Ctx *ctx) override;
+    bool real() const override { return false; }
+};
+
+struct CallbackNet : Net {
+    scz_net_vtable vt;
+    int32_t gather(Ctx *ctx, const void *d_send, void *d_recv, size_t bytes, size_t wire) override;
+    int32_t scatter(Ctx *ctx, const void *d_send, void *d_recv, size_t bytes, size_t wire) override;
+    int32_t all_gather(Ctx *ctx, const void *d_send, void *d_recv, size_t bytes, size_t wire) override;
+    int32_t sync(Ctx *ctx) override;
+    bool real() const override { return true; }
+};
+
+}   // namespace scz

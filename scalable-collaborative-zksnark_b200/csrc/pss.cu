@@ -1,0 +1,254 @@
+// Packed secret sharing on the device: secret-sharing/src/pss.rs:38-171.
+//
+// The reference runs two radix-2 (coset) FFTs per call over a vector of n = 8l
+// elements (ark-poly Radix2EvaluationDomain).  Every one of the four maps is a
+// fixed Fr-linear map, so the FFT pair is folded ONCE, at scz_pp_new, into a small
+// matrix (built on the device, no host field code):
+//   pack_from_public  shares  = F_share * IF_secret * pad_2l(secrets)            (pss.rs:93-99)
+//   pack_single       shares  = PACK * trunc_2l(PACK * [s,0,..])                 (pss.rs:103-113)
+//   unpack            secrets = first l of F_secret  * trunc_2l(IF_share * shares) (pss.rs:132-149)
+//   unpack2           secrets = even idx < 2l of F_secret2 * trunc_4l(IF_share * shares) (pss.rs:153-171)
+// where ark-poly's fft/ifft first RESIZE the vector to the domain size (truncating
+// if longer).  All domains are subgroups of <w_n>, so one power table of w_n serves
+// every twiddle.  Applying a map is then a batched small mat-vec: one thread per
+// output element over Fr, and for G1 operands (the d_msm leader closure) one CTA
+// per output point, one scalar multiplication per thread, shared-memory tree sum.
+#include "g1.cuh"
+#include "pss.h"
+
+namespace scz {
+
+__device__ __forceinline__ Fr fr_from_u32(uint32_t v) {
+    Fr x = Fr::zero();
+    x.l[0] = v;
+    return fp_from_canon(x);
+}
+
+// tables layout (Fr each): wn[n] | gpow[4l] | ginvpow[2l] | ninv | inv2l
+__global__ void __launch_bounds__(256) k_pss_setup(uint32_t l, void *tables, void *pack, void *pack_single,
+                                                    void *unpack, void *unpack2) {
+    const uint32_t n = 8 * l, s1 = 2 * l, s2 = 4 * l;
+    Fr *wn = reinterpret_cast<Fr *>(tables);
+    Fr *gpow = wn + n, *ginvpow = gpow + s2, *consts = ginvpow + s1;
+    if (threadIdx.x == 0) {
+        // F::GENERATOR = 7; TWO_ADIC_ROOT_OF_UNITY = 7^((r-1)/2^32)  (2-adicity 32)
+        Fr g = fr_from_u32(7);
+        uint32_t e[7];
+#pragma unroll
+        for (int i = 0; i < 7; i++) e[i] = FrP::mod(i + 1);
+        Fr w = fp_pow(g, e);
+        uint32_t logn = 31 - __clz(n);
+        for (uint32_t i = 0; i < 32 - logn; i++) w = fp_sqr(w);   // get_root_of_unity(n)
+        Fr acc = Fr::one();
+        for (uint32_t k = 0; k < n; k++) {
+            wn[k] = acc;
+            acc = fp_mul(acc, w);
+        }
+        acc = Fr::one();
+        for (uint32_t i = 0; i < s2; i++) {
+            gpow[i] = acc;
+            acc = fp_mul(acc, g);
+        }
+        Fr gi = fp_inv(g);
+        acc = Fr::one();
+        for (uint32_t i = 0; i < s1; i++) {
+            ginvpow[i] = acc;
+            acc = fp_mul(acc, gi);
+        }
+        consts[0] = fp_inv(fr_from_u32(n));
+        consts[1] = fp_inv(fr_from_u32(s1));
+    }
+    __threadfence_block();
+    __syncthreads();
+    const Fr ninv = consts[0], inv2l = consts[1];
+    Fr *P = reinterpret_cast<Fr *>(pack), *PS = reinterpret_cast<Fr *>(pack_single);
+    Fr *U = reinterpret_cast<Fr *>(unpack), *U2 = reinterpret_cast<Fr *>(unpack2);
+    // PACK[j][k] = sum_{i<2l} w_n^(i j) * (2l)^-1 g^-i w_2l^(-i k),  w_2l = w_n^4
+    for (uint32_t idx = threadIdx.x; idx < n * s1; idx += blockDim.x) {
+        uint32_t j = idx / s1, k = idx % s1;
+        Fr acc = Fr::zero();
+        for (uint32_t i = 0; i < s1; i++) {
+            uint32_t e1 = (i * j) % n, e2 = (n - (4 * i * k) % n) % n;
+            acc = fp_add(acc, fp_mul(fp_mul(wn[e1], wn[e2]), ginvpow[i]));
+        }
+        P[idx] = fp_mul(acc, inv2l);
+    }
+    // UNPACK[k][j]  = sum_{i<2l} (g w_2l^k)^i * n^-1 w_n^(-i j)          (rows k < l)
+    // UNPACK2[k][j] = sum_{i<4l} (g w_4l^(2k))^i * n^-1 w_n^(-i j)       (rows 2k, k < l; w_4l = w_n^2)
+    for (uint32_t idx = threadIdx.x; idx < l * n; idx += blockDim.x) {
+        uint32_t k = idx / n, j = idx % n;
+        Fr a1 = Fr::zero(), a2 = Fr::zero();
+        for (uint32_t i = 0; i < s2; i++) {
+            uint32_t ej = (n - (i * j) % n) % n;
+            if (i < s1) a1 = fp_add(a1, fp_mul(fp_mul(gpow[i], wn[(4 * k * i) % n]), wn[ej]));
+            a2 = fp_add(a2, fp_mul(fp_mul(gpow[i], wn[(2 * (2 * k) * i) % n]), wn[ej]));
+        }
+        U[idx] = fp_mul(a1, ninv);
+        U2[idx] = fp_mul(a2, ninv);
+    }
+    __threadfence_block();
+    __syncthreads();
+    // PACK_SINGLE[j] = sum_{i<2l} PACK[j][i] * PACK[i][0]
+    for (uint32_t j = threadIdx.x; j < n; j += blockDim.x) {
+        Fr acc = Fr::zero();
+        for (uint32_t i = 0; i < s1; i++) acc = fp_add(acc, fp_mul(P[j * s1 + i], P[i * s1]));
+        PS[j] = acc;
+    }
+}
+
+// out(b, o) = sum_j M[o*mcols + j] * in(b, j)   over Fr
+__global__ void __launch_bounds__(128) k_pss_apply_fr(const void *M, uint32_t mcols, uint32_t rows, uint32_t len_in,
+                                                      const void *in, size_t in_b, size_t in_j, size_t batch,
+                                                      void *out, size_t out_b, size_t out_o) {
+    size_t idx = blockIdx.x * (size_t)128 + threadIdx.x;
+    if (idx >= batch * rows) return;
+    size_t b = idx / rows;
+    uint32_t o = (uint32_t)(idx % rows);
+    Fr acc = Fr::zero();
+    for (uint32_t j = 0; j < len_in; j++)
+        acc = fp_add(acc, fp_mul(fp_load<FrP>(M, (size_t)o * mcols + j), fp_load_rw<FrP>(in, b * in_b + j * in_j)));
+    fp_store<FrP>(out, b * out_b + o * out_o, acc);
+}
+// same over G1: one CTA per output point, thread j does M[o][j] * in(b, j); tree sum in shared memory
+template <int T>
+__global__ void __launch_bounds__(T) k_pss_apply_g1(const void *M, uint32_t mcols, uint32_t rows, uint32_t len_in,
+                                                    const void *in, size_t in_b, size_t in_j, void *out, size_t out_b,
+                                                    size_t out_o) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    G1X *sh = reinterpret_cast<G1X *>(smem_raw);
+    size_t b = blockIdx.x / rows;
+    uint32_t o = blockIdx.x % rows;
+    G1X acc = G1X::inf();
+    for (uint32_t j = threadIdx.x; j < len_in; j += T) {
+        G1X p = g1x_from_jac(g1j_load(in, b * in_b + j * in_j));
+        acc = g1x_add(acc, g1x_mul_fr(p, fp_load<FrP>(M, (size_t)o * mcols + j)));
+    }
+    sh[threadIdx.x] = acc;
+    __syncthreads();
+    for (int stride = T / 2; stride > 0; stride >>= 1) {
+        if ((int)threadIdx.x < stride) {
+            acc = g1x_add(acc, sh[threadIdx.x + stride]);
+            sh[threadIdx.x] = acc;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) g1j_store(out, b * out_b + o * out_o, g1x_to_jac(acc));
+}
+
+int32_t pss_apply(Ctx *ctx, const scz_pp *pp, PssMap map, int kind, const void *d_in, size_t len_in, size_t in_b,
+                  size_t in_j, size_t batch, void *d_out, size_t out_b, size_t out_o) {
+    if (!pp || !d_in || !d_out) return ctx->fail(SCZ_ERR_BAD_ARG, "pss: null argument");
+    if (kind != 0 && kind != 1) return ctx->fail(SCZ_ERR_BAD_ARG, "pss: kind must be 0 (Fr) or 1 (G1)");
+    if (!batch) return SCZ_OK;
+    const void *M;
+    uint32_t mcols, rows;
+    switch (map) {
+        case PSS_PACK:
+            if (len_in > 2 * pp->l) len_in = 2 * pp->l;   // ifft_in_place truncates to the secret domain
+            M = pp->d_pack, mcols = (uint32_t)(2 * pp->l), rows = (uint32_t)pp->n;
+            break;
+        case PSS_PACK_SINGLE:
+            len_in = 1;
+            M = pp->d_pack_single, mcols = 1, rows = (uint32_t)pp->n;
+            break;
+        case PSS_UNPACK:
+            len_in = pp->n;
+            M = pp->d_unpack, mcols = (uint32_t)pp->n, rows = (uint32_t)pp->l;
+            break;
+        default:
+            len_in = pp->n;
+            M = pp->d_unpack2, mcols = (uint32_t)pp->n, rows = (uint32_t)pp->l;
+            break;
+    }
+    if (kind == 0) {
+        k_pss_apply_fr<<<ceil_div_u32(batch * rows, 128), 128, 0, ctx->stream>>>(M, mcols, rows, (uint32_t)len_in, d_in,
+                                                                                 in_b, in_j, batch, d_out, out_b, out_o);
+    } else {
+        // one scalar multiplication per thread; 32 threads cover n = 8l up to l = 4 in one pass
+        k_pss_apply_g1<32><<<(uint32_t)(batch * rows), 32, 32 * sizeof(G1X), ctx->stream>>>(
+            M, mcols, rows, (uint32_t)len_in, d_in, in_b, in_j, d_out, out_b, out_o);
+    }
+    SCZ_LAUNCH_CHECK(ctx);
+    return SCZ_OK;
+}
+
+}   // namespace scz
+
+using namespace scz;
+
+extern "C" {
+
+int32_t scz_pp_new(scz_ctx *h, size_t l, scz_pp **out) {
+    if (!h || !out) return SCZ_ERR_BAD_ARG;
+    Ctx *c = &h->c;
+    *out = nullptr;
+    if (l == 0 || (l & (l - 1)) || l > 1024)   // Radix2EvaluationDomain sizes; n = 8l must divide 2^32
+        return c->fail(SCZ_ERR_NOT_POW2, "PackedSharingParams: l = %zu must be a power of two <= 1024", l);
+    scz_pp *pp = new scz_pp();
+    pp->l = l;
+    pp->n = 8 * l;
+    pp->t = l - 1;
+    pp->device = c->device;
+    size_t n = pp->n;
+    char *blk = nullptr;
+    size_t total = (n * 2 * l + n + 2 * l * n) * 32;
+    cudaError_t e = cudaMalloc(&blk, total);
+    if (e != cudaSuccess) {
+        delete pp;
+        return c->cuda(e, "cudaMalloc(pss matrices)");
+    }
+    pp->d_pack = blk;
+    pp->d_pack_single = blk + n * 2 * l * 32;
+    pp->d_unpack = blk + (n * 2 * l + n) * 32;
+    pp->d_unpack2 = blk + (n * 2 * l + n + l * n) * 32;
+    DevTmp tables(c);
+    int32_t rc = tables.alloc((n + 4 * l + 2 * l + 2) * 32);
+    if (rc == SCZ_OK) {
+        k_pss_setup<<<1, 256, 0, c->stream>>>((uint32_t)l, tables.p, pp->d_pack, pp->d_pack_single, pp->d_unpack,
+                                              pp->d_unpack2);
+        c->launches++;
+        e = cudaStreamSynchronize(c->stream);
+        if (e != cudaSuccess) rc = c->cuda(e, "k_pss_setup");
+    }
+    if (rc != SCZ_OK) {
+        cudaFree(blk);
+        delete pp;
+        return rc;
+    }
+    *out = pp;
+    return SCZ_OK;
+}
+void scz_pp_free(scz_pp *pp) {
+    if (!pp) return;
+    cudaSetDevice(pp->device);
+    cudaFree(pp->d_pack);
+    delete pp;
+}
+int32_t scz_pp_info(const scz_pp *pp, size_t *t, size_t *l, size_t *n) {
+    if (!pp) return SCZ_ERR_BAD_ARG;
+    if (t) *t = pp->t;
+    if (l) *l = pp->l;
+    if (n) *n = pp->n;
+    return SCZ_OK;
+}
+static size_t esz(int kind) { return kind == 0 ? SCZ_FR_BYTES : SCZ_G1_JAC_BYTES; }
+int32_t scz_pss_pack_from_public_dev(scz_ctx *h, const scz_pp *pp, int32_t kind, const void *in, size_t len_in,
+                                     size_t batch, void *out) {
+    if (!h || !pp) return SCZ_ERR_BAD_ARG;
+    (void)esz;
+    return pss_apply(&h->c, pp, PSS_PACK, kind, in, len_in, len_in, 1, batch, out, pp->n, 1);
+}
+int32_t scz_pss_pack_single_dev(scz_ctx *h, const scz_pp *pp, int32_t kind, const void *in, size_t batch, void *out) {
+    if (!h || !pp) return SCZ_ERR_BAD_ARG;
+    return pss_apply(&h->c, pp, PSS_PACK_SINGLE, kind, in, 1, 1, 1, batch, out, pp->n, 1);
+}
+int32_t scz_pss_unpack_dev(scz_ctx *h, const scz_pp *pp, int32_t kind, const void *in, size_t batch, void *out) {
+    if (!h || !pp) return SCZ_ERR_BAD_ARG;
+    return pss_apply(&h->c, pp, PSS_UNPACK, kind, in, pp->n, pp->n, 1, batch, out, pp->l, 1);
+}
+int32_t scz_pss_unpack2_dev(scz_ctx *h, const scz_pp *pp, int32_t kind, const void *in, size_t batch, void *out) {
+    if (!h || !pp) return SCZ_ERR_BAD_ARG;
+    return pss_apply(&h->c, pp, PSS_UNPACK2, kind, in, pp->n, pp->n, 1, batch, out, pp->l, 1);
+}
+
+}   // extern "C"

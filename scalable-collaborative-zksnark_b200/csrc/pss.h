@@ -1,0 +1,26 @@
+// Packed secret sharing maps on the device (internal interface).
+#pragma once
+#include "ctx.h"
+
+struct scz_pp {
+    size_t t, l, n;       // secret-sharing/src/pss.rs:38-41
+    int device;
+    // device-resident matrices of Fr (Montgomery), row-major
+    void *d_pack;         // n x 2l : shares = PACK * (secrets zero-padded to 2l)
+    void *d_pack_single;  // n      : pack_single(s)[j] = PS[j] * s
+    void *d_unpack;       // l x n
+    void *d_unpack2;      // l x n
+};
+
+namespace scz {
+
+enum PssMap { PSS_PACK = 0, PSS_PACK_SINGLE = 1, PSS_UNPACK = 2, PSS_UNPACK2 = 3 };
+
+// Applies one of the four linear maps to `batch` vectors.
+// Element (b, j) of the input sits at element index b*in_bstride + j*in_jstride,
+// output (b, o) at b*out_bstride + o*out_ostride, so the gather / scatter layouts
+// of the leader closures (party-major) are consumed without a transpose pass.
+int32_t pss_apply(Ctx *ctx, const scz_pp *pp, PssMap map, int kind, const void *d_in, size_t len_in, size_t in_bstride,
+                  size_t in_jstride, size_t batch, void *d_out, size_t out_bstride, size_t out_ostride);
+
+}   // namespace scz

@@ -1,0 +1,77 @@
+// TEST-ONLY host build of the device arithmetic headers (csrc/field.cuh, g1.cuh,
+// msm_digits.cuh).  The authoring container has no GPU, so the limb logic that the
+// CUDA kernels inline is compiled here with g++ (carry-chain primitives fall back
+// to their host emulation) and compared with the oracle by tests/test_emu_arith.py.
+// This file is NEVER linked into libscz.so: the product has no CPU path.
+#include <cstring>
+#include "../../scalable-collaborative-zksnark_b200/csrc/field.cuh"
+#include "../../scalable-collaborative-zksnark_b200/csrc/g1.cuh"
+#include "../../scalable-collaborative-zksnark_b200/csrc/msm_digits.cuh"
+using namespace scz;
+
+template <class P> static Fp<P> ld(const uint32_t *p, size_t i) {
+    Fp<P> r;
+    memcpy(r.l, p + i * P::N, sizeof r.l);
+    return r;
+}
+template <class P> static void st(uint32_t *p, size_t i, const Fp<P> &v) { memcpy(p + i * P::N, v.l, sizeof v.l); }
+
+#define VEC2(name, P, op)                                                                  \
+    extern "C" void name(const uint32_t *a, const uint32_t *b, uint32_t *r, size_t n) {   \
+        for (size_t i = 0; i < n; i++) st<P>(r, i, op(ld<P>(a, i), ld<P>(b, i)));         \
+    }
+VEC2(emu_fr_mul, FrP, fp_mul)
+VEC2(emu_fr_add, FrP, fp_add)
+VEC2(emu_fr_sub, FrP, fp_sub)
+VEC2(emu_fq_mul, FqP, fp_mul)
+VEC2(emu_fq_add, FqP, fp_add)
+VEC2(emu_fq_sub, FqP, fp_sub)
+extern "C" void emu_fr_inv(const uint32_t *a, uint32_t *r, size_t n) {
+    for (size_t i = 0; i < n; i++) st<FrP>(r, i, fp_inv(ld<FrP>(a, i)));
+}
+extern "C" void emu_fr_canon(const uint32_t *a, uint32_t *r, size_t n, int to) {
+    for (size_t i = 0; i < n; i++) st<FrP>(r, i, to ? fp_to_canon(ld<FrP>(a, i)) : fp_from_canon(ld<FrP>(a, i)));
+}
+static G1Jac ldj(const uint32_t *p, size_t i) {
+    G1Jac r;
+    r.x = ld<FqP>(p, 3 * i);
+    r.y = ld<FqP>(p, 3 * i + 1);
+    r.z = ld<FqP>(p, 3 * i + 2);
+    return r;
+}
+static void stj(uint32_t *p, size_t i, const G1Jac &v) {
+    st<FqP>(p, 3 * i, v.x);
+    st<FqP>(p, 3 * i + 1, v.y);
+    st<FqP>(p, 3 * i + 2, v.z);
+}
+// acc (Jacobian) += affine (x|y, 24 words; all-zero = infinity), optionally negated
+extern "C" void emu_g1_add_affine(const uint32_t *acc, const uint32_t *aff, const uint8_t *neg, uint32_t *out, size_t n) {
+    for (size_t i = 0; i < n; i++) {
+        G1X a = g1x_from_jac(ldj(acc, i));
+        G1Affine p;
+        p.x = ld<FqP>(aff, 2 * i);
+        p.y = ld<FqP>(aff, 2 * i + 1);
+        g1x_add_affine(a, p, neg[i] != 0);
+        stj(out, i, g1x_to_jac(a));
+    }
+}
+extern "C" void emu_g1_add(const uint32_t *a, const uint32_t *b, uint32_t *out, size_t n) {
+    for (size_t i = 0; i < n; i++) stj(out, i, g1x_to_jac(g1x_add(g1x_from_jac(ldj(a, i)), g1x_from_jac(ldj(b, i)))));
+}
+extern "C" void emu_g1_double(const uint32_t *a, uint32_t *out, size_t n) {
+    for (size_t i = 0; i < n; i++) stj(out, i, g1x_to_jac(g1x_double(g1x_from_jac(ldj(a, i)))));
+}
+extern "C" void emu_g1_mul_fr(const uint32_t *a, const uint32_t *k, uint32_t *out, size_t n) {
+    for (size_t i = 0; i < n; i++) stj(out, i, g1x_to_jac(g1x_mul_fr(g1x_from_jac(ldj(a, i)), ld<FrP>(k, i))));
+}
+// digits[i*W + w] for canonical scalars
+extern "C" uint32_t emu_msm_digits(const uint32_t *k, size_t n, uint32_t c, int32_t *digits) {
+    uint32_t W = msm_num_windows(c);
+    for (size_t i = 0; i < n; i++) {
+        uint32_t s[8], carry = 0;
+        memcpy(s, k + 8 * i, sizeof s);
+        for (uint32_t w = 0; w < W; w++) digits[i * W + w] = msm_signed_digit(s, c, w, carry);
+        if (carry) return 0xffffffffu;   // must never happen
+    }
+    return W;
+}

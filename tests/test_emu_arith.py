@@ -1,0 +1,125 @@
+"""Host build of the DEVICE arithmetic headers (csrc/field.cuh, g1.cuh, msm_digits.cuh)
+checked against the oracle.  This exercises the limb/carry logic the CUDA kernels inline;
+it is a CI aid for the GPU-less authoring box, not a product path (tests/emu/emu.cpp)."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import py_twin as tw
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+@pytest.fixture(scope="module")
+def emu():
+    so = os.path.join(HERE, "emu", "libemu.so")
+    src = os.path.join(HERE, "emu", "emu.cpp")
+    subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", so, src], check=True)
+    return C.CDLL(so)
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _edge(orc, mod, frm, n):
+    vals = [0, 1, 2, mod - 1, mod - 2, (mod - 1) // 2, (1 << 32) - 1, 1 << 32, (1 << 64) - 1]
+    return frm(vals)
+
+
+def test_field_ops(orc, emu):
+    rng = np.random.default_rng(100)
+    for name, mod, cols, rnd, frm, omul, oadd, osub in (
+        ("fr", tw.R_MOD, 4, lambda n: orc.random_fr(rng, n), orc.fr_from_ints, orc.fr_mul, orc.fr_add, orc.fr_sub),
+        ("fq", tw.P_MOD, 6, lambda n: orc.fq_from_ints([int.from_bytes(rng.bytes(64), "little") for _ in range(n)]),
+         orc.fq_from_ints, orc.fq_mul, orc.fq_add, orc.fq_sub),
+    ):
+        e = _edge(orc, mod, frm, 0)
+        a = np.concatenate([rnd(3000), np.repeat(e, len(e), axis=0)])
+        b = np.concatenate([rnd(3000), np.tile(e, (len(e), 1))])
+        for op, ref in (("mul", omul), ("add", oadd), ("sub", osub)):
+            out = np.zeros_like(a)
+            getattr(emu, f"emu_{name}_{op}")(_p(a), _p(b), _p(out), C.c_size_t(len(a)))
+            assert np.array_equal(out, ref(a, b)), (name, op)
+
+
+def test_fr_inv_and_canon(orc, emu):
+    rng = np.random.default_rng(101)
+    a = orc.random_fr(rng, 64)
+    out = np.zeros_like(a)
+    emu.emu_fr_inv(_p(a), _p(out), C.c_size_t(len(a)))
+    assert np.array_equal(out, orc.fr_inv(a))
+    emu.emu_fr_canon(_p(a), _p(out), C.c_size_t(len(a)), 1)
+    assert [orc.limbs_to_int(r) for r in out] == orc.fr_to_ints(a)
+    back = np.zeros_like(a)
+    emu.emu_fr_canon(_p(out), _p(back), C.c_size_t(len(a)), 0)
+    assert np.array_equal(back, a)
+
+
+def _inf_jac(orc):
+    inf = np.zeros((1, 18), dtype=np.uint64)
+    inf[0, 0:6] = orc.fq_from_ints([1])[0]
+    inf[0, 6:12] = orc.fq_from_ints([1])[0]
+    return inf
+
+
+def test_g1_ops(orc, emu):
+    rng = np.random.default_rng(102)
+    n = 24
+    pa = orc.random_g1(rng, n)
+    pb = orc.random_g1(rng, n)
+    ja = orc.g1_mul(orc.g1_from_affine(pa), orc.random_fr(rng, n)) * 0 + orc.g1_double(orc.g1_from_affine(pa))  # non-trivial Z
+    jb = orc.g1_add(orc.g1_from_affine(pb), orc.g1_from_affine(pa))
+    # exceptional cases: acc == P (doubling), acc == -P (-> identity), acc identity, P identity
+    inf = _inf_jac(orc)
+    neg_flags = np.zeros(n + 4, dtype=np.uint8)
+    acc = np.concatenate([ja, orc.g1_from_affine(pb[:1]), orc.g1_from_affine(pb[1:2]), inf, ja[:1]])
+    aff = np.concatenate([pb, pb[:1], pb[1:2], pb[2:3], np.zeros((1, 13), dtype=np.uint64)])
+    neg_flags[n + 1] = 1
+    neg_flags[3] = 1
+    aff_packed = np.ascontiguousarray(aff[:, :12])
+    aff_ref = aff.copy()
+    aff_ref[-1, 12] = 1                       # oracle flags infinity explicitly
+    for i in np.nonzero(neg_flags)[0]:
+        aff_ref[i, 6:12] = orc.fq_sub(np.zeros((1, 6), dtype=np.uint64), aff_ref[i:i + 1, 6:12])[0]
+    out = np.zeros_like(acc)
+    emu.emu_g1_add_affine(_p(acc), _p(aff_packed), _p(neg_flags), _p(out), C.c_size_t(len(acc)))
+    want = orc.canon_g1(orc.g1_add_mixed(acc, aff_ref))
+    assert orc.canon_g1(out) == want
+    assert want[n] != (0, 0, 1) and want[n + 1] == (0, 0, 1)
+    # full add incl. P+P, P+(-P), identities
+    A = np.concatenate([ja, ja[:1], ja[:1], inf, ja[:1], inf])
+    negja = ja[:1].copy()
+    negja[0, 6:12] = orc.fq_sub(np.zeros((1, 6), dtype=np.uint64), ja[:1, 6:12])[0]
+    B = np.concatenate([jb, ja[:1], negja, jb[:1], inf, inf])
+    out = np.zeros_like(A)
+    emu.emu_g1_add(_p(A), _p(B), _p(out), C.c_size_t(len(A)))
+    assert orc.canon_g1(out) == orc.canon_g1(orc.g1_add(A, B))
+    out = np.zeros_like(A)
+    emu.emu_g1_double(_p(A), _p(out), C.c_size_t(len(A)))
+    assert orc.canon_g1(out) == orc.canon_g1(orc.g1_double(A))
+    k = orc.random_fr(rng, 6)
+    k[0] = 0
+    k[1] = orc.fr_from_ints([1])[0]
+    out = np.zeros_like(ja[:6])
+    emu.emu_g1_mul_fr(_p(np.ascontiguousarray(ja[:6])), _p(k), _p(out), C.c_size_t(6))
+    assert orc.canon_g1(out) == orc.canon_g1(orc.g1_mul(ja[:6], k))
+
+
+@pytest.mark.parametrize("c", [1, 2, 3, 5, 8, 13, 15, 16, 17, 20])
+def test_msm_digits_recompose(orc, emu, c):
+    rng = np.random.default_rng(103 + c)
+    ks = [int.from_bytes(rng.bytes(40), "little") % tw.R_MOD for _ in range(200)] + [0, 1, tw.R_MOD - 1, (1 << 254) - 1,
+                                                                                       1 << 254, (1 << 255) - 19 - (1 << 255) + tw.R_MOD - 2]
+    k = orc.ints_to_arr(ks, 4)
+    W = (256 + c - 1) // c
+    digits = np.zeros((len(ks), W), dtype=np.int32)
+    got_w = emu.emu_msm_digits(_p(k), C.c_size_t(len(ks)), c, _p(digits))
+    assert got_w == W
+    half = 1 << (c - 1)
+    assert digits.max() <= half and digits.min() > -half - (1 if c == 1 else 0)
+    for i, kv in enumerate(ks):
+        assert sum(int(d) << (c * w) for w, d in enumerate(digits[i])) == kv
