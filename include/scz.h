@@ -83,8 +83,10 @@ int32_t scz_ctx_create(int32_t device, uint32_t party_id, uint32_t n_parties, co
                        scz_ctx **out);
 void scz_ctx_destroy(scz_ctx *ctx);
 const char *scz_last_error(const scz_ctx *ctx);
-/* run on a caller-owned CUDA stream (cudaStream_t); NULL restores the ctx's own stream */
+/* run on a caller-owned CUDA stream (cudaStream_t, used as given: NULL is the legacy default stream) */
 int32_t scz_ctx_set_stream(scz_ctx *ctx, void *cuda_stream);
+/* go back to the ctx's private non-blocking stream (the state after scz_ctx_create) */
+int32_t scz_ctx_own_stream(scz_ctx *ctx);
 int32_t scz_ctx_sync(scz_ctx *ctx);
 /* kernels launched so far by this ctx */
 uint64_t scz_ctx_launch_count(const scz_ctx *ctx);

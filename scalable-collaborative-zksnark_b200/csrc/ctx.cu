@@ -142,13 +142,18 @@ int32_t scz_ctx_set_stream(scz_ctx *h, void *s) {
     SCZ_CUDA(c, cudaSetDevice(c->device));
     SCZ_CUDA(c, cudaStreamSynchronize(c->stream));
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
-    if (s) {
-        c->stream = (cudaStream_t)s;
-        c->own_stream = false;
-    } else {
-        SCZ_CUDA(c, cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-        c->own_stream = true;
-    }
+    c->stream = (cudaStream_t)s;
+    c->own_stream = false;
+    return SCZ_OK;
+}
+int32_t scz_ctx_own_stream(scz_ctx *h) {
+    if (!h) return SCZ_ERR_BAD_ARG;
+    Ctx *c = &h->c;
+    if (c->own_stream) return SCZ_OK;
+    SCZ_CUDA(c, cudaSetDevice(c->device));
+    SCZ_CUDA(c, cudaStreamSynchronize(c->stream));
+    SCZ_CUDA(c, cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    c->own_stream = true;
     return SCZ_OK;
 }
 int32_t scz_ctx_sync(scz_ctx *h) {
