@@ -7,21 +7,29 @@
 // the ~800 MSMs of a proof cost ~100 sequences instead of ~800.
 //
 // Pipeline (all on ctx->stream, nothing returns to the host):
-//   1 count     one thread per scalar: Montgomery -> integer, signed c-bit digits,
-//               histogram of (segment, window, |digit|) buckets            [atomics]
-//   2 scan      exclusive prefix sum of the histogram                      [3 small kernels]
-//   3 scatter   digits recomputed, point index (+ sign bit) written to its bucket's slot:
-//               a counting sort whose within-bucket order is irrelevant because
-//               group addition commutes (the result is bit-exact regardless)
-//   4 accumulate one thread per bucket: gathers its bases (96 B, 128-bit loads) and
-//               mixed-adds them into an XYZZ accumulator held in registers;
-//               oversized buckets (degenerate scalar distributions such as the
-//               all-ones test of dmsm.rs:103) go to a block-per-bucket kernel
-//   5 reduce    one CTA per window: sum_k k*B_k by chunked running sums + a
-//               shared-memory tree with R_AB = R_A + R_B + |A|*S_B
-//   6 finish    one thread per segment: Horner over the windows, XYZZ -> Jacobian
-// The bucket kernels are bound by the integer multiply pipe (a mixed add is
-// ~4.7k IMAD.WIDE for ~100 B of HBM traffic), see DESIGN.md.
+//   1 count      one thread per scalar: Montgomery -> integer, signed c-bit digits,
+//                histogram of (segment, window, |digit|) buckets               [atomics]
+//   2 scan       exclusive prefix sum of the histogram                         [3 small kernels]
+//   3 scatter    digits recomputed; (bucket id, point index | sign) written to the bucket's
+//                slot: a counting sort whose within-bucket order is irrelevant because
+//                group addition commutes (the result is bit-exact regardless)
+//   4 accumulate the sorted entry stream is cut into equal chunks of T entries, one
+//                thread per chunk: perfectly balanced whatever the digit distribution
+//                (the all-ones scalars of dmsm.rs:103 included).  A thread mixed-adds
+//                (XYZZ += affine, 96 B gathered per entry with 128-bit loads, next point
+//                prefetched during the current add) run by run; runs that are whole
+//                buckets go straight to the bucket array, the first / last run of a
+//                chunk may be a piece of a bucket shared with the neighbours
+//   5 fix-up     pieces of buckets that straddle chunk boundaries are summed
+//   6 chunks     bucket reduction, level 1: one thread per L = 8 consecutive buckets:
+//                S_q = sum B, R_q = sum j*B_j (running sums)
+//   7 planes     level 2: sum_k k*B_k = sum_q R_q + L*sum_q q*S_q + sum_q S_q with
+//                sum_q q*S_q = sum_b 2^b * (sum of S_q over q with bit b set): one CTA per
+//                (window, bit plane), plain tree sums, no doublings
+//   8 finish     per segment: windows recombine their planes in parallel, then one
+//                Horner chain over the windows, XYZZ -> Jacobian
+// The accumulate kernel is bound by the integer multiply pipe (a mixed add is ~2.9k
+// IMAD.WIDE for ~104 B of HBM traffic), see DESIGN.md.
 #include <algorithm>
 #include <vector>
 
@@ -33,12 +41,14 @@ namespace scz {
 
 constexpr int CNT_THREADS = 256;
 constexpr int ACC_THREADS = 128;
-constexpr int RED_THREADS = 128;
-constexpr int HEAVY_THREADS = 128;
-constexpr uint32_t HEAVY_CAP = 1024;   // buckets longer than this are split across a CTA
+constexpr int FIX_THREADS = 128;
+constexpr int CHK_THREADS = 64;
+constexpr int PLN_THREADS = 256;
+constexpr int FIN_THREADS = 256;       // >= max windows of a segment (c = 1 -> 256)
 constexpr int SCAN_THREADS = 256;
 constexpr int SCAN_ITEMS = 8;          // per thread
 constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
+constexpr uint32_t RED_LOGL = 3;       // level-1 reduction chunk: 8 buckets
 
 __device__ __forceinline__ int seg_by_point(const MsmSeg *segs, int K, uint32_t g) {
     int lo = 0, hi = K - 1;
@@ -67,14 +77,29 @@ __device__ __forceinline__ int seg_by_window(const MsmSeg *segs, int K, uint32_t
     }
     return lo;
 }
+__device__ __forceinline__ int seg_by_chunk(const MsmSeg *segs, int K, uint32_t q) {
+    int lo = 0, hi = K - 1;
+    while (lo < hi) {
+        int mid = (lo + hi + 1) >> 1;
+        if (__ldg(&segs[mid].chunk_base) <= q) lo = mid;
+        else hi = mid - 1;
+    }
+    return lo;
+}
+
+// Out-of-line group law for the latency-bound tail kernels: keeps their code inside the
+// instruction cache (an inlined general add is ~5k instructions) and the build fast.
+__device__ __noinline__ void g1x_add_nl(G1X &r, const G1X &a, const G1X &b) { r = g1x_add(a, b); }
+__device__ __noinline__ void g1x_double_nl(G1X &r, const G1X &a) { r = g1x_double(a); }
 
 // ---- 1 + 3: recode, then count (SCATTER = false) or place (SCATTER = true)
 template <bool SCATTER>
 __global__ void __launch_bounds__(CNT_THREADS) k_msm_recode(const MsmSeg *segs, int K, uint32_t total_points,
-                                                             uint32_t *counts, uint32_t *cursor, uint32_t *sorted) {
+                                                             uint32_t *counts, uint32_t *cursor, uint32_t *sorted,
+                                                             uint32_t *keys) {
     uint32_t g = blockIdx.x * CNT_THREADS + threadIdx.x;
     if (g >= total_points) return;
-    int s = seg_by_point(segs, K, g);
+    int s = K == 1 ? 0 : seg_by_point(segs, K, g);
     const MsmSeg sg = segs[s];
     uint32_t i = g - sg.point_base;
     Fr k = fp_to_canon(fp_load<FrP>(sg.scalars, i));
@@ -89,6 +114,7 @@ __global__ void __launch_bounds__(CNT_THREADS) k_msm_recode(const MsmSeg *segs, 
         } else {
             uint32_t pos = atomicAdd(&cursor[b], 1u);
             sorted[pos] = i | (d < 0 ? 0x80000000u : 0u);
+            keys[pos] = b;
         }
     }
 }
@@ -172,32 +198,120 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_add(uint32_t *out, const 
         if (base + j < n) out[base + j] += add;
 }
 
-// ---- 4: bucket accumulation, one thread per bucket
-// After the scatter pass cursor[b] is the END of bucket b; its entries are sorted[end - count, end).
-__global__ void __launch_bounds__(ACC_THREADS) k_msm_accumulate(const MsmSeg *segs, int K, uint32_t total_buckets,
-                                                                 const uint32_t *counts, const uint32_t *cursor,
-                                                                 const uint32_t *sorted, void *buckets,
-                                                                 uint32_t *heavy_list, uint32_t *heavy_count) {
-    uint32_t b = blockIdx.x * ACC_THREADS + threadIdx.x;
+// ---- 4: bucket accumulation over equal chunks of the sorted entry stream
+// After the scatter pass cursor[b] is the END of bucket b; it starts at cursor[b] - counts[b].
+// Chunk t covers entries [t*T, (t+1)*T).  A bucket that lies inside one chunk is written to
+// buckets[b]; a bucket cut by chunk boundaries leaves a TAIL piece in the chunk where it starts
+// (parts[2t+1]) and HEAD pieces in the following chunks (parts[2u]); k_msm_fixup* sums them.
+__global__ void __launch_bounds__(ACC_THREADS) k_msm_accumulate(const MsmSeg *segs, int K, const uint32_t *E_ptr,
+                                                                 uint32_t logT, const uint32_t *keys,
+                                                                 const uint32_t *sorted, const uint32_t *counts,
+                                                                 const uint32_t *cursor, void *buckets, void *parts) {
+    uint32_t t = blockIdx.x * ACC_THREADS + threadIdx.x;
+    const uint32_t E = __ldg(E_ptr);   // entries actually in the stream (zero digits are dropped)
+    uint64_t lo64 = (uint64_t)t << logT;
+    if (lo64 >= E) return;
+    uint32_t lo = (uint32_t)lo64;
+    uint32_t hi = lo64 + (1u << logT) < E ? lo + (1u << logT) : E;
+    uint32_t k_first = __ldg(keys + lo), k_last = __ldg(keys + hi - 1);
+    bool head_piece = cursor[k_first] - counts[k_first] < lo;   // the first bucket began in an earlier chunk
+    bool tail_piece = cursor[k_last] > hi;                      // the last bucket goes on in a later chunk
+
+    // segment of the current run (bases pointer); re-resolved when the bucket id leaves its range
+    uint32_t seg_hi = 0;
+    const void *bases = nullptr;
+    uint32_t cur = k_first;
+    bool first_run = true;
+    G1X acc = G1X::inf();
+    {
+        int s = K == 1 ? 0 : seg_by_bucket(segs, K, cur);
+        seg_hi = segs[s].bucket_base + segs[s].W * segs[s].nb;
+        bases = segs[s].bases;
+    }
+    uint32_t ent = __ldg(sorted + lo);
+    G1Affine p = g1a_load(bases, ent & 0x7fffffffu);
+    for (uint32_t j = lo; j < hi; j++) {
+        // prefetch entry j+1 (key, index, point) while entry j is being added
+        uint32_t nkey = cur, nent = 0;
+        G1Affine np;
+        bool more = j + 1 < hi;
+        if (more) {
+            nkey = __ldg(keys + j + 1);
+            nent = __ldg(sorted + j + 1);
+            if (nkey >= seg_hi) {
+                int s = seg_by_bucket(segs, K, nkey);
+                seg_hi = segs[s].bucket_base + segs[s].W * segs[s].nb;
+                bases = segs[s].bases;
+            }
+            np = g1a_load(bases, nent & 0x7fffffffu);
+        }
+        g1x_add_affine(acc, p, (ent >> 31) != 0);
+        if (!more || nkey != cur) {   // the run of bucket `cur` ends here
+            bool last_run = !more;
+            if (first_run && head_piece) g1x_store(parts, 2 * (size_t)t, acc);
+            else if (last_run && tail_piece) g1x_store(parts, 2 * (size_t)t + 1, acc);
+            else g1x_store(buckets, cur, acc);
+            first_run = false;
+            acc = G1X::inf();
+            cur = nkey;
+        }
+        if (more) {
+            p = np;
+            ent = nent;
+        }
+    }
+}
+
+// ---- 5: buckets cut by chunk boundaries.  Bucket b = entries [start, end) touches chunks t0 = start/T ..
+// t1 = (end-1)/T; when t1 > t0 its value is parts[2*t0+1] + sum_{u in (t0, t1]} parts[2u].  Short chains are
+// summed by the bucket's thread; long ones (the top window's few buckets, degenerate scalar
+// distributions such as dmsm.rs:103) go to a list served by whole CTAs.
+constexpr uint32_t FIX_SERIAL_MAX = 6;
+__global__ void __launch_bounds__(FIX_THREADS) k_msm_fixup(uint32_t total_buckets, uint32_t logT, const uint32_t *counts,
+                                                            const uint32_t *cursor, const void *parts, void *buckets,
+                                                            uint32_t *heavy_list, uint32_t *heavy_count) {
+    uint32_t b = blockIdx.x * FIX_THREADS + threadIdx.x;
     if (b >= total_buckets) return;
     uint32_t n = counts[b];
-    if (n > HEAVY_CAP) {
+    if (!n) return;
+    uint32_t end = cursor[b], start = end - n;
+    uint32_t t0 = start >> logT, t1 = (end - 1) >> logT;
+    if (t1 == t0) return;
+    if (t1 - t0 > FIX_SERIAL_MAX) {
         heavy_list[atomicAdd(heavy_count, 1u)] = b;
         return;
     }
-    G1X acc = G1X::inf();
-    if (n) {
-        int s = seg_by_bucket(segs, K, b);
-        const void *bases = segs[s].bases;
-        const uint32_t *e = sorted + (cursor[b] - n);
-        for (uint32_t j = 0; j < n; j++) {
-            uint32_t ent = __ldg(e + j);
-            G1Affine p = g1a_load(bases, ent & 0x7fffffffu);
-            g1x_add_affine(acc, p, (ent >> 31) != 0);
-        }
+    G1X acc = g1x_load(parts, 2 * (size_t)t0 + 1);
+    for (uint32_t u = t0 + 1; u <= t1; u++) {
+        G1X h = g1x_load(parts, 2 * (size_t)u);
+        g1x_add_nl(acc, acc, h);
     }
     g1x_store(buckets, b, acc);
 }
+
+// ---- 6: level-1 bucket reduction: one thread per chunk of L = 2^logL buckets
+//   S_q = sum_j B_j,   R_q = sum_j j * B_j   (j = 0 .. L-1 within the chunk)
+__global__ void __launch_bounds__(CHK_THREADS) k_msm_chunks(const MsmSeg *segs, int K, uint32_t total_chunks,
+                                                             const uint32_t *counts, const void *buckets, void *chS,
+                                                             void *chR) {
+    uint32_t q = blockIdx.x * CHK_THREADS + threadIdx.x;
+    if (q >= total_chunks) return;
+    int s = K == 1 ? 0 : seg_by_chunk(segs, K, q);
+    const MsmSeg sg = segs[s];
+    uint32_t L = 1u << sg.logL;
+    uint32_t first = sg.bucket_base + (q - sg.chunk_base) * L;   // windows are contiguous: chunk -> bucket is linear
+    G1X S = G1X::inf(), R = G1X::inf();
+    for (uint32_t j = L; j-- > 0;) {
+        if (counts[first + j]) {
+            G1X b = g1x_load(buckets, first + j);
+            g1x_add_nl(S, S, b);
+        }
+        if (j) g1x_add_nl(R, R, S);   // after the loop R = sum_j j*B_j
+    }
+    g1x_store(chS, q, S);
+    g1x_store(chR, q, R);
+}
+
 // tree-sum of one XYZZ value per thread through shared memory; result in thread 0
 template <int T>
 __device__ __forceinline__ G1X block_sum_g1x(G1X v, G1X *sh) {
@@ -205,110 +319,108 @@ __device__ __forceinline__ G1X block_sum_g1x(G1X v, G1X *sh) {
     __syncthreads();
     for (int stride = T / 2; stride > 0; stride >>= 1) {
         if ((int)threadIdx.x < stride) {
-            v = g1x_add(v, sh[threadIdx.x + stride]);
-            sh[threadIdx.x] = v;
+            G1X o = sh[threadIdx.x + stride];
+            if (!o.is_inf()) {
+                g1x_add_nl(v, v, o);
+                sh[threadIdx.x] = v;
+            }
         }
         __syncthreads();
     }
     return v;
 }
-__global__ void __launch_bounds__(HEAVY_THREADS) k_msm_accumulate_heavy(const MsmSeg *segs, int K,
-                                                                         const uint32_t *counts, const uint32_t *cursor,
-                                                                         const uint32_t *sorted, void *buckets,
-                                                                         const uint32_t *heavy_list,
-                                                                         const uint32_t *heavy_count) {
+
+__global__ void __launch_bounds__(PLN_THREADS) k_msm_fixup_heavy(uint32_t logT, const uint32_t *counts,
+                                                                  const uint32_t *cursor, const void *parts,
+                                                                  void *buckets, const uint32_t *heavy_list,
+                                                                  const uint32_t *heavy_count) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     G1X *sh = reinterpret_cast<G1X *>(smem_raw);
     for (uint32_t h = blockIdx.x; h < *heavy_count; h += gridDim.x) {
         uint32_t b = heavy_list[h];
-        uint32_t n = counts[b];
-        int s = seg_by_bucket(segs, K, b);
-        const void *bases = segs[s].bases;
-        const uint32_t *e = sorted + (cursor[b] - n);
+        uint32_t end = cursor[b], start = end - counts[b];
+        uint32_t t0 = start >> logT, t1 = (end - 1) >> logT;
         G1X acc = G1X::inf();
-        for (uint32_t j = threadIdx.x; j < n; j += HEAVY_THREADS) {
-            uint32_t ent = __ldg(e + j);
-            G1Affine p = g1a_load(bases, ent & 0x7fffffffu);
-            g1x_add_affine(acc, p, (ent >> 31) != 0);
+        if (threadIdx.x == 0) acc = g1x_load(parts, 2 * (size_t)t0 + 1);
+        for (uint32_t u = t0 + 1 + threadIdx.x; u <= t1; u += PLN_THREADS) {
+            G1X v = g1x_load(parts, 2 * (size_t)u);
+            g1x_add_nl(acc, acc, v);
         }
-        acc = block_sum_g1x<HEAVY_THREADS>(acc, sh);
+        acc = block_sum_g1x<PLN_THREADS>(acc, sh);
         if (threadIdx.x == 0) g1x_store(buckets, b, acc);
         __syncthreads();
     }
 }
 
-// ---- 5: per-window bucket reduction  sum_{k=1..nb} k * B_k
-__device__ __forceinline__ G1X g1x_mul_pow2(G1X p, uint32_t log2k) {
-    for (uint32_t i = 0; i < log2k; i++) p = g1x_double(p);
-    return p;
-}
-__global__ void __launch_bounds__(RED_THREADS) k_msm_reduce(const MsmSeg *segs, int K, const void *buckets,
-                                                             void *window_sums) {
+// ---- 7: level 2, one CTA per (window, plane):
+//   plane b < PB : sum of S_q over chunks q with bit b set
+//   plane PB     : sum of S_q          plane PB+1 : sum of R_q
+__global__ void __launch_bounds__(PLN_THREADS) k_msm_planes(const MsmSeg *segs, int K, const void *chS,
+                                                             const void *chR, void *planes) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    G1X *shS = reinterpret_cast<G1X *>(smem_raw);
-    G1X *shR = shS + RED_THREADS;
-    uint32_t gw = blockIdx.x;
-    int s = seg_by_window(segs, K, gw);
+    G1X *sh = reinterpret_cast<G1X *>(smem_raw);
+    uint32_t gw = blockIdx.x, plane = blockIdx.y;
+    int s = K == 1 ? 0 : seg_by_window(segs, K, gw);
     const MsmSeg sg = segs[s];
+    if (plane >= sg.PB + 2) return;
     uint32_t w = gw - sg.window_base;
-    uint32_t first = sg.bucket_base + w * sg.nb;
-    // chunk length L (a power of two) and number of active threads
-    uint32_t L = sg.nb >= RED_THREADS ? sg.nb / RED_THREADS : 1;
-    uint32_t active = sg.nb / L;
-    uint32_t t = threadIdx.x;
-    G1X S = G1X::inf(), R = G1X::inf();
-    if (t < active) {
-        uint32_t lo = t * L;
-        for (uint32_t j = L; j-- > 0;) {   // running sum from the chunk's top bucket down
-            S = g1x_add(S, g1x_load(buckets, first + lo + j));
-            R = g1x_add(R, S);
-        }
+    uint32_t base = sg.chunk_base + w * sg.M;
+    const void *src = plane == sg.PB + 1 ? chR : chS;
+    G1X acc = G1X::inf();
+    for (uint32_t q = threadIdx.x; q < sg.M; q += PLN_THREADS) {
+        if (plane < sg.PB && !((q >> plane) & 1)) continue;
+        G1X v = g1x_load(src, base + q);
+        if (!v.is_inf()) g1x_add_nl(acc, acc, v);
     }
-    shS[t] = S;
-    shR[t] = R;
-    __syncthreads();
-    // tree: node A = [t, t+stride), node B = [t+stride, t+2*stride);  |A| = stride * L buckets
-    uint32_t logL = 31 - __clz(L);
-    uint32_t level = 0;
-    for (uint32_t stride = 1; stride < active; stride <<= 1, level++) {
-        if ((t & (2 * stride - 1)) == 0 && t + stride < active) {
-            G1X Sb = shS[t + stride];
-            G1X Rb = shR[t + stride];
-            R = g1x_add(g1x_add(R, Rb), g1x_mul_pow2(Sb, logL + level));
-            S = g1x_add(S, Sb);
-            shS[t] = S;
-            shR[t] = R;
-        }
-        __syncthreads();
-    }
-    if (t == 0) g1x_store(window_sums, gw, R);
+    acc = block_sum_g1x<PLN_THREADS>(acc, sh);
+    if (threadIdx.x == 0) g1x_store(planes, sg.plane_base + w * (sg.PB + 2) + plane, acc);
 }
 
-// ---- 6: Horner over windows, one thread per segment
-__global__ void k_msm_finish(const MsmSeg *segs, int K, const void *window_sums, void *out_jac) {
-    int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= K) return;
-    const MsmSeg sg = segs[s];
-    G1X acc = G1X::inf();
-    if (sg.len) {
-        for (uint32_t w = sg.W; w-- > 0;) {
-            acc = g1x_mul_pow2(acc, sg.c);
-            acc = g1x_add(acc, g1x_load(window_sums, sg.window_base + w));
+// ---- 8: one CTA per segment.  Thread w: window sum = sum_q R_q + L * sum_b 2^b plane_b + sum_q S_q;
+//         then thread 0 runs Horner over the windows (the only long serial chain of the pipeline).
+__global__ void __launch_bounds__(FIN_THREADS) k_msm_finish(const MsmSeg *segs, const void *planes, void *out_jac) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    G1X *sh = reinterpret_cast<G1X *>(smem_raw);
+    const MsmSeg sg = segs[blockIdx.x];
+    uint32_t w = threadIdx.x;
+    if (sg.len && w < sg.W) {
+        size_t pb = sg.plane_base + (size_t)w * (sg.PB + 2);
+        G1X X = G1X::inf();
+        for (uint32_t b = sg.PB; b-- > 0;) {
+            g1x_double_nl(X, X);
+            G1X v = g1x_load(planes, pb + b);
+            g1x_add_nl(X, X, v);
         }
+        for (uint32_t i = 0; i < sg.logL; i++) g1x_double_nl(X, X);
+        G1X v = g1x_load(planes, pb + sg.PB + 1);
+        g1x_add_nl(X, X, v);
+        v = g1x_load(planes, pb + sg.PB);
+        g1x_add_nl(X, X, v);
+        sh[w] = X;
     }
-    g1j_store(out_jac, s, g1x_to_jac(acc));
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        G1X acc = G1X::inf();
+        if (sg.len) {
+            for (uint32_t ww = sg.W; ww-- > 0;) {
+                for (uint32_t i = 0; i < sg.c; i++) g1x_double_nl(acc, acc);
+                g1x_add_nl(acc, acc, sh[ww]);
+            }
+        }
+        g1j_store(out_jac, blockIdx.x, g1x_to_jac(acc));
+    }
 }
 
 // ------------------------------------------------------------------ host side
 uint32_t msm_pick_window(size_t len) {
     if (len == 0) return 1;
-    // cost in mixed-add equivalents: W * (len + 6 * nb): the reduction runs one CTA per
-    // window, so a bucket there costs several times a bucket addition
+    // cost in mixed-add equivalents: W * (len + 3 * nb): a bucket costs two general additions in
+    // the level-1 reduction
     uint32_t best = 1;
     double best_cost = 1e300;
     for (uint32_t c = 1; c <= 16; c++) {
         double W = (double)msm_num_windows(c), nb = (double)(1u << (c - 1));
-        double cost = W * ((double)len + 6.0 * nb);
+        double cost = W * ((double)len + 3.0 * nb);
         if (cost < best_cost) {
             best_cost = cost;
             best = c;
@@ -322,7 +434,8 @@ int32_t msm_g1_batched(Ctx *ctx, const void *const *d_bases, const void *const *
     if (batch == 0) return SCZ_OK;
     if (batch > (1u << 20)) return ctx->fail(SCZ_ERR_BAD_ARG, "msm: batch too large");
     std::vector<MsmSeg> segs(batch);
-    uint64_t points = 0, buckets = 0, windows = 0, entries = 0;
+    uint64_t points = 0, buckets = 0, windows = 0, entries = 0, chunks = 0, planes = 0;
+    uint32_t max_planes = 2;
     for (size_t k = 0; k < batch; k++) {
         if (lens[k] >= (1ull << 31)) return ctx->fail(SCZ_ERR_BAD_ARG, "msm: segment %zu too long", k);
         if (lens[k] && (!d_bases[k] || !d_scalars[k])) return ctx->fail(SCZ_ERR_BAD_ARG, "msm: null segment %zu", k);
@@ -336,11 +449,19 @@ int32_t msm_g1_batched(Ctx *ctx, const void *const *d_bases, const void *const *
         s.nb = 1u << (s.c - 1);
         s.bucket_base = (uint32_t)buckets;
         s.window_base = (uint32_t)windows;
-        s.pad_ = 0;
+        s.logL = std::min<uint32_t>(RED_LOGL, s.c - 1);
+        s.M = s.nb >> s.logL;
+        s.PB = 0;
+        while ((1u << s.PB) < s.M) s.PB++;
+        s.chunk_base = (uint32_t)chunks;
+        s.plane_base = (uint32_t)planes;
+        max_planes = std::max(max_planes, s.PB + 2);
         points += s.len;
         buckets += (uint64_t)s.W * s.nb;
         windows += s.W;
         entries += (uint64_t)s.len * s.W;
+        chunks += (uint64_t)s.W * s.M;
+        planes += (uint64_t)s.W * (s.PB + 2);
     }
     if (points >= (1ull << 31) || buckets >= (1ull << 31) || entries >= (1ull << 32))
         return ctx->fail(SCZ_ERR_BAD_ARG, "msm: batch too large (%llu points, %llu buckets)", (unsigned long long)points,
@@ -349,30 +470,39 @@ int32_t msm_g1_batched(Ctx *ctx, const void *const *d_bases, const void *const *
     ctx->msm_buckets = buckets;
     ctx->msm_windows = windows;
 
+    // entries per accumulate thread: 64 for big batches, less when that would leave SMs idle
+    uint32_t logT = 6;
+    while (logT > 3 && (entries >> logT) < (uint64_t)ctx->sm_count * 2 * ACC_THREADS) logT--;
+    uint32_t nchunks = (uint32_t)((entries + (1u << logT) - 1) >> logT);   // upper bound: zero digits shrink the stream
+
     cudaStream_t st = ctx->stream;
     uint32_t tiles = ceil_div_u32(buckets, SCAN_TILE);
-    DevTmp d_segs(ctx), d_counts(ctx), d_cursor(ctx), d_tiles(ctx), d_sorted(ctx), d_buckets(ctx), d_wsums(ctx),
-        d_heavy(ctx);
+    DevTmp d_segs(ctx), d_counts(ctx), d_cursor(ctx), d_tiles(ctx), d_sorted(ctx), d_keys(ctx), d_buckets(ctx),
+        d_parts(ctx), d_heavy(ctx), d_chS(ctx), d_chR(ctx), d_planes(ctx);
     SCZ_TRY(d_segs.alloc(batch * sizeof(MsmSeg)));
     SCZ_TRY(d_counts.alloc(buckets * 4));
     SCZ_TRY(d_cursor.alloc(buckets * 4));
     SCZ_TRY(d_tiles.alloc((size_t)tiles * 4 + 4));
     SCZ_TRY(d_sorted.alloc((entries ? entries : 1) * 4));
+    SCZ_TRY(d_keys.alloc((entries ? entries : 1) * 4));
     SCZ_TRY(d_buckets.alloc(buckets * sizeof(G1X)));
-    SCZ_TRY(d_wsums.alloc(windows * sizeof(G1X)));
+    SCZ_TRY(d_parts.alloc(((size_t)nchunks * 2 + 2) * sizeof(G1X)));
     SCZ_TRY(d_heavy.alloc((buckets + 1) * 4));   // [0] = count, [1..] = list
-    // segment table: pageable host -> device; the vector must outlive the copy, so stage through the stream
+    SCZ_TRY(d_chS.alloc(chunks * sizeof(G1X)));
+    SCZ_TRY(d_chR.alloc(chunks * sizeof(G1X)));
+    SCZ_TRY(d_planes.alloc(planes * sizeof(G1X)));
+    // segment table: pageable host -> device; the vector must outlive the copy
     SCZ_CUDA(ctx, cudaMemcpyAsync(d_segs.p, segs.data(), batch * sizeof(MsmSeg), cudaMemcpyHostToDevice, st));
-    SCZ_CUDA(ctx, cudaStreamSynchronize(st));   // pageable source: make the copy complete before `segs` dies
+    SCZ_CUDA(ctx, cudaStreamSynchronize(st));
     SCZ_CUDA(ctx, cudaMemsetAsync(d_counts.p, 0, buckets * 4, st));
     SCZ_CUDA(ctx, cudaMemsetAsync(d_heavy.p, 0, 4, st));
     const MsmSeg *sp = d_segs.as<MsmSeg>();
     int K = (int)batch;
     uint32_t *counts = d_counts.as<uint32_t>(), *cursor = d_cursor.as<uint32_t>(), *sorted = d_sorted.as<uint32_t>();
-    uint32_t *heavy = d_heavy.as<uint32_t>();
+    uint32_t *keys = d_keys.as<uint32_t>();
     if (points) {
         k_msm_recode<false><<<ceil_div_u32(points, CNT_THREADS), CNT_THREADS, 0, st>>>(sp, K, (uint32_t)points, counts,
-                                                                                       nullptr, nullptr);
+                                                                                       nullptr, nullptr, nullptr);
         SCZ_LAUNCH_CHECK(ctx);
     }
     k_scan_tiles<<<tiles, SCAN_THREADS, 0, st>>>(counts, cursor, d_tiles.as<uint32_t>(), (uint32_t)buckets);
@@ -383,29 +513,38 @@ int32_t msm_g1_batched(Ctx *ctx, const void *const *d_bases, const void *const *
     SCZ_LAUNCH_CHECK(ctx);
     if (points) {
         k_msm_recode<true><<<ceil_div_u32(points, CNT_THREADS), CNT_THREADS, 0, st>>>(sp, K, (uint32_t)points, nullptr,
-                                                                                      cursor, sorted);
+                                                                                      cursor, sorted, keys);
         SCZ_LAUNCH_CHECK(ctx);
     }
-    k_msm_accumulate<<<ceil_div_u32(buckets, ACC_THREADS), ACC_THREADS, 0, st>>>(sp, K, (uint32_t)buckets, counts,
-                                                                                 cursor, sorted, d_buckets.p, heavy + 1,
-                                                                                 heavy);
-    SCZ_LAUNCH_CHECK(ctx);
-    {
-        static bool attr_done = false;
-        size_t sh = HEAVY_THREADS * sizeof(G1X);
-        if (!attr_done) {
-            cudaFuncSetAttribute(k_msm_accumulate_heavy, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh);
-            cudaFuncSetAttribute(k_msm_reduce, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)(2 * RED_THREADS * sizeof(G1X)));
-            attr_done = true;
-        }
-        k_msm_accumulate_heavy<<<ctx->sm_count, HEAVY_THREADS, sh, st>>>(sp, K, counts, cursor, sorted, d_buckets.p,
-                                                                         heavy + 1, heavy);
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaFuncSetAttribute(k_msm_planes, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(PLN_THREADS * sizeof(G1X)));
+        cudaFuncSetAttribute(k_msm_fixup_heavy, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)(PLN_THREADS * sizeof(G1X)));
+        cudaFuncSetAttribute(k_msm_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(FIN_THREADS * sizeof(G1X)));
+        attr_done = true;
+    }
+    if (points) {
+        // after the scatter cursor[last bucket] = entries really in the stream (the host only knows the
+        // bound `entries`: zero digits are dropped); chunks past that end return at once
+        k_msm_accumulate<<<ceil_div_u32(nchunks, ACC_THREADS), ACC_THREADS, 0, st>>>(
+            sp, K, cursor + (buckets - 1), logT, keys, sorted, counts, cursor, d_buckets.p, d_parts.p);
+        SCZ_LAUNCH_CHECK(ctx);
+        uint32_t *heavy = d_heavy.as<uint32_t>();
+        k_msm_fixup<<<ceil_div_u32(buckets, FIX_THREADS), FIX_THREADS, 0, st>>>((uint32_t)buckets, logT, counts, cursor,
+                                                                                d_parts.p, d_buckets.p, heavy + 1, heavy);
+        SCZ_LAUNCH_CHECK(ctx);
+        k_msm_fixup_heavy<<<ctx->sm_count, PLN_THREADS, PLN_THREADS * sizeof(G1X), st>>>(
+            logT, counts, cursor, d_parts.p, d_buckets.p, heavy + 1, heavy);
         SCZ_LAUNCH_CHECK(ctx);
     }
-    k_msm_reduce<<<(uint32_t)windows, RED_THREADS, 2 * RED_THREADS * sizeof(G1X), st>>>(sp, K, d_buckets.p, d_wsums.p);
+    k_msm_chunks<<<ceil_div_u32(chunks, CHK_THREADS), CHK_THREADS, 0, st>>>(sp, K, (uint32_t)chunks, counts, d_buckets.p,
+                                                                           d_chS.p, d_chR.p);
     SCZ_LAUNCH_CHECK(ctx);
-    k_msm_finish<<<ceil_div_u32(batch, 32), 32, 0, st>>>(sp, K, d_wsums.p, d_out);
+    k_msm_planes<<<dim3((uint32_t)windows, max_planes), PLN_THREADS, PLN_THREADS * sizeof(G1X), st>>>(
+        sp, K, d_chS.p, d_chR.p, d_planes.p);
+    SCZ_LAUNCH_CHECK(ctx);
+    k_msm_finish<<<(uint32_t)batch, FIN_THREADS, FIN_THREADS * sizeof(G1X), st>>>(sp, d_planes.p, d_out);
     SCZ_LAUNCH_CHECK(ctx);
     return SCZ_OK;
 }

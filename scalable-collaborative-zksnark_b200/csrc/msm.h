@@ -17,11 +17,11 @@ struct MsmSeg {
     uint32_t nb;           // buckets per window = 2^(c-1)
     uint32_t bucket_base;  // first global bucket of this segment (window w starts at bucket_base + w*nb)
     uint32_t window_base;  // first global window of this segment
-    uint32_t pad_;
-};
-
-struct MsmStats {
-    uint64_t bucket_adds = 0, buckets = 0, windows = 0;
+    uint32_t logL;         // bucket-reduction chunk length L = 2^logL = min(nb, 8)
+    uint32_t M;            // chunks per window = nb / L (a power of two)
+    uint32_t PB;           // log2(M): bit planes of the chunk index
+    uint32_t chunk_base;   // first global chunk (window w starts at chunk_base + w*M)
+    uint32_t plane_base;   // first global plane slot (window w owns PB + 2 slots from plane_base + w*(PB+2))
 };
 
 // d_out: batch Jacobian points (144 B each).  Asynchronous on ctx->stream.
