@@ -90,6 +90,22 @@ int32_t scz_ctx_own_stream(scz_ctx *ctx);
 int32_t scz_ctx_sync(scz_ctx *ctx);
 /* kernels launched so far by this ctx */
 uint64_t scz_ctx_launch_count(const scz_ctx *ctx);
+/* Per-kernel-class device timing for bench.py's roofline: when enabled, every launch group of a class is
+ * bracketed by CUDA events on the ctx stream (the reference's start_timer!/end_timer! labels,
+ * mpc-net/src/utils/timer.rs:25-197, are the host-side analogue).  scz_prof_read synchronises the stream
+ * and returns the summed device time and the number of brackets of that class since scz_prof_enable. */
+#define SCZ_K_MSM_SORT 0        /* digit recode, histogram, scan, scatter */
+#define SCZ_K_MSM_ACCUMULATE 1  /* Pippenger bucket accumulation (the dominant kernel) */
+#define SCZ_K_MSM_FIXUP 2       /* buckets cut by chunk boundaries */
+#define SCZ_K_MSM_REDUCE 3      /* bucket reduction: chunks + bit planes */
+#define SCZ_K_MSM_FINISH 4      /* window recombination, Horner chain */
+#define SCZ_K_PSS 5             /* PSS maps of the leader closures */
+#define SCZ_K_SUMCHECK 6        /* fused fold + product-sum rounds */
+#define SCZ_K_OPEN_FOLD 7       /* PST open: quotient + fold rounds */
+#define SCZ_K_ACC_PRODUCT 8     /* product tree */
+#define SCZ_K_POINTWISE 9       /* element-wise Fr maps, batch inversion */
+int32_t scz_prof_enable(scz_ctx *ctx, int32_t on);
+int32_t scz_prof_read(scz_ctx *ctx, int32_t kernel_class, double *ms_total, uint64_t *brackets);
 /* MPCNet::get_comm (mpc-net/src/lib.rs:59): (upload, download) in the reference's serialised bytes */
 int32_t scz_ctx_get_comm(const scz_ctx *ctx, uint64_t *upload, uint64_t *download);
 
@@ -160,6 +176,11 @@ int32_t scz_pss_unpack2_dev(scz_ctx *ctx, const scz_pp *pp, int32_t kind, const 
  * (this party's packed shares of the batch results). */
 int32_t scz_d_msm_dev(scz_ctx *ctx, const scz_pp *pp, const void *const *d_bases, const void *const *d_scalars,
                       const size_t *lens, size_t batch, void *d_out_jac);
+/* The two halves of d_msm for hosts that run several parties in one process (fewer GPUs than parties):
+ * the local half is scz_msm_g1_batched_dev (dmsm.rs:19-24); this is the leader closure (dmsm.rs:31-38) on
+ * the gathered buffer, party-major [party][k], n_parties x batch Jacobian points in and out. */
+int32_t scz_d_msm_leader_dev(scz_ctx *ctx, const scz_pp *pp, const void *d_gathered, size_t batch,
+                             void *d_to_scatter);
 int32_t scz_d_msm(scz_ctx *ctx, const scz_pp *pp, const void *const *bases, const size_t *bases_lens,
                   const void *const *scalars, const size_t *scalars_lens, size_t batch, void *out_jac);
 

@@ -12,5 +12,7 @@ from .api import (  # noqa: F401
     Context,
     PackedSharingParams,
     d_msm,
+    d_msm_leader,
+    msm_batched,
     msm,
 )

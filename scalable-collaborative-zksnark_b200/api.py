@@ -90,6 +90,19 @@ class Context:
     def launches(self):
         return int(self.L.scz_ctx_launch_count(self.h))
 
+    KERNEL_CLASSES = {"msm_sort": 0, "msm_accumulate": 1, "msm_fixup": 2, "msm_reduce": 3, "msm_finish": 4, "pss": 5,
+                      "sumcheck": 6, "open_fold": 7, "acc_product": 8, "pointwise": 9}
+
+    def prof_enable(self, on=True):
+        """bracket every kernel class with CUDA events on the ctx stream (scz_prof_enable); clears old records"""
+        self.check(self.L.scz_prof_enable(self.h, C.c_int32(1 if on else 0)))
+
+    def prof_read(self, kernel_class):
+        """-> (summed device ms, number of brackets) of one kernel class since prof_enable"""
+        ms, n = C.c_double(), C.c_uint64()
+        self.check(self.L.scz_prof_read(self.h, C.c_int32(self.KERNEL_CLASSES[kernel_class]), C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
     def get_comm(self):
         """MPCNet::get_comm -> (upload, download) in the reference's serialised bytes"""
         up, down = C.c_uint64(), C.c_uint64()
@@ -306,4 +319,16 @@ def d_msm(ctx, pp, bases, scalars):
     return out
 
 
-__all__ = ["Context", "PackedSharingParams", "msm", "msm_batched", "d_msm", "NetVTable"]
+def d_msm_leader(ctx, pp, gathered):
+    """the leader closure of d_msm alone (dmsm.rs:31-38): gathered is (n_parties, batch, 18) Jacobian,
+    party-major; returns the (n_parties, batch, 18) buffer the leader scatters"""
+    g = gathered if _is_dev(gathered) else ctx.to_device(np.ascontiguousarray(gathered).reshape(-1, 18), 18)
+    g = g.reshape(pp.n, -1, 18).contiguous()
+    batch = g.shape[1]
+    out = torch.empty_like(g)
+    ctx.check(ctx.L.scz_d_msm_leader_dev(ctx.h, pp.h, C.c_void_p(g.data_ptr()), C.c_size_t(batch),
+                                         C.c_void_p(out.data_ptr())))
+    return out if _is_dev(gathered) else ctx.to_host(out.reshape(-1, 18)).reshape(pp.n, batch, 18)
+
+
+__all__ = ["Context", "PackedSharingParams", "msm", "msm_batched", "d_msm", "d_msm_leader", "NetVTable"]

@@ -30,6 +30,31 @@ int32_t Ctx::pinned_reserve(size_t bytes) {
     return SCZ_OK;
 }
 
+void Ctx::prof_begin(int id) {
+    ProfRec r;
+    r.id = id;
+    for (cudaEvent_t *e : {&r.a, &r.b}) {
+        if (!prof_pool.empty()) {
+            *e = prof_pool.back();
+            prof_pool.pop_back();
+        } else {
+            cudaEventCreate(e);
+        }
+    }
+    cudaEventRecord(r.a, stream);
+    prof_recs.push_back(r);
+}
+void Ctx::prof_end() {
+    if (!prof_recs.empty()) cudaEventRecord(prof_recs.back().b, stream);
+}
+void Ctx::prof_clear() {
+    for (ProfRec &r : prof_recs) {
+        prof_pool.push_back(r.a);
+        prof_pool.push_back(r.b);
+    }
+    prof_recs.clear();
+}
+
 // ------------------------------------------------------------------ leader simulator
 // serializing_net.rs:147-167: the leader "receives" n_parties clones of its own message
 int32_t LeaderSimNet::gather(Ctx *ctx, const void *d_send, void *d_recv, size_t bytes, size_t wire) {
@@ -131,6 +156,8 @@ void scz_ctx_destroy(scz_ctx *h) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     if (c->pinned) cudaFreeHost(c->pinned);
+    c->prof_clear();
+    for (cudaEvent_t e : c->prof_pool) cudaEventDestroy(e);
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
     delete c->net;
     delete h;
@@ -159,6 +186,30 @@ int32_t scz_ctx_own_stream(scz_ctx *h) {
 int32_t scz_ctx_sync(scz_ctx *h) {
     if (!h) return SCZ_ERR_BAD_ARG;
     SCZ_CUDA(&h->c, cudaStreamSynchronize(h->c.stream));
+    return SCZ_OK;
+}
+int32_t scz_prof_enable(scz_ctx *h, int32_t on) {
+    if (!h) return SCZ_ERR_BAD_ARG;
+    SCZ_CUDA(&h->c, cudaStreamSynchronize(h->c.stream));
+    h->c.prof_clear();
+    h->c.prof = on != 0;
+    return SCZ_OK;
+}
+int32_t scz_prof_read(scz_ctx *h, int32_t kernel_class, double *ms_total, uint64_t *brackets) {
+    if (!h) return SCZ_ERR_BAD_ARG;
+    Ctx *c = &h->c;
+    SCZ_CUDA(c, cudaStreamSynchronize(c->stream));
+    double ms = 0;
+    uint64_t n = 0;
+    for (const Ctx::ProfRec &r : c->prof_recs) {
+        if (r.id != kernel_class) continue;
+        float t = 0;
+        SCZ_CUDA(c, cudaEventElapsedTime(&t, r.a, r.b));
+        ms += t;
+        n++;
+    }
+    if (ms_total) *ms_total = ms;
+    if (brackets) *brackets = n;
     return SCZ_OK;
 }
 uint64_t scz_ctx_launch_count(const scz_ctx *h) { return h ? h->c.launches : 0; }

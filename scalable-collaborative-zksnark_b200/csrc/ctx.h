@@ -27,6 +27,17 @@ struct Ctx {
     uint64_t launches = 0;   // kernels launched by this ctx (bench.py reports it as gpu_launches)
     uint32_t msm_window_override = 0;
     uint64_t msm_bucket_adds = 0, msm_buckets = 0, msm_windows = 0;   // statistics of the last MSM sequence
+    // optional per-kernel-class device timing (scz_prof_*): CUDA events recorded on `stream` around the launches
+    struct ProfRec {
+        int id;
+        cudaEvent_t a, b;
+    };
+    bool prof = false;
+    std::vector<ProfRec> prof_recs;
+    std::vector<cudaEvent_t> prof_pool;
+    void prof_begin(int id);
+    void prof_end();
+    void prof_clear();
 
     int32_t fail(int32_t code, const char *fmt, ...);
     int32_t cuda(cudaError_t e, const char *what);
@@ -73,6 +84,17 @@ struct DevTmp {
         cudaError_t e__ = cudaGetLastError();                         \
         if (e__ != cudaSuccess) return (ctx)->cuda(e__, "kernel launch"); \
     } while (0)
+
+// RAII bracket: times everything launched on ctx->stream inside the scope under kernel class `id`
+struct ProfScope {
+    Ctx *c;
+    ProfScope(Ctx *ctx, int id) : c(ctx) {
+        if (c->prof) c->prof_begin(id);
+    }
+    ~ProfScope() {
+        if (c->prof) c->prof_end();
+    }
+};
 
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 static inline uint32_t ceil_div_u32(size_t a, size_t b) { return (uint32_t)((a + b - 1) / b); }

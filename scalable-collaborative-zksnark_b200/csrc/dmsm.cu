@@ -14,14 +14,13 @@
 
 namespace scz {
 
-// sec[k*l + i] <- sum_i sec[k*l + i] for every i   (dmsm.rs:34-35)
-__global__ void k_g1_sum_replicate(void *sec, uint32_t l, uint32_t batch) {
-    uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= batch) return;
-    G1X acc = G1X::inf();
-    for (uint32_t i = 0; i < l; i++) acc = g1x_add(acc, g1x_from_jac(g1j_load(sec, (size_t)k * l + i)));
-    G1Jac r = g1x_to_jac(acc);
-    for (uint32_t i = 0; i < l; i++) g1j_store(sec, (size_t)k * l + i, r);
+// The leader closure alone (dmsm.rs:31-38) on an already gathered buffer: recv is party-major
+// [party][k] (n x batch Jacobian points), send receives the same layout.  unpack2 -> sum of the l
+// secrets -> replicate -> pack_from_public is ONE fixed n x n Fr matrix (built at scz_pp_new), so the
+// closure is a single round of n^2 parallel scalar multiplications per batch entry.
+int32_t d_msm_leader(Ctx *ctx, const scz_pp *pp, const void *d_recv, size_t batch, void *d_send) {
+    ProfScope ps(ctx, SCZ_K_PSS);
+    return pss_apply(ctx, pp, PSS_DMSM, 1, d_recv, pp->n, 1, batch, batch, d_send, 1, batch);
 }
 
 int32_t d_msm_dev(Ctx *ctx, const scz_pp *pp, const void *const *d_bases, const void *const *d_scalars,
@@ -31,22 +30,18 @@ int32_t d_msm_dev(Ctx *ctx, const scz_pp *pp, const void *const *d_bases, const 
     Net *net = ctx->net;
     const size_t N = net->n_parties, PT = SCZ_G1_JAC_BYTES;
     if (N != pp->n) return ctx->fail(SCZ_ERR_BAD_ARG, "d_msm: %zu parties but pp.n = %zu", N, pp->n);
-    DevTmp c_shares(ctx), recv(ctx), sec(ctx), send(ctx);
+    DevTmp c_shares(ctx), recv(ctx), send(ctx);
     SCZ_TRY(c_shares.alloc(batch * PT));
     SCZ_TRY(msm_g1_batched(ctx, d_bases, d_scalars, lens, batch, c_shares.p));
     const size_t wire = 8 + 48 * batch;
     if (net->is_leader()) {
         SCZ_TRY(recv.alloc(N * batch * PT));
-        SCZ_TRY(sec.alloc(batch * pp->l * PT));
         SCZ_TRY(send.alloc(N * batch * PT));
     }
     SCZ_TRY(net->gather(ctx, c_shares.p, recv.p, batch * PT, wire));
     if (net->is_leader()) {
         // recv is party-major [j][k]: vector k is the stride-`batch` column
-        SCZ_TRY(pss_apply(ctx, pp, PSS_UNPACK2, 1, recv.p, pp->n, 1, batch, batch, sec.p, pp->l, 1));
-        k_g1_sum_replicate<<<ceil_div_u32(batch, 32), 32, 0, ctx->stream>>>(sec.p, (uint32_t)pp->l, (uint32_t)batch);
-        SCZ_LAUNCH_CHECK(ctx);
-        SCZ_TRY(pss_apply(ctx, pp, PSS_PACK, 1, sec.p, pp->l, pp->l, 1, batch, send.p, 1, batch));
+        SCZ_TRY(d_msm_leader(ctx, pp, recv.p, batch, send.p));
     }
     SCZ_TRY(net->scatter(ctx, send.p, d_out, batch * PT, wire));
     return SCZ_OK;
@@ -63,6 +58,13 @@ int32_t scz_d_msm_dev(scz_ctx *h, const scz_pp *pp, const void *const *d_bases, 
     if (!h) return SCZ_ERR_BAD_ARG;
     if (batch && (!d_bases || !d_scalars || !lens || !d_out)) return h->c.fail(SCZ_ERR_BAD_ARG, "d_msm: null argument");
     return d_msm_dev(&h->c, pp, d_bases, d_scalars, lens, batch, d_out);
+}
+
+int32_t scz_d_msm_leader_dev(scz_ctx *h, const scz_pp *pp, const void *d_gathered, size_t batch, void *d_to_scatter) {
+    if (!h || !pp) return SCZ_ERR_BAD_ARG;
+    if (batch && (!d_gathered || !d_to_scatter)) return h->c.fail(SCZ_ERR_BAD_ARG, "d_msm_leader: null argument");
+    if (!batch) return SCZ_OK;
+    return d_msm_leader(&h->c, pp, d_gathered, batch, d_to_scatter);
 }
 
 int32_t scz_d_msm(scz_ctx *h, const scz_pp *pp, const void *const *bases, const size_t *bases_lens,

@@ -500,22 +500,6 @@ int32_t msm_g1_batched(Ctx *ctx, const void *const *d_bases, const void *const *
     int K = (int)batch;
     uint32_t *counts = d_counts.as<uint32_t>(), *cursor = d_cursor.as<uint32_t>(), *sorted = d_sorted.as<uint32_t>();
     uint32_t *keys = d_keys.as<uint32_t>();
-    if (points) {
-        k_msm_recode<false><<<ceil_div_u32(points, CNT_THREADS), CNT_THREADS, 0, st>>>(sp, K, (uint32_t)points, counts,
-                                                                                       nullptr, nullptr, nullptr);
-        SCZ_LAUNCH_CHECK(ctx);
-    }
-    k_scan_tiles<<<tiles, SCAN_THREADS, 0, st>>>(counts, cursor, d_tiles.as<uint32_t>(), (uint32_t)buckets);
-    SCZ_LAUNCH_CHECK(ctx);
-    k_scan_tile_sums<<<1, 1024, 0, st>>>(d_tiles.as<uint32_t>(), tiles);
-    SCZ_LAUNCH_CHECK(ctx);
-    k_scan_add<<<tiles, SCAN_THREADS, 0, st>>>(cursor, d_tiles.as<uint32_t>(), (uint32_t)buckets);
-    SCZ_LAUNCH_CHECK(ctx);
-    if (points) {
-        k_msm_recode<true><<<ceil_div_u32(points, CNT_THREADS), CNT_THREADS, 0, st>>>(sp, K, (uint32_t)points, nullptr,
-                                                                                      cursor, sorted, keys);
-        SCZ_LAUNCH_CHECK(ctx);
-    }
     static bool attr_done = false;
     if (!attr_done) {
         cudaFuncSetAttribute(k_msm_planes, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(PLN_THREADS * sizeof(G1X)));
@@ -524,12 +508,35 @@ int32_t msm_g1_batched(Ctx *ctx, const void *const *d_bases, const void *const *
         cudaFuncSetAttribute(k_msm_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(FIN_THREADS * sizeof(G1X)));
         attr_done = true;
     }
-    if (points) {
-        // after the scatter cursor[last bucket] = entries really in the stream (the host only knows the
-        // bound `entries`: zero digits are dropped); chunks past that end return at once
-        k_msm_accumulate<<<ceil_div_u32(nchunks, ACC_THREADS), ACC_THREADS, 0, st>>>(
-            sp, K, cursor + (buckets - 1), logT, keys, sorted, counts, cursor, d_buckets.p, d_parts.p);
+    {
+        ProfScope ps(ctx, SCZ_K_MSM_SORT);
+        if (points) {
+            k_msm_recode<false><<<ceil_div_u32(points, CNT_THREADS), CNT_THREADS, 0, st>>>(
+                sp, K, (uint32_t)points, counts, nullptr, nullptr, nullptr);
+            SCZ_LAUNCH_CHECK(ctx);
+        }
+        k_scan_tiles<<<tiles, SCAN_THREADS, 0, st>>>(counts, cursor, d_tiles.as<uint32_t>(), (uint32_t)buckets);
         SCZ_LAUNCH_CHECK(ctx);
+        k_scan_tile_sums<<<1, 1024, 0, st>>>(d_tiles.as<uint32_t>(), tiles);
+        SCZ_LAUNCH_CHECK(ctx);
+        k_scan_add<<<tiles, SCAN_THREADS, 0, st>>>(cursor, d_tiles.as<uint32_t>(), (uint32_t)buckets);
+        SCZ_LAUNCH_CHECK(ctx);
+        if (points) {
+            k_msm_recode<true><<<ceil_div_u32(points, CNT_THREADS), CNT_THREADS, 0, st>>>(
+                sp, K, (uint32_t)points, nullptr, cursor, sorted, keys);
+            SCZ_LAUNCH_CHECK(ctx);
+        }
+    }
+    if (points) {
+        {
+            // after the scatter cursor[last bucket] = entries really in the stream (the host only knows the
+            // bound `entries`: zero digits are dropped); chunks past that end return at once
+            ProfScope ps(ctx, SCZ_K_MSM_ACCUMULATE);
+            k_msm_accumulate<<<ceil_div_u32(nchunks, ACC_THREADS), ACC_THREADS, 0, st>>>(
+                sp, K, cursor + (buckets - 1), logT, keys, sorted, counts, cursor, d_buckets.p, d_parts.p);
+            SCZ_LAUNCH_CHECK(ctx);
+        }
+        ProfScope ps(ctx, SCZ_K_MSM_FIXUP);
         uint32_t *heavy = d_heavy.as<uint32_t>();
         k_msm_fixup<<<ceil_div_u32(buckets, FIX_THREADS), FIX_THREADS, 0, st>>>((uint32_t)buckets, logT, counts, cursor,
                                                                                 d_parts.p, d_buckets.p, heavy + 1, heavy);
@@ -538,14 +545,20 @@ int32_t msm_g1_batched(Ctx *ctx, const void *const *d_bases, const void *const *
             logT, counts, cursor, d_parts.p, d_buckets.p, heavy + 1, heavy);
         SCZ_LAUNCH_CHECK(ctx);
     }
-    k_msm_chunks<<<ceil_div_u32(chunks, CHK_THREADS), CHK_THREADS, 0, st>>>(sp, K, (uint32_t)chunks, counts, d_buckets.p,
-                                                                           d_chS.p, d_chR.p);
-    SCZ_LAUNCH_CHECK(ctx);
-    k_msm_planes<<<dim3((uint32_t)windows, max_planes), PLN_THREADS, PLN_THREADS * sizeof(G1X), st>>>(
-        sp, K, d_chS.p, d_chR.p, d_planes.p);
-    SCZ_LAUNCH_CHECK(ctx);
-    k_msm_finish<<<(uint32_t)batch, FIN_THREADS, FIN_THREADS * sizeof(G1X), st>>>(sp, d_planes.p, d_out);
-    SCZ_LAUNCH_CHECK(ctx);
+    {
+        ProfScope ps(ctx, SCZ_K_MSM_REDUCE);
+        k_msm_chunks<<<ceil_div_u32(chunks, CHK_THREADS), CHK_THREADS, 0, st>>>(sp, K, (uint32_t)chunks, counts,
+                                                                               d_buckets.p, d_chS.p, d_chR.p);
+        SCZ_LAUNCH_CHECK(ctx);
+        k_msm_planes<<<dim3((uint32_t)windows, max_planes), PLN_THREADS, PLN_THREADS * sizeof(G1X), st>>>(
+            sp, K, d_chS.p, d_chR.p, d_planes.p);
+        SCZ_LAUNCH_CHECK(ctx);
+    }
+    {
+        ProfScope ps(ctx, SCZ_K_MSM_FINISH);
+        k_msm_finish<<<(uint32_t)batch, FIN_THREADS, FIN_THREADS * sizeof(G1X), st>>>(sp, d_planes.p, d_out);
+        SCZ_LAUNCH_CHECK(ctx);
+    }
     return SCZ_OK;
 }
 

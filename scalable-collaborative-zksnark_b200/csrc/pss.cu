@@ -26,7 +26,7 @@ __device__ __forceinline__ Fr fr_from_u32(uint32_t v) {
 
 // tables layout (Fr each): wn[n] | gpow[4l] | ginvpow[2l] | ninv | inv2l
 __global__ void __launch_bounds__(256) k_pss_setup(uint32_t l, void *tables, void *pack, void *pack_single,
-                                                    void *unpack, void *unpack2) {
+                                                    void *unpack, void *unpack2, void *dmsm) {
     const uint32_t n = 8 * l, s1 = 2 * l, s2 = 4 * l;
     Fr *wn = reinterpret_cast<Fr *>(tables);
     Fr *gpow = wn + n, *ginvpow = gpow + s2, *consts = ginvpow + s1;
@@ -94,6 +94,17 @@ __global__ void __launch_bounds__(256) k_pss_setup(uint32_t l, void *tables, voi
         for (uint32_t i = 0; i < s1; i++) acc = fp_add(acc, fp_mul(P[j * s1 + i], P[i * s1]));
         PS[j] = acc;
     }
+    // DMSM[j][i] = (sum_{a<l} PACK[j][a]) * (sum_{b<l} UNPACK2[b][i]): unpack2, sum the l secrets, replicate, pack
+    Fr *D = reinterpret_cast<Fr *>(dmsm);
+    for (uint32_t idx = threadIdx.x; idx < n * n; idx += blockDim.x) {
+        uint32_t j = idx / n, i = idx % n;
+        Fr pj = Fr::zero(), ui = Fr::zero();
+        for (uint32_t a = 0; a < l; a++) {
+            pj = fp_add(pj, P[j * s1 + a]);
+            ui = fp_add(ui, U2[a * n + i]);
+        }
+        D[idx] = fp_mul(pj, ui);
+    }
 }
 
 // out(b, o) = sum_j M[o*mcols + j] * in(b, j)   over Fr
@@ -155,9 +166,13 @@ int32_t pss_apply(Ctx *ctx, const scz_pp *pp, PssMap map, int kind, const void *
             len_in = pp->n;
             M = pp->d_unpack, mcols = (uint32_t)pp->n, rows = (uint32_t)pp->l;
             break;
-        default:
+        case PSS_UNPACK2:
             len_in = pp->n;
             M = pp->d_unpack2, mcols = (uint32_t)pp->n, rows = (uint32_t)pp->l;
+            break;
+        default:
+            len_in = pp->n;
+            M = pp->d_dmsm, mcols = (uint32_t)pp->n, rows = (uint32_t)pp->n;
             break;
     }
     if (kind == 0) {
@@ -191,7 +206,7 @@ int32_t scz_pp_new(scz_ctx *h, size_t l, scz_pp **out) {
     pp->device = c->device;
     size_t n = pp->n;
     char *blk = nullptr;
-    size_t total = (n * 2 * l + n + 2 * l * n) * 32;
+    size_t total = (n * 2 * l + n + 2 * l * n + n * n) * 32;
     cudaError_t e = cudaMalloc(&blk, total);
     if (e != cudaSuccess) {
         delete pp;
@@ -201,11 +216,12 @@ int32_t scz_pp_new(scz_ctx *h, size_t l, scz_pp **out) {
     pp->d_pack_single = blk + n * 2 * l * 32;
     pp->d_unpack = blk + (n * 2 * l + n) * 32;
     pp->d_unpack2 = blk + (n * 2 * l + n + l * n) * 32;
+    pp->d_dmsm = blk + (n * 2 * l + n + 2 * l * n) * 32;
     DevTmp tables(c);
     int32_t rc = tables.alloc((n + 4 * l + 2 * l + 2) * 32);
     if (rc == SCZ_OK) {
         k_pss_setup<<<1, 256, 0, c->stream>>>((uint32_t)l, tables.p, pp->d_pack, pp->d_pack_single, pp->d_unpack,
-                                              pp->d_unpack2);
+                                              pp->d_unpack2, pp->d_dmsm);
         c->launches++;
         e = cudaStreamSynchronize(c->stream);
         if (e != cudaSuccess) rc = c->cuda(e, "k_pss_setup");

@@ -10,11 +10,12 @@ struct scz_pp {
     void *d_pack_single;  // n      : pack_single(s)[j] = PS[j] * s
     void *d_unpack;       // l x n
     void *d_unpack2;      // l x n
+    void *d_dmsm;         // n x n : the whole d_msm leader closure, pack([sum_l unpack2(.)] * l)  (dmsm.rs:31-38)
 };
 
 namespace scz {
 
-enum PssMap { PSS_PACK = 0, PSS_PACK_SINGLE = 1, PSS_UNPACK = 2, PSS_UNPACK2 = 3 };
+enum PssMap { PSS_PACK = 0, PSS_PACK_SINGLE = 1, PSS_UNPACK = 2, PSS_UNPACK2 = 3, PSS_DMSM = 4 };
 
 // Applies one of the four linear maps to `batch` vectors.
 // Element (b, j) of the input sits at element index b*in_bstride + j*in_jstride,

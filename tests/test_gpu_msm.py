@@ -165,3 +165,23 @@ def test_config2_msm_2p20_trapdoor_and_linearity(orc, ctx):
     assert orc.canon_g1(ctx.to_host(ctx.g1_add(r1, r2))) == orc.canon_g1(ctx.to_host(r12))
     st = ctx.msm_last_stats()
     assert st["bucket_adds"] == n * st["windows"]
+
+
+@pytest.mark.parametrize("l", [1, 2])
+def test_d_msm_leader_closure_parties_mode(orc, ctx, l):
+    """dmsm.rs:31-38 with N real parties: per batch entry unpack2 -> sum of the l secrets -> [sum; l] -> pack.
+    The device folds the closure into one n x n matrix; the oracle runs the FFT pairs step by step."""
+    import scz_b200 as scz
+    rng = np.random.default_rng(310 + l)
+    pp = scz.PackedSharingParams(ctx, l)
+    opp = orc.pp_new(l)
+    n, batch = 8 * l, 3
+    pts = orc.g1_from_affine(orc.random_g1(rng, n * batch)).reshape(n, batch, 18)   # [party][k]
+    got = scz.d_msm_leader(ctx, pp, pts)
+    for k in range(batch):
+        sec = orc.unpack2(opp, pts[:, k, :], kind=1)
+        tot = sec[0:1]
+        for i in range(1, l):
+            tot = orc.g1_add(tot, sec[i:i + 1])
+        want = orc.pack_from_public(opp, np.repeat(tot, l, axis=0), kind=1)
+        assert orc.canon_g1(got[:, k, :]) == orc.canon_g1(want), (l, k)
