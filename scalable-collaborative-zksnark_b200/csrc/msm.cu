@@ -33,7 +33,7 @@
 #include <algorithm>
 #include <vector>
 
-#include "g1.cuh"
+#include "g1_coop.cuh"
 #include "msm.h"
 #include "msm_digits.cuh"
 
@@ -373,41 +373,49 @@ __global__ void __launch_bounds__(PLN_THREADS) k_msm_planes(const MsmSeg *segs, 
         if (!v.is_inf()) g1x_add_nl(acc, acc, v);
     }
     acc = block_sum_g1x<PLN_THREADS>(acc, sh);
-    if (threadIdx.x == 0) g1x_store(planes, sg.plane_base + w * (sg.PB + 2) + plane, acc);
+    // planes leave as Jacobian (144 B): the finish kernel works on (X, Y, Z)
+    if (threadIdx.x == 0) g1j_store(planes, sg.plane_base + w * (sg.PB + 2) + plane, g1x_to_jac(acc));
 }
 
-// ---- 8: one CTA per segment.  Thread w: window sum = sum_q R_q + L * sum_b 2^b plane_b + sum_q S_q;
-//         then thread 0 runs Horner over the windows (the only long serial chain of the pipeline).
+// ---- 8: one CTA per segment.  Both stages are serial chains in the group law, so they run on groups of 4
+//         cooperating lanes (g1_coop.cuh).  Group w: window sum = sum_q R_q + L * sum_b 2^b plane_b + sum_q S_q;
+//         then warp 0 runs Horner over the windows (255 doublings: the longest chain of the pipeline).
+constexpr int FIN_GROUPS = FIN_THREADS / 4;
 __global__ void __launch_bounds__(FIN_THREADS) k_msm_finish(const MsmSeg *segs, const void *planes, void *out_jac) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    G1X *sh = reinterpret_cast<G1X *>(smem_raw);
+    G1Jac *sh = reinterpret_cast<G1Jac *>(smem_raw);   // [W]
     const MsmSeg sg = segs[blockIdx.x];
-    uint32_t w = threadIdx.x;
-    if (sg.len && w < sg.W) {
-        size_t pb = sg.plane_base + (size_t)w * (sg.PB + 2);
-        G1X X = G1X::inf();
-        for (uint32_t b = sg.PB; b-- > 0;) {
-            g1x_double_nl(X, X);
-            G1X v = g1x_load(planes, pb + b);
-            g1x_add_nl(X, X, v);
+    const Coop g;
+    const uint32_t gi = threadIdx.x >> 2;
+    if (sg.len) {
+        for (uint32_t w = gi; w < sg.W; w += FIN_GROUPS) {
+            size_t pb = sg.plane_base + (size_t)w * (sg.PB + 2);
+            G1Jac X = g1j_inf();
+            for (uint32_t b = sg.PB; b-- > 0;) {
+                coop_double(g, X);
+                G1Jac v = g1j_load(planes, pb + b);
+                coop_add(g, X, v);
+            }
+            for (uint32_t i = 0; i < sg.logL; i++) coop_double(g, X);
+            G1Jac v = g1j_load(planes, pb + sg.PB + 1);
+            coop_add(g, X, v);
+            v = g1j_load(planes, pb + sg.PB);
+            coop_add(g, X, v);
+            if (g.role == 0) sh[w] = X;
         }
-        for (uint32_t i = 0; i < sg.logL; i++) g1x_double_nl(X, X);
-        G1X v = g1x_load(planes, pb + sg.PB + 1);
-        g1x_add_nl(X, X, v);
-        v = g1x_load(planes, pb + sg.PB);
-        g1x_add_nl(X, X, v);
-        sh[w] = X;
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
-        G1X acc = G1X::inf();
+    if (threadIdx.x < 32) {   // warp 0: its 8 groups run the same chain redundantly (lanes are free)
+        G1Jac acc = g1j_inf();
         if (sg.len) {
             for (uint32_t ww = sg.W; ww-- > 0;) {
-                for (uint32_t i = 0; i < sg.c; i++) g1x_double_nl(acc, acc);
-                g1x_add_nl(acc, acc, sh[ww]);
+                if (!acc.z.is_zero())
+                    for (uint32_t i = 0; i < sg.c; i++) coop_double(g, acc);
+                G1Jac v = sh[ww];
+                coop_add(g, acc, v);
             }
         }
-        g1j_store(out_jac, blockIdx.x, g1x_to_jac(acc));
+        if (threadIdx.x == 0) g1j_store(out_jac, blockIdx.x, acc);
     }
 }
 
@@ -490,7 +498,7 @@ int32_t msm_g1_batched(Ctx *ctx, const void *const *d_bases, const void *const *
     SCZ_TRY(d_heavy.alloc((buckets + 1) * 4));   // [0] = count, [1..] = list
     SCZ_TRY(d_chS.alloc(chunks * sizeof(G1X)));
     SCZ_TRY(d_chR.alloc(chunks * sizeof(G1X)));
-    SCZ_TRY(d_planes.alloc(planes * sizeof(G1X)));
+    SCZ_TRY(d_planes.alloc(planes * sizeof(G1Jac)));
     // segment table: pageable host -> device; the vector must outlive the copy
     SCZ_CUDA(ctx, cudaMemcpyAsync(d_segs.p, segs.data(), batch * sizeof(MsmSeg), cudaMemcpyHostToDevice, st));
     SCZ_CUDA(ctx, cudaStreamSynchronize(st));
@@ -505,7 +513,7 @@ int32_t msm_g1_batched(Ctx *ctx, const void *const *d_bases, const void *const *
         cudaFuncSetAttribute(k_msm_planes, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(PLN_THREADS * sizeof(G1X)));
         cudaFuncSetAttribute(k_msm_fixup_heavy, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)(PLN_THREADS * sizeof(G1X)));
-        cudaFuncSetAttribute(k_msm_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(FIN_THREADS * sizeof(G1X)));
+        cudaFuncSetAttribute(k_msm_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(FIN_THREADS * sizeof(G1Jac)));
         attr_done = true;
     }
     {
@@ -556,7 +564,7 @@ int32_t msm_g1_batched(Ctx *ctx, const void *const *d_bases, const void *const *
     }
     {
         ProfScope ps(ctx, SCZ_K_MSM_FINISH);
-        k_msm_finish<<<(uint32_t)batch, FIN_THREADS, FIN_THREADS * sizeof(G1X), st>>>(sp, d_planes.p, d_out);
+        k_msm_finish<<<(uint32_t)batch, FIN_THREADS, FIN_THREADS * sizeof(G1Jac), st>>>(sp, d_planes.p, d_out);
         SCZ_LAUNCH_CHECK(ctx);
     }
     return SCZ_OK;

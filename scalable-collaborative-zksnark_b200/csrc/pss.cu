@@ -13,7 +13,7 @@
 // every twiddle.  Applying a map is then a batched small mat-vec: one thread per
 // output element over Fr, and for G1 operands (the d_msm leader closure) one CTA
 // per output point, one scalar multiplication per thread, shared-memory tree sum.
-#include "g1.cuh"
+#include "g1_coop.cuh"
 #include "pss.h"
 
 namespace scz {
@@ -120,30 +120,40 @@ __global__ void __launch_bounds__(128) k_pss_apply_fr(const void *M, uint32_t mc
         acc = fp_add(acc, fp_mul(fp_load<FrP>(M, (size_t)o * mcols + j), fp_load_rw<FrP>(in, b * in_b + j * in_j)));
     fp_store<FrP>(out, b * out_b + o * out_o, acc);
 }
-// same over G1: one CTA per output point, thread j does M[o][j] * in(b, j); tree sum in shared memory
-template <int T>
-__global__ void __launch_bounds__(T) k_pss_apply_g1(const void *M, uint32_t mcols, uint32_t rows, uint32_t len_in,
-                                                    const void *in, size_t in_b, size_t in_j, void *out, size_t out_b,
-                                                    size_t out_o) {
+// same over G1: one CTA per output point.  Term j = M[o][j] * in(b, j) is a 255-bit scalar multiplication: a
+// serial chain, run by a group of 4 cooperating lanes (g1_coop.cuh) with a 4-bit window table in shared
+// memory; the groups' terms are then tree-summed.
+template <int GROUPS>
+__global__ void __launch_bounds__(GROUPS * 4) k_pss_apply_g1(const void *M, uint32_t mcols, uint32_t rows,
+                                                              uint32_t len_in, const void *in, size_t in_b, size_t in_j,
+                                                              void *out, size_t out_b, size_t out_o) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    G1X *sh = reinterpret_cast<G1X *>(smem_raw);
+    G1Jac *tab = reinterpret_cast<G1Jac *>(smem_raw);          // [GROUPS][16]
+    G1Jac *res = tab + GROUPS * 16;                             // [GROUPS]
+    const Coop g;
+    const int gi = threadIdx.x >> 2;
     size_t b = blockIdx.x / rows;
     uint32_t o = blockIdx.x % rows;
-    G1X acc = G1X::inf();
-    for (uint32_t j = threadIdx.x; j < len_in; j += T) {
-        G1X p = g1x_from_jac(g1j_load(in, b * in_b + j * in_j));
-        acc = g1x_add(acc, g1x_mul_fr(p, fp_load<FrP>(M, (size_t)o * mcols + j)));
+    G1Jac acc = g1j_inf();
+    for (uint32_t j = gi; j < len_in; j += GROUPS) {
+        G1Jac p = g1j_load(in, b * in_b + j * in_j);
+        Fr k = fp_to_canon(fp_load<FrP>(M, (size_t)o * mcols + j));
+        if (p.z.is_zero() || k.is_zero()) continue;
+        G1Jac t = coop_mul_bits(g, p, k.l, tab + gi * 16);
+        coop_add(g, acc, t);
     }
-    sh[threadIdx.x] = acc;
+    if (g.role == 0) res[gi] = acc;
     __syncthreads();
-    for (int stride = T / 2; stride > 0; stride >>= 1) {
-        if ((int)threadIdx.x < stride) {
-            acc = g1x_add(acc, sh[threadIdx.x + stride]);
-            sh[threadIdx.x] = acc;
+    for (int stride = GROUPS / 2; stride > 0; stride >>= 1) {
+        if (gi < stride) {
+            G1Jac o2 = res[gi + stride];
+            coop_add(g, acc, o2);
         }
         __syncthreads();
+        if (gi < stride && g.role == 0) res[gi] = acc;
+        __syncthreads();
     }
-    if (threadIdx.x == 0) g1j_store(out, b * out_b + o * out_o, g1x_to_jac(acc));
+    if (threadIdx.x == 0) g1j_store(out, b * out_b + o * out_o, acc);
 }
 
 int32_t pss_apply(Ctx *ctx, const scz_pp *pp, PssMap map, int kind, const void *d_in, size_t len_in, size_t in_b,
@@ -179,9 +189,18 @@ int32_t pss_apply(Ctx *ctx, const scz_pp *pp, PssMap map, int kind, const void *
         k_pss_apply_fr<<<ceil_div_u32(batch * rows, 128), 128, 0, ctx->stream>>>(M, mcols, rows, (uint32_t)len_in, d_in,
                                                                                  in_b, in_j, batch, d_out, out_b, out_o);
     } else {
-        // one scalar multiplication per thread; 32 threads cover n = 8l up to l = 4 in one pass
-        k_pss_apply_g1<32><<<(uint32_t)(batch * rows), 32, 32 * sizeof(G1X), ctx->stream>>>(
-            M, mcols, rows, (uint32_t)len_in, d_in, in_b, in_j, d_out, out_b, out_o);
+        static bool attr_done = false;
+        constexpr size_t SH8 = 8 * 17 * sizeof(G1Jac), SH32 = 32 * 17 * sizeof(G1Jac);
+        if (!attr_done) {
+            cudaFuncSetAttribute(k_pss_apply_g1<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SH32);
+            attr_done = true;
+        }
+        if (len_in <= 8)
+            k_pss_apply_g1<8><<<(uint32_t)(batch * rows), 32, SH8, ctx->stream>>>(M, mcols, rows, (uint32_t)len_in, d_in,
+                                                                                 in_b, in_j, d_out, out_b, out_o);
+        else
+            k_pss_apply_g1<32><<<(uint32_t)(batch * rows), 128, SH32, ctx->stream>>>(
+                M, mcols, rows, (uint32_t)len_in, d_in, in_b, in_j, d_out, out_b, out_o);
     }
     SCZ_LAUNCH_CHECK(ctx);
     return SCZ_OK;
