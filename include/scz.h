@@ -142,6 +142,25 @@ int32_t scz_g1_to_affine_dev(scz_ctx *ctx, const void *d_jac, void *d_out_affine
 /* synthetic bases: out[i] = k[i] * G1 generator, packed affine (stands in for G1::rand, dpoly_comm.rs:214,229) */
 int32_t scz_g1_generator_mul_dev(scz_ctx *ctx, const void *d_k, void *d_out_affine, size_t n);
 
+/* ---- Fr tables: the local loops of dsumcheck.rs, dpoly_comm.rs, dacc_product.rs, mle.rs, dhyperplonk.rs ---- */
+/* n = log2(len) rounds of the product sumcheck (dsumcheck.rs:37-85; the same loop at :167-219, :377-429):
+ * round i splits the tables top-half / bottom-half, emits (sum f0 g0, sum f1 g1, sum (2f1-f0)(2g1-g0)) and folds with
+ * challenge[i].  d_out_triples: n triples; d_last_fg: the two fully folded values (f, g).  Inputs are not modified. */
+int32_t scz_sumcheck_product_rounds_dev(scz_ctx *ctx, const void *d_f, const void *d_g, size_t len,
+                                        const void *d_challenge, void *d_out_triples, void *d_last_fg);
+/* the fold rounds of a PST opening (dpoly_comm.rs:309-323 = :337-351 = :418-432): q_i = hi - lo, r = (1-u_i) lo + u_i hi.
+ * d_q receives q_0 | q_1 | ... | q_{n-1} (len/2 + len/4 + ... + 1 = len - 1 entries), d_value the evaluation. */
+int32_t scz_open_fold_dev(scz_ctx *ctx, const void *d_peval, size_t len, const void *d_point, void *d_q, void *d_value);
+/* fix_variable (mle.rs:88-104): folds the top min(npoints, log2 len) variables; d_out gets len >> that many entries */
+int32_t scz_fix_variable_dev(scz_ctx *ctx, const void *d_evals, size_t len, const void *d_points, size_t npoints,
+                             void *d_out);
+/* acc_product's table (dacc_product.rs:30-39 = :374-381): d_tree has 2m entries: x | products level by level | 0 */
+int32_t scz_acc_product_dev(scz_ctx *ctx, const void *d_x, size_t m, void *d_tree);
+/* point-wise maps of dhyperplonk.rs:233-238, 251-256, 326-339.  mode 0: a + b; 1: b - a; 2: a + k[0]*b + k[1]
+ * (d_k: two Fr on the device); 3: a / b with one shared inversion per warp (b = 0 -> 0; arkworks would panic) */
+int32_t scz_fr_pointwise_dev(scz_ctx *ctx, int32_t mode, const void *d_a, const void *d_b, const void *d_k, void *d_out,
+                             size_t n);
+
 /* ---- MSM: ark-ec VariableBaseMSM::msm, call sites dmsm.rs:23, dpoly_comm.rs:242,274,457 ----- */
 /* One launch sequence computes `batch` independent MSMs; out_jac holds batch Jacobian points. */
 int32_t scz_msm_g1_batched_dev(scz_ctx *ctx, const void *const *d_bases, const void *const *d_scalars,
@@ -183,6 +202,52 @@ int32_t scz_d_msm_leader_dev(scz_ctx *ctx, const scz_pp *pp, const void *d_gathe
                              void *d_to_scatter);
 int32_t scz_d_msm(scz_ctx *ctx, const scz_pp *pp, const void *const *bases, const size_t *bases_lens,
                   const void *const *scalars, const size_t *scalars_lens, size_t batch, void *out_jac);
+
+/* ---- re-sharing rounds -------------------------------------------------------------------------------- */
+/* pss2ss (unpack.rs:72-97): one share in, Vec<F> of length l out (gather, leader unpack + pack_single, scatter) */
+int32_t scz_pss2ss_dev(scz_ctx *ctx, const scz_pp *pp, const void *d_share, void *d_out);
+/* degree_reduce (degree_reduce.rs:29-41): one share in, one share out (gather, unpack2, pack_from_public, scatter) */
+int32_t scz_degree_reduce_dev(scz_ctx *ctx, const scz_pp *pp, const void *d_share, void *d_out);
+
+/* ---- sumcheck family: dist-primitive/src/dsumcheck.rs ---------------------------------------------------- */
+/* sumcheck_product (:28-90): n + 1 triples, the last is (0, f*g, 0) */
+int32_t scz_sumcheck_product_dev(scz_ctx *ctx, const void *d_f, const void *d_g, size_t len, const void *d_challenge,
+                                 void *d_out);
+/* c_sumcheck_product (:148-285): n + log2(l) + 1 triples; phase 2 re-uses challenge[0..log2 l) like the reference (:230) */
+int32_t scz_c_sumcheck_product_dev(scz_ctx *ctx, const scz_pp *pp, const void *d_f, const void *d_g, size_t len,
+                                   const void *d_challenge, void *d_out);
+/* d_sumcheck_product (:359-512): d_challenge holds n + log2(N) challenges; the leader gets *count = n + log2(N)
+ * triples in d_out, every other party *count = 0 (the reference returns an empty Vec, :507-509) */
+int32_t scz_d_sumcheck_product_dev(scz_ctx *ctx, const void *d_f, const void *d_g, size_t len, const void *d_challenge,
+                                   void *d_out, size_t *count);
+/* d_acc_product (dacc_product.rs:365-414): d_subtree 2m entries; on the leader d_leader_tree 2N entries */
+int32_t scz_d_acc_product_dev(scz_ctx *ctx, const void *d_x, size_t m, void *d_subtree, void *d_leader_tree);
+
+/* ---- multilinear KZG: dist-primitive/src/dpoly_comm.rs --------------------------------------------------- */
+/* powers_of_g (:30-34): level i = packed affine bases; _device_ borrows the caller's device arrays, _host_ uploads */
+int32_t scz_srs_from_device_levels(scz_ctx *ctx, size_t levels, const void *const *d_levels, const size_t *lens,
+                                   scz_srs **out);
+int32_t scz_srs_from_host_levels(scz_ctx *ctx, size_t levels, const void *const *levels_host, const size_t *lens,
+                                 scz_srs **out);
+void scz_srs_free(scz_srs *srs);
+int32_t scz_srs_info(const scz_srs *srs, size_t *levels);
+/* commit / d_local_commit (:237-243, :269-275): len must be 2^level with level < #levels (SCZ_ERR_NOT_POW2 / LEVEL_OOB) */
+int32_t scz_commit_dev(scz_ctx *ctx, const scz_srs *srs, const void *d_peval, size_t len, void *d_out_jac);
+/* c_commit (:244-267): level = log2(len * l); one d_msm over the batch */
+int32_t scz_c_commit_dev(scz_ctx *ctx, const scz_srs *srs, const scz_pp *pp, const void *const *d_pevals,
+                         const size_t *lens, size_t batch, void *d_out_jac);
+/* d_commit (:276-297): local commit, the leader sums the N commitments, every party receives the sum */
+int32_t scz_d_commit_dev(scz_ctx *ctx, const scz_srs *srs, const void *d_peval, size_t len, void *d_out_jac);
+/* open / d_local_open (:299-325, :327-353): value (1 Fr) + n proofs */
+int32_t scz_open_dev(scz_ctx *ctx, const scz_srs *srs, const void *d_peval, size_t len, const void *d_point,
+                     void *d_value, void *d_proofs_jac);
+/* c_open (:401-464): value + n + log2(l) proofs; all n quotient commitments go out as one batched c_commit (:436) */
+int32_t scz_c_open_dev(scz_ctx *ctx, const scz_srs *srs, const scz_pp *pp, const void *d_peval, size_t len,
+                       const void *d_point, void *d_value, void *d_proofs_jac);
+/* d_open (:355-398): point has log2(N) + n coordinates; leader: value + log2(N) root proofs ++ n summed proofs
+ * (*count = log2(N) + n); others: value 0, *count = 0 (:387) */
+int32_t scz_d_open_dev(scz_ctx *ctx, const scz_srs *srs, const void *d_peval, size_t len, const void *d_point,
+                       size_t npoint, void *d_value, void *d_proofs_jac, size_t *count);
 
 #ifdef __cplusplus
 }

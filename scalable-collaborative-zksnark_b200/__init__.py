@@ -14,5 +14,16 @@ from .api import (  # noqa: F401
     d_msm,
     d_msm_leader,
     msm_batched,
+    PolynomialCommitment,
+    acc_product_tree,
+    c_sumcheck_product,
+    d_acc_product,
+    d_sumcheck_product,
+    degree_reduce,
+    fix_variable,
+    fr_pointwise,
+    pss2ss,
+    sumcheck_product,
+    sumcheck_rounds,
     msm,
 )

@@ -331,4 +331,205 @@ def d_msm_leader(ctx, pp, gathered):
     return out if _is_dev(gathered) else ctx.to_host(out.reshape(-1, 18)).reshape(pp.n, batch, 18)
 
 
-__all__ = ["Context", "PackedSharingParams", "msm", "msm_batched", "d_msm", "d_msm_leader", "NetVTable"]
+# ---------------------------------------------------------------------------- Fr tables
+def _vp(t):
+    return C.c_void_p(t.data_ptr())
+
+
+def _in(ctx, x, cols):
+    """-> (device tensor, was_host)"""
+    if _is_dev(x):
+        return _dev(x, cols), False
+    return ctx.to_device(x, cols), True
+
+
+def _out(ctx, t, host):
+    return ctx.to_host(t) if host else t
+
+
+def _log2(v):
+    return v.bit_length() - 1
+
+
+def fr_pointwise(ctx, mode, a, b, k=None):
+    """dhyperplonk.rs:233-238, 251-256, 326-339.  mode: 'add' a+b, 'rsub' b-a, 'axpb' a + k[0]*b + k[1], 'div' a/b"""
+    ad, host = _in(ctx, a, 4)
+    bd, _ = _in(ctx, b, 4)
+    kd = _in(ctx, k, 4)[0] if k is not None else None
+    out = torch.empty_like(ad)
+    m = {"add": 0, "rsub": 1, "axpb": 2, "div": 3}[mode]
+    ctx.check(ctx.L.scz_fr_pointwise_dev(ctx.h, C.c_int32(m), _vp(ad), _vp(bd), _vp(kd) if kd is not None else None,
+                                         _vp(out), C.c_size_t(len(ad))))
+    return _out(ctx, out, host)
+
+
+def fix_variable(ctx, evals, points):
+    """mle.rs:88-104"""
+    ed, host = _in(ctx, evals, 4)
+    pd, _ = _in(ctx, points, 4)
+    k = min(len(pd), _log2(len(ed)))
+    out = ctx.empty(len(ed) >> k, 4)
+    ctx.check(ctx.L.scz_fix_variable_dev(ctx.h, _vp(ed), C.c_size_t(len(ed)), _vp(pd), C.c_size_t(len(pd)), _vp(out)))
+    return _out(ctx, out, host)
+
+
+def acc_product_tree(ctx, x):
+    """the 2m-entry table of acc_product (dacc_product.rs:30-39)"""
+    xd, host = _in(ctx, x, 4)
+    out = ctx.empty(2 * len(xd), 4)
+    ctx.check(ctx.L.scz_acc_product_dev(ctx.h, _vp(xd), C.c_size_t(len(xd)), _vp(out)))
+    return _out(ctx, out, host)
+
+
+def d_acc_product(ctx, x):
+    """dacc_product.rs:365-414 -> (subtree, leader_tree or None)"""
+    xd, host = _in(ctx, x, 4)
+    sub = ctx.empty(2 * len(xd), 4)
+    lead = ctx.empty(2 * ctx.n_parties, 4) if ctx.party_id == 0 else None
+    ctx.check(ctx.L.scz_d_acc_product_dev(ctx.h, _vp(xd), C.c_size_t(len(xd)), _vp(sub),
+                                          _vp(lead) if lead is not None else None))
+    return _out(ctx, sub, host), (_out(ctx, lead, host) if lead is not None else None)
+
+
+def sumcheck_rounds(ctx, f, g, challenge):
+    """the local round loop alone -> (n triples, (f_last, g_last))"""
+    fd, host = _in(ctx, f, 4)
+    gd, _ = _in(ctx, g, 4)
+    cd, _ = _in(ctx, challenge, 4)
+    n = _log2(len(fd))
+    out = ctx.empty(max(n, 1) * 3, 4)
+    last = ctx.empty(2, 4)
+    ctx.check(ctx.L.scz_sumcheck_product_rounds_dev(ctx.h, _vp(fd), _vp(gd), C.c_size_t(len(fd)), _vp(cd), _vp(out), _vp(last)))
+    return _out(ctx, out[: n * 3].reshape(n, 3, 4), host), _out(ctx, last, host)
+
+
+def sumcheck_product(ctx, f, g, challenge):
+    """dsumcheck.rs:28-90 -> (n + 1, 3, 4)"""
+    fd, host = _in(ctx, f, 4)
+    gd, _ = _in(ctx, g, 4)
+    cd, _ = _in(ctx, challenge, 4)
+    n = _log2(len(fd))
+    out = ctx.empty((n + 1) * 3, 4)
+    ctx.check(ctx.L.scz_sumcheck_product_dev(ctx.h, _vp(fd), _vp(gd), C.c_size_t(len(fd)), _vp(cd), _vp(out)))
+    return _out(ctx, out.reshape(n + 1, 3, 4), host)
+
+
+def c_sumcheck_product(ctx, pp, f, g, challenge):
+    """dsumcheck.rs:148-285 -> (n + log2 l + 1, 3, 4)"""
+    fd, host = _in(ctx, f, 4)
+    gd, _ = _in(ctx, g, 4)
+    cd, _ = _in(ctx, challenge, 4)
+    cnt = _log2(len(fd)) + _log2(pp.l) + 1
+    out = ctx.empty(cnt * 3, 4)
+    ctx.check(ctx.L.scz_c_sumcheck_product_dev(ctx.h, pp.h, _vp(fd), _vp(gd), C.c_size_t(len(fd)), _vp(cd), _vp(out)))
+    return _out(ctx, out.reshape(cnt, 3, 4), host)
+
+
+def d_sumcheck_product(ctx, f, g, challenge):
+    """dsumcheck.rs:359-512 -> leader: (n + log2 N, 3, 4); every other party: an empty array (:507-509)"""
+    fd, host = _in(ctx, f, 4)
+    gd, _ = _in(ctx, g, 4)
+    cd, _ = _in(ctx, challenge, 4)
+    cap = _log2(len(fd)) + _log2(ctx.n_parties)
+    out = ctx.empty(max(cap, 1) * 3, 4)
+    cnt = C.c_size_t()
+    ctx.check(ctx.L.scz_d_sumcheck_product_dev(ctx.h, _vp(fd), _vp(gd), C.c_size_t(len(fd)), _vp(cd), _vp(out), C.byref(cnt)))
+    return _out(ctx, out[: cnt.value * 3].reshape(cnt.value, 3, 4), host)
+
+
+def pss2ss(ctx, pp, share):
+    """unpack.rs:72-97: one share -> Vec<F> of length l"""
+    sd, host = _in(ctx, share, 4)
+    out = ctx.empty(pp.l, 4)
+    ctx.check(ctx.L.scz_pss2ss_dev(ctx.h, pp.h, _vp(sd), _vp(out)))
+    return _out(ctx, out, host)
+
+
+def degree_reduce(ctx, pp, share):
+    """degree_reduce.rs:29-41"""
+    sd, host = _in(ctx, share, 4)
+    out = ctx.empty(1, 4)
+    ctx.check(ctx.L.scz_degree_reduce_dev(ctx.h, pp.h, _vp(sd), _vp(out)))
+    return _out(ctx, out, host)
+
+
+class PolynomialCommitment:
+    """The G1 side of dpoly_comm.rs:30-34 (`powers_of_g`) with the commit / open family (:236-464).
+    levels[i]: packed affine bases of level i, numpy (n_i, 12) or CUDA tensors."""
+
+    def __init__(self, ctx, levels):
+        self.ctx = ctx
+        self.levels = [lv if _is_dev(lv) else ctx.to_device(lv, 12) for lv in levels]   # keeps the arrays alive
+        k = len(self.levels)
+        ptrs = (C.c_void_p * k)(*[lv.data_ptr() for lv in self.levels])
+        lens = (C.c_size_t * k)(*[len(lv) for lv in self.levels])
+        h = C.c_void_p()
+        ctx.check(ctx.L.scz_srs_from_device_levels(ctx.h, C.c_size_t(k), ptrs, lens, C.byref(h)))
+        self.h = h
+
+    def __del__(self):
+        try:
+            if self.h:
+                self.ctx.L.scz_srs_free(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    def commit(self, peval):
+        ctx = self.ctx
+        pd, host = _in(ctx, peval, 4)
+        out = ctx.empty(1, 18)
+        ctx.check(ctx.L.scz_commit_dev(ctx.h, self.h, _vp(pd), C.c_size_t(len(pd)), _vp(out)))
+        return _out(ctx, out, host)
+
+    def c_commit(self, pp, pevals):
+        ctx = self.ctx
+        ins = [_in(ctx, p, 4) for p in pevals]
+        host = bool(ins) and ins[0][1]
+        k = len(ins)
+        out = ctx.empty(k, 18)
+        ptrs = (C.c_void_p * k)(*[t.data_ptr() for t, _ in ins])
+        lens = (C.c_size_t * k)(*[len(t) for t, _ in ins])
+        ctx.check(ctx.L.scz_c_commit_dev(ctx.h, self.h, pp.h, ptrs, lens, C.c_size_t(k), _vp(out)))
+        return _out(ctx, out, host)
+
+    def d_commit(self, peval):
+        ctx = self.ctx
+        pd, host = _in(ctx, peval, 4)
+        out = ctx.empty(1, 18)
+        ctx.check(ctx.L.scz_d_commit_dev(ctx.h, self.h, _vp(pd), C.c_size_t(len(pd)), _vp(out)))
+        return _out(ctx, out, host)
+
+    def open(self, peval, point):
+        ctx = self.ctx
+        pd, host = _in(ctx, peval, 4)
+        ud, _ = _in(ctx, point, 4)
+        n = _log2(len(pd))
+        val, proofs = ctx.empty(1, 4), ctx.empty(max(n, 1), 18)
+        ctx.check(ctx.L.scz_open_dev(ctx.h, self.h, _vp(pd), C.c_size_t(len(pd)), _vp(ud), _vp(val), _vp(proofs)))
+        return _out(ctx, val, host), _out(ctx, proofs[:n], host)
+
+    def c_open(self, pp, peval, point):
+        ctx = self.ctx
+        pd, host = _in(ctx, peval, 4)
+        ud, _ = _in(ctx, point, 4)
+        cnt = _log2(len(pd)) + _log2(pp.l)
+        val, proofs = ctx.empty(1, 4), ctx.empty(max(cnt, 1), 18)
+        ctx.check(ctx.L.scz_c_open_dev(ctx.h, self.h, pp.h, _vp(pd), C.c_size_t(len(pd)), _vp(ud), _vp(val), _vp(proofs)))
+        return _out(ctx, val, host), _out(ctx, proofs[:cnt], host)
+
+    def d_open(self, peval, point):
+        ctx = self.ctx
+        pd, host = _in(ctx, peval, 4)
+        ud, _ = _in(ctx, point, 4)
+        cap = _log2(len(pd)) + _log2(ctx.n_parties)
+        val, proofs = ctx.empty(1, 4), ctx.empty(max(cap, 1), 18)
+        cnt = C.c_size_t()
+        ctx.check(ctx.L.scz_d_open_dev(ctx.h, self.h, _vp(pd), C.c_size_t(len(pd)), _vp(ud), C.c_size_t(len(ud)), _vp(val),
+                                       _vp(proofs), C.byref(cnt)))
+        return _out(ctx, val, host), _out(ctx, proofs[: cnt.value], host)
+
+
+__all__ = ["Context", "PackedSharingParams", "msm", "msm_batched", "d_msm", "d_msm_leader", "NetVTable",
+           "fr_pointwise", "fix_variable", "acc_product_tree", "d_acc_product", "sumcheck_rounds", "sumcheck_product",
+           "c_sumcheck_product", "d_sumcheck_product", "pss2ss", "degree_reduce", "PolynomialCommitment"]

@@ -1,0 +1,483 @@
+// Fr-table kernels of the path: product sumcheck rounds, PST open folds, the product tree,
+// point-wise maps with batch inversion, fix_variable.
+//
+//   product sumcheck round   dist-primitive/src/dsumcheck.rs:37-85 (same loop body at :167-219, :227-279,
+//                            :377-429, :452-504)
+//   PST open fold            dist-primitive/src/dpoly_comm.rs:309-323 (= :337-351, :418-432)
+//   product tree             dist-primitive/src/dacc_product.rs:30-39 / :374-381
+//   fix_variable             dist-primitive/src/mle.rs:88-104
+//   point-wise maps          hyperplonk/src/dhyperplonk.rs:233-238, 251-256, 326-339
+//
+// A table is a dense array of 32 B Fr elements (arkworks' Montgomery limbs); every thread moves whole
+// elements with 128-bit loads and stores, consecutive threads touch consecutive elements.  The reference
+// takes every challenge up-front (dsumcheck.rs:151), so a round's fold is fused with the evaluation of the
+// SAME round's three sums: one pass reads (f_lo, f_hi, g_lo, g_hi) = 128 B per pair and writes the folded
+// pair = 64 B, five Fr products in between.  a*(1-r) + b*r is computed as a + r*(b - a): the same field
+// element with one product instead of two.
+#include "ctx.h"
+#include "field.cuh"
+
+namespace scz {
+
+constexpr int PL_THREADS = 256;
+constexpr uint32_t TAIL_PAIRS = 2048;   // rounds with at most this many pairs finish inside one CTA
+
+struct Fr3 {
+    Fr a, b, c;
+};
+
+__device__ __forceinline__ Fr fr_shfl_down(const Fr &v, int delta) {
+    Fr r;
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.l[i] = __shfl_down_sync(0xffffffffu, v.l[i], delta);
+    return r;
+}
+// block-wide sum of three Fr accumulators; result valid in thread 0.  sh: 3 * (T/32) Fr
+template <int T>
+__device__ __forceinline__ void block_sum3(Fr &s0, Fr &s1, Fr &s2, Fr *sh) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        s0 = fp_add(s0, fr_shfl_down(s0, d));
+        s1 = fp_add(s1, fr_shfl_down(s1, d));
+        s2 = fp_add(s2, fr_shfl_down(s2, d));
+    }
+    int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (lane == 0) {
+        sh[3 * wid] = s0;
+        sh[3 * wid + 1] = s1;
+        sh[3 * wid + 2] = s2;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < T / 32; w++) {
+            s0 = fp_add(s0, sh[3 * w]);
+            s1 = fp_add(s1, sh[3 * w + 1]);
+            s2 = fp_add(s2, sh[3 * w + 2]);
+        }
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ void product_pair(const Fr &f0, const Fr &f1, const Fr &g0, const Fr &g1, const Fr &r,
+                                             Fr &s0, Fr &s1, Fr &s2, Fr &fo, Fr &go) {
+    s0 = fp_add(s0, fp_mul(f0, g0));
+    s1 = fp_add(s1, fp_mul(f1, g1));
+    Fr df = fp_sub(f1, f0), dg = fp_sub(g1, g0);
+    s2 = fp_add(s2, fp_mul(fp_add(f1, df), fp_add(g1, dg)));   // (2 f1 - f0)(2 g1 - g0)
+    fo = fp_add(f0, fp_mul(r, df));                             // f0 (1 - r) + f1 r
+    go = fp_add(g0, fp_mul(r, dg));
+}
+
+// One round over h pairs.  Every CTA leaves its partial triple in `partial`; the last CTA to finish (ticket)
+// adds them up and writes the round message.
+__global__ void __launch_bounds__(PL_THREADS) k_sumcheck_round(const void *f_in, const void *g_in, void *f_out,
+                                                                void *g_out, uint32_t h, const void *challenge,
+                                                                Fr3 *partial, uint32_t *ticket, Fr3 *out) {
+    __shared__ Fr sh[3 * PL_THREADS / 32];
+    __shared__ bool last;
+    const Fr r = fp_load<FrP>(challenge, 0);
+    Fr s0 = Fr::zero(), s1 = Fr::zero(), s2 = Fr::zero();
+    for (uint32_t i = blockIdx.x * PL_THREADS + threadIdx.x; i < h; i += gridDim.x * PL_THREADS) {
+        Fr f0 = fp_load_rw<FrP>(f_in, i), f1 = fp_load_rw<FrP>(f_in, (size_t)h + i);
+        Fr g0 = fp_load_rw<FrP>(g_in, i), g1 = fp_load_rw<FrP>(g_in, (size_t)h + i);
+        Fr fo, go;
+        product_pair(f0, f1, g0, g1, r, s0, s1, s2, fo, go);
+        fp_store<FrP>(f_out, i, fo);
+        fp_store<FrP>(g_out, i, go);
+    }
+    block_sum3<PL_THREADS>(s0, s1, s2, sh);
+    if (threadIdx.x == 0) {
+        partial[blockIdx.x].a = s0;
+        partial[blockIdx.x].b = s1;
+        partial[blockIdx.x].c = s2;
+        __threadfence();
+        last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    s0 = Fr::zero(), s1 = Fr::zero(), s2 = Fr::zero();
+    for (uint32_t b = threadIdx.x; b < gridDim.x; b += PL_THREADS) {
+        const uint4 *p = reinterpret_cast<const uint4 *>(&partial[b]);   // written by other CTAs: read through L2
+        Fr3 t;
+        uint32_t *w = &t.a.l[0];
+#pragma unroll
+        for (int k = 0; k < 6; k++) {
+            uint4 v = __ldcg(p + k);
+            w[4 * k] = v.x, w[4 * k + 1] = v.y, w[4 * k + 2] = v.z, w[4 * k + 3] = v.w;
+        }
+        s0 = fp_add(s0, t.a);
+        s1 = fp_add(s1, t.b);
+        s2 = fp_add(s2, t.c);
+    }
+    block_sum3<PL_THREADS>(s0, s1, s2, sh);
+    if (threadIdx.x == 0) {
+        out->a = s0;
+        out->b = s1;
+        out->c = s2;
+        *ticket = 0;   // ready for the next round
+    }
+}
+
+// All remaining rounds (h <= TAIL_PAIRS pairs in the first of them) inside one CTA, in place on f/g.
+// challenge points at the first of these rounds' challenges; out at their first message.
+__global__ void __launch_bounds__(PL_THREADS) k_sumcheck_tail(void *f, void *g, uint32_t h, const void *challenge,
+                                                               Fr3 *out) {
+    __shared__ Fr sh[3 * PL_THREADS / 32];
+    for (uint32_t round = 0; h >= 1; h >>= 1, round++) {
+        const Fr r = fp_load<FrP>(challenge, round);
+        Fr s0 = Fr::zero(), s1 = Fr::zero(), s2 = Fr::zero();
+        Fr fo[TAIL_PAIRS / PL_THREADS], go[TAIL_PAIRS / PL_THREADS];
+#pragma unroll
+        for (uint32_t k = 0; k < TAIL_PAIRS / PL_THREADS; k++) {
+            uint32_t i = k * PL_THREADS + threadIdx.x;
+            if (i < h) {
+                Fr f0 = fp_load_rw<FrP>(f, i), f1 = fp_load_rw<FrP>(f, (size_t)h + i);
+                Fr g0 = fp_load_rw<FrP>(g, i), g1 = fp_load_rw<FrP>(g, (size_t)h + i);
+                product_pair(f0, f1, g0, g1, r, s0, s1, s2, fo[k], go[k]);
+            }
+        }
+        __syncthreads();   // every read of this round is done before any slot is overwritten
+#pragma unroll
+        for (uint32_t k = 0; k < TAIL_PAIRS / PL_THREADS; k++) {
+            uint32_t i = k * PL_THREADS + threadIdx.x;
+            if (i < h) {
+                fp_store<FrP>(f, i, fo[k]);
+                fp_store<FrP>(g, i, go[k]);
+            }
+        }
+        block_sum3<PL_THREADS>(s0, s1, s2, sh);
+        if (threadIdx.x == 0) {
+            out[round].a = s0;
+            out[round].b = s1;
+            out[round].c = s2;
+        }
+        __syncthreads();
+    }
+}
+
+// PST open fold round: q[j] = hi - lo ; cur[j] = lo + u * q[j]   (= (1-u) lo + u hi)
+__global__ void __launch_bounds__(PL_THREADS) k_open_fold(const void *in, void *cur_out, void *q, uint32_t h,
+                                                           const void *point) {
+    const Fr u = fp_load<FrP>(point, 0);
+    for (uint32_t i = blockIdx.x * PL_THREADS + threadIdx.x; i < h; i += gridDim.x * PL_THREADS) {
+        Fr lo = fp_load_rw<FrP>(in, i), hi = fp_load_rw<FrP>(in, (size_t)h + i);
+        Fr d = fp_sub(hi, lo);
+        fp_store<FrP>(q, i, d);
+        fp_store<FrP>(cur_out, i, fp_add(lo, fp_mul(u, d)));
+    }
+}
+// tail: all remaining rounds in one CTA; q arena is laid out round after round (h, h/2, ..., 1 entries)
+__global__ void __launch_bounds__(PL_THREADS) k_open_fold_tail(void *cur, void *q, uint32_t h, const void *point) {
+    size_t qoff = 0;
+    for (uint32_t round = 0; h >= 1; qoff += h, h >>= 1, round++) {
+        const Fr u = fp_load<FrP>(point, round);
+        Fr keep[TAIL_PAIRS / PL_THREADS];
+#pragma unroll
+        for (uint32_t k = 0; k < TAIL_PAIRS / PL_THREADS; k++) {
+            uint32_t i = k * PL_THREADS + threadIdx.x;
+            if (i < h) {
+                Fr lo = fp_load_rw<FrP>(cur, i), hi = fp_load_rw<FrP>(cur, (size_t)h + i);
+                Fr d = fp_sub(hi, lo);
+                fp_store<FrP>(q, qoff + i, d);
+                keep[k] = fp_add(lo, fp_mul(u, d));
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (uint32_t k = 0; k < TAIL_PAIRS / PL_THREADS; k++) {
+            uint32_t i = k * PL_THREADS + threadIdx.x;
+            if (i < h) fp_store<FrP>(cur, i, keep[k]);
+        }
+        __syncthreads();
+    }
+}
+
+// fix_variable round: out[j] = lo + p * (hi - lo)
+__global__ void __launch_bounds__(PL_THREADS) k_fix_variable(const void *in, void *out, uint32_t h, const void *point) {
+    const Fr u = fp_load<FrP>(point, 0);
+    for (uint32_t i = blockIdx.x * PL_THREADS + threadIdx.x; i < h; i += gridDim.x * PL_THREADS) {
+        Fr lo = fp_load_rw<FrP>(in, i), hi = fp_load_rw<FrP>(in, (size_t)h + i);
+        fp_store<FrP>(out, i, fp_add(lo, fp_mul(u, fp_sub(hi, lo))));
+    }
+}
+
+// product tree level: tree[dst + k] = tree[src + 2k] * tree[src + 2k + 1], k < cnt
+__global__ void __launch_bounds__(PL_THREADS) k_tree_level(void *tree, size_t src, size_t dst, uint32_t cnt) {
+    uint32_t k = blockIdx.x * PL_THREADS + threadIdx.x;
+    if (k >= cnt) return;
+    fp_store<FrP>(tree, dst + k, fp_mul(fp_load_rw<FrP>(tree, src + 2 * (size_t)k), fp_load_rw<FrP>(tree, src + 2 * (size_t)k + 1)));
+}
+// the levels with at most PL_THREADS products each, in one CTA; finally tree[2m-1] = 0 (dacc_product.rs:39,381)
+__global__ void __launch_bounds__(PL_THREADS) k_tree_tail(void *tree, size_t src, size_t dst, uint32_t cnt, size_t last) {
+    for (; cnt >= 1; cnt >>= 1) {
+        if (threadIdx.x < cnt)
+            fp_store<FrP>(tree, dst + threadIdx.x,
+                          fp_mul(fp_load_rw<FrP>(tree, src + 2 * (size_t)threadIdx.x),
+                                 fp_load_rw<FrP>(tree, src + 2 * (size_t)threadIdx.x + 1)));
+        __syncthreads();
+        src = dst;
+        dst += cnt;
+    }
+    if (threadIdx.x == 0) fp_store<FrP>(tree, last, Fr::zero());
+}
+
+// point-wise: out = a*ca + b*cb + cc with constants from a small device array k = (ca, cb, cc);
+// mode 0: out = a + b ; 1: out = b - a ; 2: out = a + k0*b + k1   (num / den of dhyperplonk.rs:326-337)
+template <int MODE>
+__global__ void __launch_bounds__(PL_THREADS) k_pointwise(const void *a, const void *b, const void *k, void *out,
+                                                           size_t n) {
+    size_t i = blockIdx.x * (size_t)PL_THREADS + threadIdx.x;
+    if (i >= n) return;
+    Fr x = fp_load_rw<FrP>(a, i), y = fp_load_rw<FrP>(b, i), r;
+    if (MODE == 0) r = fp_add(x, y);
+    else if (MODE == 1) r = fp_sub(y, x);
+    else r = fp_add(fp_add(x, fp_mul(fp_load<FrP>(k, 0), y)), fp_load<FrP>(k, 1));
+    fp_store<FrP>(out, i, r);
+}
+
+// out[i] = num[i] / den[i] (dhyperplonk.rs:338-339).  Montgomery's trick on two levels: a thread owns
+// INV_PER_THREAD consecutive elements (prefix products in registers), a warp shares ONE Fermat inversion through
+// a shuffle scan, so an element costs ~6 products instead of ~380.  den = 0 yields 0 (arkworks would panic).
+constexpr int INV_PER_THREAD = 4;
+__device__ __forceinline__ Fr fr_shfl(const Fr &v, int src) {
+    Fr r;
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.l[i] = __shfl_sync(0xffffffffu, v.l[i], src);
+    return r;
+}
+__device__ __forceinline__ Fr fr_shfl_up(const Fr &v, int d) {
+    Fr r;
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.l[i] = __shfl_up_sync(0xffffffffu, v.l[i], d);
+    return r;
+}
+__global__ void __launch_bounds__(PL_THREADS) k_div(const void *num, const void *den, void *out, size_t n) {
+    size_t base = ((size_t)blockIdx.x * PL_THREADS + threadIdx.x) * INV_PER_THREAD;
+    int lane = threadIdx.x & 31;
+    Fr d[INV_PER_THREAD], pre[INV_PER_THREAD];
+    Fr run = Fr::one();
+#pragma unroll
+    for (int j = 0; j < INV_PER_THREAD; j++) {
+        d[j] = base + j < n ? fp_load_rw<FrP>(den, base + j) : Fr::one();
+        if (d[j].is_zero()) d[j] = Fr::one();   // keeps the batch invertible; fixed up below
+        pre[j] = run;                            // product of the thread's earlier elements
+        run = fp_mul(run, d[j]);
+    }
+    // inclusive warp scan of the thread products
+    Fr incl = run;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        Fr t = fr_shfl_up(incl, o);
+        if (lane >= o) incl = fp_mul(incl, t);
+    }
+    Fr total_inv = Fr::zero();
+    if (lane == 31) total_inv = fp_inv(incl);
+    total_inv = fr_shfl(total_inv, 31);
+    // inverse of this thread's product = total_inv * (product of later lanes) * (product of earlier lanes):
+    // suffix products by a second scan
+    Fr suf = run;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        Fr t = fr_shfl_down(suf, o);
+        if (lane + o < 32) suf = fp_mul(suf, t);
+    }
+    Fr excl_pre = fr_shfl_up(incl, 1);          // product of lanes < lane
+    Fr excl_suf = fr_shfl_down(suf, 1);         // product of lanes > lane
+    Fr inv_run = total_inv;
+    if (lane > 0) inv_run = fp_mul(inv_run, excl_pre);
+    if (lane < 31) inv_run = fp_mul(inv_run, excl_suf);
+    // walk back through the thread's own elements
+#pragma unroll
+    for (int j = INV_PER_THREAD - 1; j >= 0; j--) {
+        Fr inv_j = fp_mul(inv_run, pre[j]);
+        inv_run = fp_mul(inv_run, d[j]);
+        if (base + j < n) {
+            Fr dn = fp_load_rw<FrP>(den, base + j);
+            Fr r = dn.is_zero() ? Fr::zero() : fp_mul(fp_load_rw<FrP>(num, base + j), inv_j);
+            fp_store<FrP>(out, base + j, r);
+        }
+    }
+}
+
+static uint32_t grid_for(Ctx *c, size_t items) {
+    size_t want = (items + PL_THREADS - 1) / PL_THREADS;
+    size_t cap = (size_t)c->sm_count * 8;   // a multiple of the SM count; grid-stride loops cover the rest
+    return (uint32_t)(want < cap ? (want ? want : 1) : cap);
+}
+
+// n = log2(len) rounds of the product sumcheck on device tables; writes n triples to d_out and the two
+// fully folded values (f, g) to d_last.  The inputs are left untouched (the reference clones, dsumcheck.rs:160).
+int32_t sumcheck_product_rounds(Ctx *ctx, const void *d_f, const void *d_g, size_t len, const void *d_challenge,
+                                void *d_out, void *d_last) {
+    if (len == 0 || (len & (len - 1))) return ctx->fail(SCZ_ERR_NOT_POW2, "sumcheck: table length %zu is not a power of two", len);
+    if (len >= (1ull << 32)) return ctx->fail(SCZ_ERR_BAD_ARG, "sumcheck: table too long");
+    ProfScope ps(ctx, SCZ_K_SUMCHECK);
+    cudaStream_t st = ctx->stream;
+    if (len == 1) {
+        SCZ_CUDA(ctx, cudaMemcpyAsync(d_last, d_f, 32, cudaMemcpyDeviceToDevice, st));
+        SCZ_CUDA(ctx, cudaMemcpyAsync((char *)d_last + 32, d_g, 32, cudaMemcpyDeviceToDevice, st));
+        return SCZ_OK;
+    }
+    size_t h = len / 2;
+    if (h <= TAIL_PAIRS) {   // short table: everything in one CTA, in place on a private copy
+        DevTmp ff(ctx), gg(ctx);
+        SCZ_TRY(ff.alloc(len * 32));
+        SCZ_TRY(gg.alloc(len * 32));
+        SCZ_CUDA(ctx, cudaMemcpyAsync(ff.p, d_f, len * 32, cudaMemcpyDeviceToDevice, st));
+        SCZ_CUDA(ctx, cudaMemcpyAsync(gg.p, d_g, len * 32, cudaMemcpyDeviceToDevice, st));
+        k_sumcheck_tail<<<1, PL_THREADS, 0, st>>>(ff.p, gg.p, (uint32_t)h, d_challenge, reinterpret_cast<Fr3 *>(d_out));
+        SCZ_LAUNCH_CHECK(ctx);
+        SCZ_CUDA(ctx, cudaMemcpyAsync(d_last, ff.p, 32, cudaMemcpyDeviceToDevice, st));
+        SCZ_CUDA(ctx, cudaMemcpyAsync((char *)d_last + 32, gg.p, 32, cudaMemcpyDeviceToDevice, st));
+        return SCZ_OK;
+    }
+    DevTmp tf(ctx), tg(ctx), partial(ctx), ticket(ctx);
+    SCZ_TRY(tf.alloc(h * 32));
+    SCZ_TRY(tg.alloc(h * 32));
+    SCZ_TRY(partial.alloc((size_t)grid_for(ctx, h) * sizeof(Fr3)));
+    SCZ_TRY(ticket.alloc(4));
+    SCZ_CUDA(ctx, cudaMemsetAsync(ticket.p, 0, 4, st));
+    const void *fi = d_f, *gi = d_g;
+    size_t round = 0;
+    while (h > TAIL_PAIRS) {
+        k_sumcheck_round<<<grid_for(ctx, h), PL_THREADS, 0, st>>>(fi, gi, tf.p, tg.p, (uint32_t)h,
+                                                                  (const char *)d_challenge + round * 32,
+                                                                  partial.as<Fr3>(), ticket.as<uint32_t>(),
+                                                                  reinterpret_cast<Fr3 *>(d_out) + round);
+        SCZ_LAUNCH_CHECK(ctx);
+        fi = tf.p;
+        gi = tg.p;
+        h >>= 1;
+        round++;
+    }
+    k_sumcheck_tail<<<1, PL_THREADS, 0, st>>>(tf.p, tg.p, (uint32_t)h, (const char *)d_challenge + round * 32,
+                                              reinterpret_cast<Fr3 *>(d_out) + round);
+    SCZ_LAUNCH_CHECK(ctx);
+    SCZ_CUDA(ctx, cudaMemcpyAsync(d_last, tf.p, 32, cudaMemcpyDeviceToDevice, st));
+    SCZ_CUDA(ctx, cudaMemcpyAsync((char *)d_last + 32, tg.p, 32, cudaMemcpyDeviceToDevice, st));
+    return SCZ_OK;
+}
+
+// n fold rounds of a PST opening: quotient tables q_0 .. q_{n-1} (len/2, len/4, ..., 1 entries) packed one
+// after the other into d_q (len - 1 entries), the evaluation into d_value.
+int32_t open_fold_rounds(Ctx *ctx, const void *d_peval, size_t len, const void *d_point, void *d_q, void *d_value) {
+    if (len == 0 || (len & (len - 1))) return ctx->fail(SCZ_ERR_NOT_POW2, "open: table length %zu is not a power of two", len);
+    if (len >= (1ull << 32)) return ctx->fail(SCZ_ERR_BAD_ARG, "open: table too long");
+    ProfScope ps(ctx, SCZ_K_OPEN_FOLD);
+    cudaStream_t st = ctx->stream;
+    if (len == 1) {
+        SCZ_CUDA(ctx, cudaMemcpyAsync(d_value, d_peval, 32, cudaMemcpyDeviceToDevice, st));
+        return SCZ_OK;
+    }
+    size_t h = len / 2, qoff = 0, round = 0;
+    DevTmp cur(ctx);
+    SCZ_TRY(cur.alloc((h > TAIL_PAIRS ? h : len) * 32));
+    const void *in = d_peval;
+    while (h > TAIL_PAIRS) {
+        k_open_fold<<<grid_for(ctx, h), PL_THREADS, 0, st>>>(in, cur.p, (char *)d_q + qoff * 32, (uint32_t)h,
+                                                             (const char *)d_point + round * 32);
+        SCZ_LAUNCH_CHECK(ctx);
+        in = cur.p;
+        qoff += h;
+        h >>= 1;
+        round++;
+    }
+    if (in == d_peval) SCZ_CUDA(ctx, cudaMemcpyAsync(cur.p, d_peval, len * 32, cudaMemcpyDeviceToDevice, st));
+    k_open_fold_tail<<<1, PL_THREADS, 0, st>>>(cur.p, (char *)d_q + qoff * 32, (uint32_t)h,
+                                               (const char *)d_point + round * 32);
+    SCZ_LAUNCH_CHECK(ctx);
+    SCZ_CUDA(ctx, cudaMemcpyAsync(d_value, cur.p, 32, cudaMemcpyDeviceToDevice, st));
+    return SCZ_OK;
+}
+
+int32_t fix_variable_rounds(Ctx *ctx, const void *d_evals, size_t len, const void *d_points, size_t npoints, void *d_out) {
+    if (len == 0 || (len & (len - 1))) return ctx->fail(SCZ_ERR_NOT_POW2, "fix_variable: length %zu is not a power of two", len);
+    ProfScope ps(ctx, SCZ_K_POINTWISE);
+    cudaStream_t st = ctx->stream;
+    size_t n = 0;
+    while (((size_t)1 << n) < len) n++;
+    size_t k = npoints < n ? npoints : n;
+    if (k == 0) {
+        SCZ_CUDA(ctx, cudaMemcpyAsync(d_out, d_evals, len * 32, cudaMemcpyDeviceToDevice, st));
+        return SCZ_OK;
+    }
+    DevTmp a(ctx), b(ctx);
+    SCZ_TRY(a.alloc(len / 2 * 32));
+    SCZ_TRY(b.alloc(len / 2 * 32));
+    const void *in = d_evals;
+    size_t h = len / 2;
+    for (size_t i = 0; i < k; i++, h >>= 1) {
+        void *out = i + 1 == k ? d_out : (i & 1 ? b.p : a.p);
+        k_fix_variable<<<grid_for(ctx, h), PL_THREADS, 0, st>>>(in, out, (uint32_t)h, (const char *)d_points + i * 32);
+        SCZ_LAUNCH_CHECK(ctx);
+        in = out;
+    }
+    return SCZ_OK;
+}
+
+// tree (2m entries): [0, m) = x, [m, 2m-1) products level by level, [2m-1] = 0   (dacc_product.rs:30-39)
+int32_t acc_product_tree(Ctx *ctx, const void *d_x, size_t m, void *d_tree) {
+    if (m == 0 || (m & (m - 1))) return ctx->fail(SCZ_ERR_NOT_POW2, "acc_product: length %zu is not a power of two", m);
+    if (m >= (1ull << 31)) return ctx->fail(SCZ_ERR_BAD_ARG, "acc_product: table too long");
+    ProfScope ps(ctx, SCZ_K_ACC_PRODUCT);
+    cudaStream_t st = ctx->stream;
+    SCZ_CUDA(ctx, cudaMemcpyAsync(d_tree, d_x, m * 32, cudaMemcpyDeviceToDevice, st));
+    size_t src = 0, dst = m, cnt = m / 2;
+    while (cnt > (size_t)PL_THREADS) {
+        k_tree_level<<<ceil_div_u32(cnt, PL_THREADS), PL_THREADS, 0, st>>>(d_tree, src, dst, (uint32_t)cnt);
+        SCZ_LAUNCH_CHECK(ctx);
+        src = dst;
+        dst += cnt;
+        cnt >>= 1;
+    }
+    k_tree_tail<<<1, PL_THREADS, 0, st>>>(d_tree, src, dst, (uint32_t)cnt, 2 * m - 1);
+    SCZ_LAUNCH_CHECK(ctx);
+    return SCZ_OK;
+}
+
+}   // namespace scz
+
+using namespace scz;
+
+extern "C" {
+
+int32_t scz_sumcheck_product_rounds_dev(scz_ctx *h, const void *d_f, const void *d_g, size_t len, const void *d_challenge,
+                                        void *d_out_triples, void *d_last_fg) {
+    if (!h) return SCZ_ERR_BAD_ARG;
+    if (!d_f || !d_g || !d_last_fg || (len > 1 && (!d_challenge || !d_out_triples)))
+        return h->c.fail(SCZ_ERR_BAD_ARG, "sumcheck: null argument");
+    return sumcheck_product_rounds(&h->c, d_f, d_g, len, d_challenge, d_out_triples, d_last_fg);
+}
+int32_t scz_open_fold_dev(scz_ctx *h, const void *d_peval, size_t len, const void *d_point, void *d_q, void *d_value) {
+    if (!h) return SCZ_ERR_BAD_ARG;
+    if (!d_peval || !d_value || (len > 1 && (!d_point || !d_q))) return h->c.fail(SCZ_ERR_BAD_ARG, "open_fold: null argument");
+    return open_fold_rounds(&h->c, d_peval, len, d_point, d_q, d_value);
+}
+int32_t scz_fix_variable_dev(scz_ctx *h, const void *d_evals, size_t len, const void *d_points, size_t npoints, void *d_out) {
+    if (!h) return SCZ_ERR_BAD_ARG;
+    if (!d_evals || !d_out || (npoints && !d_points)) return h->c.fail(SCZ_ERR_BAD_ARG, "fix_variable: null argument");
+    return fix_variable_rounds(&h->c, d_evals, len, d_points, npoints, d_out);
+}
+int32_t scz_acc_product_dev(scz_ctx *h, const void *d_x, size_t m, void *d_tree) {
+    if (!h) return SCZ_ERR_BAD_ARG;
+    if (!d_x || !d_tree) return h->c.fail(SCZ_ERR_BAD_ARG, "acc_product: null argument");
+    return acc_product_tree(&h->c, d_x, m, d_tree);
+}
+int32_t scz_fr_pointwise_dev(scz_ctx *h, int32_t mode, const void *d_a, const void *d_b, const void *d_k, void *d_out,
+                             size_t n) {
+    if (!h) return SCZ_ERR_BAD_ARG;
+    Ctx *c = &h->c;
+    if (!d_a || !d_b || !d_out || mode < 0 || mode > 3 || (mode == 2 && !d_k)) return c->fail(SCZ_ERR_BAD_ARG, "pointwise: bad argument");
+    if (!n) return SCZ_OK;
+    ProfScope ps(c, SCZ_K_POINTWISE);
+    uint32_t g = ceil_div_u32(n, PL_THREADS);
+    if (mode == 0) k_pointwise<0><<<g, PL_THREADS, 0, c->stream>>>(d_a, d_b, d_k, d_out, n);
+    else if (mode == 1) k_pointwise<1><<<g, PL_THREADS, 0, c->stream>>>(d_a, d_b, d_k, d_out, n);
+    else if (mode == 2) k_pointwise<2><<<g, PL_THREADS, 0, c->stream>>>(d_a, d_b, d_k, d_out, n);
+    else k_div<<<ceil_div_u32(n, (size_t)PL_THREADS * INV_PER_THREAD), PL_THREADS, 0, c->stream>>>(d_a, d_b, d_out, n);
+    SCZ_LAUNCH_CHECK(c);
+    return SCZ_OK;
+}
+
+}   // extern "C"

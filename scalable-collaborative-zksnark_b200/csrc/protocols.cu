@@ -1,0 +1,498 @@
+// The dist-primitive protocols on top of the kernels: every function here is the device-side restatement
+// of one reference function, local loops on this party's GPU and the reference's own leader rounds
+// (gather -> closure on the leader -> scatter, dist-primitive/src/utils/serializing_net.rs:128-141) through
+// ctx->net.  Payloads stay on the device in device layout; the byte counters use the reference's
+// ark-serialize compressed sizes (Fr 32 B, G1 48 B, Vec header 8 B) so get_comm() stays comparable.
+//
+//   pss2ss                 dist-primitive/src/unpack.rs:72-97
+//   degree_reduce          dist-primitive/src/degree_reduce.rs:29-41
+//   sumcheck_product       dist-primitive/src/dsumcheck.rs:28-90
+//   c_sumcheck_product     dist-primitive/src/dsumcheck.rs:148-285
+//   d_sumcheck_product     dist-primitive/src/dsumcheck.rs:359-512
+//   commit / d_local_commit, c_commit, d_commit     dist-primitive/src/dpoly_comm.rs:237-243, 269-275, 244-267, 276-297
+//   open / d_local_open, c_open, d_open             dist-primitive/src/dpoly_comm.rs:299-325, 327-353, 401-464, 355-398
+//   d_acc_product          dist-primitive/src/dacc_product.rs:365-414
+#include <vector>
+
+#include "g1.cuh"
+#include "msm.h"
+#include "net.h"
+#include "pss.h"
+
+namespace scz {
+
+int32_t sumcheck_product_rounds(Ctx *ctx, const void *d_f, const void *d_g, size_t len, const void *d_challenge,
+                                void *d_out, void *d_last);
+int32_t open_fold_rounds(Ctx *ctx, const void *d_peval, size_t len, const void *d_point, void *d_q, void *d_value);
+int32_t acc_product_tree(Ctx *ctx, const void *d_x, size_t m, void *d_tree);
+int32_t d_msm_dev(Ctx *ctx, const scz_pp *pp, const void *const *d_bases, const void *const *d_scalars,
+                  const size_t *lens, size_t batch, void *d_out);
+
+static inline size_t log2_exact(size_t v, bool *ok) {
+    size_t l = 0;
+    while (((size_t)1 << l) < v) l++;
+    *ok = v != 0 && ((size_t)1 << l) == v;
+    return l;
+}
+
+struct Fr3 {
+    Fr a, b, c;
+};
+
+// ---- tiny leader-side kernels -------------------------------------------------------------------
+// out = (0, f*g, 0)            dsumcheck.rs:87 / :282
+__global__ void k_final_triple(const void *last_fg, void *out) {
+    if (threadIdx.x) return;
+    Fr f = fp_load_rw<FrP>(last_fg, 0), g = fp_load_rw<FrP>(last_fg, 1);
+    fp_store<FrP>(out, 0, Fr::zero());
+    fp_store<FrP>(out, 1, fp_mul(f, g));
+    fp_store<FrP>(out, 2, Fr::zero());
+}
+// out = (g_last, f_last, 0)    dsumcheck.rs:433
+__global__ void k_last_triple(const void *last_fg, void *out) {
+    if (threadIdx.x) return;
+    Fr f = fp_load_rw<FrP>(last_fg, 0), g = fp_load_rw<FrP>(last_fg, 1);
+    fp_store<FrP>(out, 0, g);
+    fp_store<FrP>(out, 1, f);
+    fp_store<FrP>(out, 2, Fr::zero());
+}
+// leader of d_sumcheck_product (dsumcheck.rs:440-449): recv is [party][n+1] triples.
+// out[i] = sum over parties of round i; lf[j] = recv[j][n].b ; lg[j] = recv[j][n].a
+__global__ void k_dsum_leader(const void *recv, uint32_t N, uint32_t n, void *out, void *lf, void *lg) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < 3 * n) {
+        uint32_t i = t / 3, comp = t % 3;
+        Fr acc = Fr::zero();
+        for (uint32_t j = 0; j < N; j++) acc = fp_add(acc, fp_load_rw<FrP>(recv, ((size_t)j * (n + 1) + i) * 3 + comp));
+        fp_store<FrP>(out, (size_t)i * 3 + comp, acc);
+    } else if (t < 3 * n + N) {
+        uint32_t j = t - 3 * n;
+        fp_store<FrP>(lg, j, fp_load_rw<FrP>(recv, ((size_t)j * (n + 1) + n) * 3));
+        fp_store<FrP>(lf, j, fp_load_rw<FrP>(recv, ((size_t)j * (n + 1) + n) * 3 + 1));
+    }
+}
+// column sums of Jacobian points: out[i] = sum_j in[j*stride_pts + off_pts + i]   (in units of 144 B after a byte offset)
+__global__ void k_g1_colsum(const void *in, size_t party_stride_bytes, size_t off_bytes, uint32_t N, uint32_t cols,
+                            void *out, uint32_t replicate) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= cols) return;
+    G1X acc = G1X::inf();
+    for (uint32_t j = 0; j < N; j++) {
+        const char *p = reinterpret_cast<const char *>(in) + (size_t)j * party_stride_bytes + off_bytes;
+        acc = g1x_add(acc, g1x_from_jac(g1j_load(p, i)));
+    }
+    G1Jac r = g1x_to_jac(acc);
+    for (uint32_t k = 0; k < replicate; k++) g1j_store(out, (size_t)k * cols + i, r);
+}
+// lz[j] = first Fr of party j's payload
+__global__ void k_pick_fr(const void *in, size_t party_stride_bytes, uint32_t N, void *out) {
+    uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= N) return;
+    fp_store<FrP>(out, j, fp_load_rw<FrP>(reinterpret_cast<const char *>(in) + (size_t)j * party_stride_bytes, 0));
+}
+
+// ---- pss2ss: unpack.rs:72-97 ----------------------------------------------------------------------
+// gather one share -> leader: unpack -> pack_single each secret -> transpose -> scatter Vec<F> of length l
+int32_t pss2ss_dev(Ctx *ctx, const scz_pp *pp, const void *d_share, void *d_out) {
+    Net *net = ctx->net;
+    const size_t N = net->n_parties, l = pp->l;
+    if (N != pp->n) return ctx->fail(SCZ_ERR_BAD_ARG, "pss2ss: %zu parties but pp.n = %zu", N, pp->n);
+    DevTmp recv(ctx), sec(ctx), send(ctx);
+    if (net->is_leader()) {
+        SCZ_TRY(recv.alloc(N * 32));
+        SCZ_TRY(sec.alloc(l * 32));
+        SCZ_TRY(send.alloc(N * l * 32));
+    }
+    SCZ_TRY(net->gather(ctx, d_share, recv.p, 32, 32));
+    if (net->is_leader()) {
+        ProfScope ps(ctx, SCZ_K_PSS);
+        SCZ_TRY(pss_apply(ctx, pp, PSS_UNPACK, 0, recv.p, N, N, 1, 1, sec.p, l, 1));
+        // secret i -> shares PS[j] * sec[i], stored party-major [j][i]
+        SCZ_TRY(pss_apply(ctx, pp, PSS_PACK_SINGLE, 0, sec.p, 1, 1, 1, l, send.p, 1, l));
+    }
+    SCZ_TRY(net->scatter(ctx, send.p, d_out, l * 32, 8 + 32 * l));
+    return SCZ_OK;
+}
+
+// ---- degree_reduce: degree_reduce.rs:29-41 ----------------------------------------------------------
+int32_t degree_reduce_dev(Ctx *ctx, const scz_pp *pp, const void *d_share, void *d_out) {
+    Net *net = ctx->net;
+    const size_t N = net->n_parties, l = pp->l;
+    if (N != pp->n) return ctx->fail(SCZ_ERR_BAD_ARG, "degree_reduce: %zu parties but pp.n = %zu", N, pp->n);
+    DevTmp recv(ctx), sec(ctx), send(ctx);
+    if (net->is_leader()) {
+        SCZ_TRY(recv.alloc(N * 32));
+        SCZ_TRY(sec.alloc(l * 32));
+        SCZ_TRY(send.alloc(N * 32));
+    }
+    SCZ_TRY(net->gather(ctx, d_share, recv.p, 32, 32));
+    if (net->is_leader()) {
+        ProfScope ps(ctx, SCZ_K_PSS);
+        SCZ_TRY(pss_apply(ctx, pp, PSS_UNPACK2, 0, recv.p, N, N, 1, 1, sec.p, l, 1));
+        SCZ_TRY(pss_apply(ctx, pp, PSS_PACK, 0, sec.p, l, l, 1, 1, send.p, N, 1));
+    }
+    SCZ_TRY(net->scatter(ctx, send.p, d_out, 32, 32));
+    return SCZ_OK;
+}
+
+// ---- sumcheck_product: dsumcheck.rs:28-90 -> n + 1 triples ----------------------------------------------
+int32_t sumcheck_product_dev(Ctx *ctx, const void *d_f, const void *d_g, size_t len, const void *d_challenge,
+                             void *d_out) {
+    bool ok;
+    size_t n = log2_exact(len, &ok);
+    if (!ok) return ctx->fail(SCZ_ERR_NOT_POW2, "sumcheck_product: length %zu is not a power of two", len);
+    DevTmp last(ctx);
+    SCZ_TRY(last.alloc(64));
+    SCZ_TRY(sumcheck_product_rounds(ctx, d_f, d_g, len, d_challenge, d_out, last.p));
+    k_final_triple<<<1, 32, 0, ctx->stream>>>(last.p, (char *)d_out + n * 96);
+    SCZ_LAUNCH_CHECK(ctx);
+    return SCZ_OK;
+}
+
+// ---- c_sumcheck_product: dsumcheck.rs:148-285 -> n + log2(l) + 1 triples ---------------------------------
+int32_t c_sumcheck_product_dev(Ctx *ctx, const scz_pp *pp, const void *d_f, const void *d_g, size_t len,
+                               const void *d_challenge, void *d_out) {
+    bool ok;
+    size_t n = log2_exact(len, &ok);
+    if (!ok) return ctx->fail(SCZ_ERR_NOT_POW2, "c_sumcheck_product: length %zu is not a power of two", len);
+    size_t l = pp->l, ll = log2_exact(l, &ok);
+    DevTmp last(ctx), f2(ctx), g2(ctx), last2(ctx);
+    SCZ_TRY(last.alloc(64));
+    SCZ_TRY(f2.alloc(l * 32));
+    SCZ_TRY(g2.alloc(l * 32));
+    SCZ_TRY(last2.alloc(64));
+    SCZ_TRY(sumcheck_product_rounds(ctx, d_f, d_g, len, d_challenge, d_out, last.p));   // Phase 1 :167-219
+    SCZ_TRY(pss2ss_dev(ctx, pp, last.p, f2.p));                                         // :224
+    SCZ_TRY(pss2ss_dev(ctx, pp, (char *)last.p + 32, g2.p));                            // :225
+    // Phase 2 :227-279 -- indexes challenge[i] with i from 0 again (:230), replicated as is
+    SCZ_TRY(sumcheck_product_rounds(ctx, f2.p, g2.p, l, d_challenge, (char *)d_out + n * 96, last2.p));
+    k_final_triple<<<1, 32, 0, ctx->stream>>>(last2.p, (char *)d_out + (n + ll) * 96);   // :282
+    SCZ_LAUNCH_CHECK(ctx);
+    return SCZ_OK;
+}
+
+// ---- d_sumcheck_product: dsumcheck.rs:359-512.  Leader: n + log2(N) triples, others: none (:507-509) -----------
+int32_t d_sumcheck_product_dev(Ctx *ctx, const void *d_f, const void *d_g, size_t len, const void *d_challenge,
+                               void *d_out, size_t *count) {
+    bool ok;
+    size_t n = log2_exact(len, &ok);
+    if (!ok) return ctx->fail(SCZ_ERR_NOT_POW2, "d_sumcheck_product: length %zu is not a power of two", len);
+    Net *net = ctx->net;
+    const size_t N = net->n_parties;
+    size_t s = log2_exact(N, &ok);
+    if (!ok) return ctx->fail(SCZ_ERR_NOT_POW2, "d_sumcheck_product: %zu parties is not a power of two", N);
+    DevTmp local(ctx), last(ctx), recv(ctx), lf(ctx), lg(ctx), last2(ctx);
+    SCZ_TRY(local.alloc((n + 1) * 96));
+    SCZ_TRY(last.alloc(64));
+    SCZ_TRY(sumcheck_product_rounds(ctx, d_f, d_g, len, d_challenge, local.p, last.p));   // :377-429
+    k_last_triple<<<1, 32, 0, ctx->stream>>>(last.p, (char *)local.p + n * 96);           // :433
+    SCZ_LAUNCH_CHECK(ctx);
+    if (net->is_leader()) {
+        SCZ_TRY(recv.alloc(N * (n + 1) * 96));
+        SCZ_TRY(lf.alloc(N * 32));
+        SCZ_TRY(lg.alloc(N * 32));
+        SCZ_TRY(last2.alloc(64));
+    }
+    SCZ_TRY(net->gather(ctx, local.p, recv.p, (n + 1) * 96, 8 + 96 * (n + 1)));            // :434
+    if (!net->is_leader()) {
+        if (count) *count = 0;
+        return SCZ_OK;
+    }
+    uint32_t work = (uint32_t)(3 * n + N);
+    k_dsum_leader<<<ceil_div_u32(work, 64), 64, 0, ctx->stream>>>(recv.p, (uint32_t)N, (uint32_t)n, d_out, lf.p, lg.p);
+    SCZ_LAUNCH_CHECK(ctx);
+    SCZ_TRY(sumcheck_product_rounds(ctx, lf.p, lg.p, N, (const char *)d_challenge + n * 32, (char *)d_out + n * 96,
+                                    last2.p));                                            // :452-504
+    if (count) *count = n + s;
+    return SCZ_OK;
+}
+
+// ---- d_acc_product: dacc_product.rs:365-414 ---------------------------------------------------------------
+int32_t d_acc_product_dev(Ctx *ctx, const void *d_x, size_t m, void *d_subtree, void *d_leader_tree) {
+    Net *net = ctx->net;
+    const size_t N = net->n_parties;
+    SCZ_TRY(acc_product_tree(ctx, d_x, m, d_subtree));                                    // :374-381
+    DevTmp recv(ctx);
+    if (net->is_leader()) SCZ_TRY(recv.alloc(N * 32));
+    // the entry sent is subtree[2m-1], already forced to zero (:381, :390) -- replicated, not "fixed"
+    SCZ_TRY(net->gather(ctx, (const char *)d_subtree + (2 * m - 1) * 32, recv.p, 32, 32));
+    if (net->is_leader()) SCZ_TRY(acc_product_tree(ctx, recv.p, N, d_leader_tree));        // :392-404
+    return SCZ_OK;
+}
+
+}   // namespace scz
+
+// ---- SRS: the G1 side of PolynomialCommitment (dpoly_comm.rs:30-34) ------------------------------------------
+struct scz_srs {
+    std::vector<const void *> level;   // device pointers, packed affine
+    std::vector<size_t> len;
+    std::vector<void *> owned;
+    int device = 0;
+};
+
+namespace scz {
+
+static int32_t srs_level_for(Ctx *ctx, const scz_srs *srs, size_t need_len, size_t level_of, const char *who,
+                             const void **out) {
+    bool ok;
+    size_t level = log2_exact(level_of, &ok);
+    if (!ok) return ctx->fail(SCZ_ERR_NOT_POW2, "%s: length %zu is not a power of two", who, level_of);   // dpoly_comm.rs:240,255
+    if (level >= srs->level.size()) return ctx->fail(SCZ_ERR_LEVEL_OOB, "%s: level %zu >= %zu", who, level, srs->level.size());
+    if (srs->len[level] < need_len)
+        return ctx->fail(SCZ_ERR_LEN_MISMATCH, "%s: level %zu holds %zu bases, %zu needed", who, level, srs->len[level], need_len);
+    *out = srs->level[level];
+    return SCZ_OK;
+}
+
+// commit / d_local_commit: dpoly_comm.rs:237-243, 269-275
+int32_t commit_dev(Ctx *ctx, const scz_srs *srs, const void *d_peval, size_t len, void *d_out) {
+    const void *b;
+    SCZ_TRY(srs_level_for(ctx, srs, len, len, "commit", &b));
+    return msm_g1_batched(ctx, &b, &d_peval, &len, 1, d_out);
+}
+
+// c_commit: dpoly_comm.rs:244-267
+int32_t c_commit_dev(Ctx *ctx, const scz_srs *srs, const scz_pp *pp, const void *const *d_pevals, const size_t *lens,
+                     size_t batch, void *d_out) {
+    std::vector<const void *> bases(batch);
+    for (size_t k = 0; k < batch; k++) SCZ_TRY(srs_level_for(ctx, srs, lens[k], lens[k] * pp->l, "c_commit", &bases[k]));
+    return d_msm_dev(ctx, pp, bases.data(), d_pevals, lens, batch, d_out);
+}
+
+// d_commit: dpoly_comm.rs:276-297 -- every party ends with the sum of the N local commitments
+int32_t d_commit_dev(Ctx *ctx, const scz_srs *srs, const void *d_peval, size_t len, void *d_out) {
+    Net *net = ctx->net;
+    const size_t N = net->n_parties, PT = SCZ_G1_JAC_BYTES;
+    DevTmp loc(ctx), recv(ctx), send(ctx);
+    SCZ_TRY(loc.alloc(PT));
+    SCZ_TRY(commit_dev(ctx, srs, d_peval, len, loc.p));
+    if (net->is_leader()) {
+        SCZ_TRY(recv.alloc(N * PT));
+        SCZ_TRY(send.alloc(N * PT));
+    }
+    SCZ_TRY(net->gather(ctx, loc.p, recv.p, PT, 48));
+    if (net->is_leader()) {
+        k_g1_colsum<<<1, 32, 0, ctx->stream>>>(recv.p, PT, 0, (uint32_t)N, 1, send.p, (uint32_t)N);
+        SCZ_LAUNCH_CHECK(ctx);
+    }
+    SCZ_TRY(net->scatter(ctx, send.p, d_out, PT, 48));
+    return SCZ_OK;
+}
+
+// open / d_local_open: dpoly_comm.rs:299-325, 327-353.  The reference commits q_i inside the fold loop; here all folds run
+// first and the n MSMs go out as ONE batched launch sequence (same values).
+int32_t open_dev(Ctx *ctx, const scz_srs *srs, const void *d_peval, size_t len, const void *d_point, void *d_value,
+                 void *d_proofs) {
+    bool ok;
+    size_t n = log2_exact(len, &ok);
+    if (!ok) return ctx->fail(SCZ_ERR_NOT_POW2, "open: length %zu is not a power of two", len);
+    DevTmp q(ctx);
+    SCZ_TRY(q.alloc((len > 1 ? len - 1 : 1) * 32));
+    SCZ_TRY(open_fold_rounds(ctx, d_peval, len, d_point, q.p, d_value));
+    if (!n) return SCZ_OK;
+    std::vector<const void *> bases(n), scal(n);
+    std::vector<size_t> lens(n);
+    size_t off = 0;
+    for (size_t i = 0; i < n; i++) {
+        size_t h = len >> (i + 1);
+        SCZ_TRY(srs_level_for(ctx, srs, h, h, "open", &bases[i]));
+        scal[i] = (const char *)q.p + off * 32;
+        lens[i] = h;
+        off += h;
+    }
+    return msm_g1_batched(ctx, bases.data(), scal.data(), lens.data(), n, d_proofs);
+}
+
+// c_open: dpoly_comm.rs:401-464 -> value + n + log2(l) proofs
+int32_t c_open_dev(Ctx *ctx, const scz_srs *srs, const scz_pp *pp, const void *d_peval, size_t len, const void *d_point,
+                   void *d_value, void *d_proofs) {
+    bool ok;
+    size_t n = log2_exact(len, &ok);
+    if (!ok) return ctx->fail(SCZ_ERR_NOT_POW2, "c_open: length %zu is not a power of two", len);
+    const size_t l = pp->l, ll = log2_exact(l, &ok), PT = SCZ_G1_JAC_BYTES;
+    DevTmp q(ctx), last(ctx), r2(ctx), q2(ctx);
+    SCZ_TRY(q.alloc((len > 1 ? len - 1 : 1) * 32));
+    SCZ_TRY(last.alloc(32));
+    SCZ_TRY(open_fold_rounds(ctx, d_peval, len, d_point, q.p, last.p));                     // Phase 1 :418-432
+    if (n) {
+        std::vector<const void *> scal(n);
+        std::vector<size_t> lens(n);
+        size_t off = 0;
+        for (size_t i = 0; i < n; i++) {
+            size_t h = len >> (i + 1);
+            scal[i] = (const char *)q.p + off * 32;
+            lens[i] = h;
+            off += h;
+        }
+        SCZ_TRY(c_commit_dev(ctx, srs, pp, scal.data(), lens.data(), n, d_proofs));         // ONE batched c_commit :436
+    }
+    SCZ_TRY(r2.alloc(l * 32));
+    SCZ_TRY(pss2ss_dev(ctx, pp, last.p, r2.p));                                             // :439
+    SCZ_TRY(q2.alloc((l > 1 ? l - 1 : 1) * 32));
+    SCZ_TRY(open_fold_rounds(ctx, r2.p, l, d_point, q2.p, d_value));                        // Phase 2 :442-459, point[i] from 0
+    if (ll) {
+        std::vector<const void *> bases(ll), scal(ll);
+        std::vector<size_t> lens(ll);
+        size_t off = 0;
+        for (size_t i = 0; i < ll; i++) {
+            size_t h = l >> (i + 1);
+            SCZ_TRY(srs_level_for(ctx, srs, h, h * l, "c_open", &bases[i]));                // local G1::msm :457
+            scal[i] = (const char *)q2.p + off * 32;
+            lens[i] = h;
+            off += h;
+        }
+        SCZ_TRY(msm_g1_batched(ctx, bases.data(), scal.data(), lens.data(), ll, (char *)d_proofs + n * PT));
+    }
+    return SCZ_OK;
+}
+
+// d_open: dpoly_comm.rs:355-398.  Leader: value + log2(N) root proofs ++ n summed proofs; others (0, []) (:387)
+int32_t d_open_dev(Ctx *ctx, const scz_srs *srs, const void *d_peval, size_t len, const void *d_point, size_t npoint,
+                   void *d_value, void *d_proofs, size_t *count) {
+    bool ok;
+    size_t n = log2_exact(len, &ok);
+    if (!ok) return ctx->fail(SCZ_ERR_NOT_POW2, "d_open: length %zu is not a power of two", len);
+    Net *net = ctx->net;
+    const size_t N = net->n_parties, PT = SCZ_G1_JAC_BYTES;
+    size_t pl = log2_exact(N, &ok);
+    if (!ok) return ctx->fail(SCZ_ERR_NOT_POW2, "d_open: %zu parties is not a power of two", N);
+    if (npoint < pl + n) return ctx->fail(SCZ_ERR_BAD_ARG, "d_open: point has %zu coordinates, %zu needed", npoint, pl + n);
+    const size_t payload = 32 + n * PT;
+    DevTmp loc(ctx), recv(ctx), lz(ctx);
+    SCZ_TRY(loc.alloc(payload));
+    SCZ_TRY(open_dev(ctx, srs, d_peval, len, (const char *)d_point + pl * 32, loc.p, (char *)loc.p + 32));   // :366
+    if (net->is_leader()) {
+        SCZ_TRY(recv.alloc(N * payload));
+        SCZ_TRY(lz.alloc(N * 32));
+    }
+    SCZ_TRY(net->gather(ctx, loc.p, recv.p, payload, 32 + 8 + 48 * n));                   // :368
+    if (!net->is_leader()) {
+        SCZ_CUDA(ctx, cudaMemsetAsync(d_value, 0, 32, ctx->stream));
+        if (count) *count = 0;
+        return SCZ_OK;
+    }
+    k_pick_fr<<<1, 32 * (uint32_t)((N + 31) / 32), 0, ctx->stream>>>(recv.p, payload, (uint32_t)N, lz.p);
+    SCZ_LAUNCH_CHECK(ctx);
+    SCZ_TRY(open_dev(ctx, srs, lz.p, N, d_point, d_value, d_proofs));                       // root_open :377
+    if (n) {
+        k_g1_colsum<<<ceil_div_u32(n, 32), 32, 0, ctx->stream>>>(recv.p, payload, 32, (uint32_t)N, (uint32_t)n,
+                                                                 (char *)d_proofs + pl * PT, 1);   // :374-376
+        SCZ_LAUNCH_CHECK(ctx);
+    }
+    if (count) *count = pl + n;
+    return SCZ_OK;
+}
+
+}   // namespace scz
+
+using namespace scz;
+
+#define NEED(h, cond, what) \
+    if (!(h)) return SCZ_ERR_BAD_ARG; \
+    if (!(cond)) return (h)->c.fail(SCZ_ERR_BAD_ARG, what ": null or bad argument")
+
+extern "C" {
+
+int32_t scz_srs_from_device_levels(scz_ctx *h, size_t levels, const void *const *d_levels, const size_t *lens, scz_srs **out) {
+    NEED(h, out && (levels == 0 || (d_levels && lens)), "srs");
+    scz_srs *s = new scz_srs();
+    s->device = h->c.device;
+    for (size_t i = 0; i < levels; i++) {
+        s->level.push_back(d_levels[i]);
+        s->len.push_back(lens[i]);
+    }
+    *out = s;
+    return SCZ_OK;
+}
+int32_t scz_srs_from_host_levels(scz_ctx *h, size_t levels, const void *const *levels_host, const size_t *lens, scz_srs **out) {
+    NEED(h, out && (levels == 0 || (levels_host && lens)), "srs");
+    Ctx *c = &h->c;
+    scz_srs *s = new scz_srs();
+    s->device = c->device;
+    for (size_t i = 0; i < levels; i++) {
+        void *d = nullptr;
+        cudaError_t e = cudaMalloc(&d, lens[i] ? lens[i] * SCZ_G1_AFFINE_BYTES : 1);
+        if (e == cudaSuccess && lens[i])
+            e = cudaMemcpyAsync(d, levels_host[i], lens[i] * SCZ_G1_AFFINE_BYTES, cudaMemcpyHostToDevice, c->stream);
+        if (e != cudaSuccess) {
+            for (void *p : s->owned) cudaFree(p);
+            delete s;
+            return c->cuda(e, "srs upload");
+        }
+        s->owned.push_back(d);
+        s->level.push_back(d);
+        s->len.push_back(lens[i]);
+    }
+    SCZ_CUDA(c, cudaStreamSynchronize(c->stream));
+    *out = s;
+    return SCZ_OK;
+}
+void scz_srs_free(scz_srs *s) {
+    if (!s) return;
+    cudaSetDevice(s->device);
+    for (void *p : s->owned) cudaFree(p);
+    delete s;
+}
+int32_t scz_srs_info(const scz_srs *s, size_t *levels) {
+    if (!s) return SCZ_ERR_BAD_ARG;
+    if (levels) *levels = s->level.size();
+    return SCZ_OK;
+}
+
+int32_t scz_pss2ss_dev(scz_ctx *h, const scz_pp *pp, const void *d_share, void *d_out) {
+    NEED(h, pp && d_share && d_out, "pss2ss");
+    return pss2ss_dev(&h->c, pp, d_share, d_out);
+}
+int32_t scz_degree_reduce_dev(scz_ctx *h, const scz_pp *pp, const void *d_share, void *d_out) {
+    NEED(h, pp && d_share && d_out, "degree_reduce");
+    return degree_reduce_dev(&h->c, pp, d_share, d_out);
+}
+int32_t scz_sumcheck_product_dev(scz_ctx *h, const void *d_f, const void *d_g, size_t len, const void *d_challenge,
+                                 void *d_out) {
+    NEED(h, d_f && d_g && d_out && (len <= 1 || d_challenge), "sumcheck_product");
+    return sumcheck_product_dev(&h->c, d_f, d_g, len, d_challenge, d_out);
+}
+int32_t scz_c_sumcheck_product_dev(scz_ctx *h, const scz_pp *pp, const void *d_f, const void *d_g, size_t len,
+                                   const void *d_challenge, void *d_out) {
+    NEED(h, pp && d_f && d_g && d_out && d_challenge, "c_sumcheck_product");
+    return c_sumcheck_product_dev(&h->c, pp, d_f, d_g, len, d_challenge, d_out);
+}
+int32_t scz_d_sumcheck_product_dev(scz_ctx *h, const void *d_f, const void *d_g, size_t len, const void *d_challenge,
+                                   void *d_out, size_t *count) {
+    NEED(h, d_f && d_g && d_challenge && (d_out || h->c.net->party_id != 0), "d_sumcheck_product");
+    return d_sumcheck_product_dev(&h->c, d_f, d_g, len, d_challenge, d_out, count);
+}
+int32_t scz_d_acc_product_dev(scz_ctx *h, const void *d_x, size_t m, void *d_subtree, void *d_leader_tree) {
+    NEED(h, d_x && d_subtree && (d_leader_tree || h->c.net->party_id != 0), "d_acc_product");
+    return d_acc_product_dev(&h->c, d_x, m, d_subtree, d_leader_tree);
+}
+int32_t scz_commit_dev(scz_ctx *h, const scz_srs *srs, const void *d_peval, size_t len, void *d_out) {
+    NEED(h, srs && d_peval && d_out, "commit");
+    return commit_dev(&h->c, srs, d_peval, len, d_out);
+}
+int32_t scz_c_commit_dev(scz_ctx *h, const scz_srs *srs, const scz_pp *pp, const void *const *d_pevals, const size_t *lens,
+                         size_t batch, void *d_out) {
+    NEED(h, srs && pp && (batch == 0 || (d_pevals && lens && d_out)), "c_commit");
+    return c_commit_dev(&h->c, srs, pp, d_pevals, lens, batch, d_out);
+}
+int32_t scz_d_commit_dev(scz_ctx *h, const scz_srs *srs, const void *d_peval, size_t len, void *d_out) {
+    NEED(h, srs && d_peval && d_out, "d_commit");
+    return d_commit_dev(&h->c, srs, d_peval, len, d_out);
+}
+int32_t scz_open_dev(scz_ctx *h, const scz_srs *srs, const void *d_peval, size_t len, const void *d_point, void *d_value,
+                     void *d_proofs) {
+    NEED(h, srs && d_peval && d_value && (len <= 1 || (d_point && d_proofs)), "open");
+    return open_dev(&h->c, srs, d_peval, len, d_point, d_value, d_proofs);
+}
+int32_t scz_c_open_dev(scz_ctx *h, const scz_srs *srs, const scz_pp *pp, const void *d_peval, size_t len,
+                       const void *d_point, void *d_value, void *d_proofs) {
+    NEED(h, srs && pp && d_peval && d_value && d_point && d_proofs, "c_open");
+    return c_open_dev(&h->c, srs, pp, d_peval, len, d_point, d_value, d_proofs);
+}
+int32_t scz_d_open_dev(scz_ctx *h, const scz_srs *srs, const void *d_peval, size_t len, const void *d_point, size_t npoint,
+                       void *d_value, void *d_proofs, size_t *count) {
+    NEED(h, srs && d_peval && d_value && d_point && (d_proofs || h->c.net->party_id != 0), "d_open");
+    return d_open_dev(&h->c, srs, d_peval, len, d_point, npoint, d_value, d_proofs, count);
+}
+
+}   // extern "C"

@@ -115,3 +115,111 @@ class TorchDistNet:
         vt.sync = NetVTable._SYNC(_sync)
         self._keep = vt   # the callbacks must outlive the ctx
         return vt
+
+
+class LocalTestNet:
+    """All parties in ONE process on ONE GPU, one host thread per party -- the analogue of the reference's
+    `LocalTestNet` (mpc-net/src/multi.rs:268-362: n parties as tokio tasks over loopback TCP).  Every party's
+    ctx runs on the same CUDA stream, so a host-side barrier is all the ordering the star collectives need:
+    whatever a party enqueued before the barrier precedes the copies the receiver enqueues after it."""
+
+    def __init__(self, n_parties, device):
+        import threading
+        self.n = n_parties
+        self.device = torch.device(device)
+        self.barrier = threading.Barrier(n_parties)
+        self.slots = [None] * n_parties
+        self.leader_send = None
+
+    def party(self, party_id):
+        return _LocalParty(self, party_id)
+
+    def simulate_network_round(self, fn):
+        """run fn(party_id, net_for_that_party) on n threads (multi.rs:329-352); returns the results by party"""
+        import threading
+        out, err = [None] * self.n, [None] * self.n
+
+        def body(j):
+            try:
+                torch.cuda.set_device(self.device)
+                out[j] = fn(j, self.party(j))
+            except BaseException as e:   # noqa: BLE001 - re-raised on the caller's thread
+                err[j] = e
+                self.barrier.abort()
+        ts = [threading.Thread(target=body, args=(j,)) for j in range(self.n)]
+        for t in ts:
+            t.start()
+        for t in ts:
+            t.join()
+        for e in err:
+            if e is not None and not isinstance(e, __import__("threading").BrokenBarrierError):
+                raise e
+        for e in err:
+            if e is not None:
+                raise e
+        return out
+
+
+class _LocalParty:
+    def __init__(self, hub, party_id):
+        self.hub, self.rank, self.n_parties = hub, party_id, hub.n
+        self._keep = None
+
+    def vtable(self):
+        hub, me, dev = self.hub, self.rank, self.hub.device
+
+        def _gather(user, d_send, d_recv, nbytes, wire, stream):
+            try:
+                hub.slots[me] = d_send
+                hub.barrier.wait()
+                if me == 0:
+                    recv = _tensor(d_recv, nbytes * hub.n, dev).view(hub.n, nbytes)
+                    for j in range(hub.n):
+                        recv[j].copy_(_tensor(hub.slots[j], nbytes, dev))
+                hub.barrier.wait()
+                return 0
+            except Exception as e:
+                print(f"[scz local net] gather failed: {e!r}", flush=True)
+                return 1
+
+        def _scatter(user, d_send, d_recv, nbytes, wire, stream):
+            try:
+                if me == 0:
+                    hub.leader_send = d_send
+                hub.barrier.wait()
+                src = _tensor(hub.leader_send, nbytes * hub.n, dev).view(hub.n, nbytes)
+                _tensor(d_recv, nbytes, dev).copy_(src[me])
+                hub.barrier.wait()
+                return 0
+            except Exception as e:
+                print(f"[scz local net] scatter failed: {e!r}", flush=True)
+                return 1
+
+        def _all_gather(user, d_send, d_recv, nbytes, wire, stream):
+            try:
+                hub.slots[me] = d_send
+                hub.barrier.wait()
+                recv = _tensor(d_recv, nbytes * hub.n, dev).view(hub.n, nbytes)
+                for j in range(hub.n):
+                    recv[j].copy_(_tensor(hub.slots[j], nbytes, dev))
+                hub.barrier.wait()
+                return 0
+            except Exception as e:
+                print(f"[scz local net] all_gather failed: {e!r}", flush=True)
+                return 1
+
+        def _sync(user, stream):
+            try:
+                hub.barrier.wait()
+                return 0
+            except Exception:
+                return 1
+
+        vt = NetVTable()
+        vt.user = None
+        vt.gather = NetVTable._COLL(_gather)
+        vt.scatter = NetVTable._COLL(_scatter)
+        vt.all_gather = NetVTable._COLL(_all_gather)
+        vt.sync = NetVTable._SYNC(_sync)
+        self._keep = vt
+        return vt
