@@ -160,6 +160,8 @@ int32_t scz_acc_product_dev(scz_ctx *ctx, const void *d_x, size_t m, void *d_tre
  * (d_k: two Fr on the device); 3: a / b with one shared inversion per warp (b = 0 -> 0; arkworks would panic) */
 int32_t scz_fr_pointwise_dev(scz_ctx *ctx, int32_t mode, const void *d_a, const void *d_b, const void *d_k, void *d_out,
                              size_t n);
+/* even[i] = in[2i], odd[i] = in[2i+1]: v(x,0) and v(x,1) of the product tree (dhyperplonk.rs:349-359) */
+int32_t scz_fr_deinterleave_dev(scz_ctx *ctx, const void *d_in, size_t n_pairs, void *d_even, void *d_odd);
 
 /* ---- MSM: ark-ec VariableBaseMSM::msm, call sites dmsm.rs:23, dpoly_comm.rs:242,274,457 ----- */
 /* One launch sequence computes `batch` independent MSMs; out_jac holds batch Jacobian points. */
@@ -248,6 +250,43 @@ int32_t scz_c_open_dev(scz_ctx *ctx, const scz_srs *srs, const scz_pp *pp, const
  * (*count = log2(N) + n); others: value 0, *count = 0 (:387) */
 int32_t scz_d_open_dev(scz_ctx *ctx, const scz_srs *srs, const void *d_peval, size_t len, const void *d_point,
                        size_t npoint, void *d_value, void *d_proofs_jac, size_t *count);
+
+/* ---- the prover: hyperplonk/src/dhyperplonk.rs:159-571 ---------------------------------------------------------
+ * scz_hp_pk mirrors the fields of PackedProvingParameters (dhyperplonk.rs:22-62) that `dhyperplonk` reads: DEVICE
+ * pointers to Fr tables (lengths for circuit size 2^n, packing factor l, N parties; gc = 2^n):
+ *   V 4gc/l; a_evals, b_evals, c_evals, I, S1, S2, eq gc/l; I_p, S1_p, S2_p gc/N; ssigma_p, sid_p, eq_r1_p, eq_r2_p 4gc/N;
+ *   challenge n; challenge_r1, challenge_r2 n+2; alpha_beta 2 (alpha | beta).
+ * The three vectors the reference draws from entropy inside the function (:188-190) are explicit inputs (an API
+ * addition so that runs are reproducible): local_s_p 4gc/N, local_s 4gc/N/l, eq_leader 8l. */
+typedef struct scz_hp_pk {
+    const void *V, *a_evals, *b_evals, *c_evals, *I, *S1, *S2, *I_p, *S1_p, *S2_p, *ssigma_p, *sid_p, *eq, *eq_r1_p,
+        *eq_r2_p, *challenge, *challenge_r1, *challenge_r2, *alpha_beta;
+    const scz_srs *c_commitment; /* new_single(n + 2, pp), dhyperplonk.rs:100 */
+    const scz_srs *d_commitment; /* new_random(n + 2, N), dhyperplonk.rs:101 */
+    const void *local_s_p, *local_s, *eq_leader;
+} scz_hp_pk;
+/* One entry of the reference's return value (dhyperplonk.rs:567-570), in the order the reference pushes it into
+ * its vector.  Offsets are element indices into the three output arenas. */
+#define SCZ_HP_GATE_PROOF 0    /* gate_identity_proofs[i]: triples                                         */
+#define SCZ_HP_GATE_COMMIT 1   /* gate_identity_commitments[i]: points[0] = commitment, then the proofs; value  */
+#define SCZ_HP_WIRING_PROOF 2  /* wiring_proofs[i]: triples (empty on non-leaders for the d_ variants)        */
+#define SCZ_HP_WIRING_COMMIT 3 /* wiring_commits[i]: one point                                               */
+#define SCZ_HP_WIRING_OPEN 4   /* wiring_opens[i]: value + proofs (value 0, no proofs on non-leaders for d_open) */
+typedef struct scz_hp_item {
+    uint32_t kind;
+    uint32_t triples_off, triples_cnt; /* into d_triples (96 B each) */
+    uint32_t points_off, points_cnt;   /* into d_points  (144 B Jacobian each) */
+    uint32_t value_off, value_cnt;     /* into d_values  (32 B each); value_cnt is 0 or 1 */
+} scz_hp_item;
+/* capacities (in elements / items) that always suffice for the outputs of scz_dhyperplonk_dev */
+int32_t scz_dhyperplonk_sizes(size_t n, size_t l, size_t n_parties, size_t *triples, size_t *points, size_t *values,
+                              size_t *items);
+/* dhyperplonk (dhyperplonk.rs:159-571) from after net.sync() (:193) to the return.  Outputs go to three DEVICE arenas;
+ * `items` (HOST array) describes them entry by entry, *n_items entries.  Asynchronous on the ctx stream except for
+ * the host-side collectives of a real net. */
+int32_t scz_dhyperplonk_dev(scz_ctx *ctx, size_t n, const scz_hp_pk *pk, const scz_pp *pp, void *d_triples,
+                            size_t triples_cap, void *d_points, size_t points_cap, void *d_values, size_t values_cap,
+                            scz_hp_item *items, size_t items_cap, size_t *n_items);
 
 #ifdef __cplusplus
 }

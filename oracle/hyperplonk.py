@@ -1,0 +1,198 @@
+"""ORACLE (test infrastructure) -- CPU restatement of the collaborative HyperPlonk prover,
+`dhyperplonk` (hyperplonk/src/dhyperplonk.rs:159-571), composed from the oracle's C primitives
+(oracle/src/*.c through oracle/oracle.py).  Only tests/, __graft_entry__.smoke() and bench.py's
+CPU legs may import this module.  PARITY UNPINNED at the arkworks byte boundary (oracle/src/oracle.h).
+
+The reference draws three vectors from entropy inside the function (`local_s_p`, `local_s`, `eq`,
+dhyperplonk.rs:188-190); here (and in the product's API) they are explicit inputs so that runs can be
+compared.  Every statement below cites the reference line it restates.
+
+A "pk" is a dict of numpy arrays (Fr: (len, 4) uint64 Montgomery) mirroring PackedProvingParameters
+(dhyperplonk.rs:22-62) -- only the fields `dhyperplonk` reads -- plus:
+  'c_commitment', 'd_commitment': oracle.Srs      (dhyperplonk.rs:53-54)
+  'alpha', 'beta': (1, 4)                          (:50-51)
+  'local_s_p', 'local_s', 'eq_leader': injected entropy (:188-190)
+"""
+import numpy as np
+
+from . import oracle as orc
+
+PK_TABLES = ("V", "a_evals", "b_evals", "c_evals", "I", "S1", "S2", "I_p", "S1_p", "S2_p", "ssigma_p", "sid_p", "eq",
+             "eq_r1_p", "eq_r2_p", "challenge", "challenge_r1", "challenge_r2", "alpha", "beta", "local_s_p", "local_s",
+             "eq_leader")
+
+
+def table_sizes(n, l, N):
+    """lengths of every table `dhyperplonk` reads, PackedProvingParameters::new (dhyperplonk.rs:65-157) + :188-190"""
+    gc = 1 << n
+    return {
+        "V": gc * 4 // l, "a_evals": gc // l, "b_evals": gc // l, "c_evals": gc // l,   # :70-73 (fix_variable drops 2 vars)
+        "I": gc // l, "S1": gc // l, "S2": gc // l,                                      # :75, :79-80
+        "I_p": gc // N, "S1_p": gc // N, "S2_p": gc // N,                                # :77, :81-82
+        "ssigma_p": gc * 4 // N, "sid_p": gc * 4 // N,                                   # :85, :90
+        "eq": gc // l, "eq_r1_p": gc * 4 // N, "eq_r2_p": gc * 4 // N,                   # :93, :96, :98
+        "challenge": n, "challenge_r1": n + 2, "challenge_r2": n + 2,                    # :103-105
+        "alpha": 1, "beta": 1,                                                           # :107-108
+        "local_s_p": gc * 4 // N, "local_s": gc * 4 // N // l, "eq_leader": 8 * l,       # :188-190 (pp.n = 8 l)
+    }
+
+
+def srs_level_sizes(n, l, N):
+    """(c_commitment, d_commitment) level lengths: new_single(n+2, pp) :196-219, new_random(n+2, N) :220-233"""
+    c = [max(1, (1 << i) // l) for i in range(n + 3)]
+    d = [1 << i for i in range(n + 2 - (N.bit_length() - 1) + 1)]
+    return c, d
+
+
+def _rep(x, m):
+    return np.repeat(np.ascontiguousarray(x, dtype=np.uint64).reshape(1, 4), m, axis=0)
+
+
+def dhyperplonk(n, pks, pp, mode, N, algo="ark"):
+    """pks: one pk per party (PARTIES: N of them, LEADER_SIM: the leader's alone).
+    Returns one result dict per party:
+      gate_identity_proofs       list of (cnt, 3, 4)
+      gate_identity_commitments  list of (com (1,18), (value (1,4), proofs (k,18)))
+      wiring_proofs, wiring_commits, wiring_opens    as the reference's tuple (dhyperplonk.rs:567-570);
+    entries a non-leader gets empty from d_sumcheck_product / d_open are empty arrays there."""
+    P = N if mode == orc.PARTIES else 1
+    assert len(pks) == P
+    csrs = [pk["c_commitment"] for pk in pks]
+    dsrs = [pk["d_commitment"] for pk in pks]
+    res = [dict(gate_identity_proofs=[], gate_identity_commitments=[], wiring_proofs=[], wiring_commits=[],
+                wiring_opens=[]) for _ in range(P)]
+    col = lambda name: [pk[name] for pk in pks]   # noqa: E731
+
+    def c_commit1(name_or_tabs):
+        tabs = col(name_or_tabs) if isinstance(name_or_tabs, str) else name_or_tabs
+        out = orc.c_commit(csrs, pp, mode, [[t] for t in tabs], algo)      # (P, 1, 18)
+        return [out[j, 0:1].copy() for j in range(P)]
+
+    def d_commit(tabs):
+        com = orc.d_commit(dsrs, mode, N, tabs, algo)                      # every party gets the sum (dpoly_comm.rs:290-292)
+        return [com.copy() for _ in range(P)]
+
+    def c_sumcheck(f, g, ch):
+        out = orc.c_sumcheck_product(pp, mode, f, g, ch)
+        return [out[j].copy() for j in range(P)]
+
+    def d_sumcheck(f, g, ch):
+        lead = orc.d_sumcheck_product(mode, N, f, g, ch)
+        return [lead] + [np.zeros((0, 3, 4), dtype=np.uint64) for _ in range(P - 1)]   # dsumcheck.rs:507-509
+
+    def c_open(tabs, point):
+        val, proofs = orc.c_open(csrs, pp, mode, tabs, point, algo)
+        return [(val[j:j + 1].copy(), proofs[j].copy()) for j in range(P)]
+
+    def d_open(tabs, point):
+        val, proofs = orc.d_open(dsrs, mode, N, tabs, point, algo)
+        empty = (np.zeros((1, 4), dtype=np.uint64), np.zeros((0, 18), dtype=np.uint64))   # dpoly_comm.rs:387
+        return [(val, proofs)] + [empty for _ in range(P - 1)]
+
+    def push(key, per_party):
+        for j in range(P):
+            res[j][key].append(per_party[j])
+
+    # Step 1: commit (:196-217)
+    com_a, com_b, com_c = c_commit1("a_evals"), c_commit1("b_evals"), c_commit1("c_evals")
+    com_I, com_S1, com_S2 = d_commit(col("I_p")), d_commit(col("S1_p")), d_commit(col("S2_p"))
+
+    # Step 3: gate identity (:222-260)
+    ch = pks[0]["challenge"]
+    push("gate_identity_proofs", c_sumcheck(col("eq"), col("S1"), ch))                              # :230-231
+    sum_ab = [orc.fr_add(pk["a_evals"], pk["b_evals"]) for pk in pks]                               # :233-238
+    push("gate_identity_proofs", c_sumcheck(col("S1"), sum_ab, ch))                                 # :240-241
+    push("gate_identity_proofs", c_sumcheck(col("eq"), col("S2"), ch))                              # :243-244
+    push("gate_identity_proofs", c_sumcheck(col("a_evals"), col("b_evals"), ch))                    # :245-246
+    push("gate_identity_proofs", c_sumcheck(col("S2"), col("a_evals"), ch))                         # :247-248
+    sum_ci = [orc.fr_sub(pk["I"], pk["c_evals"]) for pk in pks]                                     # :251-256  -c + I
+    push("gate_identity_proofs", c_sumcheck(col("eq"), sum_ci, ch))                                 # :258-259
+
+    # Step 2: wiring identity (:263-513)
+    # 2.a (:270-294): N hub rounds, hub i sends its local_s to everyone -> s = local_s^(0) | ... | local_s^(N-1);
+    # without `comm` the own vector is appended N times (:289-293)
+    if mode == orc.PARTIES:
+        s_all = np.concatenate([pk["local_s"] for pk in pks])
+        s = [s_all for _ in range(P)]
+    else:
+        s = [np.concatenate([pks[0]["local_s"]] * N)]
+    local_s_p = col("local_s_p")
+    push("wiring_commits", d_commit(local_s_p))                                                     # 2.b :297-302
+    r1, r2 = pks[0]["challenge_r1"], pks[0]["challenge_r2"]
+    push("wiring_proofs", c_sumcheck(s, col("V"), r1))                                              # 2.c :304
+    push("wiring_opens", c_open(col("V"), r1))                                                      # 2.d :306-320
+    push("wiring_opens", c_open(col("V"), r2))
+    push("wiring_opens", d_open(local_s_p, r2))
+    # 2.e (:324-340)
+    num, den, h_p = [], [], []
+    for pk in pks:
+        m = len(pk["local_s_p"])
+        alpha, beta = _rep(pk["alpha"], m), _rep(pk["beta"], m)
+        nu = orc.fr_add(orc.fr_add(pk["local_s_p"], orc.fr_mul(alpha, pk["sid_p"])), beta)          # :326-331
+        de = orc.fr_add(orc.fr_add(pk["eq_r1_p"], orc.fr_mul(alpha, pk["ssigma_p"])), beta)         # :332-337
+        num.append(nu)
+        den.append(de)
+        h_p.append(orc.fr_mul(nu, orc.fr_inv(de)))                                                  # :339
+    subtrees, top = orc.d_acc_product(mode, N, h_p)                                                 # :342
+    v1x = [t[len(t) // 2:].copy() for t in subtrees]                                                # :344-348
+    vx0 = [t[0::2].copy() for t in subtrees]                                                        # :349-353
+    vx1 = [t[1::2].copy() for t in subtrees]                                                        # :354-359
+    for tabs in (col("ssigma_p"), col("sid_p"), h_p, num, den, v1x, vx0, vx1):                      # :363-380
+        push("wiring_commits", d_commit(tabs))
+    for tabs in (col("ssigma_p"), col("sid_p"), h_p, num, den):                                     # :383-407
+        push("wiring_opens", d_open(tabs, r2))
+    eq_r2_p = col("eq_r2_p")
+    push("wiring_proofs", d_sumcheck(den, eq_r2_p, r2))                                             # :411-413
+    push("wiring_proofs", d_sumcheck(h_p, den, r2))
+    push("wiring_proofs", d_sumcheck(num, eq_r2_p, r2))
+    sN = N.bit_length() - 1                                                                         # :418
+    cur_v1x = [t[:len(t) // 2] for t in v1x]                                                        # :419-422
+    cur_vx0 = [t[:len(t) // 2] for t in vx0]
+    cur_vx1 = [t[:len(t) // 2] for t in vx1]
+    cur_eq = [t[:len(t) // 2] for t in eq_r2_p]
+    for i in range(1, n - sN + 1):                                                                  # :423-478
+        chi = r2[i:]
+        push("wiring_proofs", d_sumcheck(cur_eq, cur_v1x, chi))
+        push("wiring_proofs", d_sumcheck(cur_eq, cur_vx0, chi))
+        push("wiring_proofs", d_sumcheck(cur_vx0, cur_vx1, chi))
+        push("wiring_opens", d_open(cur_v1x, chi))
+        push("wiring_opens", d_open(cur_vx0, chi))
+        push("wiring_opens", d_open(cur_vx1, chi))
+        cur_v1x = [t[len(t) // 2:] for t in cur_v1x]
+        cur_vx0 = [t[len(t) // 2:] for t in cur_vx0]
+        cur_vx1 = [t[len(t) // 2:] for t in cur_vx1]
+        cur_eq = [t[len(t) // 2:] for t in cur_eq]
+    # leader tree (:480-511): party 0 only
+    lt = top
+    lv1x, lvx0, lvx1 = lt[len(lt) // 2:].copy(), lt[0::2].copy(), lt[1::2].copy()
+    pt = r2[:sN]
+    d0 = dsrs[0]
+    for t in (lvx0, lvx1, lv1x):                                                                    # :500-505
+        res[0]["wiring_commits"].append(orc.commit(d0, t, algo))
+        res[0]["wiring_opens"].append(orc.open_(d0, t, pt, algo))
+    eql = pks[0]["eq_leader"]
+    res[0]["wiring_proofs"].append(orc.sumcheck_product(eql, lv1x, pt))                             # :507-509
+    res[0]["wiring_proofs"].append(orc.sumcheck_product(eql, lvx0, pt))
+    res[0]["wiring_proofs"].append(orc.sumcheck_product(lvx0, lvx1, pt))
+
+    # Open (:517-554)
+    for com, name in ((com_a, "a_evals"), (com_b, "b_evals"), (com_c, "c_evals")):
+        op = c_open(col(name), ch)
+        push("gate_identity_commitments", [(com[j], op[j]) for j in range(P)])
+    for com, name in ((com_I, "I_p"), (com_S1, "S1_p"), (com_S2, "S2_p")):
+        op = d_open(col(name), ch)
+        push("gate_identity_commitments", [(com[j], op[j]) for j in range(P)])
+    return res
+
+
+def random_pk(rng, n, l, N, srs_c=None, srs_d=None, shared=None):
+    """PackedProvingParameters::new with numpy randomness (tables only; SRS passed in).  `shared`: a pk whose
+    public values (challenges, alpha, beta) are reused -- all parties must agree on them."""
+    pk = {}
+    for name, ln in table_sizes(n, l, N).items():
+        pk[name] = orc.random_fr(rng, ln)
+    if shared is not None:
+        for name in ("challenge", "challenge_r1", "challenge_r2", "alpha", "beta"):
+            pk[name] = shared[name]
+    pk["c_commitment"], pk["d_commitment"] = srs_c, srs_d
+    return pk

@@ -26,4 +26,8 @@ from .api import (  # noqa: F401
     sumcheck_product,
     sumcheck_rounds,
     msm,
+    PackedProvingParameters,
+    HyperPlonkProof,
+    dhyperplonk,
+    hp_table_sizes,
 )

@@ -530,6 +530,143 @@ class PolynomialCommitment:
         return _out(ctx, val, host), _out(ctx, proofs[: cnt.value], host)
 
 
+# ---------------------------------------------------------------------------- the prover
+class HpPk(C.Structure):
+    """scz_hp_pk (include/scz.h)"""
+    _TABLES = ("V", "a_evals", "b_evals", "c_evals", "I", "S1", "S2", "I_p", "S1_p", "S2_p", "ssigma_p", "sid_p", "eq",
+               "eq_r1_p", "eq_r2_p", "challenge", "challenge_r1", "challenge_r2", "alpha_beta")
+    _INJECTED = ("local_s_p", "local_s", "eq_leader")
+    _fields_ = ([(k, C.c_void_p) for k in _TABLES] + [("c_commitment", C.c_void_p), ("d_commitment", C.c_void_p)]
+                + [(k, C.c_void_p) for k in _INJECTED])
+
+
+class HpItem(C.Structure):
+    """scz_hp_item (include/scz.h)"""
+    _fields_ = [(k, C.c_uint32) for k in ("kind", "triples_off", "triples_cnt", "points_off", "points_cnt", "value_off",
+                                           "value_cnt")]
+
+
+def hp_table_sizes(n, l, n_parties):
+    """lengths of the tables `dhyperplonk` reads: PackedProvingParameters::new (dhyperplonk.rs:65-157) and :188-190"""
+    gc = 1 << n
+    return {"V": gc * 4 // l, "a_evals": gc // l, "b_evals": gc // l, "c_evals": gc // l, "I": gc // l, "S1": gc // l,
+            "S2": gc // l, "I_p": gc // n_parties, "S1_p": gc // n_parties, "S2_p": gc // n_parties,
+            "ssigma_p": gc * 4 // n_parties, "sid_p": gc * 4 // n_parties, "eq": gc // l, "eq_r1_p": gc * 4 // n_parties,
+            "eq_r2_p": gc * 4 // n_parties, "challenge": n, "challenge_r1": n + 2, "challenge_r2": n + 2, "alpha_beta": 2,
+            "local_s_p": gc * 4 // n_parties, "local_s": gc * 4 // n_parties // l, "eq_leader": 8 * l}
+
+
+class PackedProvingParameters:
+    """The fields of PackedProvingParameters (hyperplonk/src/dhyperplonk.rs:22-62) that `dhyperplonk` reads, as
+    device-resident Fr tables, plus the three vectors the reference draws from entropy inside the function
+    (:188-190), here explicit inputs.  `tables`: dict name -> (len, 4) array (numpy or CUDA tensor), names and
+    lengths as hp_table_sizes; c_commitment / d_commitment: PolynomialCommitment (:53-54)."""
+
+    def __init__(self, ctx, n, l, tables, c_commitment, d_commitment):
+        self.ctx, self.n, self.l = ctx, n, l
+        want = hp_table_sizes(n, l, ctx.n_parties)
+        self.t = {}
+        for name, ln in want.items():
+            x = tables[name]
+            x = _dev(x, 4) if _is_dev(x) else ctx.to_device(x, 4)
+            if len(x) != ln:
+                raise SczError(-2, f"PackedProvingParameters: {name} has {len(x)} entries, {ln} expected")
+            self.t[name] = x
+        self.c_commitment, self.d_commitment = c_commitment, d_commitment
+
+    @classmethod
+    def new(cls, ctx, n, l, seed=0, shared_seed=None):
+        """PackedProvingParameters::new(n, l, pp) (:65-157) with synthetic random tables generated ON the device
+        (the reference draws them with F::rand from entropy) and random-point SRS levels (new_single / new_random,
+        dpoly_comm.rs:196-233: random points, not a valid SRS).  Challenges, alpha and beta come from `shared_seed`
+        so that all parties agree on them."""
+        N = ctx.n_parties
+        gen = torch.Generator(device=ctx.device).manual_seed(0x5CA1AB1E ^ (seed << 32))
+        pub = torch.Generator(device=ctx.device).manual_seed(0x5CA1AB1E ^ ((shared_seed if shared_seed is not None else seed) << 32) ^ 0xFFFF)
+
+        def rand_fr(m, g):
+            # uniform 254-bit integers used directly as Montgomery limbs: every value is a valid element (< r)
+            t = torch.randint(-2**63, 2**63 - 1, (m, 4), dtype=torch.int64, device=ctx.device, generator=g)
+            t[:, 3] &= (1 << 62) - 1
+            return t
+        tables = {}
+        for name, ln in hp_table_sizes(n, l, N).items():
+            public = name in ("challenge", "challenge_r1", "challenge_r2", "alpha_beta")
+            tables[name] = rand_fr(ln, pub if public else gen)
+        # a, b, c are fix_variable(V, .) of the witness table (:71-73): bind the two top variables to (0,0), (0,1), (1,0)
+        zero, one = torch.zeros((1, 4), dtype=torch.int64, device=ctx.device), _fr_one(ctx)
+        for name, pt in (("a_evals", (zero, zero)), ("b_evals", (zero, one)), ("c_evals", (one, zero))):
+            tables[name] = fix_variable(ctx, tables["V"], torch.cat(pt))
+
+        def levels(sizes):
+            return [ctx.g1_generator_mul(rand_fr(m, gen)) for m in sizes]
+        csz = [max(1, (1 << i) // l) for i in range(n + 3)]                      # new_single(n + 2, pp)
+        dsz = [1 << i for i in range(n + 2 - (N.bit_length() - 1) + 1)]          # new_random(n + 2, N)
+        return cls(ctx, n, l, tables, PolynomialCommitment(ctx, levels(csz)), PolynomialCommitment(ctx, levels(dsz)))
+
+    def c_struct(self):
+        pk = HpPk()
+        for name in HpPk._TABLES + HpPk._INJECTED:
+            setattr(pk, name, self.t[name].data_ptr())
+        pk.c_commitment, pk.d_commitment = self.c_commitment.h, self.d_commitment.h
+        return pk
+
+
+def _fr_one(ctx):
+    one = np.array([[0x00000001fffffffe, 0x5884b7fa00034802, 0x998c4fefecbc4ff5, 0x1824b159acc5056f]], dtype=np.uint64)
+    return ctx.to_device(one, 4)
+
+
+class HyperPlonkProof:
+    """The return value of `dhyperplonk` (dhyperplonk.rs:567-570) on the device: three arenas + the item table.
+    `nested()` rebuilds the reference's tuple
+        ((gate_identity_proofs, gate_identity_commitments), (wiring_proofs, wiring_commits, wiring_opens))
+    with numpy arrays: proofs (cnt, 3, 4); commitments (1, 18); opens (value (1, 4), proofs (k, 18))."""
+
+    def __init__(self, ctx, triples, points, values, items):
+        self.ctx, self.triples, self.points, self.values, self.items = ctx, triples, points, values, items
+
+    def nested(self):
+        tri = self.ctx.to_host(self.triples).reshape(-1, 3, 4)
+        pts = self.ctx.to_host(self.points)
+        val = self.ctx.to_host(self.values)
+        gp, gc, wp, wc, wo = [], [], [], [], []
+        for it in self.items:
+            t = tri[it.triples_off: it.triples_off + it.triples_cnt]
+            p = pts[it.points_off: it.points_off + it.points_cnt]
+            v = val[it.value_off: it.value_off + it.value_cnt]
+            if it.kind == 0:
+                gp.append(t)
+            elif it.kind == 1:
+                gc.append((p[:1], (v, p[1:])))
+            elif it.kind == 2:
+                wp.append(t)
+            elif it.kind == 3:
+                wc.append(p)
+            else:
+                wo.append((v, p))
+        return (gp, gc), (wp, wc, wo)
+
+
+def dhyperplonk(ctx, n, pk, pp):
+    """hyperplonk/src/dhyperplonk.rs:159-571 (after net.sync(), :193) -> HyperPlonkProof.  Asynchronous on the
+    ctx stream in leader mode; call ctx.sync() or .nested() to wait."""
+    L = ctx.L
+    nt, npt, nv, ni = C.c_size_t(), C.c_size_t(), C.c_size_t(), C.c_size_t()
+    ctx.check(L.scz_dhyperplonk_sizes(C.c_size_t(n), C.c_size_t(pp.l), C.c_size_t(ctx.n_parties), C.byref(nt), C.byref(npt),
+                                      C.byref(nv), C.byref(ni)))
+    tri = ctx.empty(nt.value * 3, 4)
+    pts = ctx.empty(npt.value, 18)
+    val = ctx.empty(nv.value, 4)
+    items = (HpItem * ni.value)()
+    cnt = C.c_size_t()
+    cpk = pk.c_struct()
+    ctx.check(L.scz_dhyperplonk_dev(ctx.h, C.c_size_t(n), C.byref(cpk), pp.h, _vp(tri), nt, _vp(pts), npt, _vp(val), nv,
+                                    items, ni, C.byref(cnt)))
+    return HyperPlonkProof(ctx, tri, pts, val, list(items[: cnt.value]))
+
+
 __all__ = ["Context", "PackedSharingParams", "msm", "msm_batched", "d_msm", "d_msm_leader", "NetVTable",
            "fr_pointwise", "fix_variable", "acc_product_tree", "d_acc_product", "sumcheck_rounds", "sumcheck_product",
-           "c_sumcheck_product", "d_sumcheck_product", "pss2ss", "degree_reduce", "PolynomialCommitment"]
+           "c_sumcheck_product", "d_sumcheck_product", "pss2ss", "degree_reduce", "PolynomialCommitment",
+           "PackedProvingParameters", "HyperPlonkProof", "dhyperplonk", "hp_table_sizes"]

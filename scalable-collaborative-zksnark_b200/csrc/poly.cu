@@ -436,6 +436,36 @@ int32_t acc_product_tree(Ctx *ctx, const void *d_x, size_t m, void *d_tree) {
     return SCZ_OK;
 }
 
+// point-wise maps of dhyperplonk.rs:233-238, 251-256, 326-339 (modes: see scz_fr_pointwise_dev)
+int32_t fr_pointwise(Ctx *c, int32_t mode, const void *d_a, const void *d_b, const void *d_k, void *d_out, size_t n) {
+    if (!d_a || !d_b || !d_out || mode < 0 || mode > 3 || (mode == 2 && !d_k)) return c->fail(SCZ_ERR_BAD_ARG, "pointwise: bad argument");
+    if (!n) return SCZ_OK;
+    ProfScope ps(c, SCZ_K_POINTWISE);
+    uint32_t g = ceil_div_u32(n, PL_THREADS);
+    if (mode == 0) k_pointwise<0><<<g, PL_THREADS, 0, c->stream>>>(d_a, d_b, d_k, d_out, n);
+    else if (mode == 1) k_pointwise<1><<<g, PL_THREADS, 0, c->stream>>>(d_a, d_b, d_k, d_out, n);
+    else if (mode == 2) k_pointwise<2><<<g, PL_THREADS, 0, c->stream>>>(d_a, d_b, d_k, d_out, n);
+    else k_div<<<ceil_div_u32(n, (size_t)PL_THREADS * INV_PER_THREAD), PL_THREADS, 0, c->stream>>>(d_a, d_b, d_out, n);
+    SCZ_LAUNCH_CHECK(c);
+    return SCZ_OK;
+}
+
+// even[i] = in[2i], odd[i] = in[2i+1]: v(x,0) / v(x,1) of the product tree (dhyperplonk.rs:349-359, dacc_product.rs:41-52)
+__global__ void __launch_bounds__(PL_THREADS) k_deinterleave(const void *in, void *even, void *odd, size_t n_pairs) {
+    size_t i = blockIdx.x * (size_t)PL_THREADS + threadIdx.x;
+    if (i >= n_pairs) return;
+    fp_store<FrP>(even, i, fp_load_rw<FrP>(in, 2 * i));
+    fp_store<FrP>(odd, i, fp_load_rw<FrP>(in, 2 * i + 1));
+}
+int32_t fr_deinterleave(Ctx *c, const void *d_in, size_t n_pairs, void *d_even, void *d_odd) {
+    if (!d_in || !d_even || !d_odd) return c->fail(SCZ_ERR_BAD_ARG, "deinterleave: null argument");
+    if (!n_pairs) return SCZ_OK;
+    ProfScope ps(c, SCZ_K_POINTWISE);
+    k_deinterleave<<<ceil_div_u32(n_pairs, PL_THREADS), PL_THREADS, 0, c->stream>>>(d_in, d_even, d_odd, n_pairs);
+    SCZ_LAUNCH_CHECK(c);
+    return SCZ_OK;
+}
+
 }   // namespace scz
 
 using namespace scz;
@@ -467,17 +497,11 @@ int32_t scz_acc_product_dev(scz_ctx *h, const void *d_x, size_t m, void *d_tree)
 int32_t scz_fr_pointwise_dev(scz_ctx *h, int32_t mode, const void *d_a, const void *d_b, const void *d_k, void *d_out,
                              size_t n) {
     if (!h) return SCZ_ERR_BAD_ARG;
-    Ctx *c = &h->c;
-    if (!d_a || !d_b || !d_out || mode < 0 || mode > 3 || (mode == 2 && !d_k)) return c->fail(SCZ_ERR_BAD_ARG, "pointwise: bad argument");
-    if (!n) return SCZ_OK;
-    ProfScope ps(c, SCZ_K_POINTWISE);
-    uint32_t g = ceil_div_u32(n, PL_THREADS);
-    if (mode == 0) k_pointwise<0><<<g, PL_THREADS, 0, c->stream>>>(d_a, d_b, d_k, d_out, n);
-    else if (mode == 1) k_pointwise<1><<<g, PL_THREADS, 0, c->stream>>>(d_a, d_b, d_k, d_out, n);
-    else if (mode == 2) k_pointwise<2><<<g, PL_THREADS, 0, c->stream>>>(d_a, d_b, d_k, d_out, n);
-    else k_div<<<ceil_div_u32(n, (size_t)PL_THREADS * INV_PER_THREAD), PL_THREADS, 0, c->stream>>>(d_a, d_b, d_out, n);
-    SCZ_LAUNCH_CHECK(c);
-    return SCZ_OK;
+    return fr_pointwise(&h->c, mode, d_a, d_b, d_k, d_out, n);
+}
+int32_t scz_fr_deinterleave_dev(scz_ctx *h, const void *d_in, size_t n_pairs, void *d_even, void *d_odd) {
+    if (!h) return SCZ_ERR_BAD_ARG;
+    return fr_deinterleave(&h->c, d_in, n_pairs, d_even, d_odd);
 }
 
 }   // extern "C"

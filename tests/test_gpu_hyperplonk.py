@@ -1,0 +1,141 @@
+"""-m gpu: the collaborative HyperPlonk prover (`dhyperplonk`, hyperplonk/src/dhyperplonk.rs:159-571) through the
+C ABI (scz_dhyperplonk_dev), entry by entry against the oracle's restatement (oracle/hyperplonk.py): leader mode on
+one ctx and parties mode (N = 8 ctxs on one GPU under LocalTestNet)."""
+import numpy as np
+import pytest
+
+from tests.gpu_util import oracle_affine
+
+pytestmark = pytest.mark.gpu
+
+
+def _tables_for_product(pk):
+    """oracle pk (alpha, beta separate) -> product tables (alpha_beta)"""
+    t = {k: v for k, v in pk.items() if k not in ("c_commitment", "d_commitment", "alpha", "beta")}
+    t["alpha_beta"] = np.concatenate([pk["alpha"], pk["beta"]])
+    return t
+
+
+def _make_srs(seed_ctx, orc, rng, sizes):
+    dev, host = [], []
+    for m in sizes:
+        b = seed_ctx.g1_generator_mul(seed_ctx.to_device(orc.random_fr(rng, m), 4))
+        dev.append(b)
+        host.append(oracle_affine(seed_ctx.to_host(b)))
+    return dev, orc.Srs.from_levels(host)
+
+
+def _same_proof(orc, got, want, who):
+    (gp, gc), (wp, wc, wo) = got
+    assert len(gp) == len(want["gate_identity_proofs"]), who
+    for a, b in zip(gp, want["gate_identity_proofs"]):
+        assert np.array_equal(a, b), who
+    assert len(gc) == len(want["gate_identity_commitments"]), who
+    for (com, (val, proofs)), (ocom, (oval, oproofs)) in zip(gc, want["gate_identity_commitments"]):
+        assert orc.canon_g1(com) == orc.canon_g1(ocom), who
+        assert np.array_equal(val, oval), who
+        assert len(proofs) == len(oproofs) and orc.canon_g1(proofs) == orc.canon_g1(oproofs), who
+    assert len(wp) == len(want["wiring_proofs"]), (who, len(wp), len(want["wiring_proofs"]))
+    for k, (a, b) in enumerate(zip(wp, want["wiring_proofs"])):
+        assert a.shape == b.shape and np.array_equal(a, b), (who, k)
+    assert len(wc) == len(want["wiring_commits"]), who
+    for a, b in zip(wc, want["wiring_commits"]):
+        assert orc.canon_g1(a) == orc.canon_g1(b), who
+    assert len(wo) == len(want["wiring_opens"]), who
+    for k, ((val, proofs), (oval, oproofs)) in enumerate(zip(wo, want["wiring_opens"])):
+        assert np.array_equal(val, oval), (who, k)
+        assert len(proofs) == len(oproofs) and orc.canon_g1(proofs) == orc.canon_g1(oproofs), (who, k)
+
+
+@pytest.mark.parametrize("n,l", [(4, 1), (6, 1), (6, 2)])
+def test_dhyperplonk_leader_mode(orc, n, l):
+    import scz_b200 as scz
+    from oracle import hyperplonk as ohp
+    N = 8 * l
+    rng = np.random.default_rng(600 + 10 * n + l)
+    ctx = scz.Context(device=0, n_parties=N)
+    pp, opp = scz.PackedSharingParams(ctx, l), orc.pp_new(l)
+    csz, dsz = ohp.srs_level_sizes(n, l, N)
+    cdev, csrs = _make_srs(ctx, orc, rng, csz)
+    ddev, dsrs = _make_srs(ctx, orc, rng, dsz)
+    opk = ohp.random_pk(rng, n, l, N, csrs, dsrs)
+    want = ohp.dhyperplonk(n, [opk], opp, orc.LEADER_SIM, N)[0]
+    pk = scz.PackedProvingParameters(ctx, n, l, _tables_for_product(opk), scz.PolynomialCommitment(ctx, cdev),
+                                     scz.PolynomialCommitment(ctx, ddev))
+    got = scz.dhyperplonk(ctx, n, pk, pp).nested()
+    _same_proof(orc, got, want, "leader")
+    # shape of the reference's return value at l = 1 (dhyperplonk.rs:567-570)
+    (gp, gc), (wp, wc, wo) = got
+    s = N.bit_length() - 1
+    assert len(gp) == 6 and len(gc) == 6
+    assert len(wp) == 1 + 3 + 3 * (n - s) + 3 and len(wc) == 1 + 8 + 3 and len(wo) == 3 + 5 + 3 * (n - s) + 3
+    up, down = ctx.get_comm()
+    assert up > 0 and down > 0
+    ctx.close()
+
+
+def test_dhyperplonk_generated_parameters_round_identities(orc):
+    """PackedProvingParameters.new (device-generated synthetic tables, a = fix_variable(V, (0,0)) etc.) at n = 10:
+    every sumcheck proof of the gate identity satisfies the verifier's round identity (dsumcheck.rs:558-588) and
+    the a / b / c tables are the right quarters of V (mle.rs:88-104 with points in {0, 1})."""
+    import scz_b200 as scz
+    from oracle import py_twin as tw
+    n, l, N = 10, 1, 8
+    ctx = scz.Context(device=0, n_parties=N)
+    pp = scz.PackedSharingParams(ctx, l)
+    pk = scz.PackedProvingParameters.new(ctx, n, l, seed=3)
+    V = ctx.to_host(pk.t["V"])
+    q = len(V) // 4
+    assert np.array_equal(ctx.to_host(pk.t["a_evals"]), V[:q])          # (0, 0): top two variables zero
+    assert np.array_equal(ctx.to_host(pk.t["b_evals"]), V[q:2 * q])     # (0, 1)
+    assert np.array_equal(ctx.to_host(pk.t["c_evals"]), V[2 * q:3 * q])  # (1, 0)
+    (gp, gc), (wp, wc, wo) = scz.dhyperplonk(ctx, n, pk, pp).nested()
+    R = tw.R_MOD
+    inv2 = pow(2, R - 2, R)
+    chi = orc.fr_to_ints(ctx.to_host(pk.t["challenge"]))
+    for proof in gp:
+        tri = [[orc.fr_to_ints(proof[i, j:j + 1])[0] for j in range(3)] for i in range(len(proof))]
+        for i in range(n - 1):
+            p0, p1, p2 = tri[i]
+            r = chi[i]
+            val = (p0 * (r - 1) * (r - 2) * inv2 - p1 * r * (r - 2) + p2 * r * (r - 1) * inv2) % R
+            assert val == (tri[i + 1][0] + tri[i + 1][1]) % R
+    assert all(len(p) == n for _, (_, p) in gc)
+    ctx.close()
+
+
+def test_dhyperplonk_parties_mode(orc):
+    """N = 8 parties (l = 1) on one GPU under LocalTestNet; every party's proof against the oracle's 8-party run."""
+    import scz_b200 as scz
+    from oracle import hyperplonk as ohp
+    from scz_b200.net import LocalTestNet
+    n, l, N = 5, 1, 8
+    rng = np.random.default_rng(640)
+    opp = orc.pp_new(l)
+    seed_ctx = scz.Context(device=0, n_parties=N)
+    csz, dsz = ohp.srs_level_sizes(n, l, N)
+    opks, srs_dev = [], []
+    for j in range(N):
+        cdev, csrs = _make_srs(seed_ctx, orc, rng, csz)
+        ddev, dsrs = _make_srs(seed_ctx, orc, rng, dsz)
+        opks.append(ohp.random_pk(rng, n, l, N, csrs, dsrs, shared=opks[0] if opks else None))
+        srs_dev.append((cdev, ddev))
+    want = ohp.dhyperplonk(n, opks, opp, orc.PARTIES, N)
+
+    def party(j, net):
+        c = scz.Context(device=0, party_id=j, n_parties=N, net=net)
+        pp = scz.PackedSharingParams(c, l)
+        pk = scz.PackedProvingParameters(c, n, l, _tables_for_product(opks[j]), scz.PolynomialCommitment(c, srs_dev[j][0]),
+                                         scz.PolynomialCommitment(c, srs_dev[j][1]))
+        got = scz.dhyperplonk(c, n, pk, pp).nested()
+        comm = c.get_comm()
+        c.sync()
+        c.close()
+        return got, comm
+
+    res = LocalTestNet(N, "cuda:0").simulate_network_round(party)
+    for j in range(N):
+        _same_proof(orc, res[j][0], want[j], f"party {j}")
+    (gp, gc), (wp, wc, wo) = res[3][0]
+    assert all(len(t) == 0 for t in wp[1:]) and len(wp) == 1 + 3 + 3 * (n - 3)     # workers: empty d_ proofs, no leader tail
+    seed_ctx.close()
