@@ -174,6 +174,9 @@ int32_t scz_msm_g1(scz_ctx *ctx, const void *bases, const uint8_t *inf_mask, siz
 int32_t scz_msm_set_window(scz_ctx *ctx, uint32_t c);
 /* statistics of the last MSM launch sequence: total (point, window) pairs = bucket additions, buckets, windows */
 int32_t scz_msm_last_stats(const scz_ctx *ctx, uint64_t *bucket_adds, uint64_t *buckets, uint64_t *windows);
+/* cumulative since scz_ctx_create: bucket additions, (base, scalar) pairs, launch sequences, MSMs (segments) */
+int32_t scz_msm_cum_stats(const scz_ctx *ctx, uint64_t *bucket_adds, uint64_t *pairs, uint64_t *sequences,
+                          uint64_t *segments);
 
 /* ---- PSS: secret-sharing/src/pss.rs ------------------------------------------------------- */
 int32_t scz_pp_new(scz_ctx *ctx, size_t l, scz_pp **out);          /* PackedSharingParams::new, pss.rs:38-65 */

@@ -234,6 +234,11 @@ def canon_g1(j):
     return [(0, 0, 1) if int(aff[i, 12]) & 0xFFFFFFFF else (xs[i], ys[i], 0) for i in range(len(aff))]
 
 
+def set_msm_threads(t):
+    """threads used by the ark-style MSM inside every protocol function (default 1, like the reference)"""
+    lib().orc_set_msm_threads(C.c_int(t))
+
+
 def msm(bases, scalars, algo="ark", threads=1):
     b, s = _u64(bases, 13), _u64(scalars, 4)
     assert len(b) == len(s)

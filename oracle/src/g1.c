@@ -300,8 +300,12 @@ void g1_msm_ark_mt(g1j_t *r, const g1a_t *bases, const fr_t *scalars, size_t n, 
     free(wsum);
     free(digits);
 }
+/* threads used by g1_msm_ark (and so by every protocol function): 1 = what the reference does per party
+ * (ark `parallel` is off, dist-primitive/Cargo.toml:18-22); bench.py --impl reference raises it */
+static int g_msm_threads = 1;
+void orc_set_msm_threads(int t) { g_msm_threads = t < 1 ? 1 : t; }
 void g1_msm_ark(g1j_t *r, const g1a_t *bases, const fr_t *scalars, size_t n) {
-    g1_msm_ark_mt(r, bases, scalars, n, 1);
+    g1_msm_ark_mt(r, bases, scalars, n, g_msm_threads);
 }
 
 /* ---- vector helpers for the Python side ---- */

@@ -57,6 +57,7 @@ void g1_msm_naive(g1j_t *r, const g1a_t *bases, const fr_t *scalars, size_t n);
 /* ark-ec 0.4.2 VariableBaseMSM::msm restated (signed-digit Pippenger) */
 void g1_msm_ark(g1j_t *r, const g1a_t *bases, const fr_t *scalars, size_t n);
 void g1_msm_ark_mt(g1j_t *r, const g1a_t *bases, const fr_t *scalars, size_t n, int threads);
+void orc_set_msm_threads(int threads);
 
 /* ---- PSS (pss.c): secret-sharing/src/pss.rs ---- */
 typedef struct {

@@ -199,6 +199,12 @@ class Context:
         return {"bucket_adds": a.value, "buckets": b.value, "windows": w.value}
 
 
+    def msm_cum_stats(self):
+        a, p, q, g = C.c_uint64(), C.c_uint64(), C.c_uint64(), C.c_uint64()
+        self.check(self.L.scz_msm_cum_stats(self.h, C.byref(a), C.byref(p), C.byref(q), C.byref(g)))
+        return {"bucket_adds": a.value, "pairs": p.value, "sequences": q.value, "segments": g.value}
+
+
 # ---------------------------------------------------------------------------- MSM
 def msm(ctx, bases, scalars, inf_mask=None):
     """G1::msm(bases, scalars) (ark-ec VariableBaseMSM; dmsm.rs:23).  Raises SczError
@@ -604,6 +610,15 @@ class PackedProvingParameters:
         dsz = [1 << i for i in range(n + 2 - (N.bit_length() - 1) + 1)]          # new_random(n + 2, N)
         return cls(ctx, n, l, tables, PolynomialCommitment(ctx, levels(csz)), PolynomialCommitment(ctx, levels(dsz)))
 
+    def upload(self, host_tables):
+        """copy HOST tables (name -> pinned int64 tensor or numpy array) into the resident device tables, on the ctx
+        stream: the per-proof host -> device traffic of a caller whose witness lives in host memory"""
+        for name, src in host_tables.items():
+            dst = self.t[name]
+            if not isinstance(src, torch.Tensor):
+                src = torch.from_numpy(np.ascontiguousarray(src, dtype=np.uint64).view(np.int64))
+            dst.copy_(src.view(dst.shape), non_blocking=True)
+
     def c_struct(self):
         pk = HpPk()
         for name in HpPk._TABLES + HpPk._INJECTED:
@@ -625,6 +640,18 @@ class HyperPlonkProof:
 
     def __init__(self, ctx, triples, points, values, items):
         self.ctx, self.triples, self.points, self.values, self.items = ctx, triples, points, values, items
+
+    def used(self):
+        """(triples, points, values) element counts actually written"""
+        t = max([it.triples_off + it.triples_cnt for it in self.items] + [0])
+        p = max([it.points_off + it.points_cnt for it in self.items] + [0])
+        v = max([it.value_off + it.value_cnt for it in self.items] + [0])
+        return t, p, v
+
+    def to_host(self):
+        """device -> host copy of the written part of the three arenas (numpy, synchronous)"""
+        t, p, v = self.used()
+        return (self.ctx.to_host(self.triples[: 3 * t]), self.ctx.to_host(self.points[:p]), self.ctx.to_host(self.values[:v]))
 
     def nested(self):
         tri = self.ctx.to_host(self.triples).reshape(-1, 3, 4)

@@ -7,6 +7,7 @@
 // 8 + 48 * batch (ark-serialize, serializing_net.rs:17).
 #include <vector>
 
+#include "deferred.h"
 #include "g1.cuh"
 #include "msm.h"
 #include "net.h"
@@ -23,28 +24,41 @@ int32_t d_msm_leader(Ctx *ctx, const scz_pp *pp, const void *d_recv, size_t batc
     return pss_apply(ctx, pp, PSS_DMSM, 1, d_recv, pp->n, 1, batch, batch, d_send, 1, batch);
 }
 
-int32_t d_msm_dev(Ctx *ctx, const scz_pp *pp, const void *const *d_bases, const void *const *d_scalars,
-                  const size_t *lens, size_t batch, void *d_out) {
+// Queues the local MSMs (dmsm.rs:19-24) on `D` and registers the leader round (:29-40) as their continuation.
+int32_t d_msm_defer(Ctx *ctx, Deferred &D, const scz_pp *pp, const void *const *d_bases, const void *const *d_scalars,
+                    const size_t *lens, size_t batch, void *d_out) {
     if (!pp) return ctx->fail(SCZ_ERR_BAD_ARG, "d_msm: null pp");
     if (batch == 0) return SCZ_OK;
     Net *net = ctx->net;
     const size_t N = net->n_parties, PT = SCZ_G1_JAC_BYTES;
     if (N != pp->n) return ctx->fail(SCZ_ERR_BAD_ARG, "d_msm: %zu parties but pp.n = %zu", N, pp->n);
-    DevTmp c_shares(ctx), recv(ctx), send(ctx);
-    SCZ_TRY(c_shares.alloc(batch * PT));
-    SCZ_TRY(msm_g1_batched(ctx, d_bases, d_scalars, lens, batch, c_shares.p));
-    const size_t wire = 8 + 48 * batch;
-    if (net->is_leader()) {
-        SCZ_TRY(recv.alloc(N * batch * PT));
-        SCZ_TRY(send.alloc(N * batch * PT));
-    }
-    SCZ_TRY(net->gather(ctx, c_shares.p, recv.p, batch * PT, wire));
-    if (net->is_leader()) {
-        // recv is party-major [j][k]: vector k is the stride-`batch` column
-        SCZ_TRY(d_msm_leader(ctx, pp, recv.p, batch, send.p));
-    }
-    SCZ_TRY(net->scatter(ctx, send.p, d_out, batch * PT, wire));
+    DevTmp *c_shares = nullptr;
+    SCZ_TRY(D.tmp(batch * PT, &c_shares));
+    for (size_t k = 0; k < batch; k++)
+        SCZ_TRY(D.add_msm(d_bases[k], d_scalars[k], lens[k], (char *)c_shares->p + k * PT));
+    D.then([=]() -> int32_t {
+        const size_t wire = 8 + 48 * batch;
+        DevTmp recv(ctx), send(ctx);
+        if (net->is_leader()) {
+            SCZ_TRY(recv.alloc(N * batch * PT));
+            SCZ_TRY(send.alloc(N * batch * PT));
+        }
+        SCZ_TRY(net->gather(ctx, c_shares->p, recv.p, batch * PT, wire));
+        if (net->is_leader()) {
+            // recv is party-major [j][k]: vector k is the stride-`batch` column
+            SCZ_TRY(d_msm_leader(ctx, pp, recv.p, batch, send.p));
+        }
+        SCZ_TRY(net->scatter(ctx, send.p, d_out, batch * PT, wire));
+        return SCZ_OK;
+    });
     return SCZ_OK;
+}
+
+int32_t d_msm_dev(Ctx *ctx, const scz_pp *pp, const void *const *d_bases, const void *const *d_scalars,
+                  const size_t *lens, size_t batch, void *d_out) {
+    Deferred D(ctx);
+    SCZ_TRY(d_msm_defer(ctx, D, pp, d_bases, d_scalars, lens, batch, d_out));
+    return D.run();
 }
 
 }   // namespace scz

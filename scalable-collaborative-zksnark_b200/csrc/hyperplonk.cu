@@ -61,6 +61,7 @@ int32_t dhyperplonk_dev(Ctx *ctx, size_t n, const scz_hp_pk *pk, const scz_pp *p
     const bool leader = net->is_leader();
     const size_t nc = ilog2(share_len) + ll + 1;   // triples of a c_sumcheck_product on 2^n/l shares
     cudaStream_t st = ctx->stream;
+    Deferred D(ctx);   // every MSM of the proof is queued here and runs in (at most a few) batched launch sequences
 
     // ---- Step 1: commit (:196-217).  The six commitments leave with the openings at the very end (:518-553).
     DevTmp coms(ctx);
@@ -68,10 +69,10 @@ int32_t dhyperplonk_dev(Ctx *ctx, size_t n, const scz_hp_pk *pk, const scz_pp *p
     {
         const void *tabs[3] = {pk->a_evals, pk->b_evals, pk->c_evals};
         for (int k = 0; k < 3; k++)   // three separate c_commit calls, one leader round each (:198-212)
-            SCZ_TRY(c_commit_dev(ctx, pk->c_commitment, pp, &tabs[k], &share_len, 1, (char *)coms.p + k * PT));
+            SCZ_TRY(c_commit_defer(ctx, D, pk->c_commitment, pp, &tabs[k], &share_len, 1, (char *)coms.p + k * PT));
         const void *slc[3] = {pk->I_p, pk->S1_p, pk->S2_p};
         for (int k = 0; k < 3; k++)   // :213-215
-            SCZ_TRY(d_commit_dev(ctx, pk->d_commitment, slc[k], slice_len, (char *)coms.p + (3 + k) * PT));
+            SCZ_TRY(d_commit_defer(ctx, D, pk->d_commitment, slc[k], slice_len, (char *)coms.p + (3 + k) * PT));
     }
 
     // ---- Step 3: gate identity (:222-260): six collaborative product sumchecks on 2^n/l shares
@@ -97,7 +98,7 @@ int32_t dhyperplonk_dev(Ctx *ctx, size_t n, const scz_hp_pk *pk, const scz_pp *p
     // ---- Step 2: wiring identity (:263-513)
     auto d_commit = [&](const void *tab, size_t len) -> int32_t {
         SCZ_TRY(o.reserve(0, 1));
-        SCZ_TRY(d_commit_dev(ctx, pk->d_commitment, tab, len, o.pts_at()));
+        SCZ_TRY(d_commit_defer(ctx, D, pk->d_commitment, tab, len, o.pts_at()));
         o.push(SCZ_HP_WIRING_COMMIT, 0, 1, 0);
         return SCZ_OK;
     };
@@ -105,14 +106,14 @@ int32_t dhyperplonk_dev(Ctx *ctx, size_t n, const scz_hp_pk *pk, const scz_pp *p
         // `lead` points precede the proofs (the commitment of a gate_identity_commitments entry)
         size_t cap = s + ilog2(len), cnt = 0;
         SCZ_TRY(o.reserve(0, lead + cap));
-        SCZ_TRY(d_open_dev(ctx, pk->d_commitment, tab, len, point, npoint, o.val_at(), o.pts_at(lead), &cnt));
+        SCZ_TRY(d_open_defer(ctx, D, pk->d_commitment, tab, len, point, npoint, o.val_at(), o.pts_at(lead), &cnt));
         o.push(kind, 0, lead + cnt, 1);
         return SCZ_OK;
     };
     auto c_open = [&](uint32_t kind, const void *tab, size_t len, const void *point, size_t lead) -> int32_t {
         size_t cnt = ilog2(len) + ll;
         SCZ_TRY(o.reserve(0, lead + cnt));
-        SCZ_TRY(c_open_dev(ctx, pk->c_commitment, pp, tab, len, point, o.val_at(), o.pts_at(lead)));
+        SCZ_TRY(c_open_defer(ctx, D, pk->c_commitment, pp, tab, len, point, o.val_at(), o.pts_at(lead)));
         o.push(kind, 0, lead + cnt, 1);
         return SCZ_OK;
     };
@@ -185,21 +186,21 @@ int32_t dhyperplonk_dev(Ctx *ctx, size_t n, const scz_hp_pk *pk, const scz_pp *p
         }
     }
     if (leader) {   // :480-511  `if let Some(leader_tree) = top`
-        DevTmp lx0(ctx), lx1(ctx);
-        SCZ_TRY(lx0.alloc(N * 32));
-        SCZ_TRY(lx1.alloc(N * 32));
+        DevTmp *lx = nullptr;   // vx0 | vx1 of the leader tree; read by queued MSMs, so it lives in D
+        SCZ_TRY(D.tmp(2 * N * 32, &lx));
+        void *lx0 = lx->p, *lx1 = (char *)lx->p + N * 32;
         const void *l1x = (const char *)ltree.p + N * 32;
-        SCZ_TRY(fr_deinterleave(ctx, ltree.p, N, lx0.p, lx1.p));
-        const void *tabs[3] = {lx0.p, lx1.p, l1x};                                          // vx0, vx1, v1x :500-505
+        SCZ_TRY(fr_deinterleave(ctx, ltree.p, N, lx0, lx1));
+        const void *tabs[3] = {lx0, lx1, l1x};                                          // vx0, vx1, v1x :500-505
         for (int k = 0; k < 3; k++) {
             SCZ_TRY(o.reserve(0, 1));
-            SCZ_TRY(commit_dev(ctx, pk->d_commitment, tabs[k], N, o.pts_at()));
+            SCZ_TRY(commit_defer(ctx, D, pk->d_commitment, tabs[k], N, o.pts_at()));
             o.push(SCZ_HP_WIRING_COMMIT, 0, 1, 0);
             SCZ_TRY(o.reserve(0, s));
-            SCZ_TRY(open_dev(ctx, pk->d_commitment, tabs[k], N, r2, o.val_at(), o.pts_at()));
+            SCZ_TRY(open_defer(ctx, D, pk->d_commitment, tabs[k], N, r2, o.val_at(), o.pts_at()));
             o.push(SCZ_HP_WIRING_OPEN, 0, s, 1);
         }
-        const void *fs[3] = {pk->eq_leader, pk->eq_leader, lx0.p}, *gs[3] = {l1x, lx0.p, lx1.p};   // :507-509
+        const void *fs[3] = {pk->eq_leader, pk->eq_leader, lx0}, *gs[3] = {l1x, lx0, lx1};   // :507-509
         for (int k = 0; k < 3; k++) {
             SCZ_TRY(o.reserve(s + 1, 0));
             SCZ_TRY(sumcheck_product_dev(ctx, fs[k], gs[k], N, r2, o.tri_at()));
@@ -209,20 +210,27 @@ int32_t dhyperplonk_dev(Ctx *ctx, size_t n, const scz_hp_pk *pk, const scz_pp *p
 
     // ---- Open (:517-554)
     {
+        void *coms_p = coms.p;
+        auto copy_com = [&](void *dst, int k) {   // the commitments of step 1 exist once D has run their leader rounds
+            D.then([=]() -> int32_t {
+                SCZ_CUDA(ctx, cudaMemcpyAsync(dst, (char *)coms_p + k * PT, PT, cudaMemcpyDeviceToDevice, st));
+                return SCZ_OK;
+            });
+        };
         const void *tabs[3] = {pk->a_evals, pk->b_evals, pk->c_evals};
         for (int k = 0; k < 3; k++) {
             SCZ_TRY(o.reserve(0, 1));
-            SCZ_CUDA(ctx, cudaMemcpyAsync(o.pts_at(), (char *)coms.p + k * PT, PT, cudaMemcpyDeviceToDevice, st));
+            copy_com(o.pts_at(), k);
             SCZ_TRY(c_open(SCZ_HP_GATE_COMMIT, tabs[k], share_len, pk->challenge, 1));
         }
         const void *slc[3] = {pk->I_p, pk->S1_p, pk->S2_p};
         for (int k = 0; k < 3; k++) {
             SCZ_TRY(o.reserve(0, 1));
-            SCZ_CUDA(ctx, cudaMemcpyAsync(o.pts_at(), (char *)coms.p + (3 + k) * PT, PT, cudaMemcpyDeviceToDevice, st));
+            copy_com(o.pts_at(), 3 + k);
             SCZ_TRY(d_open(SCZ_HP_GATE_COMMIT, slc[k], slice_len, pk->challenge, n, 1));
         }
     }
-    return SCZ_OK;
+    return D.run();
 }
 
 }   // namespace scz

@@ -33,6 +33,7 @@
 #include <algorithm>
 #include <vector>
 
+#include "deferred.h"
 #include "g1_coop.cuh"
 #include "msm.h"
 #include "msm_digits.cuh"
@@ -415,7 +416,10 @@ __global__ void __launch_bounds__(FIN_THREADS) k_msm_finish(const MsmSeg *segs, 
                 coop_add(g, acc, v);
             }
         }
-        if (threadIdx.x == 0) g1j_store(out_jac, blockIdx.x, acc);
+        if (threadIdx.x == 0) {
+            if (sg.out) g1j_store(sg.out, 0, acc);
+            else g1j_store(out_jac, blockIdx.x, acc);
+        }
     }
 }
 
@@ -438,7 +442,7 @@ uint32_t msm_pick_window(size_t len) {
 }
 
 int32_t msm_g1_batched(Ctx *ctx, const void *const *d_bases, const void *const *d_scalars, const size_t *lens,
-                       size_t batch, void *d_out) {
+                       size_t batch, void *d_out, void *const *d_outs) {
     if (batch == 0) return SCZ_OK;
     if (batch > (1u << 20)) return ctx->fail(SCZ_ERR_BAD_ARG, "msm: batch too large");
     std::vector<MsmSeg> segs(batch);
@@ -463,6 +467,7 @@ int32_t msm_g1_batched(Ctx *ctx, const void *const *d_bases, const void *const *
         while ((1u << s.PB) < s.M) s.PB++;
         s.chunk_base = (uint32_t)chunks;
         s.plane_base = (uint32_t)planes;
+        s.out = d_outs ? d_outs[k] : nullptr;
         max_planes = std::max(max_planes, s.PB + 2);
         points += s.len;
         buckets += (uint64_t)s.W * s.nb;
@@ -477,6 +482,7 @@ int32_t msm_g1_batched(Ctx *ctx, const void *const *d_bases, const void *const *
     ctx->msm_bucket_adds = entries;
     ctx->msm_buckets = buckets;
     ctx->msm_windows = windows;
+    ctx->msm_cum_adds += entries, ctx->msm_cum_pairs += points, ctx->msm_cum_sequences++, ctx->msm_cum_segments += batch;
 
     // entries per accumulate thread: 64 for big batches, less when that would leave SMs idle
     uint32_t logT = 6;
@@ -570,6 +576,41 @@ int32_t msm_g1_batched(Ctx *ctx, const void *const *d_bases, const void *const *
     return SCZ_OK;
 }
 
+// ------------------------------------------------------------------ deferred execution (deferred.h)
+// One launch sequence is bounded by 32-bit entry / point indices; stay well inside and flush early otherwise.
+constexpr uint64_t DEFER_MAX_ENTRIES = 3ull << 30, DEFER_MAX_POINTS = 1ull << 30, DEFER_MAX_SEGS = 1u << 16;
+
+int32_t Deferred::add_msm(const void *b, const void *s, size_t len, void *out) {
+    if (!out || (len && (!b || !s))) return ctx->fail(SCZ_ERR_BAD_ARG, "msm: null argument");
+    uint32_t c = ctx->msm_window_override ? ctx->msm_window_override : msm_pick_window(len);
+    uint64_t e = (uint64_t)len * msm_num_windows(c);
+    if (!lens.empty() && (entries + e > DEFER_MAX_ENTRIES || points + len > DEFER_MAX_POINTS || lens.size() >= DEFER_MAX_SEGS))
+        SCZ_TRY(flush_msm());
+    bases.push_back(b);
+    scalars.push_back(s);
+    lens.push_back(len);
+    outs.push_back(out);
+    entries += e;
+    points += len;
+    return SCZ_OK;
+}
+int32_t Deferred::flush_msm() {
+    if (lens.empty()) return SCZ_OK;
+    int32_t rc = msm_g1_batched(ctx, bases.data(), scalars.data(), lens.data(), lens.size(), nullptr, outs.data());
+    bases.clear(), scalars.clear(), lens.clear(), outs.clear();
+    entries = points = 0;
+    return rc;
+}
+int32_t Deferred::run() {
+    while (!lens.empty() || !after.empty()) {
+        SCZ_TRY(flush_msm());
+        std::vector<std::function<int32_t()>> now;
+        now.swap(after);
+        for (auto &f : now) SCZ_TRY(f());
+    }
+    return SCZ_OK;
+}
+
 }   // namespace scz
 
 using namespace scz;
@@ -615,6 +656,14 @@ int32_t scz_msm_g1(scz_ctx *h, const void *bases, const uint8_t *inf_mask, size_
 int32_t scz_msm_set_window(scz_ctx *h, uint32_t cbits) {
     if (!h || cbits > 20) return SCZ_ERR_BAD_ARG;
     h->c.msm_window_override = cbits;
+    return SCZ_OK;
+}
+int32_t scz_msm_cum_stats(const scz_ctx *h, uint64_t *adds, uint64_t *pairs, uint64_t *sequences, uint64_t *segments) {
+    if (!h) return SCZ_ERR_BAD_ARG;
+    if (adds) *adds = h->c.msm_cum_adds;
+    if (pairs) *pairs = h->c.msm_cum_pairs;
+    if (sequences) *sequences = h->c.msm_cum_sequences;
+    if (segments) *segments = h->c.msm_cum_segments;
     return SCZ_OK;
 }
 int32_t scz_msm_last_stats(const scz_ctx *h, uint64_t *adds, uint64_t *buckets, uint64_t *windows) {

@@ -22,11 +22,13 @@ struct MsmSeg {
     uint32_t PB;           // log2(M): bit planes of the chunk index
     uint32_t chunk_base;   // first global chunk (window w starts at chunk_base + w*M)
     uint32_t plane_base;   // first global plane slot (window w owns PB + 2 slots from plane_base + w*(PB+2))
+    void *out;             // where this segment's result goes (one Jacobian point); null: slot `k` of d_out_jac
 };
 
 // d_out: batch Jacobian points (144 B each).  Asynchronous on ctx->stream.
+// d_outs (optional, host array of `batch` device pointers) sends each result to its own address instead.
 int32_t msm_g1_batched(Ctx *ctx, const void *const *d_bases, const void *const *d_scalars, const size_t *lens,
-                       size_t batch, void *d_out_jac);
+                       size_t batch, void *d_out_jac, void *const *d_outs = nullptr);
 uint32_t msm_pick_window(size_t len);
 
 }   // namespace scz

@@ -14,6 +14,7 @@
 //   d_acc_product          dist-primitive/src/dacc_product.rs:365-414
 #include <vector>
 
+#include "deferred.h"
 #include "g1.cuh"
 #include "msm.h"
 #include "net.h"
@@ -25,8 +26,8 @@ int32_t sumcheck_product_rounds(Ctx *ctx, const void *d_f, const void *d_g, size
                                 void *d_out, void *d_last);
 int32_t open_fold_rounds(Ctx *ctx, const void *d_peval, size_t len, const void *d_point, void *d_q, void *d_value);
 int32_t acc_product_tree(Ctx *ctx, const void *d_x, size_t m, void *d_tree);
-int32_t d_msm_dev(Ctx *ctx, const scz_pp *pp, const void *const *d_bases, const void *const *d_scalars,
-                  const size_t *lens, size_t batch, void *d_out);
+int32_t d_msm_defer(Ctx *ctx, Deferred &D, const scz_pp *pp, const void *const *d_bases, const void *const *d_scalars,
+                    const size_t *lens, size_t batch, void *d_out);
 
 static inline size_t log2_exact(size_t v, bool *ok) {
     size_t l = 0;
@@ -244,111 +245,111 @@ static int32_t srs_level_for(Ctx *ctx, const scz_srs *srs, size_t need_len, size
     return SCZ_OK;
 }
 
+// Every function of the commit / open family comes as `*_defer` (queues its MSMs on `D`, registers its leader round
+// as a continuation; see deferred.h) and as `*_dev` = defer + run for stand-alone calls.
+
 // commit / d_local_commit: dpoly_comm.rs:237-243, 269-275
-int32_t commit_dev(Ctx *ctx, const scz_srs *srs, const void *d_peval, size_t len, void *d_out) {
-    const void *b;
+int32_t commit_defer(Ctx *ctx, Deferred &D, const scz_srs *srs, const void *d_peval, size_t len, void *d_out) {
+    const void *b = nullptr;
     SCZ_TRY(srs_level_for(ctx, srs, len, len, "commit", &b));
-    return msm_g1_batched(ctx, &b, &d_peval, &len, 1, d_out);
+    return D.add_msm(b, d_peval, len, d_out);
 }
 
 // c_commit: dpoly_comm.rs:244-267
-int32_t c_commit_dev(Ctx *ctx, const scz_srs *srs, const scz_pp *pp, const void *const *d_pevals, const size_t *lens,
-                     size_t batch, void *d_out) {
+int32_t c_commit_defer(Ctx *ctx, Deferred &D, const scz_srs *srs, const scz_pp *pp, const void *const *d_pevals,
+                       const size_t *lens, size_t batch, void *d_out) {
     std::vector<const void *> bases(batch);
     for (size_t k = 0; k < batch; k++) SCZ_TRY(srs_level_for(ctx, srs, lens[k], lens[k] * pp->l, "c_commit", &bases[k]));
-    return d_msm_dev(ctx, pp, bases.data(), d_pevals, lens, batch, d_out);
+    return d_msm_defer(ctx, D, pp, bases.data(), d_pevals, lens, batch, d_out);
 }
 
 // d_commit: dpoly_comm.rs:276-297 -- every party ends with the sum of the N local commitments
-int32_t d_commit_dev(Ctx *ctx, const scz_srs *srs, const void *d_peval, size_t len, void *d_out) {
+int32_t d_commit_defer(Ctx *ctx, Deferred &D, const scz_srs *srs, const void *d_peval, size_t len, void *d_out) {
     Net *net = ctx->net;
     const size_t N = net->n_parties, PT = SCZ_G1_JAC_BYTES;
-    DevTmp loc(ctx), recv(ctx), send(ctx);
-    SCZ_TRY(loc.alloc(PT));
-    SCZ_TRY(commit_dev(ctx, srs, d_peval, len, loc.p));
-    if (net->is_leader()) {
-        SCZ_TRY(recv.alloc(N * PT));
-        SCZ_TRY(send.alloc(N * PT));
-    }
-    SCZ_TRY(net->gather(ctx, loc.p, recv.p, PT, 48));
-    if (net->is_leader()) {
-        k_g1_colsum<<<1, 32, 0, ctx->stream>>>(recv.p, PT, 0, (uint32_t)N, 1, send.p, (uint32_t)N);
-        SCZ_LAUNCH_CHECK(ctx);
-    }
-    SCZ_TRY(net->scatter(ctx, send.p, d_out, PT, 48));
+    DevTmp *loc = nullptr;
+    SCZ_TRY(D.tmp(PT, &loc));
+    SCZ_TRY(commit_defer(ctx, D, srs, d_peval, len, loc->p));
+    D.then([=]() -> int32_t {
+        DevTmp recv(ctx), send(ctx);
+        if (net->is_leader()) {
+            SCZ_TRY(recv.alloc(N * PT));
+            SCZ_TRY(send.alloc(N * PT));
+        }
+        SCZ_TRY(net->gather(ctx, loc->p, recv.p, PT, 48));
+        if (net->is_leader()) {
+            k_g1_colsum<<<1, 32, 0, ctx->stream>>>(recv.p, PT, 0, (uint32_t)N, 1, send.p, (uint32_t)N);
+            SCZ_LAUNCH_CHECK(ctx);
+        }
+        SCZ_TRY(net->scatter(ctx, send.p, d_out, PT, 48));
+        return SCZ_OK;
+    });
     return SCZ_OK;
 }
 
-// open / d_local_open: dpoly_comm.rs:299-325, 327-353.  The reference commits q_i inside the fold loop; here all folds run
-// first and the n MSMs go out as ONE batched launch sequence (same values).
-int32_t open_dev(Ctx *ctx, const scz_srs *srs, const void *d_peval, size_t len, const void *d_point, void *d_value,
-                 void *d_proofs) {
+// open / d_local_open: dpoly_comm.rs:299-325, 327-353.  The reference commits q_i inside the fold loop; here all folds
+// run first (now) and the n MSMs are queued (same values).
+int32_t open_defer(Ctx *ctx, Deferred &D, const scz_srs *srs, const void *d_peval, size_t len, const void *d_point,
+                   void *d_value, void *d_proofs) {
     bool ok;
     size_t n = log2_exact(len, &ok);
     if (!ok) return ctx->fail(SCZ_ERR_NOT_POW2, "open: length %zu is not a power of two", len);
-    DevTmp q(ctx);
-    SCZ_TRY(q.alloc((len > 1 ? len - 1 : 1) * 32));
-    SCZ_TRY(open_fold_rounds(ctx, d_peval, len, d_point, q.p, d_value));
-    if (!n) return SCZ_OK;
-    std::vector<const void *> bases(n), scal(n);
-    std::vector<size_t> lens(n);
+    DevTmp *q = nullptr;
+    SCZ_TRY(D.tmp((len > 1 ? len - 1 : 1) * 32, &q));
+    SCZ_TRY(open_fold_rounds(ctx, d_peval, len, d_point, q->p, d_value));
     size_t off = 0;
     for (size_t i = 0; i < n; i++) {
         size_t h = len >> (i + 1);
-        SCZ_TRY(srs_level_for(ctx, srs, h, h, "open", &bases[i]));
-        scal[i] = (const char *)q.p + off * 32;
-        lens[i] = h;
+        const void *b = nullptr;
+        SCZ_TRY(srs_level_for(ctx, srs, h, h, "open", &b));
+        SCZ_TRY(D.add_msm(b, (const char *)q->p + off * 32, h, (char *)d_proofs + i * SCZ_G1_JAC_BYTES));
         off += h;
     }
-    return msm_g1_batched(ctx, bases.data(), scal.data(), lens.data(), n, d_proofs);
+    return SCZ_OK;
 }
 
 // c_open: dpoly_comm.rs:401-464 -> value + n + log2(l) proofs
-int32_t c_open_dev(Ctx *ctx, const scz_srs *srs, const scz_pp *pp, const void *d_peval, size_t len, const void *d_point,
-                   void *d_value, void *d_proofs) {
+int32_t c_open_defer(Ctx *ctx, Deferred &D, const scz_srs *srs, const scz_pp *pp, const void *d_peval, size_t len,
+                     const void *d_point, void *d_value, void *d_proofs) {
     bool ok;
     size_t n = log2_exact(len, &ok);
     if (!ok) return ctx->fail(SCZ_ERR_NOT_POW2, "c_open: length %zu is not a power of two", len);
     const size_t l = pp->l, ll = log2_exact(l, &ok), PT = SCZ_G1_JAC_BYTES;
-    DevTmp q(ctx), last(ctx), r2(ctx), q2(ctx);
-    SCZ_TRY(q.alloc((len > 1 ? len - 1 : 1) * 32));
-    SCZ_TRY(last.alloc(32));
-    SCZ_TRY(open_fold_rounds(ctx, d_peval, len, d_point, q.p, last.p));                     // Phase 1 :418-432
+    DevTmp *q = nullptr, *last = nullptr, *r2 = nullptr, *q2 = nullptr;
+    SCZ_TRY(D.tmp((len > 1 ? len - 1 : 1) * 32, &q));
+    SCZ_TRY(D.tmp(32, &last));
+    SCZ_TRY(open_fold_rounds(ctx, d_peval, len, d_point, q->p, last->p));                   // Phase 1 :418-432
     if (n) {
         std::vector<const void *> scal(n);
         std::vector<size_t> lens(n);
         size_t off = 0;
         for (size_t i = 0; i < n; i++) {
             size_t h = len >> (i + 1);
-            scal[i] = (const char *)q.p + off * 32;
+            scal[i] = (const char *)q->p + off * 32;
             lens[i] = h;
             off += h;
         }
-        SCZ_TRY(c_commit_dev(ctx, srs, pp, scal.data(), lens.data(), n, d_proofs));         // ONE batched c_commit :436
+        SCZ_TRY(c_commit_defer(ctx, D, srs, pp, scal.data(), lens.data(), n, d_proofs));    // ONE batched c_commit :436
     }
-    SCZ_TRY(r2.alloc(l * 32));
-    SCZ_TRY(pss2ss_dev(ctx, pp, last.p, r2.p));                                             // :439
-    SCZ_TRY(q2.alloc((l > 1 ? l - 1 : 1) * 32));
-    SCZ_TRY(open_fold_rounds(ctx, r2.p, l, d_point, q2.p, d_value));                        // Phase 2 :442-459, point[i] from 0
-    if (ll) {
-        std::vector<const void *> bases(ll), scal(ll);
-        std::vector<size_t> lens(ll);
-        size_t off = 0;
-        for (size_t i = 0; i < ll; i++) {
-            size_t h = l >> (i + 1);
-            SCZ_TRY(srs_level_for(ctx, srs, h, h * l, "c_open", &bases[i]));                // local G1::msm :457
-            scal[i] = (const char *)q2.p + off * 32;
-            lens[i] = h;
-            off += h;
-        }
-        SCZ_TRY(msm_g1_batched(ctx, bases.data(), scal.data(), lens.data(), ll, (char *)d_proofs + n * PT));
+    SCZ_TRY(D.tmp(l * 32, &r2));
+    SCZ_TRY(pss2ss_dev(ctx, pp, last->p, r2->p));                                           // :439
+    SCZ_TRY(D.tmp((l > 1 ? l - 1 : 1) * 32, &q2));
+    SCZ_TRY(open_fold_rounds(ctx, r2->p, l, d_point, q2->p, d_value));                      // Phase 2 :442-459, point[i] from 0
+    size_t off = 0;
+    for (size_t i = 0; i < ll; i++) {
+        size_t h = l >> (i + 1);
+        const void *b = nullptr;
+        SCZ_TRY(srs_level_for(ctx, srs, h, h * l, "c_open", &b));                           // local G1::msm :457
+        SCZ_TRY(D.add_msm(b, (const char *)q2->p + off * 32, h, (char *)d_proofs + (n + i) * PT));
+        off += h;
     }
     return SCZ_OK;
 }
 
-// d_open: dpoly_comm.rs:355-398.  Leader: value + log2(N) root proofs ++ n summed proofs; others (0, []) (:387)
-int32_t d_open_dev(Ctx *ctx, const scz_srs *srs, const void *d_peval, size_t len, const void *d_point, size_t npoint,
-                   void *d_value, void *d_proofs, size_t *count) {
+// d_open: dpoly_comm.rs:355-398.  Leader: value + log2(N) root proofs ++ n summed proofs; others (0, []) (:387).
+// *count is known at once (it depends on the role only); the values arrive when `D` has run.
+int32_t d_open_defer(Ctx *ctx, Deferred &D, const scz_srs *srs, const void *d_peval, size_t len, const void *d_point,
+                     size_t npoint, void *d_value, void *d_proofs, size_t *count) {
     bool ok;
     size_t n = log2_exact(len, &ok);
     if (!ok) return ctx->fail(SCZ_ERR_NOT_POW2, "d_open: length %zu is not a power of two", len);
@@ -358,29 +359,63 @@ int32_t d_open_dev(Ctx *ctx, const scz_srs *srs, const void *d_peval, size_t len
     if (!ok) return ctx->fail(SCZ_ERR_NOT_POW2, "d_open: %zu parties is not a power of two", N);
     if (npoint < pl + n) return ctx->fail(SCZ_ERR_BAD_ARG, "d_open: point has %zu coordinates, %zu needed", npoint, pl + n);
     const size_t payload = 32 + n * PT;
-    DevTmp loc(ctx), recv(ctx), lz(ctx);
-    SCZ_TRY(loc.alloc(payload));
-    SCZ_TRY(open_dev(ctx, srs, d_peval, len, (const char *)d_point + pl * 32, loc.p, (char *)loc.p + 32));   // :366
-    if (net->is_leader()) {
-        SCZ_TRY(recv.alloc(N * payload));
-        SCZ_TRY(lz.alloc(N * 32));
-    }
-    SCZ_TRY(net->gather(ctx, loc.p, recv.p, payload, 32 + 8 + 48 * n));                   // :368
-    if (!net->is_leader()) {
-        SCZ_CUDA(ctx, cudaMemsetAsync(d_value, 0, 32, ctx->stream));
-        if (count) *count = 0;
-        return SCZ_OK;
-    }
-    k_pick_fr<<<1, 32 * (uint32_t)((N + 31) / 32), 0, ctx->stream>>>(recv.p, payload, (uint32_t)N, lz.p);
-    SCZ_LAUNCH_CHECK(ctx);
-    SCZ_TRY(open_dev(ctx, srs, lz.p, N, d_point, d_value, d_proofs));                       // root_open :377
-    if (n) {
-        k_g1_colsum<<<ceil_div_u32(n, 32), 32, 0, ctx->stream>>>(recv.p, payload, 32, (uint32_t)N, (uint32_t)n,
-                                                                 (char *)d_proofs + pl * PT, 1);   // :374-376
+    DevTmp *loc = nullptr;
+    SCZ_TRY(D.tmp(payload, &loc));
+    SCZ_TRY(open_defer(ctx, D, srs, d_peval, len, (const char *)d_point + pl * 32, loc->p, (char *)loc->p + 32));   // :366
+    if (count) *count = net->is_leader() ? pl + n : 0;
+    Deferred *Dp = &D;
+    D.then([=]() -> int32_t {
+        DevTmp recv(ctx);
+        DevTmp *lz = nullptr;
+        if (net->is_leader()) {
+            SCZ_TRY(recv.alloc(N * payload));
+            SCZ_TRY(Dp->tmp(N * 32, &lz));
+        }
+        SCZ_TRY(net->gather(ctx, loc->p, recv.p, payload, 32 + 8 + 48 * n));                // :368
+        if (!net->is_leader()) {
+            SCZ_CUDA(ctx, cudaMemsetAsync(d_value, 0, 32, ctx->stream));
+            return SCZ_OK;
+        }
+        k_pick_fr<<<1, 32 * (uint32_t)((N + 31) / 32), 0, ctx->stream>>>(recv.p, payload, (uint32_t)N, lz->p);
         SCZ_LAUNCH_CHECK(ctx);
-    }
-    if (count) *count = pl + n;
+        SCZ_TRY(open_defer(ctx, *Dp, srs, lz->p, N, d_point, d_value, d_proofs));           // root_open :377 (next flush)
+        if (n) {
+            k_g1_colsum<<<ceil_div_u32(n, 32), 32, 0, ctx->stream>>>(recv.p, payload, 32, (uint32_t)N, (uint32_t)n,
+                                                                     (char *)d_proofs + pl * PT, 1);   // :374-376
+            SCZ_LAUNCH_CHECK(ctx);
+        }
+        return SCZ_OK;
+    });
     return SCZ_OK;
+}
+
+#define SCZ_RUN_NOW(call)        \
+    do {                         \
+        Deferred D(ctx);         \
+        SCZ_TRY(call);           \
+        return D.run();          \
+    } while (0)
+int32_t commit_dev(Ctx *ctx, const scz_srs *srs, const void *d_peval, size_t len, void *d_out) {
+    SCZ_RUN_NOW(commit_defer(ctx, D, srs, d_peval, len, d_out));
+}
+int32_t c_commit_dev(Ctx *ctx, const scz_srs *srs, const scz_pp *pp, const void *const *d_pevals, const size_t *lens,
+                     size_t batch, void *d_out) {
+    SCZ_RUN_NOW(c_commit_defer(ctx, D, srs, pp, d_pevals, lens, batch, d_out));
+}
+int32_t d_commit_dev(Ctx *ctx, const scz_srs *srs, const void *d_peval, size_t len, void *d_out) {
+    SCZ_RUN_NOW(d_commit_defer(ctx, D, srs, d_peval, len, d_out));
+}
+int32_t open_dev(Ctx *ctx, const scz_srs *srs, const void *d_peval, size_t len, const void *d_point, void *d_value,
+                 void *d_proofs) {
+    SCZ_RUN_NOW(open_defer(ctx, D, srs, d_peval, len, d_point, d_value, d_proofs));
+}
+int32_t c_open_dev(Ctx *ctx, const scz_srs *srs, const scz_pp *pp, const void *d_peval, size_t len, const void *d_point,
+                   void *d_value, void *d_proofs) {
+    SCZ_RUN_NOW(c_open_defer(ctx, D, srs, pp, d_peval, len, d_point, d_value, d_proofs));
+}
+int32_t d_open_dev(Ctx *ctx, const scz_srs *srs, const void *d_peval, size_t len, const void *d_point, size_t npoint,
+                   void *d_value, void *d_proofs, size_t *count) {
+    SCZ_RUN_NOW(d_open_defer(ctx, D, srs, d_peval, len, d_point, npoint, d_value, d_proofs, count));
 }
 
 }   // namespace scz

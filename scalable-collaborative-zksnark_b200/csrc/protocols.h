@@ -3,6 +3,7 @@
 // definitions for the file:line each follows.
 #pragma once
 #include "ctx.h"
+#include "deferred.h"
 #include "pss.h"
 
 struct scz_srs;
@@ -40,5 +41,20 @@ int32_t c_open_dev(Ctx *ctx, const scz_srs *srs, const scz_pp *pp, const void *d
                    void *d_value, void *d_proofs);
 int32_t d_open_dev(Ctx *ctx, const scz_srs *srs, const void *d_peval, size_t len, const void *d_point, size_t npoint,
                    void *d_value, void *d_proofs, size_t *count);
+
+
+// deferred variants (deferred.h): MSMs are queued on D, leader rounds become continuations
+int32_t d_msm_defer(Ctx *ctx, Deferred &D, const scz_pp *pp, const void *const *d_bases, const void *const *d_scalars,
+                    const size_t *lens, size_t batch, void *d_out);
+int32_t commit_defer(Ctx *ctx, Deferred &D, const scz_srs *srs, const void *d_peval, size_t len, void *d_out);
+int32_t c_commit_defer(Ctx *ctx, Deferred &D, const scz_srs *srs, const scz_pp *pp, const void *const *d_pevals,
+                       const size_t *lens, size_t batch, void *d_out);
+int32_t d_commit_defer(Ctx *ctx, Deferred &D, const scz_srs *srs, const void *d_peval, size_t len, void *d_out);
+int32_t open_defer(Ctx *ctx, Deferred &D, const scz_srs *srs, const void *d_peval, size_t len, const void *d_point,
+                   void *d_value, void *d_proofs);
+int32_t c_open_defer(Ctx *ctx, Deferred &D, const scz_srs *srs, const scz_pp *pp, const void *d_peval, size_t len,
+                     const void *d_point, void *d_value, void *d_proofs);
+int32_t d_open_defer(Ctx *ctx, Deferred &D, const scz_srs *srs, const void *d_peval, size_t len, const void *d_point,
+                     size_t npoint, void *d_value, void *d_proofs, size_t *count);
 
 }   // namespace scz

@@ -223,3 +223,163 @@ class _LocalParty:
         vt.sync = NetVTable._SYNC(_sync)
         self._keep = vt
         return vt
+
+
+class HybridNet:
+    """Fewer GPUs than parties: every rank hosts `per_rank` parties (one host thread and one ctx each, all on the
+    rank's GPU and on the same CUDA stream), party id = rank * per_rank + local index; party 0 is the leader.
+    A collective is a host barrier among the local parties, ONE torch.distributed collective per rank issued by
+    local party 0 on the concatenated payloads, and a second host barrier.  With per_rank = 1 this is
+    TorchDistNet; with world = 1 it is LocalTestNet."""
+
+    def __init__(self, device, per_rank, group=None):
+        import threading
+        self.device = torch.device(device)
+        self.per_rank = per_rank
+        self.group = group
+        self.dist = dist.is_available() and dist.is_initialized()
+        self.rank = dist.get_rank(group) if self.dist else 0
+        self.world = dist.get_world_size(group) if self.dist else 1
+        self.n = self.world * per_rank
+        self.barrier = threading.Barrier(per_rank)
+        self.slots = [None] * per_rank
+        self.stage = None
+        self.calls = {"gather": 0, "scatter": 0, "all_gather": 0, "sync": 0}
+
+    def party(self, local_index):
+        return _HybridParty(self, local_index)
+
+    def _buf(self, nbytes):
+        return torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+
+    def run_parties(self, fn):
+        """fn(party_id, local_index, net) on one thread per hosted party; returns the results by local index"""
+        import threading
+        out, err = [None] * self.per_rank, [None] * self.per_rank
+
+        def body(p):
+            try:
+                if self.device.type == "cuda":
+                    torch.cuda.set_device(self.device)
+                out[p] = fn(self.rank * self.per_rank + p, p, self.party(p))
+            except BaseException as e:   # noqa: BLE001
+                err[p] = e
+                self.barrier.abort()
+        if self.per_rank == 1:
+            body(0)
+        else:
+            ts = [threading.Thread(target=body, args=(p,)) for p in range(self.per_rank)]
+            for t in ts:
+                t.start()
+            for t in ts:
+                t.join()
+        for e in err:
+            if e is not None and not isinstance(e, __import__("threading").BrokenBarrierError):
+                raise e
+        for e in err:
+            if e is not None:
+                raise e
+        return out
+
+
+class _HybridParty:
+    def __init__(self, hub, p):
+        self.hub, self.p = hub, p
+        self.rank = hub.rank * hub.per_rank + p      # party id
+        self.n_parties = hub.n
+        self._keep = None
+
+    def vtable(self):
+        hub, p, dev, P, W = self.hub, self.p, self.hub.device, self.hub.per_rank, self.hub.world
+
+        def _gather(user, d_send, d_recv, nbytes, wire, stream):
+            try:
+                hub.slots[p] = d_send
+                hub.barrier.wait()
+                if p == 0:
+                    hub.calls["gather"] += 1
+                    if W == 1:
+                        recv = _tensor(d_recv, nbytes * hub.n, dev).view(P, nbytes)
+                        for q in range(P):
+                            recv[q].copy_(_tensor(hub.slots[q], nbytes, dev))
+                    else:
+                        loc = hub._buf(P * nbytes).view(P, nbytes)
+                        for q in range(P):
+                            loc[q].copy_(_tensor(hub.slots[q], nbytes, dev))
+                        if hub.rank == 0:
+                            recv = _tensor(d_recv, nbytes * hub.n, dev).view(W, P * nbytes)
+                            dist.gather(loc.view(-1), list(recv.unbind(0)), dst=0, group=hub.group)
+                        else:
+                            dist.gather(loc.view(-1), None, dst=0, group=hub.group)
+                hub.barrier.wait()
+                return 0
+            except Exception as e:
+                print(f"[scz hybrid net] gather failed: {e!r}", flush=True)
+                return 1
+
+        def _scatter(user, d_send, d_recv, nbytes, wire, stream):
+            try:
+                if p == 0:
+                    if W == 1:
+                        hub.stage = _tensor(d_send, nbytes * hub.n, dev).view(P, nbytes)
+                    else:
+                        hub.calls["scatter"] += 1
+                        loc = hub._buf(P * nbytes)
+                        if hub.rank == 0:
+                            send = _tensor(d_send, nbytes * hub.n, dev).view(W, P * nbytes)
+                            dist.scatter(loc, list(send.unbind(0)), src=0, group=hub.group)
+                        else:
+                            dist.scatter(loc, None, src=0, group=hub.group)
+                        hub.stage = loc.view(P, nbytes)
+                hub.barrier.wait()
+                _tensor(d_recv, nbytes, dev).copy_(hub.stage[p])
+                hub.barrier.wait()
+                return 0
+            except Exception as e:
+                print(f"[scz hybrid net] scatter failed: {e!r}", flush=True)
+                return 1
+
+        def _all_gather(user, d_send, d_recv, nbytes, wire, stream):
+            try:
+                hub.slots[p] = d_send
+                hub.barrier.wait()
+                if p == 0:
+                    hub.calls["all_gather"] += 1
+                    full = _tensor(d_recv, nbytes * hub.n, dev)
+                    if W == 1:
+                        for q in range(P):
+                            full.view(P, nbytes)[q].copy_(_tensor(hub.slots[q], nbytes, dev))
+                    else:
+                        loc = hub._buf(P * nbytes).view(P, nbytes)
+                        for q in range(P):
+                            loc[q].copy_(_tensor(hub.slots[q], nbytes, dev))
+                        dist.all_gather_into_tensor(full, loc.view(-1), group=hub.group)
+                    hub.stage = full
+                hub.barrier.wait()
+                if p != 0:
+                    _tensor(d_recv, nbytes * hub.n, dev).copy_(hub.stage)
+                hub.barrier.wait()
+                return 0
+            except Exception as e:
+                print(f"[scz hybrid net] all_gather failed: {e!r}", flush=True)
+                return 1
+
+        def _sync(user, stream):
+            try:
+                hub.barrier.wait()
+                if p == 0 and W > 1:
+                    hub.calls["sync"] += 1
+                    dist.barrier(group=hub.group)
+                hub.barrier.wait()
+                return 0
+            except Exception:
+                return 1
+
+        vt = NetVTable()
+        vt.user = None
+        vt.gather = NetVTable._COLL(_gather)
+        vt.scatter = NetVTable._COLL(_scatter)
+        vt.all_gather = NetVTable._COLL(_all_gather)
+        vt.sync = NetVTable._SYNC(_sync)
+        self._keep = vt
+        return vt
