@@ -19,6 +19,8 @@
 #include "ctx.h"
 #include "msm.h"
 
+struct scz_pp;
+
 namespace scz {
 
 struct Deferred {
@@ -28,6 +30,24 @@ struct Deferred {
     std::vector<void *> outs;
     uint64_t points = 0, entries = 0;                  // queued so far (entries = sum of len * windows)
     std::vector<std::function<int32_t()>> after;       // continuations, run after the next flush
+    // Leader closures queued by the continuations (one multi-job launch each instead of one launch per call):
+    //   PssJob    the d_msm closure (dmsm.rs:31-38) on a gathered buffer, party-major [party][k]
+    //   ColsumJob out[r][i] = sum_j in[j * stride + off + i * 144] for r < replicate (d_commit / d_open sums)
+    struct PssJob {
+        const void *in;
+        void *out;
+        uint32_t batch, cta_base;
+    };
+    struct ColsumJob {
+        const void *in;
+        void *out;
+        uint64_t stride, off;
+        uint32_t parties, cols, replicate, col_base;
+    };
+    std::vector<PssJob> pss_jobs;
+    const scz_pp *pss_pp = nullptr;
+    std::vector<ColsumJob> colsum_jobs;
+    std::vector<std::function<int32_t()>> after2;      // run after the queued closures (the scatters)
     std::vector<std::shared_ptr<DevTmp>> keep;         // temporaries that must stay alive until run() returns
 
     explicit Deferred(Ctx *c) : ctx(c) {}
@@ -45,7 +65,16 @@ struct Deferred {
     // queue out = sum_i scalars[i] * bases[i]; `out` is one Jacobian point (144 B) on the device
     int32_t add_msm(const void *b, const void *s, size_t len, void *out);
     void then(std::function<int32_t()> f) { after.push_back(std::move(f)); }
+    void then2(std::function<int32_t()> f) { after2.push_back(std::move(f)); }
+    void add_pss(const scz_pp *pp, const void *in, uint32_t batch, void *out) {
+        pss_pp = pp;
+        pss_jobs.push_back(PssJob{in, out, batch, 0});
+    }
+    void add_colsum(const void *in, size_t stride, size_t off, uint32_t parties, uint32_t cols, void *out, uint32_t replicate) {
+        colsum_jobs.push_back(ColsumJob{in, out, stride, off, parties, cols, replicate, 0});
+    }
     int32_t flush_msm();
+    int32_t flush_closures();   // protocols.cu
     int32_t run();
 };
 

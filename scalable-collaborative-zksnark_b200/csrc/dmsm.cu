@@ -36,19 +36,19 @@ int32_t d_msm_defer(Ctx *ctx, Deferred &D, const scz_pp *pp, const void *const *
     SCZ_TRY(D.tmp(batch * PT, &c_shares));
     for (size_t k = 0; k < batch; k++)
         SCZ_TRY(D.add_msm(d_bases[k], d_scalars[k], lens[k], (char *)c_shares->p + k * PT));
+    Deferred *Dp = &D;
     D.then([=]() -> int32_t {
         const size_t wire = 8 + 48 * batch;
-        DevTmp recv(ctx), send(ctx);
+        DevTmp *recv = nullptr, *send = nullptr;
         if (net->is_leader()) {
-            SCZ_TRY(recv.alloc(N * batch * PT));
-            SCZ_TRY(send.alloc(N * batch * PT));
+            SCZ_TRY(Dp->tmp(N * batch * PT, &recv));
+            SCZ_TRY(Dp->tmp(N * batch * PT, &send));
         }
-        SCZ_TRY(net->gather(ctx, c_shares->p, recv.p, batch * PT, wire));
-        if (net->is_leader()) {
-            // recv is party-major [j][k]: vector k is the stride-`batch` column
-            SCZ_TRY(d_msm_leader(ctx, pp, recv.p, batch, send.p));
-        }
-        SCZ_TRY(net->scatter(ctx, send.p, d_out, batch * PT, wire));
+        SCZ_TRY(net->gather(ctx, c_shares->p, recv ? recv->p : nullptr, batch * PT, wire));
+        // recv is party-major [j][k]: vector k is the stride-`batch` column.  The closure (dmsm.rs:31-38) is queued:
+        // all d_msm calls of a round share one launch (deferred.h)
+        if (net->is_leader()) Dp->add_pss(pp, recv->p, (uint32_t)batch, send->p);
+        Dp->then2([=]() -> int32_t { return net->scatter(ctx, send ? send->p : nullptr, d_out, batch * PT, wire); });
         return SCZ_OK;
     });
     return SCZ_OK;

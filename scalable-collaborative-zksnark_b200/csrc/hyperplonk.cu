@@ -212,8 +212,12 @@ int32_t dhyperplonk_dev(Ctx *ctx, size_t n, const scz_hp_pk *pk, const scz_pp *p
     {
         void *coms_p = coms.p;
         auto copy_com = [&](void *dst, int k) {   // the commitments of step 1 exist once D has run their leader rounds
-            D.then([=]() -> int32_t {
-                SCZ_CUDA(ctx, cudaMemcpyAsync(dst, (char *)coms_p + k * PT, PT, cudaMemcpyDeviceToDevice, st));
+            Deferred *Dp = &D;
+            D.then([=]() -> int32_t {   // queued behind the scatters that deliver the commitments (stage 2 of the round)
+                Dp->then2([=]() -> int32_t {
+                    SCZ_CUDA(ctx, cudaMemcpyAsync(dst, (char *)coms_p + k * PT, PT, cudaMemcpyDeviceToDevice, st));
+                    return SCZ_OK;
+                });
                 return SCZ_OK;
             });
         };

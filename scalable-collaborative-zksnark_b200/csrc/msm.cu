@@ -49,7 +49,6 @@ constexpr int FIN_THREADS = 256;       // >= max windows of a segment (c = 1 -> 
 constexpr int SCAN_THREADS = 256;
 constexpr int SCAN_ITEMS = 8;          // per thread
 constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
-constexpr uint32_t RED_LOGL = 3;       // level-1 reduction chunk: 8 buckets
 
 __device__ __forceinline__ int seg_by_point(const MsmSeg *segs, int K, uint32_t g) {
     int lo = 0, hi = K - 1;
@@ -78,11 +77,11 @@ __device__ __forceinline__ int seg_by_window(const MsmSeg *segs, int K, uint32_t
     }
     return lo;
 }
-__device__ __forceinline__ int seg_by_chunk(const MsmSeg *segs, int K, uint32_t q) {
+__device__ __forceinline__ int seg_by_level(const MsmSeg *segs, int K, int lvl, uint32_t t) {
     int lo = 0, hi = K - 1;
     while (lo < hi) {
         int mid = (lo + hi + 1) >> 1;
-        if (__ldg(&segs[mid].chunk_base) <= q) lo = mid;
+        if (__ldg(&segs[mid].lvl_base[lvl]) <= t) lo = mid;
         else hi = mid - 1;
     }
     return lo;
@@ -264,53 +263,89 @@ __global__ void __launch_bounds__(ACC_THREADS) k_msm_accumulate(const MsmSeg *se
 }
 
 // ---- 5: buckets cut by chunk boundaries.  Bucket b = entries [start, end) touches chunks t0 = start/T ..
-// t1 = (end-1)/T; when t1 > t0 its value is parts[2*t0+1] + sum_{u in (t0, t1]} parts[2u].  Short chains are
-// summed by the bucket's thread; long ones (the top window's few buckets, degenerate scalar
-// distributions such as dmsm.rs:103) go to a list served by whole CTAs.
+// t1 = (end-1)/T; when t1 > t0 its value is parts[2*t0+1] + sum_{u in (t0, t1]} parts[2u].  One thread per CHUNK:
+// chunk t owns the bucket that starts in it and runs past its end (nearly every chunk has one, so the kernel is
+// dense).  Long chains (the top window's few buckets, degenerate scalar distributions such as dmsm.rs:103) go
+// to a list served by whole CTAs.
 constexpr uint32_t FIX_SERIAL_MAX = 6;
-__global__ void __launch_bounds__(FIX_THREADS) k_msm_fixup(uint32_t total_buckets, uint32_t logT, const uint32_t *counts,
-                                                            const uint32_t *cursor, const void *parts, void *buckets,
-                                                            uint32_t *heavy_list, uint32_t *heavy_count) {
-    uint32_t b = blockIdx.x * FIX_THREADS + threadIdx.x;
-    if (b >= total_buckets) return;
-    uint32_t n = counts[b];
-    if (!n) return;
-    uint32_t end = cursor[b], start = end - n;
-    uint32_t t0 = start >> logT, t1 = (end - 1) >> logT;
-    if (t1 == t0) return;
-    if (t1 - t0 > FIX_SERIAL_MAX) {
+__global__ void __launch_bounds__(FIX_THREADS) k_msm_fixup(const uint32_t *E_ptr, uint32_t logT, const uint32_t *keys,
+                                                            const uint32_t *counts, const uint32_t *cursor,
+                                                            const void *parts, void *buckets, uint32_t *heavy_list,
+                                                            uint32_t *heavy_count) {
+    uint32_t t = blockIdx.x * FIX_THREADS + threadIdx.x;
+    const uint32_t E = __ldg(E_ptr);
+    uint64_t lo64 = (uint64_t)t << logT;
+    if (lo64 >= E) return;
+    uint32_t lo = (uint32_t)lo64;
+    uint32_t hi = lo64 + (1u << logT) < E ? lo + (1u << logT) : E;
+    uint32_t b = __ldg(keys + hi - 1);
+    uint32_t end = cursor[b];
+    if (end <= hi) return;                      // the chunk's last bucket ends inside it
+    uint32_t start = end - counts[b];
+    if (start < lo) return;                     // began in an earlier chunk: that chunk owns it
+    uint32_t t1 = (end - 1) >> logT;
+    if (t1 - t > FIX_SERIAL_MAX) {
         heavy_list[atomicAdd(heavy_count, 1u)] = b;
         return;
     }
-    G1X acc = g1x_load(parts, 2 * (size_t)t0 + 1);
-    for (uint32_t u = t0 + 1; u <= t1; u++) {
+    G1X acc = g1x_load(parts, 2 * (size_t)t + 1);
+    for (uint32_t u = t + 1; u <= t1; u++) {
         G1X h = g1x_load(parts, 2 * (size_t)u);
         g1x_add_nl(acc, acc, h);
     }
     g1x_store(buckets, b, acc);
 }
 
-// ---- 6: level-1 bucket reduction: one thread per chunk of L = 2^logL buckets
-//   S_q = sum_j B_j,   R_q = sum_j j * B_j   (j = 0 .. L-1 within the chunk)
-__global__ void __launch_bounds__(CHK_THREADS) k_msm_chunks(const MsmSeg *segs, int K, uint32_t total_chunks,
-                                                             const uint32_t *counts, const void *buckets, void *chS,
-                                                             void *chR) {
-    uint32_t q = blockIdx.x * CHK_THREADS + threadIdx.x;
-    if (q >= total_chunks) return;
-    int s = K == 1 ? 0 : seg_by_chunk(segs, K, q);
+// ---- 6: bucket reduction, sum_j (j+1) B_j per window, as a tree of fan-in 8.  A node over the bucket range
+//   [base, base + span) keeps S = sum B_j and T = sum (j - base) B_j.  A parent over children c_0 .. c_7 (each of
+//   span s): S = sum S_i (running sum, high child first), R = sum_i i*S_i (sum of the running sums), T = sum_i T_i + s*R
+//   (s = 8^level: 3*level doublings).  Two general additions per bucket at level 0, three per node above:
+//   ~2.4 additions per bucket in total, all in dense thread-per-node kernels.  The root writes S + T, the window sum.
+struct MsmNode {
+    G1X S, T;
+};
+template <bool FIRST>
+__global__ void __launch_bounds__(CHK_THREADS) k_msm_tree(const MsmSeg *segs, int K, int lvl, uint32_t first, uint32_t count,
+                                                           const uint32_t *counts, const void *buckets, MsmNode *nodes,
+                                                           void *wsum) {
+    uint32_t t = blockIdx.x * CHK_THREADS + threadIdx.x;
+    if (t >= count) return;
+    t += first;                                        // global node index
+    int s = K == 1 ? 0 : seg_by_level(segs, K, lvl, t);
     const MsmSeg sg = segs[s];
-    uint32_t L = 1u << sg.logL;
-    uint32_t first = sg.bucket_base + (q - sg.chunk_base) * L;   // windows are contiguous: chunk -> bucket is linear
-    G1X S = G1X::inf(), R = G1X::inf();
-    for (uint32_t j = L; j-- > 0;) {
-        if (counts[first + j]) {
-            G1X b = g1x_load(buckets, first + j);
-            g1x_add_nl(S, S, b);
+    uint32_t per_w = sg.lvl_nodes[lvl];
+    uint32_t rel = t - sg.lvl_base[lvl];
+    uint32_t w = rel / per_w, i = rel - w * per_w;
+    uint32_t below = FIRST ? sg.nb : sg.lvl_nodes[lvl - 1];
+    uint32_t nchild = below / per_w;                  // 8, or fewer at the root / for tiny windows
+    G1X S = G1X::inf(), R = G1X::inf(), Tsum = G1X::inf();
+    if (FIRST) {
+        uint32_t b0 = sg.bucket_base + w * sg.nb + i * nchild;
+        for (uint32_t j = nchild; j-- > 0;) {
+            if (counts[b0 + j]) {
+                G1X b = g1x_load(buckets, b0 + j);
+                g1x_add_nl(S, S, b);
+            }
+            if (j) g1x_add_nl(R, R, S);
         }
-        if (j) g1x_add_nl(R, R, S);   // after the loop R = sum_j j*B_j
+    } else {
+        const MsmNode *ch = nodes + sg.lvl_base[lvl - 1] + (size_t)w * below + (size_t)i * nchild;
+        for (uint32_t j = nchild; j-- > 0;) {
+            G1X cs = g1x_load(&ch[j].S, 0), ct = g1x_load(&ch[j].T, 0);
+            g1x_add_nl(S, S, cs);
+            g1x_add_nl(Tsum, Tsum, ct);
+            if (j) g1x_add_nl(R, R, S);
+        }
+        for (int d = 0; d < 3 * lvl; d++) g1x_double_nl(R, R);
+        g1x_add_nl(R, R, Tsum);
     }
-    g1x_store(chS, q, S);
-    g1x_store(chR, q, R);
+    if (lvl + 1 == (int)sg.levels) {                   // root: window sum = sum_j (j + 1) B_j = T + S
+        g1x_add_nl(R, R, S);
+        g1j_store(wsum, sg.window_base + w, g1x_to_jac(R));
+    } else {
+        g1x_store(&nodes[t].S, 0, S);
+        g1x_store(&nodes[t].T, 0, R);
+    }
 }
 
 // tree-sum of one XYZZ value per thread through shared memory; result in thread 0
@@ -353,60 +388,17 @@ __global__ void __launch_bounds__(PLN_THREADS) k_msm_fixup_heavy(uint32_t logT, 
     }
 }
 
-// ---- 7: level 2, one CTA per (window, plane):
-//   plane b < PB : sum of S_q over chunks q with bit b set
-//   plane PB     : sum of S_q          plane PB+1 : sum of R_q
-__global__ void __launch_bounds__(PLN_THREADS) k_msm_planes(const MsmSeg *segs, int K, const void *chS,
-                                                             const void *chR, void *planes) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    G1X *sh = reinterpret_cast<G1X *>(smem_raw);
-    uint32_t gw = blockIdx.x, plane = blockIdx.y;
-    int s = K == 1 ? 0 : seg_by_window(segs, K, gw);
-    const MsmSeg sg = segs[s];
-    if (plane >= sg.PB + 2) return;
-    uint32_t w = gw - sg.window_base;
-    uint32_t base = sg.chunk_base + w * sg.M;
-    const void *src = plane == sg.PB + 1 ? chR : chS;
-    G1X acc = G1X::inf();
-    for (uint32_t q = threadIdx.x; q < sg.M; q += PLN_THREADS) {
-        if (plane < sg.PB && !((q >> plane) & 1)) continue;
-        G1X v = g1x_load(src, base + q);
-        if (!v.is_inf()) g1x_add_nl(acc, acc, v);
-    }
-    acc = block_sum_g1x<PLN_THREADS>(acc, sh);
-    // planes leave as Jacobian (144 B): the finish kernel works on (X, Y, Z)
-    if (threadIdx.x == 0) g1j_store(planes, sg.plane_base + w * (sg.PB + 2) + plane, g1x_to_jac(acc));
-}
-
-// ---- 8: one CTA per segment.  Both stages are serial chains in the group law, so they run on groups of 4
-//         cooperating lanes (g1_coop.cuh).  Group w: window sum = sum_q R_q + L * sum_b 2^b plane_b + sum_q S_q;
-//         then warp 0 runs Horner over the windows (255 doublings: the longest chain of the pipeline).
-constexpr int FIN_GROUPS = FIN_THREADS / 4;
-__global__ void __launch_bounds__(FIN_THREADS) k_msm_finish(const MsmSeg *segs, const void *planes, void *out_jac) {
+// ---- 7: one CTA per segment: Horner over the window sums (255 doublings: the longest chain of the pipeline),
+//         run by groups of 4 cooperating lanes (g1_coop.cuh); warp 0's 8 groups run the same chain redundantly.
+__global__ void __launch_bounds__(FIN_THREADS) k_msm_finish(const MsmSeg *segs, const void *wsum, void *out_jac) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     G1Jac *sh = reinterpret_cast<G1Jac *>(smem_raw);   // [W]
     const MsmSeg sg = segs[blockIdx.x];
     const Coop g;
-    const uint32_t gi = threadIdx.x >> 2;
-    if (sg.len) {
-        for (uint32_t w = gi; w < sg.W; w += FIN_GROUPS) {
-            size_t pb = sg.plane_base + (size_t)w * (sg.PB + 2);
-            G1Jac X = g1j_inf();
-            for (uint32_t b = sg.PB; b-- > 0;) {
-                coop_double(g, X);
-                G1Jac v = g1j_load(planes, pb + b);
-                coop_add(g, X, v);
-            }
-            for (uint32_t i = 0; i < sg.logL; i++) coop_double(g, X);
-            G1Jac v = g1j_load(planes, pb + sg.PB + 1);
-            coop_add(g, X, v);
-            v = g1j_load(planes, pb + sg.PB);
-            coop_add(g, X, v);
-            if (g.role == 0) sh[w] = X;
-        }
-    }
+    if (sg.len)
+        for (uint32_t w = threadIdx.x; w < sg.W; w += FIN_THREADS) sh[w] = g1j_load(wsum, sg.window_base + w);
     __syncthreads();
-    if (threadIdx.x < 32) {   // warp 0: its 8 groups run the same chain redundantly (lanes are free)
+    if (threadIdx.x < 32) {
         G1Jac acc = g1j_inf();
         if (sg.len) {
             for (uint32_t ww = sg.W; ww-- > 0;) {
@@ -446,8 +438,8 @@ int32_t msm_g1_batched(Ctx *ctx, const void *const *d_bases, const void *const *
     if (batch == 0) return SCZ_OK;
     if (batch > (1u << 20)) return ctx->fail(SCZ_ERR_BAD_ARG, "msm: batch too large");
     std::vector<MsmSeg> segs(batch);
-    uint64_t points = 0, buckets = 0, windows = 0, entries = 0, chunks = 0, planes = 0;
-    uint32_t max_planes = 2;
+    uint64_t points = 0, buckets = 0, windows = 0, entries = 0, lvl_count[MSM_MAX_LEVELS] = {0};
+    uint32_t max_levels = 1;
     for (size_t k = 0; k < batch; k++) {
         if (lens[k] >= (1ull << 31)) return ctx->fail(SCZ_ERR_BAD_ARG, "msm: segment %zu too long", k);
         if (lens[k] && (!d_bases[k] || !d_scalars[k])) return ctx->fail(SCZ_ERR_BAD_ARG, "msm: null segment %zu", k);
@@ -461,22 +453,37 @@ int32_t msm_g1_batched(Ctx *ctx, const void *const *d_bases, const void *const *
         s.nb = 1u << (s.c - 1);
         s.bucket_base = (uint32_t)buckets;
         s.window_base = (uint32_t)windows;
-        s.logL = std::min<uint32_t>(RED_LOGL, s.c - 1);
-        s.M = s.nb >> s.logL;
-        s.PB = 0;
-        while ((1u << s.PB) < s.M) s.PB++;
-        s.chunk_base = (uint32_t)chunks;
-        s.plane_base = (uint32_t)planes;
+        s.levels = 0;
+        for (uint32_t below = s.nb; s.levels == 0 || below > 1;) {
+            if (s.levels == MSM_MAX_LEVELS) return ctx->fail(SCZ_ERR_BAD_ARG, "msm: window of %u bits is too wide", s.c);
+            uint32_t here = std::max<uint32_t>(1, below >> 3);
+            s.lvl_nodes[s.levels] = here;
+            lvl_count[s.levels] += (uint64_t)s.W * here;
+            s.levels++;
+            below = here;
+        }
+        for (uint32_t k2 = s.levels; k2 < MSM_MAX_LEVELS; k2++) s.lvl_nodes[k2] = 0;
+        max_levels = std::max(max_levels, s.levels);
         s.out = d_outs ? d_outs[k] : nullptr;
-        max_planes = std::max(max_planes, s.PB + 2);
         points += s.len;
         buckets += (uint64_t)s.W * s.nb;
         windows += s.W;
         entries += (uint64_t)s.len * s.W;
-        chunks += (uint64_t)s.W * s.M;
-        planes += (uint64_t)s.W * (s.PB + 2);
     }
-    if (points >= (1ull << 31) || buckets >= (1ull << 31) || entries >= (1ull << 32))
+    // node index space: level 0 of all segments, then level 1 of all segments, ...
+    uint64_t lvl_first[MSM_MAX_LEVELS + 1] = {0};
+    for (int k2 = 0; k2 < MSM_MAX_LEVELS; k2++) lvl_first[k2 + 1] = lvl_first[k2] + lvl_count[k2];
+    {
+        uint64_t run[MSM_MAX_LEVELS];
+        for (int k2 = 0; k2 < MSM_MAX_LEVELS; k2++) run[k2] = lvl_first[k2];
+        for (size_t k = 0; k < batch; k++)
+            for (int k2 = 0; k2 < MSM_MAX_LEVELS; k2++) {
+                segs[k].lvl_base[k2] = (uint32_t)run[k2];
+                run[k2] += (uint64_t)segs[k].W * segs[k].lvl_nodes[k2];
+            }
+    }
+    const uint64_t nodes_total = lvl_first[MSM_MAX_LEVELS];
+    if (points >= (1ull << 31) || buckets >= (1ull << 31) || entries >= (1ull << 32) || nodes_total >= (1ull << 32))
         return ctx->fail(SCZ_ERR_BAD_ARG, "msm: batch too large (%llu points, %llu buckets)", (unsigned long long)points,
                          (unsigned long long)buckets);
     ctx->msm_bucket_adds = entries;
@@ -492,7 +499,7 @@ int32_t msm_g1_batched(Ctx *ctx, const void *const *d_bases, const void *const *
     cudaStream_t st = ctx->stream;
     uint32_t tiles = ceil_div_u32(buckets, SCAN_TILE);
     DevTmp d_segs(ctx), d_counts(ctx), d_cursor(ctx), d_tiles(ctx), d_sorted(ctx), d_keys(ctx), d_buckets(ctx),
-        d_parts(ctx), d_heavy(ctx), d_chS(ctx), d_chR(ctx), d_planes(ctx);
+        d_parts(ctx), d_heavy(ctx), d_nodes(ctx), d_wsum(ctx);
     SCZ_TRY(d_segs.alloc(batch * sizeof(MsmSeg)));
     SCZ_TRY(d_counts.alloc(buckets * 4));
     SCZ_TRY(d_cursor.alloc(buckets * 4));
@@ -501,10 +508,9 @@ int32_t msm_g1_batched(Ctx *ctx, const void *const *d_bases, const void *const *
     SCZ_TRY(d_keys.alloc((entries ? entries : 1) * 4));
     SCZ_TRY(d_buckets.alloc(buckets * sizeof(G1X)));
     SCZ_TRY(d_parts.alloc(((size_t)nchunks * 2 + 2) * sizeof(G1X)));
-    SCZ_TRY(d_heavy.alloc((buckets + 1) * 4));   // [0] = count, [1..] = list
-    SCZ_TRY(d_chS.alloc(chunks * sizeof(G1X)));
-    SCZ_TRY(d_chR.alloc(chunks * sizeof(G1X)));
-    SCZ_TRY(d_planes.alloc(planes * sizeof(G1Jac)));
+    SCZ_TRY(d_heavy.alloc(((size_t)nchunks + 1) * 4));   // [0] = count, [1..] = list (at most one bucket per chunk)
+    SCZ_TRY(d_nodes.alloc(nodes_total * sizeof(MsmNode)));
+    SCZ_TRY(d_wsum.alloc(windows * sizeof(G1Jac)));
     // segment table: pageable host -> device; the vector must outlive the copy
     SCZ_CUDA(ctx, cudaMemcpyAsync(d_segs.p, segs.data(), batch * sizeof(MsmSeg), cudaMemcpyHostToDevice, st));
     SCZ_CUDA(ctx, cudaStreamSynchronize(st));
@@ -516,7 +522,6 @@ int32_t msm_g1_batched(Ctx *ctx, const void *const *d_bases, const void *const *
     uint32_t *keys = d_keys.as<uint32_t>();
     static bool attr_done = false;
     if (!attr_done) {
-        cudaFuncSetAttribute(k_msm_planes, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(PLN_THREADS * sizeof(G1X)));
         cudaFuncSetAttribute(k_msm_fixup_heavy, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)(PLN_THREADS * sizeof(G1X)));
         cudaFuncSetAttribute(k_msm_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(FIN_THREADS * sizeof(G1Jac)));
@@ -552,8 +557,9 @@ int32_t msm_g1_batched(Ctx *ctx, const void *const *d_bases, const void *const *
         }
         ProfScope ps(ctx, SCZ_K_MSM_FIXUP);
         uint32_t *heavy = d_heavy.as<uint32_t>();
-        k_msm_fixup<<<ceil_div_u32(buckets, FIX_THREADS), FIX_THREADS, 0, st>>>((uint32_t)buckets, logT, counts, cursor,
-                                                                                d_parts.p, d_buckets.p, heavy + 1, heavy);
+        k_msm_fixup<<<ceil_div_u32(nchunks, FIX_THREADS), FIX_THREADS, 0, st>>>(cursor + (buckets - 1), logT, keys, counts,
+                                                                                cursor, d_parts.p, d_buckets.p, heavy + 1,
+                                                                                heavy);
         SCZ_LAUNCH_CHECK(ctx);
         k_msm_fixup_heavy<<<ctx->sm_count, PLN_THREADS, PLN_THREADS * sizeof(G1X), st>>>(
             logT, counts, cursor, d_parts.p, d_buckets.p, heavy + 1, heavy);
@@ -561,16 +567,21 @@ int32_t msm_g1_batched(Ctx *ctx, const void *const *d_bases, const void *const *
     }
     {
         ProfScope ps(ctx, SCZ_K_MSM_REDUCE);
-        k_msm_chunks<<<ceil_div_u32(chunks, CHK_THREADS), CHK_THREADS, 0, st>>>(sp, K, (uint32_t)chunks, counts,
-                                                                               d_buckets.p, d_chS.p, d_chR.p);
-        SCZ_LAUNCH_CHECK(ctx);
-        k_msm_planes<<<dim3((uint32_t)windows, max_planes), PLN_THREADS, PLN_THREADS * sizeof(G1X), st>>>(
-            sp, K, d_chS.p, d_chR.p, d_planes.p);
-        SCZ_LAUNCH_CHECK(ctx);
+        for (uint32_t lv = 0; lv < max_levels; lv++) {
+            uint32_t cnt = (uint32_t)lvl_count[lv];
+            if (!cnt) continue;
+            if (lv == 0)
+                k_msm_tree<true><<<ceil_div_u32(cnt, CHK_THREADS), CHK_THREADS, 0, st>>>(
+                    sp, K, 0, 0, cnt, counts, d_buckets.p, d_nodes.as<MsmNode>(), d_wsum.p);
+            else
+                k_msm_tree<false><<<ceil_div_u32(cnt, CHK_THREADS), CHK_THREADS, 0, st>>>(
+                    sp, K, (int)lv, (uint32_t)lvl_first[lv], cnt, counts, d_buckets.p, d_nodes.as<MsmNode>(), d_wsum.p);
+            SCZ_LAUNCH_CHECK(ctx);
+        }
     }
     {
         ProfScope ps(ctx, SCZ_K_MSM_FINISH);
-        k_msm_finish<<<(uint32_t)batch, FIN_THREADS, FIN_THREADS * sizeof(G1Jac), st>>>(sp, d_planes.p, d_out);
+        k_msm_finish<<<(uint32_t)batch, FIN_THREADS, FIN_THREADS * sizeof(G1Jac), st>>>(sp, d_wsum.p, d_out);
         SCZ_LAUNCH_CHECK(ctx);
     }
     return SCZ_OK;
@@ -602,10 +613,14 @@ int32_t Deferred::flush_msm() {
     return rc;
 }
 int32_t Deferred::run() {
-    while (!lens.empty() || !after.empty()) {
+    while (!lens.empty() || !after.empty() || !pss_jobs.empty() || !colsum_jobs.empty() || !after2.empty()) {
         SCZ_TRY(flush_msm());
         std::vector<std::function<int32_t()>> now;
         now.swap(after);
+        for (auto &f : now) SCZ_TRY(f());
+        SCZ_TRY(flush_closures());
+        now.clear();
+        now.swap(after2);
         for (auto &f : now) SCZ_TRY(f());
     }
     return SCZ_OK;

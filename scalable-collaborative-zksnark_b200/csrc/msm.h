@@ -6,6 +6,8 @@
 
 namespace scz {
 
+constexpr int MSM_MAX_LEVELS = 7;   // 8^7 = 2^21 buckets per window: window sizes up to 22 bits
+
 // one MSM of a batch ("segment"); lives in device memory, read by every kernel of the pipeline
 struct MsmSeg {
     const void *bases;     // packed affine, 96 B per point
@@ -17,11 +19,11 @@ struct MsmSeg {
     uint32_t nb;           // buckets per window = 2^(c-1)
     uint32_t bucket_base;  // first global bucket of this segment (window w starts at bucket_base + w*nb)
     uint32_t window_base;  // first global window of this segment
-    uint32_t logL;         // bucket-reduction chunk length L = 2^logL = min(nb, 8)
-    uint32_t M;            // chunks per window = nb / L (a power of two)
-    uint32_t PB;           // log2(M): bit planes of the chunk index
-    uint32_t chunk_base;   // first global chunk (window w starts at chunk_base + w*M)
-    uint32_t plane_base;   // first global plane slot (window w owns PB + 2 slots from plane_base + w*(PB+2))
+    // bucket-reduction tree: level k (0-based) has lvl_nodes[k] = max(1, nb >> 3(k+1)) nodes per window, each over
+    // (up to) 8 children of the level below (level 0's children are the buckets); the last level has one node
+    uint32_t levels;
+    uint32_t lvl_nodes[MSM_MAX_LEVELS];
+    uint32_t lvl_base[MSM_MAX_LEVELS];   // global node index of (window 0, node 0) at level k
     void *out;             // where this segment's result goes (one Jacobian point); null: slot `k` of d_out_jac
 };
 

@@ -72,19 +72,6 @@ __global__ void k_dsum_leader(const void *recv, uint32_t N, uint32_t n, void *ou
         fp_store<FrP>(lf, j, fp_load_rw<FrP>(recv, ((size_t)j * (n + 1) + n) * 3 + 1));
     }
 }
-// column sums of Jacobian points: out[i] = sum_j in[j*stride_pts + off_pts + i]   (in units of 144 B after a byte offset)
-__global__ void k_g1_colsum(const void *in, size_t party_stride_bytes, size_t off_bytes, uint32_t N, uint32_t cols,
-                            void *out, uint32_t replicate) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= cols) return;
-    G1X acc = G1X::inf();
-    for (uint32_t j = 0; j < N; j++) {
-        const char *p = reinterpret_cast<const char *>(in) + (size_t)j * party_stride_bytes + off_bytes;
-        acc = g1x_add(acc, g1x_from_jac(g1j_load(p, i)));
-    }
-    G1Jac r = g1x_to_jac(acc);
-    for (uint32_t k = 0; k < replicate; k++) g1j_store(out, (size_t)k * cols + i, r);
-}
 // lz[j] = first Fr of party j's payload
 __global__ void k_pick_fr(const void *in, size_t party_stride_bytes, uint32_t N, void *out) {
     uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
@@ -270,18 +257,16 @@ int32_t d_commit_defer(Ctx *ctx, Deferred &D, const scz_srs *srs, const void *d_
     DevTmp *loc = nullptr;
     SCZ_TRY(D.tmp(PT, &loc));
     SCZ_TRY(commit_defer(ctx, D, srs, d_peval, len, loc->p));
+    Deferred *Dp = &D;
     D.then([=]() -> int32_t {
-        DevTmp recv(ctx), send(ctx);
+        DevTmp *recv = nullptr, *send = nullptr;
         if (net->is_leader()) {
-            SCZ_TRY(recv.alloc(N * PT));
-            SCZ_TRY(send.alloc(N * PT));
+            SCZ_TRY(Dp->tmp(N * PT, &recv));
+            SCZ_TRY(Dp->tmp(N * PT, &send));
         }
-        SCZ_TRY(net->gather(ctx, loc->p, recv.p, PT, 48));
-        if (net->is_leader()) {
-            k_g1_colsum<<<1, 32, 0, ctx->stream>>>(recv.p, PT, 0, (uint32_t)N, 1, send.p, (uint32_t)N);
-            SCZ_LAUNCH_CHECK(ctx);
-        }
-        SCZ_TRY(net->scatter(ctx, send.p, d_out, PT, 48));
+        SCZ_TRY(net->gather(ctx, loc->p, recv ? recv->p : nullptr, PT, 48));
+        if (net->is_leader()) Dp->add_colsum(recv->p, PT, 0, (uint32_t)N, 1, send->p, (uint32_t)N);   // sum, N copies :290-292
+        Dp->then2([=]() -> int32_t { return net->scatter(ctx, send ? send->p : nullptr, d_out, PT, 48); });
         return SCZ_OK;
     });
     return SCZ_OK;
@@ -365,27 +350,68 @@ int32_t d_open_defer(Ctx *ctx, Deferred &D, const scz_srs *srs, const void *d_pe
     if (count) *count = net->is_leader() ? pl + n : 0;
     Deferred *Dp = &D;
     D.then([=]() -> int32_t {
-        DevTmp recv(ctx);
-        DevTmp *lz = nullptr;
+        DevTmp *recv = nullptr, *lz = nullptr;
         if (net->is_leader()) {
-            SCZ_TRY(recv.alloc(N * payload));
+            SCZ_TRY(Dp->tmp(N * payload, &recv));
             SCZ_TRY(Dp->tmp(N * 32, &lz));
         }
-        SCZ_TRY(net->gather(ctx, loc->p, recv.p, payload, 32 + 8 + 48 * n));                // :368
+        SCZ_TRY(net->gather(ctx, loc->p, recv ? recv->p : nullptr, payload, 32 + 8 + 48 * n));   // :368
         if (!net->is_leader()) {
             SCZ_CUDA(ctx, cudaMemsetAsync(d_value, 0, 32, ctx->stream));
             return SCZ_OK;
         }
-        k_pick_fr<<<1, 32 * (uint32_t)((N + 31) / 32), 0, ctx->stream>>>(recv.p, payload, (uint32_t)N, lz->p);
+        k_pick_fr<<<1, 32 * (uint32_t)((N + 31) / 32), 0, ctx->stream>>>(recv->p, payload, (uint32_t)N, lz->p);
         SCZ_LAUNCH_CHECK(ctx);
         SCZ_TRY(open_defer(ctx, *Dp, srs, lz->p, N, d_point, d_value, d_proofs));           // root_open :377 (next flush)
-        if (n) {
-            k_g1_colsum<<<ceil_div_u32(n, 32), 32, 0, ctx->stream>>>(recv.p, payload, 32, (uint32_t)N, (uint32_t)n,
-                                                                     (char *)d_proofs + pl * PT, 1);   // :374-376
-            SCZ_LAUNCH_CHECK(ctx);
-        }
+        if (n) Dp->add_colsum(recv->p, payload, 32, (uint32_t)N, (uint32_t)n, (char *)d_proofs + pl * PT, 1);   // :374-376
         return SCZ_OK;
     });
+    return SCZ_OK;
+}
+
+// ---- the queued leader closures of a round, one launch per kind (deferred.h)
+__global__ void __launch_bounds__(64) k_g1_colsum_multi(const Deferred::ColsumJob *jobs, uint32_t njobs, uint32_t total_cols) {
+    uint32_t t = blockIdx.x * 64 + threadIdx.x;
+    if (t >= total_cols) return;
+    uint32_t lo = 0, hi = njobs - 1;
+    while (lo < hi) {
+        uint32_t mid = (lo + hi + 1) >> 1;
+        if (jobs[mid].col_base <= t) lo = mid;
+        else hi = mid - 1;
+    }
+    const Deferred::ColsumJob job = jobs[lo];
+    uint32_t i = t - job.col_base;
+    G1X acc = G1X::inf();
+    for (uint32_t j = 0; j < job.parties; j++) {
+        const char *p = reinterpret_cast<const char *>(job.in) + (size_t)j * job.stride + job.off;
+        acc = g1x_add(acc, g1x_from_jac(g1j_load(p, i)));
+    }
+    G1Jac r = g1x_to_jac(acc);
+    for (uint32_t k = 0; k < job.replicate; k++) g1j_store(job.out, (size_t)k * job.cols + i, r);
+}
+
+int32_t Deferred::flush_closures() {
+    if (!pss_jobs.empty()) {
+        ProfScope ps(ctx, SCZ_K_PSS);
+        int32_t rc = pss_dmsm_multi(ctx, pss_pp, pss_jobs.data(), pss_jobs.size());
+        pss_jobs.clear();
+        SCZ_TRY(rc);
+    }
+    if (!colsum_jobs.empty()) {
+        ProfScope ps(ctx, SCZ_K_PSS);
+        uint32_t cols = 0;
+        for (auto &j : colsum_jobs) {
+            j.col_base = cols;
+            cols += j.cols;
+        }
+        DevTmp d(ctx);
+        SCZ_TRY(d.alloc(colsum_jobs.size() * sizeof(ColsumJob)));
+        SCZ_CUDA(ctx, cudaMemcpyAsync(d.p, colsum_jobs.data(), colsum_jobs.size() * sizeof(ColsumJob), cudaMemcpyHostToDevice,
+                                      ctx->stream));
+        k_g1_colsum_multi<<<ceil_div_u32(cols, 64), 64, 0, ctx->stream>>>(d.as<ColsumJob>(), (uint32_t)colsum_jobs.size(), cols);
+        colsum_jobs.clear();
+        SCZ_LAUNCH_CHECK(ctx);
+    }
     return SCZ_OK;
 }
 

@@ -14,6 +14,9 @@
 // output element over Fr, and for G1 operands (the d_msm leader closure) one CTA
 // per output point, one scalar multiplication per thread, shared-memory tree sum.
 #include "g1_coop.cuh"
+#include <string.h>
+#include <vector>
+
 #include "pss.h"
 
 namespace scz {
@@ -154,6 +157,70 @@ __global__ void __launch_bounds__(GROUPS * 4) k_pss_apply_g1(const void *M, uint
         __syncthreads();
     }
     if (threadIdx.x == 0) g1j_store(out, b * out_b + o * out_o, acc);
+}
+
+// The d_msm leader closure for a LIST of gathered buffers in one launch: job q maps its party-major input
+// [party][k] (n x batch Jacobian points) through the n x n matrix M; CTA = one output point.
+struct PssG1Job {
+    const void *in;
+    void *out;
+    uint32_t batch, cta_base;
+};
+__global__ void __launch_bounds__(32) k_pss_dmsm_multi(const void *M, uint32_t n, const PssG1Job *jobs, uint32_t njobs) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int GROUPS = 8;
+    G1Jac *tab = reinterpret_cast<G1Jac *>(smem_raw);          // [GROUPS][16]
+    G1Jac *res = tab + GROUPS * 16;                             // [GROUPS]
+    uint32_t lo = 0, hi = njobs - 1;
+    while (lo < hi) {
+        uint32_t mid = (lo + hi + 1) >> 1;
+        if (jobs[mid].cta_base <= blockIdx.x) lo = mid;
+        else hi = mid - 1;
+    }
+    const PssG1Job job = jobs[lo];
+    uint32_t rel = blockIdx.x - job.cta_base;
+    uint32_t b = rel / n, o = rel % n;                          // batch entry, output party
+    const Coop g;
+    const int gi = threadIdx.x >> 2;
+    G1Jac acc = g1j_inf();
+    for (uint32_t j = gi; j < n; j += GROUPS) {
+        G1Jac p = g1j_load(job.in, (size_t)j * job.batch + b);
+        Fr k = fp_to_canon(fp_load<FrP>(M, (size_t)o * n + j));
+        if (p.z.is_zero() || k.is_zero()) continue;
+        G1Jac t = coop_mul_bits(g, p, k.l, tab + gi * 16);
+        coop_add(g, acc, t);
+    }
+    if (g.role == 0) res[gi] = acc;
+    __syncwarp();
+    for (int stride = GROUPS / 2; stride > 0; stride >>= 1) {
+        if (gi < stride) {
+            G1Jac o2 = res[gi + stride];
+            coop_add(g, acc, o2);
+        }
+        __syncwarp();
+        if (gi < stride && g.role == 0) res[gi] = acc;
+        __syncwarp();
+    }
+    if (threadIdx.x == 0) g1j_store(job.out, (size_t)o * job.batch + b, acc);
+}
+// jobs: host array of (in, out, batch, -) ; cta_base is filled here
+int32_t pss_dmsm_multi(Ctx *ctx, const scz_pp *pp, const void *jobs_host, size_t njobs) {
+    if (!njobs) return SCZ_OK;
+    std::vector<PssG1Job> jobs(njobs);
+    memcpy(jobs.data(), jobs_host, njobs * sizeof(PssG1Job));
+    uint32_t ctas = 0;
+    for (auto &j : jobs) {
+        j.cta_base = ctas;
+        ctas += j.batch * (uint32_t)pp->n;
+    }
+    if (!ctas) return SCZ_OK;
+    DevTmp d(ctx);
+    SCZ_TRY(d.alloc(njobs * sizeof(PssG1Job)));
+    SCZ_CUDA(ctx, cudaMemcpyAsync(d.p, jobs.data(), njobs * sizeof(PssG1Job), cudaMemcpyHostToDevice, ctx->stream));
+    constexpr size_t SH8 = 8 * 17 * sizeof(G1Jac);
+    k_pss_dmsm_multi<<<ctas, 32, SH8, ctx->stream>>>(pp->d_dmsm, (uint32_t)pp->n, d.as<PssG1Job>(), (uint32_t)njobs);
+    SCZ_LAUNCH_CHECK(ctx);
+    return SCZ_OK;
 }
 
 int32_t pss_apply(Ctx *ctx, const scz_pp *pp, PssMap map, int kind, const void *d_in, size_t len_in, size_t in_b,

@@ -24,4 +24,7 @@ enum PssMap { PSS_PACK = 0, PSS_PACK_SINGLE = 1, PSS_UNPACK = 2, PSS_UNPACK2 = 3
 int32_t pss_apply(Ctx *ctx, const scz_pp *pp, PssMap map, int kind, const void *d_in, size_t len_in, size_t in_bstride,
                   size_t in_jstride, size_t batch, void *d_out, size_t out_bstride, size_t out_ostride);
 
+// the d_msm leader closure on a list of gathered buffers (Deferred::PssJob array) in one launch
+int32_t pss_dmsm_multi(Ctx *ctx, const scz_pp *pp, const void *jobs_host, size_t njobs);
+
 }   // namespace scz
