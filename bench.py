@@ -216,7 +216,7 @@ def run_own(args):
         ctx = scz.Context(device=local_rank, party_id=pid if world > 1 else 0, n_parties=N_PARTIES,
                           net=hub.party(p) if hub else None)
         pp = scz.PackedSharingParams(ctx, 1)
-        pk = scz.PackedProvingParameters.new(ctx, n, 1, seed=1 + pid, shared_seed=0)
+        pk = scz.PackedProvingParameters.new(ctx, n, 1, seed=1 + pid, shared_seed=0, precompute=not args.no_precompute)
         parties.append((ctx, pp, pk))
     torch.cuda.synchronize()
 
@@ -269,6 +269,27 @@ def run_own(args):
         ms, launches = float(t[0]), int(t[1])
     parties_total = 1 if world == 1 else N_PARTIES
     value = parties_total * (1 << n) * args.steps / (ms * 1e-3)
+
+    # ---- the same proof with the fixed-base tables of the SRS ignored (plain Pippenger on the level's points)
+    plain_ms = None
+    if not args.no_precompute:
+        for ctx, _, _ in parties:
+            ctx.msm_use_precompute(False)
+        prove_all()
+        barrier()
+        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        p0.record()
+        for _ in range(2):
+            prove_all()
+        p1.record()
+        barrier()
+        plain_ms = p0.elapsed_time(p1) / 2
+        if world > 1:
+            t = torch.tensor([plain_ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            plain_ms = float(t[0])
+        for ctx, _, _ in parties:
+            ctx.msm_use_precompute(True)
 
     # ---- end to end: the witness / selector / challenge tables start in pinned HOST memory every proof, the proof
     #      ends in host memory; the SRS (proving key, reused across proofs) stays resident
@@ -330,6 +351,10 @@ def run_own(args):
             "log2_constraints": n, "parties_per_gpu": P,
             "value_counts": "2^n constraints per party per proof, summed over the parties that ran",
             "proofs_per_s": args.steps / (ms * 1e-3),
+            "srs_fixed_base_tables": (not args.no_precompute) and "window multiples of every SRS level beside the points "
+                                     "(csrc/srs.cu), 12.4 GB per party, built at set-up like the SRS itself",
+            "value_plain_srs": parties_total * (1 << n) / (plain_ms * 1e-3) if plain_ms else None,
+            "ms_per_step_plain_srs": plain_ms,
             "l2": "one proof streams > 1.2 GB of tables and bases and ~4 GB of MSM temporaries: nothing survives in "
                   "the 126 MB L2 from one step to the next (inputs larger than L2)",
             "msm_per_proof": {"msms": (stats1["segments"] - stats0["segments"]) // args.steps,
@@ -377,6 +402,7 @@ def main():
     ap.add_argument("--ref-logn", type=int, default=15, help="--impl reference: circuit size of the bounded CPU sample")
     ap.add_argument("--ref-steps", type=int, default=2, help="--impl reference: at most this many timed proofs")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-precompute", action="store_true", help="do not build the fixed-base tables of the SRS")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

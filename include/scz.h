@@ -235,6 +235,12 @@ int32_t scz_srs_from_device_levels(scz_ctx *ctx, size_t levels, const void *cons
 int32_t scz_srs_from_host_levels(scz_ctx *ctx, size_t levels, const void *const *levels_host, const size_t *lens,
                                  scz_srs **out);
 void scz_srs_free(scz_srs *srs);
+/* Fixed-base tables for every level: the window multiples 2^(c w) * P_j next to the points, so that all windows of a
+ * scalar share one bucket set (fewer bucket additions, no Horner recombination; see csrc/srs.cu).  Same results,
+ * about 13 extra copies of the SRS in HBM.  MSMs of the commit / open family that cover a whole level use the table. */
+int32_t scz_srs_precompute(scz_ctx *ctx, scz_srs *srs);
+/* on = 0: this ctx ignores fixed-base tables (A/B measurements); default 1 */
+int32_t scz_msm_use_precompute(scz_ctx *ctx, int32_t on);
 int32_t scz_srs_info(const scz_srs *srs, size_t *levels);
 /* commit / d_local_commit (:237-243, :269-275): len must be 2^level with level < #levels (SCZ_ERR_NOT_POW2 / LEVEL_OOB) */
 int32_t scz_commit_dev(scz_ctx *ctx, const scz_srs *srs, const void *d_peval, size_t len, void *d_out_jac);

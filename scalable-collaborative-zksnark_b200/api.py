@@ -199,6 +199,10 @@ class Context:
         return {"bucket_adds": a.value, "buckets": b.value, "windows": w.value}
 
 
+    def msm_use_precompute(self, on=True):
+        """A/B switch: ignore the SRS fixed-base tables on this ctx when off"""
+        self.check(self.L.scz_msm_use_precompute(self.h, C.c_int32(1 if on else 0)))
+
     def msm_cum_stats(self):
         a, p, q, g = C.c_uint64(), C.c_uint64(), C.c_uint64(), C.c_uint64()
         self.check(self.L.scz_msm_cum_stats(self.h, C.byref(a), C.byref(p), C.byref(q), C.byref(g)))
@@ -481,6 +485,11 @@ class PolynomialCommitment:
         except Exception:
             pass
 
+    def precompute(self):
+        """build the fixed-base tables of every level (scz_srs_precompute): same results, fewer bucket additions"""
+        self.ctx.check(self.ctx.L.scz_srs_precompute(self.ctx.h, self.h))
+        return self
+
     def commit(self, peval):
         ctx = self.ctx
         pd, host = _in(ctx, peval, 4)
@@ -581,7 +590,7 @@ class PackedProvingParameters:
         self.c_commitment, self.d_commitment = c_commitment, d_commitment
 
     @classmethod
-    def new(cls, ctx, n, l, seed=0, shared_seed=None):
+    def new(cls, ctx, n, l, seed=0, shared_seed=None, precompute=False):
         """PackedProvingParameters::new(n, l, pp) (:65-157) with synthetic random tables generated ON the device
         (the reference draws them with F::rand from entropy) and random-point SRS levels (new_single / new_random,
         dpoly_comm.rs:196-233: random points, not a valid SRS).  Challenges, alpha and beta come from `shared_seed`
@@ -608,7 +617,11 @@ class PackedProvingParameters:
             return [ctx.g1_generator_mul(rand_fr(m, gen)) for m in sizes]
         csz = [max(1, (1 << i) // l) for i in range(n + 3)]                      # new_single(n + 2, pp)
         dsz = [1 << i for i in range(n + 2 - (N.bit_length() - 1) + 1)]          # new_random(n + 2, N)
-        return cls(ctx, n, l, tables, PolynomialCommitment(ctx, levels(csz)), PolynomialCommitment(ctx, levels(dsz)))
+        c_srs, d_srs = PolynomialCommitment(ctx, levels(csz)), PolynomialCommitment(ctx, levels(dsz))
+        if precompute:   # fixed-base tables: part of the proving key, built once (csrc/srs.cu)
+            c_srs.precompute()
+            d_srs.precompute()
+        return cls(ctx, n, l, tables, c_srs, d_srs)
 
     def upload(self, host_tables):
         """copy HOST tables (name -> pinned int64 tensor or numpy array) into the resident device tables, on the ctx

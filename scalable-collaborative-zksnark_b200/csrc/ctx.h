@@ -26,6 +26,7 @@ struct Ctx {
     Net *net = nullptr;
     uint64_t launches = 0;   // kernels launched by this ctx (bench.py reports it as gpu_launches)
     uint32_t msm_window_override = 0;
+    bool msm_no_precompute = false;   // ignore fixed-base tables (for A/B measurements)
     uint64_t msm_bucket_adds = 0, msm_buckets = 0, msm_windows = 0;   // statistics of the last MSM sequence
     uint64_t msm_cum_adds = 0, msm_cum_pairs = 0, msm_cum_sequences = 0, msm_cum_segments = 0;   // since ctx creation
     // optional per-kernel-class device timing (scz_prof_*): CUDA events recorded on `stream` around the launches

@@ -28,6 +28,7 @@ struct Deferred {
     std::vector<const void *> bases, scalars;
     std::vector<size_t> lens;
     std::vector<void *> outs;
+    std::vector<uint32_t> pre;                         // per job: window of the fixed-base table in `bases`, 0 = plain
     uint64_t points = 0, entries = 0;                  // queued so far (entries = sum of len * windows)
     std::vector<std::function<int32_t()>> after;       // continuations, run after the next flush
     // Leader closures queued by the continuations (one multi-job launch each instead of one launch per call):
@@ -63,7 +64,8 @@ struct Deferred {
         return SCZ_OK;
     }
     // queue out = sum_i scalars[i] * bases[i]; `out` is one Jacobian point (144 B) on the device
-    int32_t add_msm(const void *b, const void *s, size_t len, void *out);
+    // pre_c != 0: `b` is a fixed-base table built for pre_c-bit windows (srs.cu), laid out [window][point]
+    int32_t add_msm(const void *b, const void *s, size_t len, void *out, uint32_t pre_c = 0);
     void then(std::function<int32_t()> f) { after.push_back(std::move(f)); }
     void then2(std::function<int32_t()> f) { after2.push_back(std::move(f)); }
     void add_pss(const scz_pp *pp, const void *in, uint32_t batch, void *out) {

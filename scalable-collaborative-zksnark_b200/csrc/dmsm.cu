@@ -25,8 +25,9 @@ int32_t d_msm_leader(Ctx *ctx, const scz_pp *pp, const void *d_recv, size_t batc
 }
 
 // Queues the local MSMs (dmsm.rs:19-24) on `D` and registers the leader round (:29-40) as their continuation.
+// pre_c (optional): per entry, the window of a fixed-base table passed as `d_bases[k]` (srs.cu); 0 = plain bases
 int32_t d_msm_defer(Ctx *ctx, Deferred &D, const scz_pp *pp, const void *const *d_bases, const void *const *d_scalars,
-                    const size_t *lens, size_t batch, void *d_out) {
+                    const size_t *lens, size_t batch, void *d_out, const uint32_t *pre_c) {
     if (!pp) return ctx->fail(SCZ_ERR_BAD_ARG, "d_msm: null pp");
     if (batch == 0) return SCZ_OK;
     Net *net = ctx->net;
@@ -35,7 +36,7 @@ int32_t d_msm_defer(Ctx *ctx, Deferred &D, const scz_pp *pp, const void *const *
     DevTmp *c_shares = nullptr;
     SCZ_TRY(D.tmp(batch * PT, &c_shares));
     for (size_t k = 0; k < batch; k++)
-        SCZ_TRY(D.add_msm(d_bases[k], d_scalars[k], lens[k], (char *)c_shares->p + k * PT));
+        SCZ_TRY(D.add_msm(d_bases[k], d_scalars[k], lens[k], (char *)c_shares->p + k * PT, pre_c ? pre_c[k] : 0));
     Deferred *Dp = &D;
     D.then([=]() -> int32_t {
         const size_t wire = 8 + 48 * batch;
@@ -57,7 +58,7 @@ int32_t d_msm_defer(Ctx *ctx, Deferred &D, const scz_pp *pp, const void *const *
 int32_t d_msm_dev(Ctx *ctx, const scz_pp *pp, const void *const *d_bases, const void *const *d_scalars,
                   const size_t *lens, size_t batch, void *d_out) {
     Deferred D(ctx);
-    SCZ_TRY(d_msm_defer(ctx, D, pp, d_bases, d_scalars, lens, batch, d_out));
+    SCZ_TRY(d_msm_defer(ctx, D, pp, d_bases, d_scalars, lens, batch, d_out, nullptr));
     return D.run();
 }
 

@@ -104,16 +104,18 @@ __global__ void __launch_bounds__(CNT_THREADS) k_msm_recode(const MsmSeg *segs, 
     uint32_t i = g - sg.point_base;
     Fr k = fp_to_canon(fp_load<FrP>(sg.scalars, i));
     uint32_t carry = 0;
-    for (uint32_t w = 0; w < sg.W; w++) {
+    for (uint32_t w = 0; w < sg.Wd; w++) {
         int32_t d = msm_signed_digit(k.l, sg.c, w, carry);
         if (d == 0) continue;
         uint32_t mag = d < 0 ? (uint32_t)(-d) : (uint32_t)d;
-        uint32_t b = sg.bucket_base + w * sg.nb + (mag - 1);
+        // with a fixed-base table every window lands in the same bucket set and refers to the multiple 2^(c w) P_i
+        uint32_t b = sg.bucket_base + (sg.pre ? 0 : w * sg.nb) + (mag - 1);
+        uint32_t ref = sg.pre ? w * sg.len + i : i;
         if (!SCATTER) {
             atomicAdd(&counts[b], 1u);
         } else {
             uint32_t pos = atomicAdd(&cursor[b], 1u);
-            sorted[pos] = i | (d < 0 ? 0x80000000u : 0u);
+            sorted[pos] = ref | (d < 0 ? 0x80000000u : 0u);
             keys[pos] = b;
         }
     }
@@ -434,7 +436,7 @@ uint32_t msm_pick_window(size_t len) {
 }
 
 int32_t msm_g1_batched(Ctx *ctx, const void *const *d_bases, const void *const *d_scalars, const size_t *lens,
-                       size_t batch, void *d_out, void *const *d_outs) {
+                       size_t batch, void *d_out, void *const *d_outs, const uint32_t *pre_c) {
     if (batch == 0) return SCZ_OK;
     if (batch > (1u << 20)) return ctx->fail(SCZ_ERR_BAD_ARG, "msm: batch too large");
     std::vector<MsmSeg> segs(batch);
@@ -448,8 +450,11 @@ int32_t msm_g1_batched(Ctx *ctx, const void *const *d_bases, const void *const *
         s.scalars = d_scalars[k];
         s.len = (uint32_t)lens[k];
         s.point_base = (uint32_t)points;
-        s.c = ctx->msm_window_override ? ctx->msm_window_override : msm_pick_window(lens[k]);
-        s.W = msm_num_windows(s.c);
+        s.pre = pre_c && pre_c[k] ? 1 : 0;
+        s.c = s.pre ? pre_c[k] : (ctx->msm_window_override ? ctx->msm_window_override : msm_pick_window(lens[k]));
+        s.Wd = msm_num_windows(s.c);
+        s.W = s.pre ? 1 : s.Wd;
+        if ((uint64_t)s.len * s.Wd >= (1ull << 31)) return ctx->fail(SCZ_ERR_BAD_ARG, "msm: segment %zu too long", k);
         s.nb = 1u << (s.c - 1);
         s.bucket_base = (uint32_t)buckets;
         s.window_base = (uint32_t)windows;
@@ -468,7 +473,7 @@ int32_t msm_g1_batched(Ctx *ctx, const void *const *d_bases, const void *const *
         points += s.len;
         buckets += (uint64_t)s.W * s.nb;
         windows += s.W;
-        entries += (uint64_t)s.len * s.W;
+        entries += (uint64_t)s.len * s.Wd;
     }
     // node index space: level 0 of all segments, then level 1 of all segments, ...
     uint64_t lvl_first[MSM_MAX_LEVELS + 1] = {0};
@@ -591,9 +596,9 @@ int32_t msm_g1_batched(Ctx *ctx, const void *const *d_bases, const void *const *
 // One launch sequence is bounded by 32-bit entry / point indices; stay well inside and flush early otherwise.
 constexpr uint64_t DEFER_MAX_ENTRIES = 3ull << 30, DEFER_MAX_POINTS = 1ull << 30, DEFER_MAX_SEGS = 1u << 16;
 
-int32_t Deferred::add_msm(const void *b, const void *s, size_t len, void *out) {
+int32_t Deferred::add_msm(const void *b, const void *s, size_t len, void *out, uint32_t pre_c) {
     if (!out || (len && (!b || !s))) return ctx->fail(SCZ_ERR_BAD_ARG, "msm: null argument");
-    uint32_t c = ctx->msm_window_override ? ctx->msm_window_override : msm_pick_window(len);
+    uint32_t c = pre_c ? pre_c : (ctx->msm_window_override ? ctx->msm_window_override : msm_pick_window(len));
     uint64_t e = (uint64_t)len * msm_num_windows(c);
     if (!lens.empty() && (entries + e > DEFER_MAX_ENTRIES || points + len > DEFER_MAX_POINTS || lens.size() >= DEFER_MAX_SEGS))
         SCZ_TRY(flush_msm());
@@ -601,14 +606,15 @@ int32_t Deferred::add_msm(const void *b, const void *s, size_t len, void *out) {
     scalars.push_back(s);
     lens.push_back(len);
     outs.push_back(out);
+    pre.push_back(pre_c);
     entries += e;
     points += len;
     return SCZ_OK;
 }
 int32_t Deferred::flush_msm() {
     if (lens.empty()) return SCZ_OK;
-    int32_t rc = msm_g1_batched(ctx, bases.data(), scalars.data(), lens.data(), lens.size(), nullptr, outs.data());
-    bases.clear(), scalars.clear(), lens.clear(), outs.clear();
+    int32_t rc = msm_g1_batched(ctx, bases.data(), scalars.data(), lens.data(), lens.size(), nullptr, outs.data(), pre.data());
+    bases.clear(), scalars.clear(), lens.clear(), outs.clear(), pre.clear();
     entries = points = 0;
     return rc;
 }
@@ -671,6 +677,11 @@ int32_t scz_msm_g1(scz_ctx *h, const void *bases, const uint8_t *inf_mask, size_
 int32_t scz_msm_set_window(scz_ctx *h, uint32_t cbits) {
     if (!h || cbits > 20) return SCZ_ERR_BAD_ARG;
     h->c.msm_window_override = cbits;
+    return SCZ_OK;
+}
+int32_t scz_msm_use_precompute(scz_ctx *h, int32_t on) {
+    if (!h) return SCZ_ERR_BAD_ARG;
+    h->c.msm_no_precompute = on == 0;
     return SCZ_OK;
 }
 int32_t scz_msm_cum_stats(const scz_ctx *h, uint64_t *adds, uint64_t *pairs, uint64_t *sequences, uint64_t *segments) {

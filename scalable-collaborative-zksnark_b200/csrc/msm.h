@@ -15,7 +15,9 @@ struct MsmSeg {
     uint32_t len;
     uint32_t point_base;   // prefix sum of len over the batch
     uint32_t c;            // window bits
-    uint32_t W;            // windows = ceil(256 / c)
+    uint32_t W;            // bucket windows: ceil(256 / c), or 1 with a fixed-base table (all digits share one bucket set)
+    uint32_t Wd;           // digits per scalar = ceil(256 / c)
+    uint32_t pre;          // 1: `bases` is a fixed-base table [digit window][point] (srs.cu)
     uint32_t nb;           // buckets per window = 2^(c-1)
     uint32_t bucket_base;  // first global bucket of this segment (window w starts at bucket_base + w*nb)
     uint32_t window_base;  // first global window of this segment
@@ -29,8 +31,10 @@ struct MsmSeg {
 
 // d_out: batch Jacobian points (144 B each).  Asynchronous on ctx->stream.
 // d_outs (optional, host array of `batch` device pointers) sends each result to its own address instead.
+// pre_c (optional, host array): per segment the window of a fixed-base table passed as its bases, 0 = plain bases.
 int32_t msm_g1_batched(Ctx *ctx, const void *const *d_bases, const void *const *d_scalars, const size_t *lens,
-                       size_t batch, void *d_out_jac, void *const *d_outs = nullptr);
+                       size_t batch, void *d_out_jac, void *const *d_outs = nullptr, const uint32_t *pre_c = nullptr);
+uint32_t msm_pick_window_pre(size_t len);
 uint32_t msm_pick_window(size_t len);
 
 }   // namespace scz

@@ -19,6 +19,7 @@
 #include "msm.h"
 #include "net.h"
 #include "pss.h"
+#include "srs.h"
 
 namespace scz {
 
@@ -27,7 +28,7 @@ int32_t sumcheck_product_rounds(Ctx *ctx, const void *d_f, const void *d_g, size
 int32_t open_fold_rounds(Ctx *ctx, const void *d_peval, size_t len, const void *d_point, void *d_q, void *d_value);
 int32_t acc_product_tree(Ctx *ctx, const void *d_x, size_t m, void *d_tree);
 int32_t d_msm_defer(Ctx *ctx, Deferred &D, const scz_pp *pp, const void *const *d_bases, const void *const *d_scalars,
-                    const size_t *lens, size_t batch, void *d_out);
+                    const size_t *lens, size_t batch, void *d_out, const uint32_t *pre_c = nullptr);
 
 static inline size_t log2_exact(size_t v, bool *ok) {
     size_t l = 0;
@@ -211,24 +212,21 @@ int32_t d_acc_product_dev(Ctx *ctx, const void *d_x, size_t m, void *d_subtree, 
 }   // namespace scz
 
 // ---- SRS: the G1 side of PolynomialCommitment (dpoly_comm.rs:30-34) ------------------------------------------
-struct scz_srs {
-    std::vector<const void *> level;   // device pointers, packed affine
-    std::vector<size_t> len;
-    std::vector<void *> owned;
-    int device = 0;
-};
-
 namespace scz {
 
+// bases of `level_of`'s level; when the level has a fixed-base table (srs.cu) *out is the table and *pre_c its window
 static int32_t srs_level_for(Ctx *ctx, const scz_srs *srs, size_t need_len, size_t level_of, const char *who,
-                             const void **out) {
+                             const void **out, uint32_t *pre_c) {
     bool ok;
     size_t level = log2_exact(level_of, &ok);
     if (!ok) return ctx->fail(SCZ_ERR_NOT_POW2, "%s: length %zu is not a power of two", who, level_of);   // dpoly_comm.rs:240,255
     if (level >= srs->level.size()) return ctx->fail(SCZ_ERR_LEVEL_OOB, "%s: level %zu >= %zu", who, level, srs->level.size());
     if (srs->len[level] < need_len)
         return ctx->fail(SCZ_ERR_LEN_MISMATCH, "%s: level %zu holds %zu bases, %zu needed", who, level, srs->len[level], need_len);
-    *out = srs->level[level];
+    // a table is laid out [window][point] for the level's full length: usable when the MSM covers the whole level
+    bool pre = level < srs->table.size() && srs->table[level] && srs->len[level] == need_len && !ctx->msm_no_precompute;
+    *out = pre ? srs->table[level] : srs->level[level];
+    *pre_c = pre ? srs->table_c[level] : 0;
     return SCZ_OK;
 }
 
@@ -238,16 +236,19 @@ static int32_t srs_level_for(Ctx *ctx, const scz_srs *srs, size_t need_len, size
 // commit / d_local_commit: dpoly_comm.rs:237-243, 269-275
 int32_t commit_defer(Ctx *ctx, Deferred &D, const scz_srs *srs, const void *d_peval, size_t len, void *d_out) {
     const void *b = nullptr;
-    SCZ_TRY(srs_level_for(ctx, srs, len, len, "commit", &b));
-    return D.add_msm(b, d_peval, len, d_out);
+    uint32_t pre = 0;
+    SCZ_TRY(srs_level_for(ctx, srs, len, len, "commit", &b, &pre));
+    return D.add_msm(b, d_peval, len, d_out, pre);
 }
 
 // c_commit: dpoly_comm.rs:244-267
 int32_t c_commit_defer(Ctx *ctx, Deferred &D, const scz_srs *srs, const scz_pp *pp, const void *const *d_pevals,
                        const size_t *lens, size_t batch, void *d_out) {
     std::vector<const void *> bases(batch);
-    for (size_t k = 0; k < batch; k++) SCZ_TRY(srs_level_for(ctx, srs, lens[k], lens[k] * pp->l, "c_commit", &bases[k]));
-    return d_msm_defer(ctx, D, pp, bases.data(), d_pevals, lens, batch, d_out);
+    std::vector<uint32_t> pre(batch);
+    for (size_t k = 0; k < batch; k++)
+        SCZ_TRY(srs_level_for(ctx, srs, lens[k], lens[k] * pp->l, "c_commit", &bases[k], &pre[k]));
+    return d_msm_defer(ctx, D, pp, bases.data(), d_pevals, lens, batch, d_out, pre.data());
 }
 
 // d_commit: dpoly_comm.rs:276-297 -- every party ends with the sum of the N local commitments
@@ -286,8 +287,9 @@ int32_t open_defer(Ctx *ctx, Deferred &D, const scz_srs *srs, const void *d_peva
     for (size_t i = 0; i < n; i++) {
         size_t h = len >> (i + 1);
         const void *b = nullptr;
-        SCZ_TRY(srs_level_for(ctx, srs, h, h, "open", &b));
-        SCZ_TRY(D.add_msm(b, (const char *)q->p + off * 32, h, (char *)d_proofs + i * SCZ_G1_JAC_BYTES));
+        uint32_t pre = 0;
+        SCZ_TRY(srs_level_for(ctx, srs, h, h, "open", &b, &pre));
+        SCZ_TRY(D.add_msm(b, (const char *)q->p + off * 32, h, (char *)d_proofs + i * SCZ_G1_JAC_BYTES, pre));
         off += h;
     }
     return SCZ_OK;
@@ -324,8 +326,9 @@ int32_t c_open_defer(Ctx *ctx, Deferred &D, const scz_srs *srs, const scz_pp *pp
     for (size_t i = 0; i < ll; i++) {
         size_t h = l >> (i + 1);
         const void *b = nullptr;
-        SCZ_TRY(srs_level_for(ctx, srs, h, h * l, "c_open", &b));                           // local G1::msm :457
-        SCZ_TRY(D.add_msm(b, (const char *)q2->p + off * 32, h, (char *)d_proofs + (n + i) * PT));
+        uint32_t pre = 0;
+        SCZ_TRY(srs_level_for(ctx, srs, h, h * l, "c_open", &b, &pre));                     // local G1::msm :457
+        SCZ_TRY(D.add_msm(b, (const char *)q2->p + off * 32, h, (char *)d_proofs + (n + i) * PT, pre));
         off += h;
     }
     return SCZ_OK;

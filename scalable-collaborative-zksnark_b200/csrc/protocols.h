@@ -45,7 +45,7 @@ int32_t d_open_dev(Ctx *ctx, const scz_srs *srs, const void *d_peval, size_t len
 
 // deferred variants (deferred.h): MSMs are queued on D, leader rounds become continuations
 int32_t d_msm_defer(Ctx *ctx, Deferred &D, const scz_pp *pp, const void *const *d_bases, const void *const *d_scalars,
-                    const size_t *lens, size_t batch, void *d_out);
+                    const size_t *lens, size_t batch, void *d_out, const uint32_t *pre_c = nullptr);
 int32_t commit_defer(Ctx *ctx, Deferred &D, const scz_srs *srs, const void *d_peval, size_t len, void *d_out);
 int32_t c_commit_defer(Ctx *ctx, Deferred &D, const scz_srs *srs, const scz_pp *pp, const void *const *d_pevals,
                        const size_t *lens, size_t batch, void *d_out);

@@ -47,8 +47,8 @@ def _same_proof(orc, got, want, who):
         assert len(proofs) == len(oproofs) and orc.canon_g1(proofs) == orc.canon_g1(oproofs), (who, k)
 
 
-@pytest.mark.parametrize("n,l", [(4, 1), (6, 1), (6, 2)])
-def test_dhyperplonk_leader_mode(orc, n, l):
+@pytest.mark.parametrize("n,l,pre", [(4, 1, False), (6, 1, False), (6, 2, False), (6, 1, True), (7, 2, True)])
+def test_dhyperplonk_leader_mode(orc, n, l, pre):
     import scz_b200 as scz
     from oracle import hyperplonk as ohp
     N = 8 * l
@@ -60,10 +60,18 @@ def test_dhyperplonk_leader_mode(orc, n, l):
     ddev, dsrs = _make_srs(ctx, orc, rng, dsz)
     opk = ohp.random_pk(rng, n, l, N, csrs, dsrs)
     want = ohp.dhyperplonk(n, [opk], opp, orc.LEADER_SIM, N)[0]
-    pk = scz.PackedProvingParameters(ctx, n, l, _tables_for_product(opk), scz.PolynomialCommitment(ctx, cdev),
-                                     scz.PolynomialCommitment(ctx, ddev))
+    c_srs, d_srs = scz.PolynomialCommitment(ctx, cdev), scz.PolynomialCommitment(ctx, ddev)
+    if pre:   # fixed-base tables (csrc/srs.cu): same group elements
+        c_srs.precompute()
+        d_srs.precompute()
+    pk = scz.PackedProvingParameters(ctx, n, l, _tables_for_product(opk), c_srs, d_srs)
     got = scz.dhyperplonk(ctx, n, pk, pp).nested()
     _same_proof(orc, got, want, "leader")
+    if pre:
+        adds_pre = ctx.msm_cum_stats()["bucket_adds"]
+        ctx.msm_use_precompute(False)
+        _same_proof(orc, scz.dhyperplonk(ctx, n, pk, pp).nested(), want, "leader, tables ignored")
+        assert ctx.msm_cum_stats()["bucket_adds"] - adds_pre != adds_pre    # the two runs really took different paths
     # shape of the reference's return value at l = 1 (dhyperplonk.rs:567-570)
     (gp, gc), (wp, wc, wo) = got
     s = N.bit_length() - 1

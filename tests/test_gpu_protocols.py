@@ -252,6 +252,39 @@ def test_d_commit_d_open_leader_mode(orc, ctx):
     assert up > 0 and down > 0
 
 
+def test_fixed_base_tables_same_results(orc, ctx):
+    """scz_srs_precompute: commit / open / d_commit / d_open / c_open over levels of 2^0 .. 2^11 points (window sizes
+    4 .. 11 bits, 24 .. 64 windows), an infinity base included, against the oracle and against the plain path"""
+    import scz_b200 as scz
+    rng = np.random.default_rng(525)
+    nv = 11
+    dev, host = _levels(ctx, orc, rng, [1 << i for i in range(nv + 1)])
+    dev[5][3] = 0                                   # a point at infinity inside a level
+    host[5][3] = 0
+    host[5][3, 12] = 1
+    pc, osrs = scz.PolynomialCommitment(ctx, dev).precompute(), orc.Srs.from_levels(host)
+    plain = scz.PolynomialCommitment(ctx, dev)
+    pp, opp = scz.PackedSharingParams(ctx, 1), orc.pp_new(1)
+    for lv in (0, 1, 5, 8, nv):
+        p = orc.random_fr(rng, 1 << lv)
+        want = orc.canon_g1(orc.commit(osrs, p))
+        assert orc.canon_g1(pc.commit(p)) == want == orc.canon_g1(plain.commit(p)), lv
+    p = orc.random_fr(rng, 1 << nv)
+    p[7] = 0                                        # zero scalar
+    p[9] = orc.fr_from_ints([tw.R_MOD - 1])[0]      # largest scalar: every signed digit carries
+    u = orc.random_fr(rng, nv + 3)
+    val, proofs = pc.open(p, u)
+    oval, oproofs = orc.open_(osrs, p, u)
+    assert np.array_equal(val, oval) and orc.canon_g1(proofs) == orc.canon_g1(oproofs)
+    assert orc.canon_g1(pc.d_commit(p)) == orc.canon_g1(orc.d_commit([osrs], orc.LEADER_SIM, 8, [p]))
+    val, proofs = pc.d_open(p, u)
+    oval, oproofs = orc.d_open([osrs], orc.LEADER_SIM, 8, [p], u)
+    assert np.array_equal(val, oval) and orc.canon_g1(proofs) == orc.canon_g1(oproofs)
+    val, proofs = pc.c_open(pp, p, u)
+    oval, oproofs = orc.c_open([osrs], opp, orc.LEADER_SIM, [p], u)
+    assert np.array_equal(val[0], oval[0]) and orc.canon_g1(proofs) == orc.canon_g1(oproofs[0])
+
+
 # ------------------------------------------------------------------------------------------- parties mode
 def test_parties_mode_local_test_net(orc):
     """N = 8 parties (l = 1), one ctx each, star collectives through LocalTestNet: d_msm, pss2ss,

@@ -14,7 +14,8 @@ reps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 ctx = scz.Context(device=0, n_parties=8)
 pp = scz.PackedSharingParams(ctx, 1)
 t0 = time.time()
-pk = scz.PackedProvingParameters.new(ctx, n, 1, seed=1)
+pre = (sys.argv[3] if len(sys.argv) > 3 else 'pre') == 'pre'
+pk = scz.PackedProvingParameters.new(ctx, n, 1, seed=1, precompute=pre)
 ctx.sync()
 print(f"setup {time.time() - t0:.2f} s, {torch.cuda.memory_allocated() / 2**30:.2f} GiB", flush=True)
 for r in range(reps):
