@@ -4,7 +4,7 @@ import os
 import re
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libscz.so")
+LIB_PATH = os.environ.get("SCZ_LIB") or os.path.join(_HERE, "libscz.so")   # SCZ_LIB: dev override (kernel variants)
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "scz.h")
 
 _LIB = None

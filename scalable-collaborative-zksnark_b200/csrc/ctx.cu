@@ -55,14 +55,31 @@ void Ctx::prof_clear() {
     prof_recs.clear();
 }
 
+// dst[j] = src for j < copies, 16-byte words (every payload of the path is a multiple of 16 B)
+__global__ void k_replicate16(uint4 *dst, const uint4 *src, uint32_t words, uint32_t copies) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= words) return;
+    uint4 v = src[i];
+    for (uint32_t j = 0; j < copies; j++) dst[(size_t)j * words + i] = v;
+}
+static int32_t replicate(Ctx *ctx, void *d_recv, const void *d_send, size_t bytes, uint32_t copies) {
+    if (bytes % 16 == 0 && bytes / 16 < (1u << 31) && ((uintptr_t)d_recv % 16) == 0 && ((uintptr_t)d_send % 16) == 0) {
+        uint32_t words = (uint32_t)(bytes / 16);
+        if (!words) return SCZ_OK;
+        k_replicate16<<<ceil_div_u32(words, 256), 256, 0, ctx->stream>>>((uint4 *)d_recv, (const uint4 *)d_send, words, copies);
+        SCZ_LAUNCH_CHECK(ctx);
+        return SCZ_OK;
+    }
+    for (uint32_t j = 0; j < copies; j++)
+        SCZ_CUDA(ctx, cudaMemcpyAsync((char *)d_recv + (size_t)j * bytes, d_send, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+    return SCZ_OK;
+}
+
 // ------------------------------------------------------------------ leader simulator
 // serializing_net.rs:147-167: the leader "receives" n_parties clones of its own message
 int32_t LeaderSimNet::gather(Ctx *ctx, const void *d_send, void *d_recv, size_t bytes, size_t wire) {
     download += wire * (n_parties - 1);
-    for (uint32_t j = 0; j < n_parties; j++)
-        SCZ_CUDA(ctx, cudaMemcpyAsync((char *)d_recv + (size_t)j * bytes, d_send, bytes, cudaMemcpyDeviceToDevice,
-                                      ctx->stream));
-    return SCZ_OK;
+    return replicate(ctx, d_recv, d_send, bytes, n_parties);
 }
 // serializing_net.rs:192-215: counts the N-1 outgoing messages, keeps element 0
 int32_t LeaderSimNet::scatter(Ctx *ctx, const void *d_send, void *d_recv, size_t bytes, size_t wire) {
@@ -73,10 +90,7 @@ int32_t LeaderSimNet::scatter(Ctx *ctx, const void *d_send, void *d_recv, size_t
 // hyperplonk/src/dhyperplonk.rs:271-294 without `comm`: the own vector is used N times (:289-293)
 int32_t LeaderSimNet::all_gather(Ctx *ctx, const void *d_send, void *d_recv, size_t bytes, size_t wire) {
     upload += wire * (n_parties - 1);
-    for (uint32_t j = 0; j < n_parties; j++)
-        SCZ_CUDA(ctx, cudaMemcpyAsync((char *)d_recv + (size_t)j * bytes, d_send, bytes, cudaMemcpyDeviceToDevice,
-                                      ctx->stream));
-    return SCZ_OK;
+    return replicate(ctx, d_recv, d_send, bytes, n_parties);
 }
 int32_t LeaderSimNet::sync(Ctx *) { return SCZ_OK; }
 

@@ -205,7 +205,10 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_add(uint32_t *out, const 
 // Chunk t covers entries [t*T, (t+1)*T).  A bucket that lies inside one chunk is written to
 // buckets[b]; a bucket cut by chunk boundaries leaves a TAIL piece in the chunk where it starts
 // (parts[2t+1]) and HEAD pieces in the following chunks (parts[2u]); k_msm_fixup* sums them.
-__global__ void __launch_bounds__(ACC_THREADS) k_msm_accumulate(const MsmSeg *segs, int K, const uint32_t *E_ptr,
+#ifndef ACC_MIN_BLOCKS
+#define ACC_MIN_BLOCKS 1
+#endif
+__global__ void __launch_bounds__(ACC_THREADS, ACC_MIN_BLOCKS) k_msm_accumulate(const MsmSeg *segs, int K, const uint32_t *E_ptr,
                                                                  uint32_t logT, const uint32_t *keys,
                                                                  const uint32_t *sorted, const uint32_t *counts,
                                                                  const uint32_t *cursor, void *buckets, void *parts) {

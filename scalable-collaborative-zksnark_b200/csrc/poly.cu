@@ -20,7 +20,7 @@
 namespace scz {
 
 constexpr int PL_THREADS = 256;
-constexpr uint32_t TAIL_PAIRS = 2048;   // rounds with at most this many pairs finish inside one CTA
+constexpr uint32_t TAIL_PAIRS = 256;    // rounds with at most this many pairs finish inside one CTA (one pair per thread)
 
 struct Fr3 {
     Fr a, b, c;
