@@ -225,6 +225,12 @@ int32_t scz_c_sumcheck_product_dev(scz_ctx *ctx, const scz_pp *pp, const void *d
  * triples in d_out, every other party *count = 0 (the reference returns an empty Vec, :507-509) */
 int32_t scz_d_sumcheck_product_dev(scz_ctx *ctx, const void *d_f, const void *d_g, size_t len, const void *d_challenge,
                                    void *d_out, size_t *count);
+/* single-MLE variants (round message = (sum lo, sum hi), 64 B): sumcheck (:6-26) n + 1 pairs, the last is (0, f(r));
+ * c_sumcheck (:92-146) n + log2(l) + 1 pairs; d_sumcheck (:287-357) leader n + log2(N) pairs, others *count = 0 */
+int32_t scz_sumcheck_dev(scz_ctx *ctx, const void *d_f, size_t len, const void *d_challenge, void *d_out);
+int32_t scz_c_sumcheck_dev(scz_ctx *ctx, const scz_pp *pp, const void *d_f, size_t len, const void *d_challenge,
+                           void *d_out);
+int32_t scz_d_sumcheck_dev(scz_ctx *ctx, const void *d_f, size_t len, const void *d_challenge, void *d_out, size_t *count);
 /* d_acc_product (dacc_product.rs:365-414): d_subtree 2m entries; on the leader d_leader_tree 2N entries */
 int32_t scz_d_acc_product_dev(scz_ctx *ctx, const void *d_x, size_t m, void *d_subtree, void *d_leader_tree);
 
@@ -296,6 +302,16 @@ int32_t scz_dhyperplonk_sizes(size_t n, size_t l, size_t n_parties, size_t *trip
 int32_t scz_dhyperplonk_dev(scz_ctx *ctx, size_t n, const scz_hp_pk *pk, const scz_pp *pp, void *d_triples,
                             size_t triples_cap, void *d_points, size_t points_cap, void *d_values, size_t values_cap,
                             scz_hp_item *items, size_t items_cap, size_t *n_items);
+/* dhyperplonk_data_parallel (dhyperplonk.rs:573-960): the same schedule, but `s` of step 2.a is an input instead of an
+ * exchange (:603): pk->local_s holds 4gc/l entries.  Same outputs layout. */
+int32_t scz_dhyperplonk_data_parallel_dev(scz_ctx *ctx, size_t n, const scz_hp_pk *pk, const scz_pp *pp, void *d_triples,
+                                          size_t triples_cap, void *d_points, size_t points_cap, void *d_values,
+                                          size_t values_cap, scz_hp_item *items, size_t items_cap, size_t *n_items);
+/* dpermcheck (dhyperplonk.rs:962-1247): the wiring identity (step 2) alone; only SCZ_HP_WIRING_* items come back.
+ * The gate-side fields of pk (a/b/c_evals, I, S1, S2, eq, challenge, *_p selectors) are not read but must be non-null. */
+int32_t scz_dpermcheck_dev(scz_ctx *ctx, size_t n, const scz_hp_pk *pk, const scz_pp *pp, void *d_triples, size_t triples_cap,
+                           void *d_points, size_t points_cap, void *d_values, size_t values_cap, scz_hp_item *items,
+                           size_t items_cap, size_t *n_items);
 
 #ifdef __cplusplus
 }

@@ -48,13 +48,17 @@ def _rep(x, m):
     return np.repeat(np.ascontiguousarray(x, dtype=np.uint64).reshape(1, 4), m, axis=0)
 
 
-def dhyperplonk(n, pks, pp, mode, N, algo="ark"):
+def dhyperplonk(n, pks, pp, mode, N, algo="ark", variant="full"):
     """pks: one pk per party (PARTIES: N of them, LEADER_SIM: the leader's alone).
     Returns one result dict per party:
       gate_identity_proofs       list of (cnt, 3, 4)
       gate_identity_commitments  list of (com (1,18), (value (1,4), proofs (k,18)))
       wiring_proofs, wiring_commits, wiring_opens    as the reference's tuple (dhyperplonk.rs:567-570);
-    entries a non-leader gets empty from d_sumcheck_product / d_open are empty arrays there."""
+    entries a non-leader gets empty from d_sumcheck_product / d_open are empty arrays there.
+    variant: "full" = dhyperplonk (:159-571); "data_parallel" = dhyperplonk_data_parallel (:573-960: pk["local_s"] is the
+    whole s, 4 * 2^n / l entries, :603; no exchange); "permcheck" = dpermcheck (:962-1247: step 2 alone)."""
+    assert variant in ("full", "data_parallel", "permcheck")
+    gate = variant != "permcheck"
     P = N if mode == orc.PARTIES else 1
     assert len(pks) == P
     csrs = [pk["c_commitment"] for pk in pks]
@@ -94,24 +98,28 @@ def dhyperplonk(n, pks, pp, mode, N, algo="ark"):
             res[j][key].append(per_party[j])
 
     # Step 1: commit (:196-217)
-    com_a, com_b, com_c = c_commit1("a_evals"), c_commit1("b_evals"), c_commit1("c_evals")
-    com_I, com_S1, com_S2 = d_commit(col("I_p")), d_commit(col("S1_p")), d_commit(col("S2_p"))
+    if gate:
+        com_a, com_b, com_c = c_commit1("a_evals"), c_commit1("b_evals"), c_commit1("c_evals")
+        com_I, com_S1, com_S2 = d_commit(col("I_p")), d_commit(col("S1_p")), d_commit(col("S2_p"))
 
     # Step 3: gate identity (:222-260)
     ch = pks[0]["challenge"]
-    push("gate_identity_proofs", c_sumcheck(col("eq"), col("S1"), ch))                              # :230-231
-    sum_ab = [orc.fr_add(pk["a_evals"], pk["b_evals"]) for pk in pks]                               # :233-238
-    push("gate_identity_proofs", c_sumcheck(col("S1"), sum_ab, ch))                                 # :240-241
-    push("gate_identity_proofs", c_sumcheck(col("eq"), col("S2"), ch))                              # :243-244
-    push("gate_identity_proofs", c_sumcheck(col("a_evals"), col("b_evals"), ch))                    # :245-246
-    push("gate_identity_proofs", c_sumcheck(col("S2"), col("a_evals"), ch))                         # :247-248
-    sum_ci = [orc.fr_sub(pk["I"], pk["c_evals"]) for pk in pks]                                     # :251-256  -c + I
-    push("gate_identity_proofs", c_sumcheck(col("eq"), sum_ci, ch))                                 # :258-259
+    if gate:
+        push("gate_identity_proofs", c_sumcheck(col("eq"), col("S1"), ch))                          # :230-231
+        sum_ab = [orc.fr_add(pk["a_evals"], pk["b_evals"]) for pk in pks]                           # :233-238
+        push("gate_identity_proofs", c_sumcheck(col("S1"), sum_ab, ch))                             # :240-241
+        push("gate_identity_proofs", c_sumcheck(col("eq"), col("S2"), ch))                          # :243-244
+        push("gate_identity_proofs", c_sumcheck(col("a_evals"), col("b_evals"), ch))                # :245-246
+        push("gate_identity_proofs", c_sumcheck(col("S2"), col("a_evals"), ch))                     # :247-248
+        sum_ci = [orc.fr_sub(pk["I"], pk["c_evals"]) for pk in pks]                                 # :251-256  -c + I
+        push("gate_identity_proofs", c_sumcheck(col("eq"), sum_ci, ch))                             # :258-259
 
     # Step 2: wiring identity (:263-513)
     # 2.a (:270-294): N hub rounds, hub i sends its local_s to everyone -> s = local_s^(0) | ... | local_s^(N-1);
     # without `comm` the own vector is appended N times (:289-293)
-    if mode == orc.PARTIES:
+    if variant == "data_parallel":                       # s drawn locally by every party (:603)
+        s = col("local_s")
+    elif mode == orc.PARTIES:
         s_all = np.concatenate([pk["local_s"] for pk in pks])
         s = [s_all for _ in range(P)]
     else:
@@ -176,6 +184,8 @@ def dhyperplonk(n, pks, pp, mode, N, algo="ark"):
     res[0]["wiring_proofs"].append(orc.sumcheck_product(lvx0, lvx1, pt))
 
     # Open (:517-554)
+    if not gate:
+        return res
     for com, name in ((com_a, "a_evals"), (com_b, "b_evals"), (com_c, "c_evals")):
         op = c_open(col(name), ch)
         push("gate_identity_commitments", [(com[j], op[j]) for j in range(P)])
@@ -185,11 +195,14 @@ def dhyperplonk(n, pks, pp, mode, N, algo="ark"):
     return res
 
 
-def random_pk(rng, n, l, N, srs_c=None, srs_d=None, shared=None):
+def random_pk(rng, n, l, N, srs_c=None, srs_d=None, shared=None, data_parallel=False):
     """PackedProvingParameters::new with numpy randomness (tables only; SRS passed in).  `shared`: a pk whose
     public values (challenges, alpha, beta) are reused -- all parties must agree on them."""
     pk = {}
-    for name, ln in table_sizes(n, l, N).items():
+    sizes = table_sizes(n, l, N)
+    if data_parallel:
+        sizes["local_s"] = (1 << n) * 4 // l             # dhyperplonk_data_parallel: the whole s (:603)
+    for name, ln in sizes.items():
         pk[name] = orc.random_fr(rng, ln)
     if shared is not None:
         for name in ("challenge", "challenge_r1", "challenge_r2", "alpha", "beta"):

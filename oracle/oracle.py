@@ -39,7 +39,7 @@ def lib():
         _LIB = C.CDLL(so)
         _LIB.orc_init()
         for name in ("orc_sumcheck_product", "orc_c_sumcheck_product", "orc_d_sumcheck_product", "orc_c_open",
-                     "orc_d_open"):
+                     "orc_d_open", "orc_sumcheck", "orc_c_sumcheck", "orc_d_sumcheck"):
             getattr(_LIB, name).restype = C.c_size_t
     return _LIB
 
@@ -317,6 +317,37 @@ def sumcheck_product(f, g, challenge):
     n = len(f).bit_length() - 1
     out = np.zeros((n + 1, 3, 4), dtype=np.uint64)
     lib().orc_sumcheck_product(_p(f), _p(g), C.c_size_t(len(f)), _p(ch), _p(out))
+    return out
+
+
+def sumcheck(f, challenge):
+    """dsumcheck.rs:6-26 -> (n + 1, 2, 4)"""
+    f, ch = _u64(f, 4), _u64(challenge, 4)
+    n = len(f).bit_length() - 1
+    out = np.zeros((n + 1, 2, 4), dtype=np.uint64)
+    lib().orc_sumcheck(_p(f), C.c_size_t(len(f)), _p(ch), _p(out))
+    return out
+
+
+def c_sumcheck(pp, mode, f, challenge):
+    """dsumcheck.rs:92-146 -> (P, n + log2 l + 1, 2, 4)"""
+    P = _nparties(pp, mode)
+    fs = [_u64(x, 4) for x in f]
+    assert len(fs) == P
+    ch = _u64(challenge, 4)
+    cnt = (len(fs[0]).bit_length() - 1) + (pp.l.bit_length() - 1) + 1
+    out = np.zeros((P, cnt, 2, 4), dtype=np.uint64)
+    lib().orc_c_sumcheck(C.byref(pp), mode, _ptr_array(fs), C.c_size_t(len(fs[0])), _p(ch), _p(out))
+    return out
+
+
+def d_sumcheck(mode, nparties, f, challenge):
+    """dsumcheck.rs:287-357 -> the leader's (n + log2 N, 2, 4)"""
+    fs = [_u64(x, 4) for x in f]
+    ch = _u64(challenge, 4)
+    cnt = (len(fs[0]).bit_length() - 1) + (nparties.bit_length() - 1)
+    out = np.zeros((cnt, 2, 4), dtype=np.uint64)
+    lib().orc_d_sumcheck(mode, C.c_size_t(nparties), _ptr_array(fs), C.c_size_t(len(fs[0])), _p(ch), _p(out))
     return out
 
 

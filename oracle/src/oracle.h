@@ -87,6 +87,11 @@ void orc_d_msm(const orc_pp_t *pp, int mode, size_t batch, const size_t *lens,
 
 /* ---- sumcheck.c: dist-primitive/src/dsumcheck.rs ---- */
 typedef struct { fr_t a, b, c; } fr3_t;
+typedef struct { fr_t a, b; } fr2_t;
+/* single-MLE variants (dsumcheck.rs:6-26, 92-146, 287-357); same conventions as the product ones below */
+size_t orc_sumcheck(const fr_t *f, size_t len, const fr_t *challenge, fr2_t *out);
+size_t orc_c_sumcheck(const orc_pp_t *pp, int mode, const fr_t *const *f, size_t len, const fr_t *challenge, fr2_t *out);
+size_t orc_d_sumcheck(int mode, size_t nparties, const fr_t *const *f, size_t len, const fr_t *challenge, fr2_t *out);
 /* returns number of triples written (n+1) */
 size_t orc_sumcheck_product(const fr_t *f, const fr_t *g, size_t len, const fr_t *challenge, fr3_t *out);
 /* c_sumcheck_product, one party's view in LEADER_SIM; in PARTIES f/g are [party] pointers, out [party][n+logl+1] */

@@ -103,6 +103,88 @@ size_t orc_sumcheck_product(const fr_t *f, const fr_t *g, size_t len, const fr_t
     return n + 1;
 }
 
+/* ---- single-MLE sumchecks: dsumcheck.rs:6-26, 92-146, 287-357 ---- */
+static void sum_round(fr_t *f, size_t len, const fr_t *ch, fr2_t *res) {
+    size_t h = len / 2;
+    fr_t one, omc, t, u, s0, s1;
+    fr_set_one(&one);
+    fr_sub(&omc, &one, ch);                   /* F::ONE - challenge[i] */
+    fr_set_zero(&s0);
+    fr_set_zero(&s1);
+    for (size_t i = 0; i < h; i++) {
+        fr_add(&s0, &s0, &f[i]);
+        fr_add(&s1, &s1, &f[h + i]);
+    }
+    res->a = s0;
+    res->b = s1;
+    for (size_t i = 0; i < h; i++) {
+        fr_mul(&t, &f[i], &omc);
+        fr_mul(&u, &f[h + i], ch);
+        fr_add(&f[i], &t, &u);                /* a*(1-r) + b*r */
+    }
+}
+/* dsumcheck.rs:6-26 */
+size_t orc_sumcheck(const fr_t *f, size_t len, const fr_t *challenge, fr2_t *out) {
+    size_t n = log2sz(len);
+    fr_t *ff = dupv(f, len);
+    for (size_t i = 0; i < n; i++) sum_round(ff, len >> i, &challenge[i], &out[i]);
+    fr_set_zero(&out[n].a);
+    out[n].b = ff[0];
+    free(ff);
+    return n + 1;
+}
+/* dsumcheck.rs:92-146.  out is [P][n + log2(l) + 1]. */
+size_t orc_c_sumcheck(const orc_pp_t *pp, int mode, const fr_t *const *f, size_t len, const fr_t *challenge, fr2_t *out) {
+    size_t N = pp->n, P = mode == ORC_PARTIES ? N : 1, l = pp->l;
+    size_t n = log2sz(len), ll = log2sz(l), cnt = n + ll + 1;
+    fr_t *last = malloc(P * sizeof *last);
+    for (size_t p = 0; p < P; p++) {                                   /* Phase 1 :105-121 */
+        fr_t *ff = dupv(f[p], len);
+        for (size_t i = 0; i < n; i++) sum_round(ff, len >> i, &challenge[i], &out[p * cnt + i]);
+        last[p] = ff[0];
+        free(ff);
+    }
+    fr_t *f2 = malloc(P * l * sizeof *f2);
+    orc_pss2ss(pp, mode, last, f2);                                    /* :124 */
+    for (size_t p = 0; p < P; p++) {
+        fr_t *ff = f2 + p * l;
+        for (size_t i = 0; i < ll; i++) sum_round(ff, l >> i, &challenge[i], &out[p * cnt + n + i]);   /* :127-141 */
+        fr_set_zero(&out[p * cnt + n + ll].a);
+        out[p * cnt + n + ll].b = ff[0];                               /* :143 */
+    }
+    free(last);
+    free(f2);
+    return cnt;
+}
+/* dsumcheck.rs:287-357; only the leader's result (workers return an empty Vec, :351-353) */
+size_t orc_d_sumcheck(int mode, size_t nparties, const fr_t *const *f, size_t len, const fr_t *challenge, fr2_t *out) {
+    size_t N = nparties, P = mode == ORC_PARTIES ? N : 1;
+    size_t n = log2sz(len), s = log2sz(N);
+    fr2_t *local = malloc(P * (n + 1) * sizeof *local);
+    for (size_t p = 0; p < P; p++) {
+        fr_t *ff = dupv(f[p], len);
+        for (size_t i = 0; i < n; i++) sum_round(ff, len >> i, &challenge[i], &local[p * (n + 1) + i]);
+        fr_set_zero(&local[p * (n + 1) + n].a);
+        local[p * (n + 1) + n].b = ff[0];                              /* :318 */
+        free(ff);
+    }
+    fr_t *lf = malloc(N * sizeof *lf);
+    for (size_t i = 0; i < n; i++) {                                   /* :323-331 */
+        fr_set_zero(&out[i].a);
+        fr_set_zero(&out[i].b);
+        for (size_t j = 0; j < N; j++) {
+            const fr2_t *x = &local[(mode == ORC_PARTIES ? j : 0) * (n + 1) + i];
+            fr_add(&out[i].a, &out[i].a, &x->a);
+            fr_add(&out[i].b, &out[i].b, &x->b);
+        }
+    }
+    for (size_t j = 0; j < N; j++) lf[j] = local[(mode == ORC_PARTIES ? j : 0) * (n + 1) + n].b;   /* :332 */
+    for (size_t i = 0; i < s; i++) sum_round(lf, N >> i, &challenge[n + i], &out[n + i]);           /* :334-347 */
+    free(local);
+    free(lf);
+    return n + s;
+}
+
 /* unpack.rs:72-97 */
 void orc_pss2ss(const orc_pp_t *pp, int mode, const fr_t *share_per_party, fr_t *out /* [P][l] */) {
     size_t N = pp->n, P = mode == ORC_PARTIES ? N : 1, l = pp->l;

@@ -24,10 +24,15 @@ from .api import (  # noqa: F401
     fr_pointwise,
     pss2ss,
     sumcheck_product,
+    sumcheck,
+    c_sumcheck,
+    d_sumcheck,
     sumcheck_rounds,
     msm,
     PackedProvingParameters,
     HyperPlonkProof,
     dhyperplonk,
+    dhyperplonk_data_parallel,
+    dpermcheck,
     hp_table_sizes,
 )

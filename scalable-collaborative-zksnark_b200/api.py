@@ -447,6 +447,37 @@ def d_sumcheck_product(ctx, f, g, challenge):
     return _out(ctx, out[: cnt.value * 3].reshape(cnt.value, 3, 4), host)
 
 
+def sumcheck(ctx, f, challenge):
+    """dsumcheck.rs:6-26 -> (n + 1, 2, 4)"""
+    fd, host = _in(ctx, f, 4)
+    cd, _ = _in(ctx, challenge, 4)
+    n = _log2(len(fd))
+    out = ctx.empty((n + 1) * 2, 4)
+    ctx.check(ctx.L.scz_sumcheck_dev(ctx.h, _vp(fd), C.c_size_t(len(fd)), _vp(cd), _vp(out)))
+    return _out(ctx, out.reshape(n + 1, 2, 4), host)
+
+
+def c_sumcheck(ctx, pp, f, challenge):
+    """dsumcheck.rs:92-146 -> (n + log2 l + 1, 2, 4)"""
+    fd, host = _in(ctx, f, 4)
+    cd, _ = _in(ctx, challenge, 4)
+    cnt = _log2(len(fd)) + _log2(pp.l) + 1
+    out = ctx.empty(cnt * 2, 4)
+    ctx.check(ctx.L.scz_c_sumcheck_dev(ctx.h, pp.h, _vp(fd), C.c_size_t(len(fd)), _vp(cd), _vp(out)))
+    return _out(ctx, out.reshape(cnt, 2, 4), host)
+
+
+def d_sumcheck(ctx, f, challenge):
+    """dsumcheck.rs:287-357 -> leader: (n + log2 N, 2, 4); every other party: an empty array (:351-353)"""
+    fd, host = _in(ctx, f, 4)
+    cd, _ = _in(ctx, challenge, 4)
+    cap = _log2(len(fd)) + _log2(ctx.n_parties)
+    out = ctx.empty(max(cap, 1) * 2, 4)
+    cnt = C.c_size_t()
+    ctx.check(ctx.L.scz_d_sumcheck_dev(ctx.h, _vp(fd), C.c_size_t(len(fd)), _vp(cd), _vp(out), C.byref(cnt)))
+    return _out(ctx, out[: cnt.value * 2].reshape(cnt.value, 2, 4), host)
+
+
 def pss2ss(ctx, pp, share):
     """unpack.rs:72-97: one share -> Vec<F> of length l"""
     sd, host = _in(ctx, share, 4)
@@ -577,9 +608,11 @@ class PackedProvingParameters:
     (:188-190), here explicit inputs.  `tables`: dict name -> (len, 4) array (numpy or CUDA tensor), names and
     lengths as hp_table_sizes; c_commitment / d_commitment: PolynomialCommitment (:53-54)."""
 
-    def __init__(self, ctx, n, l, tables, c_commitment, d_commitment):
+    def __init__(self, ctx, n, l, tables, c_commitment, d_commitment, data_parallel=False):
         self.ctx, self.n, self.l = ctx, n, l
         want = hp_table_sizes(n, l, ctx.n_parties)
+        if data_parallel:   # dhyperplonk_data_parallel draws the whole s locally (dhyperplonk.rs:603)
+            want["local_s"] = (1 << n) * 4 // l
         self.t = {}
         for name, ln in want.items():
             x = tables[name]
@@ -688,7 +721,7 @@ class HyperPlonkProof:
         return (gp, gc), (wp, wc, wo)
 
 
-def dhyperplonk(ctx, n, pk, pp):
+def dhyperplonk(ctx, n, pk, pp, _entry="scz_dhyperplonk_dev"):
     """hyperplonk/src/dhyperplonk.rs:159-571 (after net.sync(), :193) -> HyperPlonkProof.  Asynchronous on the
     ctx stream in leader mode; call ctx.sync() or .nested() to wait."""
     L = ctx.L
@@ -701,12 +734,23 @@ def dhyperplonk(ctx, n, pk, pp):
     items = (HpItem * ni.value)()
     cnt = C.c_size_t()
     cpk = pk.c_struct()
-    ctx.check(L.scz_dhyperplonk_dev(ctx.h, C.c_size_t(n), C.byref(cpk), pp.h, _vp(tri), nt, _vp(pts), npt, _vp(val), nv,
-                                    items, ni, C.byref(cnt)))
+    ctx.check(getattr(L, _entry)(ctx.h, C.c_size_t(n), C.byref(cpk), pp.h, _vp(tri), nt, _vp(pts), npt, _vp(val), nv,
+                                 items, ni, C.byref(cnt)))
     return HyperPlonkProof(ctx, tri, pts, val, list(items[: cnt.value]))
+
+
+def dhyperplonk_data_parallel(ctx, n, pk, pp):
+    """dhyperplonk.rs:573-960: pk.t['local_s'] holds the whole `s` (4 * 2^n / l entries, :603); no step-2.a exchange"""
+    return dhyperplonk(ctx, n, pk, pp, "scz_dhyperplonk_data_parallel_dev")
+
+
+def dpermcheck(ctx, n, pk, pp):
+    """dhyperplonk.rs:962-1247: the wiring identity alone; .nested() returns ((), (proofs, commits, opens)) with empty gate lists"""
+    return dhyperplonk(ctx, n, pk, pp, "scz_dpermcheck_dev")
 
 
 __all__ = ["Context", "PackedSharingParams", "msm", "msm_batched", "d_msm", "d_msm_leader", "NetVTable",
            "fr_pointwise", "fix_variable", "acc_product_tree", "d_acc_product", "sumcheck_rounds", "sumcheck_product",
-           "c_sumcheck_product", "d_sumcheck_product", "pss2ss", "degree_reduce", "PolynomialCommitment",
-           "PackedProvingParameters", "HyperPlonkProof", "dhyperplonk", "hp_table_sizes"]
+           "c_sumcheck_product", "d_sumcheck_product", "sumcheck", "c_sumcheck", "d_sumcheck", "pss2ss", "degree_reduce", "PolynomialCommitment",
+           "PackedProvingParameters", "HyperPlonkProof", "dhyperplonk", "dhyperplonk_data_parallel", "dpermcheck",
+           "hp_table_sizes"]

@@ -45,7 +45,14 @@ struct HpOut {
     }
 };
 
-int32_t dhyperplonk_dev(Ctx *ctx, size_t n, const scz_hp_pk *pk, const scz_pp *pp, HpOut &o) {
+// variant: the three provers of hyperplonk/src/dhyperplonk.rs share one schedule
+//   HP_FULL           dhyperplonk                (:159-571)
+//   HP_DATA_PARALLEL  dhyperplonk_data_parallel  (:573-960): `s` is an input (pk->local_s holds 4gc/l entries, :603)
+//                     instead of the all-gather of step 2.a -- nothing else differs
+//   HP_PERMCHECK      dpermcheck                 (:962-1247): step 2 alone; returns the wiring triple only
+enum HpVariant { HP_FULL = 0, HP_DATA_PARALLEL = 1, HP_PERMCHECK = 2 };
+
+int32_t dhyperplonk_dev(Ctx *ctx, size_t n, const scz_hp_pk *pk, const scz_pp *pp, HpOut &o, HpVariant variant) {
     Net *net = ctx->net;
     const size_t N = net->n_parties, l = pp->l, ll = ilog2(l), s = ilog2(N);
     if (N != pp->n) return ctx->fail(SCZ_ERR_BAD_ARG, "dhyperplonk: %zu parties but pp.n = %zu", N, pp->n);
@@ -66,7 +73,7 @@ int32_t dhyperplonk_dev(Ctx *ctx, size_t n, const scz_hp_pk *pk, const scz_pp *p
     // ---- Step 1: commit (:196-217).  The six commitments leave with the openings at the very end (:518-553).
     DevTmp coms(ctx);
     SCZ_TRY(coms.alloc(6 * PT));
-    {
+    if (variant != HP_PERMCHECK) {
         const void *tabs[3] = {pk->a_evals, pk->b_evals, pk->c_evals};
         for (int k = 0; k < 3; k++)   // three separate c_commit calls, one leader round each (:198-212)
             SCZ_TRY(c_commit_defer(ctx, D, pk->c_commitment, pp, &tabs[k], &share_len, 1, (char *)coms.p + k * PT));
@@ -76,7 +83,7 @@ int32_t dhyperplonk_dev(Ctx *ctx, size_t n, const scz_hp_pk *pk, const scz_pp *p
     }
 
     // ---- Step 3: gate identity (:222-260): six collaborative product sumchecks on 2^n/l shares
-    {
+    if (variant != HP_PERMCHECK) {
         DevTmp tmp(ctx);
         SCZ_TRY(tmp.alloc(share_len * 32));
         auto c_sum = [&](const void *f, const void *g) -> int32_t {
@@ -130,7 +137,10 @@ int32_t dhyperplonk_dev(Ctx *ctx, size_t n, const scz_hp_pk *pk, const scz_pp *p
         // s = local_s^(0) | ... | local_s^(N-1).  The leader simulator repeats the own vector N times (:289-293).
         DevTmp sv(ctx);
         SCZ_TRY(sv.alloc(v_len * 32));
-        SCZ_TRY(net->all_gather(ctx, pk->local_s, sv.p, ls_len * 32, 8 + 32 * ls_len));
+        if (variant == HP_DATA_PARALLEL)   // s drawn locally (:603): no exchange
+            SCZ_CUDA(ctx, cudaMemcpyAsync(sv.p, pk->local_s, v_len * 32, cudaMemcpyDeviceToDevice, st));
+        else
+            SCZ_TRY(net->all_gather(ctx, pk->local_s, sv.p, ls_len * 32, 8 + 32 * ls_len));
         SCZ_TRY(d_commit(pk->local_s_p, hl));                                               // 2.b :297-302
         {                                                                                    // 2.c :304
             size_t cnt = ilog2(v_len) + ll + 1;
@@ -209,7 +219,7 @@ int32_t dhyperplonk_dev(Ctx *ctx, size_t n, const scz_hp_pk *pk, const scz_pp *p
     }
 
     // ---- Open (:517-554)
-    {
+    if (variant != HP_PERMCHECK) {
         void *coms_p = coms.p;
         auto copy_com = [&](void *dst, int k) {   // the commitments of step 1 exist once D has run their leader rounds
             Deferred *Dp = &D;
@@ -256,9 +266,9 @@ int32_t scz_dhyperplonk_sizes(size_t n, size_t l, size_t n_parties, size_t *trip
     return SCZ_OK;
 }
 
-int32_t scz_dhyperplonk_dev(scz_ctx *h, size_t n, const scz_hp_pk *pk, const scz_pp *pp, void *d_triples, size_t triples_cap,
-                            void *d_points, size_t points_cap, void *d_values, size_t values_cap, scz_hp_item *items,
-                            size_t items_cap, size_t *n_items) {
+static int32_t hp_entry(scz_ctx *h, size_t n, const scz_hp_pk *pk, const scz_pp *pp, void *d_triples, size_t triples_cap,
+                        void *d_points, size_t points_cap, void *d_values, size_t values_cap, scz_hp_item *items,
+                        size_t items_cap, size_t *n_items, HpVariant variant) {
     if (!h) return SCZ_ERR_BAD_ARG;
     Ctx *c = &h->c;
     if (!pk || !pp || !d_triples || !d_points || !d_values || !items || !n_items)
@@ -274,9 +284,28 @@ int32_t scz_dhyperplonk_dev(scz_ctx *h, size_t n, const scz_hp_pk *pk, const scz
     o.tri = (char *)d_triples, o.pts = (char *)d_points, o.val = (char *)d_values;
     o.tri_cap = triples_cap, o.pts_cap = points_cap, o.val_cap = values_cap, o.items_cap = items_cap;
     o.items = items;
-    int32_t rc = dhyperplonk_dev(c, n, pk, pp, o);
+    int32_t rc = dhyperplonk_dev(c, n, pk, pp, o, variant);
     *n_items = o.items_n;
     return rc;
+}
+
+int32_t scz_dhyperplonk_dev(scz_ctx *h, size_t n, const scz_hp_pk *pk, const scz_pp *pp, void *d_triples, size_t triples_cap,
+                            void *d_points, size_t points_cap, void *d_values, size_t values_cap, scz_hp_item *items,
+                            size_t items_cap, size_t *n_items) {
+    return hp_entry(h, n, pk, pp, d_triples, triples_cap, d_points, points_cap, d_values, values_cap, items, items_cap, n_items,
+                    HP_FULL);
+}
+int32_t scz_dhyperplonk_data_parallel_dev(scz_ctx *h, size_t n, const scz_hp_pk *pk, const scz_pp *pp, void *d_triples,
+                                          size_t triples_cap, void *d_points, size_t points_cap, void *d_values,
+                                          size_t values_cap, scz_hp_item *items, size_t items_cap, size_t *n_items) {
+    return hp_entry(h, n, pk, pp, d_triples, triples_cap, d_points, points_cap, d_values, values_cap, items, items_cap, n_items,
+                    HP_DATA_PARALLEL);
+}
+int32_t scz_dpermcheck_dev(scz_ctx *h, size_t n, const scz_hp_pk *pk, const scz_pp *pp, void *d_triples, size_t triples_cap,
+                           void *d_points, size_t points_cap, void *d_values, size_t values_cap, scz_hp_item *items,
+                           size_t items_cap, size_t *n_items) {
+    return hp_entry(h, n, pk, pp, d_triples, triples_cap, d_points, points_cap, d_values, values_cap, items, items_cap, n_items,
+                    HP_PERMCHECK);
 }
 
 }   // extern "C"

@@ -156,6 +156,77 @@ __global__ void __launch_bounds__(PL_THREADS) k_sumcheck_tail(void *f, void *g, 
     }
 }
 
+// ---- single-MLE sumcheck (dsumcheck.rs:6-26; the same loop at :107-121, :128-141, :303-316, :335-347): the round message
+// is (sum lo, sum hi), the fold is lo + r (hi - lo).  One Fr product per pair against 64 B read + 32 B written.
+struct Fr2 {
+    Fr a, b;
+};
+__global__ void __launch_bounds__(PL_THREADS) k_sum_round(const void *f_in, void *f_out, uint32_t h, const void *challenge,
+                                                           Fr3 *partial, uint32_t *ticket, Fr2 *out) {
+    __shared__ Fr sh[3 * PL_THREADS / 32];
+    __shared__ bool last;
+    const Fr r = fp_load<FrP>(challenge, 0);
+    Fr s0 = Fr::zero(), s1 = Fr::zero(), s2 = Fr::zero();
+    for (uint32_t i = blockIdx.x * PL_THREADS + threadIdx.x; i < h; i += gridDim.x * PL_THREADS) {
+        Fr f0 = fp_load_rw<FrP>(f_in, i), f1 = fp_load_rw<FrP>(f_in, (size_t)h + i);
+        s0 = fp_add(s0, f0);
+        s1 = fp_add(s1, f1);
+        fp_store<FrP>(f_out, i, fp_add(f0, fp_mul(r, fp_sub(f1, f0))));
+    }
+    block_sum3<PL_THREADS>(s0, s1, s2, sh);
+    if (threadIdx.x == 0) {
+        partial[blockIdx.x].a = s0;
+        partial[blockIdx.x].b = s1;
+        __threadfence();
+        last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    s0 = Fr::zero(), s1 = Fr::zero();
+    for (uint32_t b = threadIdx.x; b < gridDim.x; b += PL_THREADS) {
+        const uint4 *p = reinterpret_cast<const uint4 *>(&partial[b]);   // written by other CTAs: read through L2
+        Fr2 t;
+        uint32_t *w = &t.a.l[0];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            uint4 v = __ldcg(p + k);
+            w[4 * k] = v.x, w[4 * k + 1] = v.y, w[4 * k + 2] = v.z, w[4 * k + 3] = v.w;
+        }
+        s0 = fp_add(s0, t.a);
+        s1 = fp_add(s1, t.b);
+    }
+    block_sum3<PL_THREADS>(s0, s1, s2, sh);
+    if (threadIdx.x == 0) {
+        out->a = s0;
+        out->b = s1;
+        *ticket = 0;
+    }
+}
+// all remaining rounds (h <= TAIL_PAIRS) in one CTA, in place on f
+__global__ void __launch_bounds__(PL_THREADS) k_sum_tail(void *f, uint32_t h, const void *challenge, Fr2 *out) {
+    __shared__ Fr sh[3 * PL_THREADS / 32];
+    for (uint32_t round = 0; h >= 1; h >>= 1, round++) {
+        const Fr r = fp_load<FrP>(challenge, round);
+        Fr s0 = Fr::zero(), s1 = Fr::zero(), s2 = Fr::zero(), fo = Fr::zero();
+        uint32_t i = threadIdx.x;
+        if (i < h) {
+            Fr f0 = fp_load_rw<FrP>(f, i), f1 = fp_load_rw<FrP>(f, (size_t)h + i);
+            s0 = f0;
+            s1 = f1;
+            fo = fp_add(f0, fp_mul(r, fp_sub(f1, f0)));
+        }
+        __syncthreads();
+        if (i < h) fp_store<FrP>(f, i, fo);
+        block_sum3<PL_THREADS>(s0, s1, s2, sh);
+        if (threadIdx.x == 0) {
+            out[round].a = s0;
+            out[round].b = s1;
+        }
+        __syncthreads();
+    }
+}
+
 // PST open fold round: q[j] = hi - lo ; cur[j] = lo + u * q[j]   (= (1-u) lo + u hi)
 __global__ void __launch_bounds__(PL_THREADS) k_open_fold(const void *in, void *cur_out, void *q, uint32_t h,
                                                            const void *point) {
@@ -356,6 +427,41 @@ int32_t sumcheck_product_rounds(Ctx *ctx, const void *d_f, const void *d_g, size
     SCZ_LAUNCH_CHECK(ctx);
     SCZ_CUDA(ctx, cudaMemcpyAsync(d_last, tf.p, 32, cudaMemcpyDeviceToDevice, st));
     SCZ_CUDA(ctx, cudaMemcpyAsync((char *)d_last + 32, tg.p, 32, cudaMemcpyDeviceToDevice, st));
+    return SCZ_OK;
+}
+
+// n = log2(len) rounds of the single-MLE sumcheck: n pairs to d_out, the fully folded value to d_last (32 B)
+int32_t sumcheck_rounds(Ctx *ctx, const void *d_f, size_t len, const void *d_challenge, void *d_out, void *d_last) {
+    if (len == 0 || (len & (len - 1))) return ctx->fail(SCZ_ERR_NOT_POW2, "sumcheck: table length %zu is not a power of two", len);
+    if (len >= (1ull << 32)) return ctx->fail(SCZ_ERR_BAD_ARG, "sumcheck: table too long");
+    static_assert(TAIL_PAIRS == PL_THREADS, "k_sum_tail handles one pair per thread");
+    ProfScope ps(ctx, SCZ_K_SUMCHECK);
+    cudaStream_t st = ctx->stream;
+    if (len == 1) {
+        SCZ_CUDA(ctx, cudaMemcpyAsync(d_last, d_f, 32, cudaMemcpyDeviceToDevice, st));
+        return SCZ_OK;
+    }
+    size_t h = len / 2, round = 0;
+    DevTmp tf(ctx), partial(ctx), ticket(ctx);
+    SCZ_TRY(tf.alloc((h > TAIL_PAIRS ? h : len) * 32));
+    SCZ_TRY(partial.alloc((size_t)grid_for(ctx, h) * sizeof(Fr3)));
+    SCZ_TRY(ticket.alloc(4));
+    SCZ_CUDA(ctx, cudaMemsetAsync(ticket.p, 0, 4, st));
+    const void *fi = d_f;
+    while (h > TAIL_PAIRS) {
+        k_sum_round<<<grid_for(ctx, h), PL_THREADS, 0, st>>>(fi, tf.p, (uint32_t)h, (const char *)d_challenge + round * 32,
+                                                             partial.as<Fr3>(), ticket.as<uint32_t>(),
+                                                             reinterpret_cast<Fr2 *>(d_out) + round);
+        SCZ_LAUNCH_CHECK(ctx);
+        fi = tf.p;
+        h >>= 1;
+        round++;
+    }
+    if (fi == d_f) SCZ_CUDA(ctx, cudaMemcpyAsync(tf.p, d_f, len * 32, cudaMemcpyDeviceToDevice, st));
+    k_sum_tail<<<1, PL_THREADS, 0, st>>>(tf.p, (uint32_t)h, (const char *)d_challenge + round * 32,
+                                         reinterpret_cast<Fr2 *>(d_out) + round);
+    SCZ_LAUNCH_CHECK(ctx);
+    SCZ_CUDA(ctx, cudaMemcpyAsync(d_last, tf.p, 32, cudaMemcpyDeviceToDevice, st));
     return SCZ_OK;
 }
 

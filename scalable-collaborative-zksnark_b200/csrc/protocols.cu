@@ -26,6 +26,7 @@ namespace scz {
 int32_t sumcheck_product_rounds(Ctx *ctx, const void *d_f, const void *d_g, size_t len, const void *d_challenge,
                                 void *d_out, void *d_last);
 int32_t open_fold_rounds(Ctx *ctx, const void *d_peval, size_t len, const void *d_point, void *d_q, void *d_value);
+int32_t sumcheck_rounds(Ctx *ctx, const void *d_f, size_t len, const void *d_challenge, void *d_out, void *d_last);
 int32_t acc_product_tree(Ctx *ctx, const void *d_x, size_t m, void *d_tree);
 int32_t d_msm_defer(Ctx *ctx, Deferred &D, const scz_pp *pp, const void *const *d_bases, const void *const *d_scalars,
                     const size_t *lens, size_t batch, void *d_out, const uint32_t *pre_c = nullptr);
@@ -192,6 +193,88 @@ int32_t d_sumcheck_product_dev(Ctx *ctx, const void *d_f, const void *d_g, size_
     SCZ_LAUNCH_CHECK(ctx);
     SCZ_TRY(sumcheck_product_rounds(ctx, lf.p, lg.p, N, (const char *)d_challenge + n * 32, (char *)d_out + n * 96,
                                     last2.p));                                            // :452-504
+    if (count) *count = n + s;
+    return SCZ_OK;
+}
+
+// ---- single-MLE sumchecks: dsumcheck.rs:6-26, 92-146, 287-357 (round message = (sum lo, sum hi), 64 B) --------------
+// out = (0, v)
+__global__ void k_final_pair(const void *last, void *out) {
+    if (threadIdx.x) return;
+    fp_store<FrP>(out, 0, Fr::zero());
+    fp_store<FrP>(out, 1, fp_load_rw<FrP>(last, 0));
+}
+// leader of d_sumcheck (:321-333): recv is [party][n+1] pairs.  out[i] = sum over parties of round i; lf[j] = recv[j][n].b
+__global__ void k_dsum1_leader(const void *recv, uint32_t N, uint32_t n, void *out, void *lf) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < 2 * n) {
+        uint32_t i = t / 2, comp = t % 2;
+        Fr acc = Fr::zero();
+        for (uint32_t j = 0; j < N; j++) acc = fp_add(acc, fp_load_rw<FrP>(recv, ((size_t)j * (n + 1) + i) * 2 + comp));
+        fp_store<FrP>(out, (size_t)i * 2 + comp, acc);
+    } else if (t < 2 * n + N) {
+        uint32_t j = t - 2 * n;
+        fp_store<FrP>(lf, j, fp_load_rw<FrP>(recv, ((size_t)j * (n + 1) + n) * 2 + 1));
+    }
+}
+// sumcheck (:6-26) -> n + 1 pairs, the last is (0, f(challenge))
+int32_t sumcheck_dev(Ctx *ctx, const void *d_f, size_t len, const void *d_challenge, void *d_out) {
+    bool ok;
+    size_t n = log2_exact(len, &ok);
+    if (!ok) return ctx->fail(SCZ_ERR_NOT_POW2, "sumcheck: length %zu is not a power of two", len);
+    DevTmp last(ctx);
+    SCZ_TRY(last.alloc(32));
+    SCZ_TRY(sumcheck_rounds(ctx, d_f, len, d_challenge, d_out, last.p));
+    k_final_pair<<<1, 32, 0, ctx->stream>>>(last.p, (char *)d_out + n * 64);
+    SCZ_LAUNCH_CHECK(ctx);
+    return SCZ_OK;
+}
+// c_sumcheck (:92-146) -> n + log2(l) + 1 pairs; phase 2 re-uses challenge[0..log2 l) (:129) like the product variant
+int32_t c_sumcheck_dev(Ctx *ctx, const scz_pp *pp, const void *d_f, size_t len, const void *d_challenge, void *d_out) {
+    bool ok;
+    size_t n = log2_exact(len, &ok);
+    if (!ok) return ctx->fail(SCZ_ERR_NOT_POW2, "c_sumcheck: length %zu is not a power of two", len);
+    size_t l = pp->l, ll = log2_exact(l, &ok);
+    DevTmp last(ctx), f2(ctx), last2(ctx);
+    SCZ_TRY(last.alloc(32));
+    SCZ_TRY(f2.alloc(l * 32));
+    SCZ_TRY(last2.alloc(32));
+    SCZ_TRY(sumcheck_rounds(ctx, d_f, len, d_challenge, d_out, last.p));                  // Phase 1 :105-121
+    SCZ_TRY(pss2ss_dev(ctx, pp, last.p, f2.p));                                           // :124
+    SCZ_TRY(sumcheck_rounds(ctx, f2.p, l, d_challenge, (char *)d_out + n * 64, last2.p)); // Phase 2 :127-141
+    k_final_pair<<<1, 32, 0, ctx->stream>>>(last2.p, (char *)d_out + (n + ll) * 64);      // :143
+    SCZ_LAUNCH_CHECK(ctx);
+    return SCZ_OK;
+}
+// d_sumcheck (:287-357).  Leader: n + log2(N) pairs, others: none (:351-353)
+int32_t d_sumcheck_dev(Ctx *ctx, const void *d_f, size_t len, const void *d_challenge, void *d_out, size_t *count) {
+    bool ok;
+    size_t n = log2_exact(len, &ok);
+    if (!ok) return ctx->fail(SCZ_ERR_NOT_POW2, "d_sumcheck: length %zu is not a power of two", len);
+    Net *net = ctx->net;
+    const size_t N = net->n_parties;
+    size_t s = log2_exact(N, &ok);
+    if (!ok) return ctx->fail(SCZ_ERR_NOT_POW2, "d_sumcheck: %zu parties is not a power of two", N);
+    DevTmp local(ctx), last(ctx), recv(ctx), lf(ctx), last2(ctx);
+    SCZ_TRY(local.alloc((n + 1) * 64));
+    SCZ_TRY(last.alloc(32));
+    SCZ_TRY(sumcheck_rounds(ctx, d_f, len, d_challenge, local.p, last.p));                // :301-316
+    k_final_pair<<<1, 32, 0, ctx->stream>>>(last.p, (char *)local.p + n * 64);            // :318
+    SCZ_LAUNCH_CHECK(ctx);
+    if (net->is_leader()) {
+        SCZ_TRY(recv.alloc(N * (n + 1) * 64));
+        SCZ_TRY(lf.alloc(N * 32));
+        SCZ_TRY(last2.alloc(32));
+    }
+    SCZ_TRY(net->gather(ctx, local.p, recv.p, (n + 1) * 64, 8 + 64 * (n + 1)));            // :320-322
+    if (!net->is_leader()) {
+        if (count) *count = 0;
+        return SCZ_OK;
+    }
+    uint32_t work = (uint32_t)(2 * n + N);
+    k_dsum1_leader<<<ceil_div_u32(work, 64), 64, 0, ctx->stream>>>(recv.p, (uint32_t)N, (uint32_t)n, d_out, lf.p);
+    SCZ_LAUNCH_CHECK(ctx);
+    SCZ_TRY(sumcheck_rounds(ctx, lf.p, N, (const char *)d_challenge + n * 32, (char *)d_out + n * 64, last2.p));   // :334-347
     if (count) *count = n + s;
     return SCZ_OK;
 }
@@ -525,6 +608,18 @@ int32_t scz_d_sumcheck_product_dev(scz_ctx *h, const void *d_f, const void *d_g,
                                    void *d_out, size_t *count) {
     NEED(h, d_f && d_g && d_challenge && (d_out || h->c.net->party_id != 0), "d_sumcheck_product");
     return d_sumcheck_product_dev(&h->c, d_f, d_g, len, d_challenge, d_out, count);
+}
+int32_t scz_sumcheck_dev(scz_ctx *h, const void *d_f, size_t len, const void *d_challenge, void *d_out) {
+    NEED(h, d_f && d_out && (len <= 1 || d_challenge), "sumcheck");
+    return sumcheck_dev(&h->c, d_f, len, d_challenge, d_out);
+}
+int32_t scz_c_sumcheck_dev(scz_ctx *h, const scz_pp *pp, const void *d_f, size_t len, const void *d_challenge, void *d_out) {
+    NEED(h, pp && d_f && d_out && d_challenge, "c_sumcheck");
+    return c_sumcheck_dev(&h->c, pp, d_f, len, d_challenge, d_out);
+}
+int32_t scz_d_sumcheck_dev(scz_ctx *h, const void *d_f, size_t len, const void *d_challenge, void *d_out, size_t *count) {
+    NEED(h, d_f && d_challenge && (d_out || h->c.net->party_id != 0), "d_sumcheck");
+    return d_sumcheck_dev(&h->c, d_f, len, d_challenge, d_out, count);
 }
 int32_t scz_d_acc_product_dev(scz_ctx *h, const void *d_x, size_t m, void *d_subtree, void *d_leader_tree) {
     NEED(h, d_x && d_subtree && (d_leader_tree || h->c.net->party_id != 0), "d_acc_product");

@@ -13,6 +13,7 @@ namespace scz {
 // poly.cu
 int32_t sumcheck_product_rounds(Ctx *ctx, const void *d_f, const void *d_g, size_t len, const void *d_challenge,
                                 void *d_out, void *d_last);
+int32_t sumcheck_rounds(Ctx *ctx, const void *d_f, size_t len, const void *d_challenge, void *d_out, void *d_last);
 int32_t open_fold_rounds(Ctx *ctx, const void *d_peval, size_t len, const void *d_point, void *d_q, void *d_value);
 int32_t acc_product_tree(Ctx *ctx, const void *d_x, size_t m, void *d_tree);
 int32_t fr_pointwise(Ctx *c, int32_t mode, const void *d_a, const void *d_b, const void *d_k, void *d_out, size_t n);
@@ -30,6 +31,9 @@ int32_t c_sumcheck_product_dev(Ctx *ctx, const scz_pp *pp, const void *d_f, cons
                                const void *d_challenge, void *d_out);
 int32_t d_sumcheck_product_dev(Ctx *ctx, const void *d_f, const void *d_g, size_t len, const void *d_challenge,
                                void *d_out, size_t *count);
+int32_t sumcheck_dev(Ctx *ctx, const void *d_f, size_t len, const void *d_challenge, void *d_out);
+int32_t c_sumcheck_dev(Ctx *ctx, const scz_pp *pp, const void *d_f, size_t len, const void *d_challenge, void *d_out);
+int32_t d_sumcheck_dev(Ctx *ctx, const void *d_f, size_t len, const void *d_challenge, void *d_out, size_t *count);
 int32_t d_acc_product_dev(Ctx *ctx, const void *d_x, size_t m, void *d_subtree, void *d_leader_tree);
 int32_t commit_dev(Ctx *ctx, const scz_srs *srs, const void *d_peval, size_t len, void *d_out);
 int32_t c_commit_dev(Ctx *ctx, const scz_srs *srs, const scz_pp *pp, const void *const *d_pevals, const size_t *lens,

@@ -147,3 +147,29 @@ def test_dhyperplonk_parties_mode(orc):
     (gp, gc), (wp, wc, wo) = res[3][0]
     assert all(len(t) == 0 for t in wp[1:]) and len(wp) == 1 + 3 + 3 * (n - 3)     # workers: empty d_ proofs, no leader tail
     seed_ctx.close()
+
+
+@pytest.mark.parametrize("variant", ["data_parallel", "permcheck"])
+def test_prover_variants_leader_mode(orc, variant):
+    """dhyperplonk_data_parallel (dhyperplonk.rs:573-960) and dpermcheck (:962-1247): same schedule, s as an input /
+    step 2 alone"""
+    import scz_b200 as scz
+    from oracle import hyperplonk as ohp
+    n, l, N = 5, 1, 8
+    rng = np.random.default_rng(660)
+    ctx = scz.Context(device=0, n_parties=N)
+    pp, opp = scz.PackedSharingParams(ctx, l), orc.pp_new(l)
+    csz, dsz = ohp.srs_level_sizes(n, l, N)
+    cdev, csrs = _make_srs(ctx, orc, rng, csz)
+    ddev, dsrs = _make_srs(ctx, orc, rng, dsz)
+    dp = variant == "data_parallel"
+    opk = ohp.random_pk(rng, n, l, N, csrs, dsrs, data_parallel=dp)
+    want = ohp.dhyperplonk(n, [opk], opp, orc.LEADER_SIM, N, variant=variant)[0]
+    pk = scz.PackedProvingParameters(ctx, n, l, _tables_for_product(opk), scz.PolynomialCommitment(ctx, cdev),
+                                     scz.PolynomialCommitment(ctx, ddev), data_parallel=dp)
+    fn = scz.dhyperplonk_data_parallel if dp else scz.dpermcheck
+    got = fn(ctx, n, pk, pp).nested()
+    _same_proof(orc, got, want, variant)
+    if not dp:
+        assert got[0] == ([], []) and len(got[1][0]) == 1 + 3 + 3 * (n - 3) + 3
+    ctx.close()

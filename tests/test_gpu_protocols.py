@@ -177,6 +177,19 @@ def test_d_sumcheck_product_leader_mode(orc, ctx, logn):
     assert np.array_equal(got, orc.d_sumcheck_product(orc.LEADER_SIM, 8, [f], [g], ch))
 
 
+@pytest.mark.parametrize("logn", [0, 1, 3, 8, 9, 13, 16])
+def test_single_mle_sumcheck_family(orc, ctx, logn):
+    """sumcheck / c_sumcheck / d_sumcheck (dsumcheck.rs:6-26, 92-146, 287-357), leader mode, against the oracle"""
+    import scz_b200 as scz
+    rng = np.random.default_rng(485 + logn)
+    n = 1 << logn
+    f, ch = orc.random_fr(rng, n), orc.random_fr(rng, logn + 3)
+    assert np.array_equal(scz.sumcheck(ctx, f, ch), orc.sumcheck(f, ch))
+    pp, opp = scz.PackedSharingParams(ctx, 1), orc.pp_new(1)
+    assert np.array_equal(scz.c_sumcheck(ctx, pp, f, ch), orc.c_sumcheck(opp, orc.LEADER_SIM, [f], ch)[0])
+    assert np.array_equal(scz.d_sumcheck(ctx, f, ch), orc.d_sumcheck(orc.LEADER_SIM, 8, [f], ch))
+
+
 def test_d_acc_product_leader_mode(orc, ctx):
     import scz_b200 as scz
     rng = np.random.default_rng(490)
@@ -312,6 +325,8 @@ def test_parties_mode_local_test_net(orc):
     want_p2s = orc.pss2ss(opp, orc.PARTIES, x1)
     want_cs = orc.c_sumcheck_product(opp, orc.PARTIES, f, g, ch)
     want_ds = orc.d_sumcheck_product(orc.PARTIES, N, f, g, ch)
+    want_cs1 = orc.c_sumcheck(opp, orc.PARTIES, f, ch)
+    want_ds1 = orc.d_sumcheck(orc.PARTIES, N, g, ch)
     want_co = orc.c_open(srs_host, opp, orc.PARTIES, f, ch)
     want_dc = orc.d_commit(srs_host, orc.PARTIES, N, g)
     want_do = orc.d_open(srs_host, orc.PARTIES, N, g, ch)
@@ -326,6 +341,8 @@ def test_parties_mode_local_test_net(orc):
         r["p2s"] = scz.pss2ss(c, pp, x1[j:j + 1])
         r["cs"] = scz.c_sumcheck_product(c, pp, f[j], g[j], ch)
         r["ds"] = scz.d_sumcheck_product(c, f[j], g[j], ch)
+        r["cs1"] = scz.c_sumcheck(c, pp, f[j], ch)
+        r["ds1"] = scz.d_sumcheck(c, g[j], ch)
         r["co"] = pc.c_open(pp, f[j], ch)
         r["dc"] = pc.d_commit(g[j])
         r["do"] = pc.d_open(g[j], ch)
@@ -341,6 +358,8 @@ def test_parties_mode_local_test_net(orc):
         assert orc.canon_g1(r["msm"]) == orc.canon_g1(want_msm[j]), j
         assert np.array_equal(r["p2s"], want_p2s[j]), j
         assert np.array_equal(r["cs"], want_cs[j]), j
+        assert np.array_equal(r["cs1"], want_cs1[j]), j
+        assert np.array_equal(r["ds1"], want_ds1) if j == 0 else len(r["ds1"]) == 0, j
         if j == 0:
             assert np.array_equal(r["ds"], want_ds)
             assert np.array_equal(r["do"][0], want_do[0]) and orc.canon_g1(r["do"][1]) == orc.canon_g1(want_do[1])

@@ -296,3 +296,42 @@ def test_fix_variable(orc):                    # mle.rs:88-104
     assert got == v
     a = orc.fr_to_ints(orc.fix_variable(orc.fr_from_ints(e), orc.fr_from_ints([0, 1])))
     assert a == e[8:16]
+
+
+def test_single_mle_sumcheck_properties(orc):
+    """sumcheck (dsumcheck.rs:6-26): round i's two sums add up to the previous round's polynomial at the challenge,
+    round 0 sums to the table total, the final pair is (0, f(challenge)) = (0, fix_variable(f, challenge));
+    d_sumcheck over 8 slices of a table equals sumcheck of the whole table with the slice index as the top variables
+    (the reference's dsumcheck_test, :617-645, re-expressed)"""
+    import numpy as np
+    from oracle import py_twin as tw
+    R = tw.R_MOD
+    rng = np.random.default_rng(77)
+    nv = 7
+    f = orc.random_fr(rng, 1 << nv)
+    ch = orc.random_fr(rng, nv)
+    out = orc.sumcheck(f, ch)
+    fi, ci = orc.fr_to_ints(f), orc.fr_to_ints(ch)
+    pairs = [[orc.fr_to_ints(out[i, j:j + 1])[0] for j in range(2)] for i in range(nv + 1)]
+    assert (pairs[0][0] + pairs[0][1]) % R == sum(fi) % R
+    for i in range(nv):
+        a, b = pairs[i]
+        val = (a * (1 - ci[i]) + b * ci[i]) % R
+        nxt = (pairs[i + 1][0] + pairs[i + 1][1]) % R
+        assert val == nxt, i
+    assert pairs[nv][0] == 0 and pairs[nv][1] == orc.fr_to_ints(orc.fix_variable(f, ch))[0]
+    # distributed: party j holds slice j (the top three variables select the party)
+    N, s = 8, 3
+    slices = [f[j * (len(f) // N):(j + 1) * (len(f) // N)] for j in range(N)]
+    ch_d = np.concatenate([ch[s:], ch[:s]])          # local rounds use challenge[..n], the leader challenge[n..n+s]
+    lead = orc.d_sumcheck(orc.PARTIES, N, slices, ch_d)
+    assert len(lead) == nv
+    # the first local round's sums over all parties = sums over (x_top3 free, x_3 = 0 / 1)
+    lo = sum(sum(orc.fr_to_ints(sl[:len(sl) // 2])) for sl in slices) % R
+    hi = sum(sum(orc.fr_to_ints(sl[len(sl) // 2:])) for sl in slices) % R
+    assert orc.fr_to_ints(lead[0, 0:1])[0] == lo and orc.fr_to_ints(lead[0, 1:2])[0] == hi
+    # last leader round folds to the full evaluation: a*(1-r) + b*r at the final challenge = f(point)
+    a, b = orc.fr_to_ints(lead[nv - 1, 0:1])[0], orc.fr_to_ints(lead[nv - 1, 1:2])[0]
+    r_last = orc.fr_to_ints(ch_d[nv - 1:nv])[0]
+    point = np.concatenate([ch_d[nv - s:], ch_d[:nv - s]])   # top variables first for fix_variable
+    assert (a * (1 - r_last) + b * r_last) % R == orc.fr_to_ints(orc.fix_variable(f, point))[0]
