@@ -86,7 +86,7 @@ SCZ_HD G1X g1x_double(const G1X &p) {
     Fq m = fp_add(fp_dbl(xx), xx);
     G1X r;
     r.x = fp_sub(fp_sub(fp_sqr(m), s), s);
-    r.y = fp_sub(fp_mul(m, fp_sub(s, r.x)), fp_mul(w, p.y));
+    r.y = fp_dot2_sub(m, fp_sub(s, r.x), w, p.y);          // m (s - x3) - w y, one reduction
     r.zz = fp_mul(v, p.zz);
     r.zzz = fp_mul(w, p.zzz);
     return r;
@@ -101,7 +101,7 @@ SCZ_HD G1X g1x_double_affine(const Fq &x, const Fq &y) {
     Fq m = fp_add(fp_dbl(xx), xx);
     G1X r;
     r.x = fp_sub(fp_sub(fp_sqr(m), s), s);
-    r.y = fp_sub(fp_mul(m, fp_sub(s, r.x)), fp_mul(w, y));
+    r.y = fp_dot2_sub(m, fp_sub(s, r.x), w, y);
     r.zz = v;
     r.zzz = w;
     return r;
@@ -128,7 +128,7 @@ SCZ_HD void g1x_add_affine(G1X &acc, const Fq &x2, const Fq &y2) {
     Fq ppp = fp_mul(p, pp);
     Fq q = fp_mul(acc.x, pp);
     Fq x3 = fp_sub(fp_sub(fp_sub(fp_sqr(r), ppp), q), q);
-    Fq y3 = fp_sub(fp_mul(r, fp_sub(q, x3)), fp_mul(acc.y, ppp));
+    Fq y3 = fp_dot2_sub(r, fp_sub(q, x3), acc.y, ppp);      // r (q - x3) - y1 ppp, one reduction
     acc.x = x3;
     acc.y = y3;
     acc.zz = fp_mul(acc.zz, pp);
@@ -158,7 +158,7 @@ SCZ_HD G1X g1x_add(const G1X &a, const G1X &b) {
     Fq q = fp_mul(u1, pp);
     G1X o;
     o.x = fp_sub(fp_sub(fp_sub(fp_sqr(r), ppp), q), q);
-    o.y = fp_sub(fp_mul(r, fp_sub(q, o.x)), fp_mul(s1, ppp));
+    o.y = fp_dot2_sub(r, fp_sub(q, o.x), s1, ppp);
     o.zz = fp_mul(fp_mul(a.zz, b.zz), pp);
     o.zzz = fp_mul(fp_mul(a.zzz, b.zzz), ppp);
     return o;

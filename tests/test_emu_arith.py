@@ -46,6 +46,26 @@ def test_field_ops(orc, emu):
             assert np.array_equal(out, ref(a, b)), (name, op)
 
 
+def test_fq_dot2_sub(orc, emu):
+    """a*b - c*d with one shared Montgomery reduction (field.cuh fp_dot2_sub): the Y coordinate of every G1 formula"""
+    rng = np.random.default_rng(102)
+    rnd = lambda n: orc.fq_from_ints([int.from_bytes(rng.bytes(64), "little") for _ in range(n)])   # noqa: E731
+    e = _edge(orc, tw.P_MOD, orc.fq_from_ints, 0)
+    k = len(e)
+    cols = [np.concatenate([rnd(2000), e[(np.arange(k ** 2) // (k ** s)) % k][: k * k]]) for s in (0, 1, 0, 1)]
+    cols[2] = np.concatenate([rnd(2000), np.roll(e, 3, axis=0)[np.arange(k * k) % k]])
+    cols[3] = np.concatenate([rnd(2000), np.roll(e, 5, axis=0)[(np.arange(k * k) // k) % k]])
+    a, b, c, d = cols
+    out = np.zeros_like(a)
+    emu.emu_fq_dot2_sub(_p(a), _p(b), _p(c), _p(d), _p(out), C.c_size_t(len(a)))
+    assert np.array_equal(out, orc.fq_sub(orc.fq_mul(a, b), orc.fq_mul(c, d)))
+    # worst case for the accumulator bound: all four operands p - 1
+    m = orc.fq_from_ints([tw.P_MOD - 1] * 4)
+    o1 = np.zeros_like(m)
+    emu.emu_fq_dot2_sub(_p(m), _p(m), _p(orc.fq_from_ints([1] * 4)), _p(m), _p(o1), C.c_size_t(4))
+    assert np.array_equal(o1, orc.fq_sub(orc.fq_mul(m, m), orc.fq_mul(orc.fq_from_ints([1] * 4), m)))
+
+
 def test_fr_inv_and_canon(orc, emu):
     rng = np.random.default_rng(101)
     a = orc.random_fr(rng, 64)
