@@ -69,7 +69,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "50"],
+                                          "--format=csv,noheader,nounits", "-lms", "250"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
@@ -100,7 +100,7 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        inside = [r for t, r in self.rows if self.t0 is not None and self.t0 <= t <= (self.t1 or t) + 0.06]
+        inside = [r for t, r in self.rows if self.t0 is not None and self.t0 <= t <= (self.t1 or t) + 0.3]
         rows = inside or [r for _, r in self.rows]
         sm = [int(r[0]) for r in rows if r and r[0].isdigit()]
         mx = [int(r[1]) for r in rows if len(r) > 1 and r[1].isdigit()]
@@ -181,6 +181,55 @@ def cpu_baseline_leg(n=14):
     return {"value": (1 << n) / dt, "unit": UNIT, "cores": 1, "kind": "port",
             "sample": f"one leader-mode dhyperplonk proof at 2^{n} constraints (l=1, N=8), 1 thread, {dt:.1f} s of CPU work; "
                       f"oracle C restatement of the arkworks path (portable C field arithmetic, no assembly backend)"}
+
+
+def fr_kernel_rooflines(scz, ctx, torch, peak):
+    """the HBM-side kernels of the path, each timed alone on a 2^22-entry table (128 MiB > L2) with CUDA events:
+    algorithmic bytes / time against the measured HBM peak"""
+    n = 1 << 22
+    g = torch.Generator(device=ctx.device).manual_seed(7)
+
+    def rand_fr(m):
+        t = torch.randint(-2**63, 2**63 - 1, (m, 4), dtype=torch.int64, device=ctx.device, generator=g)
+        t[:, 3] &= (1 << 62) - 1
+        return t
+    f, h, ch = rand_fr(n), rand_fr(n), rand_fr(24)
+    C = __import__("ctypes")
+    vp = lambda t: C.c_void_p(t.data_ptr())   # noqa: E731
+    q, val = ctx.empty(n, 4), ctx.empty(1, 4)
+    out3, last = ctx.empty(3 * 24, 4), ctx.empty(2, 4)
+    cases = {
+        # first round only would need a private entry point; the whole call is the geometric series 2 * first round
+        "open_fold (dpoly_comm.rs:309-323), all 22 rounds": (
+            lambda: ctx.check(ctx.L.scz_open_fold_dev(ctx.h, vp(f), C.c_size_t(n), vp(ch), vp(q), vp(val))), (n - 1) * 128),
+        "product sumcheck rounds (dsumcheck.rs:37-85), all 22 rounds": (
+            lambda: ctx.check(ctx.L.scz_sumcheck_product_rounds_dev(ctx.h, vp(f), vp(h), C.c_size_t(n), vp(ch), vp(out3), vp(last))),
+            (n - 1) * 192),
+        "single-MLE sumcheck (dsumcheck.rs:6-26), all 22 rounds": (
+            lambda: ctx.check(ctx.L.scz_sumcheck_dev(ctx.h, vp(f), C.c_size_t(n), vp(ch), vp(out3))), (n - 1) * 96),
+        "pointwise a + k0*b + k1 (dhyperplonk.rs:326-337)": (
+            lambda: ctx.check(ctx.L.scz_fr_pointwise_dev(ctx.h, 2, vp(f), vp(h), vp(ch), vp(q), C.c_size_t(n))), n * 96),
+        "division num/den, batched inversion (dhyperplonk.rs:339)": (
+            lambda: ctx.check(ctx.L.scz_fr_pointwise_dev(ctx.h, 3, vp(f), vp(h), None, vp(q), C.c_size_t(n))), n * 96),
+        "fix_variable, 2 variables (mle.rs:88-104)": (
+            lambda: ctx.check(ctx.L.scz_fix_variable_dev(ctx.h, vp(f), C.c_size_t(n), vp(ch), C.c_size_t(2), vp(q))),
+            (n // 2) * 96 + (n // 4) * 96),
+    }
+    res = []
+    for name, (fn, nbytes) in cases.items():
+        for _ in range(3):
+            fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(5):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 5
+        gbs = nbytes / (ms * 1e-3) / 1e9
+        res.append({"kernel": name, "table_entries": n, "alg_bytes": nbytes, "ms": ms, "achieved_gbs": gbs, "frac_of_hbm_peak": gbs / peak})
+    return res
 
 
 # ------------------------------------------------------------------------------------------ own arm
@@ -385,6 +434,8 @@ def run_own(args):
                              "mixed add vs ~100 B of traffic; ncu shows sm__pipe_fmaheavy_cycles_active ~84 % "
                              "(profiles/), see DESIGN.md 3.1"},
     }
+    if world == 1:
+        line["roofline_fr_kernels"] = fr_kernel_rooflines(scz, ctx0, torch, peak)
     if world == 1 and not args.no_cpu:
         line["cpu_baseline"] = cpu_baseline_leg()
     for ctx, _, _ in parties:

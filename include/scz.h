@@ -74,6 +74,13 @@ typedef struct scz_net_vtable {
     int32_t (*all_gather)(void *user, const void *d_send, void *d_recv, size_t bytes, size_t wire_bytes, void *stream);
     /* MPCNet::sync (mpc-net/src/lib.rs:275-286) */
     int32_t (*sync)(void *user, void *stream);
+    /* the "dynamic" variants with a movable hub (serializing_net.rs:41-74, 98-126; used by c_acc_product_and_share):
+     * everybody sends `bytes` to party `root`, whose d_recv (n_parties * bytes, party-major) is filled /
+     * party `root`'s d_send holds n_parties * bytes, party j receives slice j.  May be NULL when cpermcheck is not used. */
+    int32_t (*gather_to)(void *user, uint32_t root, const void *d_send, void *d_recv, size_t bytes, size_t wire_bytes,
+                         void *stream);
+    int32_t (*scatter_from)(void *user, uint32_t root, const void *d_send, void *d_recv, size_t bytes, size_t wire_bytes,
+                            void *stream);
 } scz_net_vtable;
 
 /* ---- context ---------------------------------------------------------------------------- */
@@ -312,6 +319,25 @@ int32_t scz_dhyperplonk_data_parallel_dev(scz_ctx *ctx, size_t n, const scz_hp_p
 int32_t scz_dpermcheck_dev(scz_ctx *ctx, size_t n, const scz_hp_pk *pk, const scz_pp *pp, void *d_triples, size_t triples_cap,
                            void *d_points, size_t points_cap, void *d_values, size_t values_cap, scz_hp_item *items,
                            size_t items_cap, size_t *n_items);
+
+/* ---- the collaborative (PSS) permutation check, the paper's baseline: hyperplonk/src/dhyperplonk.rs:1249-1385 -----
+ * c_acc_product_and_share (dacc_product.rs:66-292): masked product accumulation over N hub rounds with a moving hub.
+ * shares / masks / unmask0..2 and the three outputs (v(x,0), v(x,1), v(1,x) shares) hold `len` entries each; len / N * l
+ * must be a power of two >= N.  Needs the gather_to / scatter_from callbacks of a real net. */
+int32_t scz_c_acc_product_and_share_dev(scz_ctx *ctx, const scz_pp *pp, const void *d_shares, const void *d_masks,
+                                        const void *d_unmask0, const void *d_unmask1, const void *d_unmask2, size_t len,
+                                        void *d_share0, void *d_share1, void *d_share2);
+/* the fields of PackedProvingParameters that cpermcheck reads: DEVICE tables of 4 * 2^n / l entries (V, sid, ssigma,
+ * eq_r1, mask, unmask0..2), challenge_r1 (n + 2), alpha_beta (2) and the collaborative SRS */
+typedef struct scz_cperm_pk {
+    const void *V, *sid, *ssigma, *eq_r1, *mask, *unmask0, *unmask1, *unmask2, *challenge_r1, *alpha_beta;
+    const scz_srs *c_commitment;
+} scz_cperm_pk;
+/* cpermcheck: 6 SCZ_HP_WIRING_PROOF, 10 SCZ_HP_WIRING_COMMIT and 12 SCZ_HP_WIRING_OPEN items in the reference's push
+ * order; arenas sized by scz_dhyperplonk_sizes */
+int32_t scz_cpermcheck_dev(scz_ctx *ctx, size_t n, const scz_cperm_pk *pk, const scz_pp *pp, void *d_triples,
+                           size_t triples_cap, void *d_points, size_t points_cap, void *d_values, size_t values_cap,
+                           scz_hp_item *items, size_t items_cap, size_t *n_items);
 
 #ifdef __cplusplus
 }

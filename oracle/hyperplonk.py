@@ -209,3 +209,148 @@ def random_pk(rng, n, l, N, srs_c=None, srs_d=None, shared=None, data_parallel=F
             pk[name] = shared[name]
     pk["c_commitment"], pk["d_commitment"] = srs_c, srs_d
     return pk
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# The collaborative (PSS) permutation check: hyperplonk/src/dhyperplonk.rs:1249-1385 and its masked product
+# accumulation dist-primitive/src/dacc_product.rs:66-363.  Restated statement by statement, including what the build
+# without `comm` substitutes for received data; the reference itself says "We do not guarantee correctness here"
+# (dacc_product.rs:353).
+def _pack_chunks(pp, vals):
+    """vals.chunks(l).map(pack_from_public) then transpose (dacc_product.rs:121-130): -> (n, len(vals) / l, 4)"""
+    l = pp.l
+    packs = [orc.pack_from_public(pp, vals[c:c + l]) for c in range(0, len(vals), l)]
+    if not packs:
+        return np.zeros((pp.n, 0, 4), dtype=np.uint64)
+    return np.stack(packs, axis=1)
+
+
+def _merge(rows):
+    """merge (dacc_product.rs:416-428)"""
+    r = len(rows[0])
+    num = 1
+    while num < r + 1:
+        num <<= 1
+    num >>= 1
+    out, start = [], 0
+    while num and start + num <= r:
+        for row in rows:
+            out.append(row[start:start + num])
+        start += num
+        num >>= 1
+    return np.concatenate(out) if out else np.zeros((0, 4), dtype=np.uint64)
+
+
+def c_acc_product(pp, mode, inputs):
+    """dacc_product.rs:296-363 -> (subtrees per party, leader tree of N * N entries)"""
+    N = pp.n
+    P = N if mode == orc.PARTIES else 1
+    subtrees = [orc.acc_product_tree(x) for x in inputs]
+    assert 2 * len(inputs[0]) >= N
+    tails = [subtrees[j if mode == orc.PARTIES else 0][-N:] for j in range(N)]          # :320-328, N clones without comm
+    lt, start, layer = [], 0, N >> 1
+    while layer > 0:                                                                     # :338-349
+        for j in range(N):
+            lt.append(tails[j][start:start + layer])
+        start += layer
+        layer >>= 1
+    lt = list(np.concatenate(lt))
+    for i in range(N * N - N, N * N - 1):                                                # :354-357
+        x0, x1 = orc.sub_index(i)
+        lt.append(orc.fr_mul(lt[x0].reshape(1, 4), lt[x1].reshape(1, 4))[0])
+    lt.append(np.zeros(4, dtype=np.uint64))
+    assert P == len(subtrees)
+    return subtrees, np.array(lt, dtype=np.uint64)
+
+
+def c_acc_product_and_share(pp, mode, shares, masks, unmask0, unmask1, unmask2):
+    """dacc_product.rs:66-292.  Every argument is a list with one array per party (LEADER_SIM: one).
+    -> list per party of (share0, share1, share2)"""
+    N, l = pp.n, pp.l
+    P = N if mode == orc.PARTIES else 1
+    L = len(shares[0])
+    assert L > N and L % N == 0
+    block = L // N
+    masked = [orc.fr_mul(shares[p], masks[p]) for p in range(P)]                         # :88-93
+    # d_unpack2_many with receiver i (:95-107): party i ends with unpack2 of block i of everybody's masked shares
+    masked_x = []
+    for p in range(P):
+        rows = [masked[j if mode == orc.PARTIES else 0][p * block:(p + 1) * block] for j in range(N)]
+        masked_x.append(np.concatenate([orc.unpack2(pp, np.stack([rows[j][b] for j in range(N)])) for b in range(block)]))
+    subtrees, ltree = c_acc_product(pp, mode, masked_x)                                  # :111-113
+    m = block * l
+    sm = []
+    for p in range(P):
+        st = subtrees[p]
+        to_share = st[:len(st) - N]                                                      # :119
+        sm.append((_pack_chunks(pp, to_share[0::2]), _pack_chunks(pp, to_share[1::2]),
+                   _pack_chunks(pp, to_share[len(st) // 2:])))                           # :120-152
+    out = []
+    q0 = N * N // 2 // l
+    lead = (_pack_chunks(pp, ltree[0::2]), _pack_chunks(pp, ltree[1::2]), _pack_chunks(pp, ltree))   # :212-249 (whole tree for v1x)
+    for p in range(P):
+        res = []
+        for k in range(3):
+            if mode == orc.PARTIES:
+                rows = [sm[i][k][p] for i in range(N)]                                   # hub i sends row p (:154-193)
+            else:
+                rows = [sm[0][k][i] for i in range(N)]                                   # :196-202 placeholder
+            merged = _merge(rows)                                                        # :204-209
+            full = np.concatenate([merged, lead[k][p]])                                  # :251-262 (leader keeps row 0)
+            assert len(full) == L, (len(merged), len(lead[k][p]), L, q0, m)
+            res.append(orc.fr_mul(full, (unmask0, unmask1, unmask2)[k][p]))              # :265-275
+        out.append(tuple(res))                                                           # degree_reduce_many results are dropped (:278-285)
+    return out
+
+
+def cpermcheck(n, pks, pp, mode, N, algo="ark"):
+    """hyperplonk/src/dhyperplonk.rs:1249-1385.  pks: per party dict with V, sid, ssigma, eq_r1, mask, unmask0..2
+    (4 * 2^n / l entries each), challenge_r1, alpha, beta, c_commitment.  -> per party dict like dhyperplonk's."""
+    P = N if mode == orc.PARTIES else 1
+    assert len(pks) == P
+    csrs = [pk["c_commitment"] for pk in pks]
+    res = [dict(gate_identity_proofs=[], gate_identity_commitments=[], wiring_proofs=[], wiring_commits=[],
+                wiring_opens=[]) for _ in range(P)]
+    col = lambda name: [pk[name] for pk in pks]   # noqa: E731
+    r1 = pks[0]["challenge_r1"]
+
+    def commit(tabs):
+        o = orc.c_commit(csrs, pp, mode, [[t] for t in tabs], algo)
+        for j in range(P):
+            res[j]["wiring_commits"].append(o[j, 0:1].copy())
+
+    def open_(tabs):
+        val, proofs = orc.c_open(csrs, pp, mode, tabs, r1, algo)
+        for j in range(P):
+            res[j]["wiring_opens"].append((val[j:j + 1].copy(), proofs[j].copy()))
+
+    def sumcheck(f, g):
+        o = orc.c_sumcheck_product(pp, mode, f, g, r1)
+        for j in range(P):
+            res[j]["wiring_proofs"].append(o[j].copy())
+    num, den = [], []
+    for pk in pks:
+        L = len(pk["V"])
+        alpha, beta = _rep(pk["alpha"], L), _rep(pk["beta"], L)
+        num.append(orc.fr_add(orc.fr_add(pk["V"], orc.fr_mul(alpha, pk["sid"])), beta))          # :1278-1280
+        den.append(orc.fr_add(orc.fr_add(pk["eq_r1"], orc.fr_mul(alpha, pk["ssigma"])), beta))   # :1281-1283
+    commit(col("ssigma"))
+    open_(col("ssigma"))
+    commit(col("sid"))
+    open_(col("sid"))
+    for ev in (num, den):                                                                        # :1311-1376
+        sh = c_acc_product_and_share(pp, mode, ev, col("mask"), col("unmask0"), col("unmask1"), col("unmask2"))
+        vx0, vx1, v1x = [s[0] for s in sh], [s[1] for s in sh], [s[2] for s in sh]
+        commit(ev)
+        open_(ev)
+        commit(vx0)
+        open_(vx0)
+        commit(vx1)
+        open_(vx1)
+        commit(v1x)
+        open_(v1x)
+        sumcheck(col("eq_r1"), v1x)
+        sumcheck(col("eq_r1"), vx0)
+        sumcheck(vx0, vx1)
+        open_(ev)
+    return res

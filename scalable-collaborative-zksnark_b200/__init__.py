@@ -34,5 +34,7 @@ from .api import (  # noqa: F401
     dhyperplonk,
     dhyperplonk_data_parallel,
     dpermcheck,
+    cpermcheck,
+    c_acc_product_and_share,
     hp_table_sizes,
 )

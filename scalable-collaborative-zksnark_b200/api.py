@@ -739,6 +739,45 @@ def dhyperplonk(ctx, n, pk, pp, _entry="scz_dhyperplonk_dev"):
     return HyperPlonkProof(ctx, tri, pts, val, list(items[: cnt.value]))
 
 
+class CpermPk(C.Structure):
+    """scz_cperm_pk (include/scz.h)"""
+    _TABLES = ("V", "sid", "ssigma", "eq_r1", "mask", "unmask0", "unmask1", "unmask2", "challenge_r1", "alpha_beta")
+    _fields_ = [(k, C.c_void_p) for k in _TABLES] + [("c_commitment", C.c_void_p)]
+
+
+def c_acc_product_and_share(ctx, pp, shares, masks, unmask0, unmask1, unmask2):
+    """dacc_product.rs:66-292 -> (v(x,0), v(x,1), v(1,x)) shares, each as long as `shares`"""
+    ins = [_in(ctx, x, 4) for x in (shares, masks, unmask0, unmask1, unmask2)]
+    host = ins[0][1]
+    n = len(ins[0][0])
+    outs = [ctx.empty(n, 4) for _ in range(3)]
+    ctx.check(ctx.L.scz_c_acc_product_and_share_dev(ctx.h, pp.h, *[_vp(t) for t, _ in ins], C.c_size_t(n),
+                                                    *[_vp(t) for t in outs]))
+    return tuple(_out(ctx, t, host) for t in outs)
+
+
+def cpermcheck(ctx, n, tables, c_commitment, pp):
+    """hyperplonk/src/dhyperplonk.rs:1249-1385.  tables: dict with the CpermPk._TABLES entries ((len, 4) arrays, numpy or
+    CUDA tensors).  Returns a HyperPlonkProof whose nested() is ((), (wiring_proofs, wiring_commits, wiring_opens))."""
+    L = ctx.L
+    keep = {k: (_dev(tables[k], 4) if _is_dev(tables[k]) else ctx.to_device(tables[k], 4)) for k in CpermPk._TABLES}
+    cpk = CpermPk()
+    for k, t in keep.items():
+        setattr(cpk, k, t.data_ptr())
+    cpk.c_commitment = c_commitment.h
+    nt, npt, nv, ni = C.c_size_t(), C.c_size_t(), C.c_size_t(), C.c_size_t()
+    ctx.check(L.scz_dhyperplonk_sizes(C.c_size_t(n), C.c_size_t(pp.l), C.c_size_t(ctx.n_parties), C.byref(nt), C.byref(npt),
+                                      C.byref(nv), C.byref(ni)))
+    tri, pts, val = ctx.empty(nt.value * 3, 4), ctx.empty(npt.value, 18), ctx.empty(nv.value, 4)
+    items = (HpItem * ni.value)()
+    cnt = C.c_size_t()
+    ctx.check(L.scz_cpermcheck_dev(ctx.h, C.c_size_t(n), C.byref(cpk), pp.h, _vp(tri), nt, _vp(pts), npt, _vp(val), nv, items, ni,
+                                   C.byref(cnt)))
+    proof = HyperPlonkProof(ctx, tri, pts, val, list(items[: cnt.value]))
+    proof._keep = keep
+    return proof
+
+
 def dhyperplonk_data_parallel(ctx, n, pk, pp):
     """dhyperplonk.rs:573-960: pk.t['local_s'] holds the whole `s` (4 * 2^n / l entries, :603); no step-2.a exchange"""
     return dhyperplonk(ctx, n, pk, pp, "scz_dhyperplonk_data_parallel_dev")
@@ -752,5 +791,5 @@ def dpermcheck(ctx, n, pk, pp):
 __all__ = ["Context", "PackedSharingParams", "msm", "msm_batched", "d_msm", "d_msm_leader", "NetVTable",
            "fr_pointwise", "fix_variable", "acc_product_tree", "d_acc_product", "sumcheck_rounds", "sumcheck_product",
            "c_sumcheck_product", "d_sumcheck_product", "sumcheck", "c_sumcheck", "d_sumcheck", "pss2ss", "degree_reduce", "PolynomialCommitment",
-           "PackedProvingParameters", "HyperPlonkProof", "dhyperplonk", "dhyperplonk_data_parallel", "dpermcheck",
+           "PackedProvingParameters", "HyperPlonkProof", "dhyperplonk", "dhyperplonk_data_parallel", "dpermcheck", "cpermcheck", "c_acc_product_and_share",
            "hp_table_sizes"]

@@ -24,7 +24,9 @@ class SczError(RuntimeError):
 class NetVTable(C.Structure):
     _COLL = C.CFUNCTYPE(C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p)
     _SYNC = C.CFUNCTYPE(C.c_int32, C.c_void_p, C.c_void_p)
-    _fields_ = [("user", C.c_void_p), ("gather", _COLL), ("scatter", _COLL), ("all_gather", _COLL), ("sync", _SYNC)]
+    _ROOTED = C.CFUNCTYPE(C.c_int32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p)
+    _fields_ = [("user", C.c_void_p), ("gather", _COLL), ("scatter", _COLL), ("all_gather", _COLL), ("sync", _SYNC),
+                ("gather_to", _ROOTED), ("scatter_from", _ROOTED)]
 
 
 def declared_symbols():

@@ -92,6 +92,28 @@ int32_t LeaderSimNet::all_gather(Ctx *ctx, const void *d_send, void *d_recv, siz
     upload += wire * (n_parties - 1);
     return replicate(ctx, d_recv, d_send, bytes, n_parties);
 }
+// serializing_net.rs:170-190: only the receiver "receives" (N clones of its own message); everybody else just counts
+int32_t LeaderSimNet::gather_to(Ctx *ctx, uint32_t root, const void *d_send, void *d_recv, size_t bytes, size_t wire) {
+    if (root != party_id) {
+        upload += wire;
+        return SCZ_OK;
+    }
+    download += wire * (n_parties - 1);
+    return replicate(ctx, d_recv, d_send, bytes, n_parties);
+}
+// serializing_net.rs:217-241: the hub counts its N - 1 messages and keeps element 0; everybody else gets T::default()
+int32_t LeaderSimNet::scatter_from(Ctx *ctx, uint32_t root, const void *d_send, void *d_recv, size_t bytes, size_t wire,
+                                   bool *got) {
+    if (root == party_id) {
+        upload += wire * (n_parties - 1);
+        SCZ_CUDA(ctx, cudaMemcpyAsync(d_recv, d_send, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+        if (got) *got = true;
+    } else {
+        SCZ_CUDA(ctx, cudaMemsetAsync(d_recv, 0, bytes, ctx->stream));
+        if (got) *got = false;
+    }
+    return SCZ_OK;
+}
 int32_t LeaderSimNet::sync(Ctx *) { return SCZ_OK; }
 
 // ------------------------------------------------------------------ host-supplied collectives
@@ -112,6 +134,22 @@ int32_t CallbackNet::all_gather(Ctx *ctx, const void *d_send, void *d_recv, size
     download += wire * (n_parties - 1);
     if (vt.all_gather(vt.user, d_send, d_recv, bytes, wire, ctx->stream) != 0)
         return ctx->fail(SCZ_ERR_NET, "net all_gather failed");
+    return SCZ_OK;
+}
+int32_t CallbackNet::gather_to(Ctx *ctx, uint32_t root, const void *d_send, void *d_recv, size_t bytes, size_t wire) {
+    if (root == party_id) download += wire * (n_parties - 1);
+    else upload += wire;
+    if (!vt.gather_to || vt.gather_to(vt.user, root, d_send, d_recv, bytes, wire, ctx->stream) != 0)
+        return ctx->fail(SCZ_ERR_NET, "net gather_to failed");
+    return SCZ_OK;
+}
+int32_t CallbackNet::scatter_from(Ctx *ctx, uint32_t root, const void *d_send, void *d_recv, size_t bytes, size_t wire,
+                                  bool *got) {
+    if (root == party_id) upload += wire * (n_parties - 1);
+    else download += wire;
+    if (!vt.scatter_from || vt.scatter_from(vt.user, root, d_send, d_recv, bytes, wire, ctx->stream) != 0)
+        return ctx->fail(SCZ_ERR_NET, "net scatter_from failed");
+    if (got) *got = true;
     return SCZ_OK;
 }
 int32_t CallbackNet::sync(Ctx *ctx) {

@@ -23,6 +23,12 @@ struct Net {
     // d_send: n_parties * bytes on the leader; d_recv: bytes on everyone
     virtual int32_t scatter(Ctx *ctx, const void *d_send, void *d_recv, size_t bytes, size_t wire) = 0;
     virtual int32_t all_gather(Ctx *ctx, const void *d_send, void *d_recv, size_t bytes, size_t wire) = 0;
+    // the "dynamic" variants with a movable hub (serializing_net.rs:41-74, 98-126): every party sends `bytes` to `root`
+    // (d_recv: n_parties * bytes there) / `root` sends slice j of d_send to party j.  *got tells the caller whether it
+    // received real data (the leader simulator only does when it is the root / never on a foreign scatter).
+    virtual int32_t gather_to(Ctx *ctx, uint32_t root, const void *d_send, void *d_recv, size_t bytes, size_t wire) = 0;
+    virtual int32_t scatter_from(Ctx *ctx, uint32_t root, const void *d_send, void *d_recv, size_t bytes, size_t wire,
+                                 bool *got) = 0;
     virtual int32_t sync(Ctx *ctx) = 0;
     // true when non-leaders receive real data on scatter (false in the leader simulator: there are none)
     virtual bool real() const = 0;
@@ -32,6 +38,9 @@ struct LeaderSimNet : Net {
     int32_t gather(Ctx *ctx, const void *d_send, void *d_recv, size_t bytes, size_t wire) override;
     int32_t scatter(Ctx *ctx, const void *d_send, void *d_recv, size_t bytes, size_t wire) override;
     int32_t all_gather(Ctx *ctx, const void *d_send, void *d_recv, size_t bytes, size_t wire) override;
+    int32_t gather_to(Ctx *ctx, uint32_t root, const void *d_send, void *d_recv, size_t bytes, size_t wire) override;
+    int32_t scatter_from(Ctx *ctx, uint32_t root, const void *d_send, void *d_recv, size_t bytes, size_t wire,
+                         bool *got) override;
     int32_t sync(Ctx *ctx) override;
     bool real() const override { return false; }
 };
@@ -41,6 +50,9 @@ struct CallbackNet : Net {
     int32_t gather(Ctx *ctx, const void *d_send, void *d_recv, size_t bytes, size_t wire) override;
     int32_t scatter(Ctx *ctx, const void *d_send, void *d_recv, size_t bytes, size_t wire) override;
     int32_t all_gather(Ctx *ctx, const void *d_send, void *d_recv, size_t bytes, size_t wire) override;
+    int32_t gather_to(Ctx *ctx, uint32_t root, const void *d_send, void *d_recv, size_t bytes, size_t wire) override;
+    int32_t scatter_from(Ctx *ctx, uint32_t root, const void *d_send, void *d_recv, size_t bytes, size_t wire,
+                         bool *got) override;
     int32_t sync(Ctx *ctx) override;
     bool real() const override { return true; }
 };

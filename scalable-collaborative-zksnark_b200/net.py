@@ -67,9 +67,45 @@ class TorchDistNet:
         self.calls["sync"] += 1
         dist.barrier(group=self.group)
 
+    def gather_to_t(self, root, send, recv):
+        """dynamic_worker_send_or_leader_receive_element (serializing_net.rs:41-74): hub = `root`"""
+        self.calls["gather"] += 1
+        if self.rank == root:
+            dist.gather(send, list(recv.view(self.n_parties, -1).unbind(0)), dst=root, group=self.group)
+        else:
+            dist.gather(send, None, dst=root, group=self.group)
+
+    def scatter_from_t(self, root, send, recv):
+        """dynamic_worker_receive_or_worker_send_element (serializing_net.rs:98-126)"""
+        self.calls["scatter"] += 1
+        if self.rank == root:
+            dist.scatter(recv, list(send.view(self.n_parties, -1).unbind(0)), src=root, group=self.group)
+        else:
+            dist.scatter(recv, None, src=root, group=self.group)
+
     # -- C callbacks
     def vtable(self):
         dev = self.device
+
+        def _gather_to(user, root, d_send, d_recv, nbytes, wire, stream):
+            try:
+                send = _tensor(d_send, nbytes, dev)
+                recv = _tensor(d_recv, nbytes * self.n_parties, dev) if self.rank == root else None
+                self.gather_to_t(root, send, recv)
+                return 0
+            except Exception as e:
+                print(f"[scz net] gather_to failed: {e!r}", flush=True)
+                return 1
+
+        def _scatter_from(user, root, d_send, d_recv, nbytes, wire, stream):
+            try:
+                recv = _tensor(d_recv, nbytes, dev)
+                send = _tensor(d_send, nbytes * self.n_parties, dev) if self.rank == root else None
+                self.scatter_from_t(root, send, recv)
+                return 0
+            except Exception as e:
+                print(f"[scz net] scatter_from failed: {e!r}", flush=True)
+                return 1
 
         def _gather(user, d_send, d_recv, nbytes, wire, stream):
             try:
@@ -113,6 +149,8 @@ class TorchDistNet:
         vt.scatter = NetVTable._COLL(_scatter)
         vt.all_gather = NetVTable._COLL(_all_gather)
         vt.sync = NetVTable._SYNC(_sync)
+        vt.gather_to = NetVTable._ROOTED(_gather_to)
+        vt.scatter_from = NetVTable._ROOTED(_scatter_from)
         self._keep = vt   # the callbacks must outlive the ctx
         return vt
 
@@ -215,12 +253,41 @@ class _LocalParty:
             except Exception:
                 return 1
 
+        def _gather_to(user, root, d_send, d_recv, nbytes, wire, stream):
+            try:
+                hub.slots[me] = d_send
+                hub.barrier.wait()
+                if me == root:
+                    recv = _tensor(d_recv, nbytes * hub.n, dev).view(hub.n, nbytes)
+                    for j in range(hub.n):
+                        recv[j].copy_(_tensor(hub.slots[j], nbytes, dev))
+                hub.barrier.wait()
+                return 0
+            except Exception as e:
+                print(f"[scz local net] gather_to failed: {e!r}", flush=True)
+                return 1
+
+        def _scatter_from(user, root, d_send, d_recv, nbytes, wire, stream):
+            try:
+                if me == root:
+                    hub.leader_send = d_send
+                hub.barrier.wait()
+                src = _tensor(hub.leader_send, nbytes * hub.n, dev).view(hub.n, nbytes)
+                _tensor(d_recv, nbytes, dev).copy_(src[me])
+                hub.barrier.wait()
+                return 0
+            except Exception as e:
+                print(f"[scz local net] scatter_from failed: {e!r}", flush=True)
+                return 1
+
         vt = NetVTable()
         vt.user = None
         vt.gather = NetVTable._COLL(_gather)
         vt.scatter = NetVTable._COLL(_scatter)
         vt.all_gather = NetVTable._COLL(_all_gather)
         vt.sync = NetVTable._SYNC(_sync)
+        vt.gather_to = NetVTable._ROOTED(_gather_to)
+        vt.scatter_from = NetVTable._ROOTED(_scatter_from)
         self._keep = vt
         return vt
 
@@ -292,44 +359,52 @@ class _HybridParty:
     def vtable(self):
         hub, p, dev, P, W = self.hub, self.p, self.hub.device, self.hub.per_rank, self.hub.world
 
-        def _gather(user, d_send, d_recv, nbytes, wire, stream):
+        def _gather_to(user, root, d_send, d_recv, nbytes, wire, stream):
+            # the root party lives on rank root // P as local party root % P; local party 0 of every rank drives
             try:
+                rr, rp = root // P, root % P
                 hub.slots[p] = d_send
+                if hub.rank == rr and p == rp:
+                    hub.root_recv = d_recv
                 hub.barrier.wait()
                 if p == 0:
                     hub.calls["gather"] += 1
                     if W == 1:
-                        recv = _tensor(d_recv, nbytes * hub.n, dev).view(P, nbytes)
+                        recv = _tensor(hub.root_recv, nbytes * hub.n, dev).view(P, nbytes)
                         for q in range(P):
                             recv[q].copy_(_tensor(hub.slots[q], nbytes, dev))
                     else:
                         loc = hub._buf(P * nbytes).view(P, nbytes)
                         for q in range(P):
                             loc[q].copy_(_tensor(hub.slots[q], nbytes, dev))
-                        if hub.rank == 0:
-                            recv = _tensor(d_recv, nbytes * hub.n, dev).view(W, P * nbytes)
-                            dist.gather(loc.view(-1), list(recv.unbind(0)), dst=0, group=hub.group)
+                        if hub.rank == rr:
+                            recv = _tensor(hub.root_recv, nbytes * hub.n, dev).view(W, P * nbytes)
+                            dist.gather(loc.view(-1), list(recv.unbind(0)), dst=rr, group=hub.group)
                         else:
-                            dist.gather(loc.view(-1), None, dst=0, group=hub.group)
+                            dist.gather(loc.view(-1), None, dst=rr, group=hub.group)
                 hub.barrier.wait()
                 return 0
             except Exception as e:
                 print(f"[scz hybrid net] gather failed: {e!r}", flush=True)
                 return 1
 
-        def _scatter(user, d_send, d_recv, nbytes, wire, stream):
+        def _scatter_from(user, root, d_send, d_recv, nbytes, wire, stream):
             try:
+                rr, rp = root // P, root % P
+                if hub.rank == rr and p == rp:
+                    hub.root_send = d_send
+                hub.barrier.wait()
                 if p == 0:
                     if W == 1:
-                        hub.stage = _tensor(d_send, nbytes * hub.n, dev).view(P, nbytes)
+                        hub.stage = _tensor(hub.root_send, nbytes * hub.n, dev).view(P, nbytes)
                     else:
                         hub.calls["scatter"] += 1
                         loc = hub._buf(P * nbytes)
-                        if hub.rank == 0:
-                            send = _tensor(d_send, nbytes * hub.n, dev).view(W, P * nbytes)
-                            dist.scatter(loc, list(send.unbind(0)), src=0, group=hub.group)
+                        if hub.rank == rr:
+                            send = _tensor(hub.root_send, nbytes * hub.n, dev).view(W, P * nbytes)
+                            dist.scatter(loc, list(send.unbind(0)), src=rr, group=hub.group)
                         else:
-                            dist.scatter(loc, None, src=0, group=hub.group)
+                            dist.scatter(loc, None, src=rr, group=hub.group)
                         hub.stage = loc.view(P, nbytes)
                 hub.barrier.wait()
                 _tensor(d_recv, nbytes, dev).copy_(hub.stage[p])
@@ -338,6 +413,12 @@ class _HybridParty:
             except Exception as e:
                 print(f"[scz hybrid net] scatter failed: {e!r}", flush=True)
                 return 1
+
+        def _gather(user, d_send, d_recv, nbytes, wire, stream):
+            return _gather_to(user, 0, d_send, d_recv, nbytes, wire, stream)
+
+        def _scatter(user, d_send, d_recv, nbytes, wire, stream):
+            return _scatter_from(user, 0, d_send, d_recv, nbytes, wire, stream)
 
         def _all_gather(user, d_send, d_recv, nbytes, wire, stream):
             try:
@@ -381,5 +462,7 @@ class _HybridParty:
         vt.scatter = NetVTable._COLL(_scatter)
         vt.all_gather = NetVTable._COLL(_all_gather)
         vt.sync = NetVTable._SYNC(_sync)
+        vt.gather_to = NetVTable._ROOTED(_gather_to)
+        vt.scatter_from = NetVTable._ROOTED(_scatter_from)
         self._keep = vt
         return vt

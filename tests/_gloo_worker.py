@@ -31,6 +31,16 @@ def check_party(vt, pid, n, leader):
     full = np.zeros(n * nb, dtype=np.uint8)
     assert vt.all_gather(None, ptr(mine), ptr(full), nb, nb, None) == 0
     assert all((full[j * nb:(j + 1) * nb] == 10 + j).all() for j in range(n)), (pid, full)
+    # moving hub (serializing_net.rs:41-74, 98-126): every party takes a turn as the root
+    for root in range(n):
+        recv = np.zeros(n * nb, dtype=np.uint8) if pid == root else None
+        assert vt.gather_to(None, root, ptr(mine), ptr(recv), nb, nb, None) == 0
+        if pid == root:
+            assert all((recv[j * nb:(j + 1) * nb] == 10 + j).all() for j in range(n)), (root, recv)
+        send = np.repeat(np.arange(n, dtype=np.uint8) + 100 + root, nb) if pid == root else None
+        got = np.zeros(nb, dtype=np.uint8)
+        assert vt.scatter_from(None, root, ptr(send), ptr(got), nb, nb, None) == 0
+        assert (got == 100 + root + pid).all(), (root, pid, got)
     assert vt.sync(None, None) == 0
     return True
 
