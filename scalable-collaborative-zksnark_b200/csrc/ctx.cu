@@ -30,6 +30,27 @@ int32_t Ctx::pinned_reserve(size_t bytes) {
     return SCZ_OK;
 }
 
+int32_t Ctx::h2d_staged(void *d_dst, const void *h_src, size_t bytes) {
+    if (!bytes) return SCZ_OK;
+    if (bytes > STAGE_BYTES) {   // rare (tens of thousands of segments): pageable copy, which the runtime stages itself
+        SCZ_CUDA(this, cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, stream));
+        SCZ_CUDA(this, cudaStreamSynchronize(stream));
+        return SCZ_OK;
+    }
+    Stage &s = stage[stage_next];
+    stage_next = (stage_next + 1) % STAGE_SLOTS;
+    if (!s.p) {
+        SCZ_CUDA(this, cudaMallocHost(&s.p, STAGE_BYTES));
+        SCZ_CUDA(this, cudaEventCreateWithFlags(&s.ev, cudaEventDisableTiming));
+    }
+    if (s.busy) SCZ_CUDA(this, cudaEventSynchronize(s.ev));
+    memcpy(s.p, h_src, bytes);
+    SCZ_CUDA(this, cudaMemcpyAsync(d_dst, s.p, bytes, cudaMemcpyHostToDevice, stream));
+    SCZ_CUDA(this, cudaEventRecord(s.ev, stream));
+    s.busy = true;
+    return SCZ_OK;
+}
+
 void Ctx::prof_begin(int id) {
     ProfRec r;
     r.id = id;
@@ -208,6 +229,10 @@ void scz_ctx_destroy(scz_ctx *h) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     if (c->pinned) cudaFreeHost(c->pinned);
+    for (auto &st : c->stage) {
+        if (st.p) cudaFreeHost(st.p);
+        if (st.ev) cudaEventDestroy(st.ev);
+    }
     c->prof_clear();
     for (cudaEvent_t e : c->prof_pool) cudaEventDestroy(e);
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);

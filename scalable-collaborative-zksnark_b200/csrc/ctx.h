@@ -41,6 +41,19 @@ struct Ctx {
     void prof_end();
     void prof_clear();
 
+    // Small host -> device tables (MSM segment tables, closure job lists) go through a ring of pinned slots so that
+    // the copy is truly asynchronous and the host can run ahead of the GPU; a slot is reused only after the copy
+    // that last used it has executed.
+    static constexpr int STAGE_SLOTS = 8;
+    static constexpr size_t STAGE_BYTES = 1 << 20;
+    struct Stage {
+        char *p = nullptr;
+        cudaEvent_t ev = nullptr;
+        bool busy = false;
+    } stage[STAGE_SLOTS];
+    int stage_next = 0;
+    int32_t h2d_staged(void *d_dst, const void *h_src, size_t bytes);
+
     int32_t fail(int32_t code, const char *fmt, ...);
     int32_t cuda(cudaError_t e, const char *what);
     int32_t pinned_reserve(size_t bytes);

@@ -519,9 +519,7 @@ int32_t msm_g1_batched(Ctx *ctx, const void *const *d_bases, const void *const *
     SCZ_TRY(d_heavy.alloc(((size_t)nchunks + 1) * 4));   // [0] = count, [1..] = list (at most one bucket per chunk)
     SCZ_TRY(d_nodes.alloc(nodes_total * sizeof(MsmNode)));
     SCZ_TRY(d_wsum.alloc(windows * sizeof(G1Jac)));
-    // segment table: pageable host -> device; the vector must outlive the copy
-    SCZ_CUDA(ctx, cudaMemcpyAsync(d_segs.p, segs.data(), batch * sizeof(MsmSeg), cudaMemcpyHostToDevice, st));
-    SCZ_CUDA(ctx, cudaStreamSynchronize(st));
+    SCZ_TRY(ctx->h2d_staged(d_segs.p, segs.data(), batch * sizeof(MsmSeg)));   // asynchronous: the host runs ahead
     SCZ_CUDA(ctx, cudaMemsetAsync(d_counts.p, 0, buckets * 4, st));
     SCZ_CUDA(ctx, cudaMemsetAsync(d_heavy.p, 0, 4, st));
     const MsmSeg *sp = d_segs.as<MsmSeg>();

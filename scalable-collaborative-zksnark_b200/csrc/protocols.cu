@@ -492,8 +492,7 @@ int32_t Deferred::flush_closures() {
         }
         DevTmp d(ctx);
         SCZ_TRY(d.alloc(colsum_jobs.size() * sizeof(ColsumJob)));
-        SCZ_CUDA(ctx, cudaMemcpyAsync(d.p, colsum_jobs.data(), colsum_jobs.size() * sizeof(ColsumJob), cudaMemcpyHostToDevice,
-                                      ctx->stream));
+        SCZ_TRY(ctx->h2d_staged(d.p, colsum_jobs.data(), colsum_jobs.size() * sizeof(ColsumJob)));
         k_g1_colsum_multi<<<ceil_div_u32(cols, 64), 64, 0, ctx->stream>>>(d.as<ColsumJob>(), (uint32_t)colsum_jobs.size(), cols);
         colsum_jobs.clear();
         SCZ_LAUNCH_CHECK(ctx);

@@ -216,7 +216,7 @@ int32_t pss_dmsm_multi(Ctx *ctx, const scz_pp *pp, const void *jobs_host, size_t
     if (!ctas) return SCZ_OK;
     DevTmp d(ctx);
     SCZ_TRY(d.alloc(njobs * sizeof(PssG1Job)));
-    SCZ_CUDA(ctx, cudaMemcpyAsync(d.p, jobs.data(), njobs * sizeof(PssG1Job), cudaMemcpyHostToDevice, ctx->stream));
+    SCZ_TRY(ctx->h2d_staged(d.p, jobs.data(), njobs * sizeof(PssG1Job)));
     constexpr size_t SH8 = 8 * 17 * sizeof(G1Jac);
     k_pss_dmsm_multi<<<ctas, 32, SH8, ctx->stream>>>(pp->d_dmsm, (uint32_t)pp->n, d.as<PssG1Job>(), (uint32_t)njobs);
     SCZ_LAUNCH_CHECK(ctx);
