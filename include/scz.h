@@ -146,6 +146,14 @@ int32_t scz_g1_vec_op_dev(scz_ctx *ctx, int32_t op, const void *d_a_jac, const v
 int32_t scz_g1_mul_fr_dev(scz_ctx *ctx, const void *d_jac, const void *d_k, void *d_out_jac, size_t n);
 /* Projective::into_affine / CurveGroup::normalize_batch: Jacobian -> packed affine (infinity -> 0,0) */
 int32_t scz_g1_to_affine_dev(scz_ctx *ctx, const void *d_jac, void *d_out_affine, size_t n);
+/* ---- wire formats (ark-serialize compressed, what serializing_net.rs:17,25,50,60,88,95 put on the wire) ----
+ * Fr: 32 B canonical little endian = scz_fr_to_canonical_dev; scz_fr_deserialize_dev also rejects values >= r
+ * (status 1, like ark-ff's deserialize).  G1 (ark-bls12-381 0.4.0 = the Zcash / IETF encoding): 48 B, x big endian,
+ * top bits of byte 0: compressed | infinity | y is the larger root.  Deserialisation validates like
+ * deserialize_compressed (Validate::Yes): status 0 ok, 1 malformed / not on the curve, 2 not in the r-torsion. */
+int32_t scz_g1_serialize_compressed_dev(scz_ctx *ctx, const void *d_jac, void *d_bytes48, size_t n);
+int32_t scz_g1_deserialize_compressed_dev(scz_ctx *ctx, const void *d_bytes48, void *d_out_jac, uint8_t *d_status, size_t n);
+int32_t scz_fr_deserialize_dev(scz_ctx *ctx, const void *d_bytes32, void *d_out, uint8_t *d_status, size_t n);
 /* synthetic bases: out[i] = k[i] * G1 generator, packed affine (stands in for G1::rand, dpoly_comm.rs:214,229) */
 int32_t scz_g1_generator_mul_dev(scz_ctx *ctx, const void *d_k, void *d_out_affine, size_t n);
 

@@ -201,3 +201,42 @@ def acc_product(x):
         t[i] = t[a] * t[b] % R_MOD
     t[2 * len(x) - 1] = 0
     return t[0::2], t[1::2], t[len(t) // 2:]
+
+
+# ---------------------------------------------------------------- wire format (ark-bls12-381 0.4.0 compressed G1 = Zcash / IETF)
+def g1_serialize_compressed(pt):
+    """pt: (x, y) ints or None (infinity) -> 48 bytes: x big endian, flags compressed | infinity | y larger root"""
+    if pt is None:
+        return bytes([0xC0]) + bytes(47)
+    x, y = pt
+    b = bytearray(x.to_bytes(48, "big"))
+    b[0] |= 0x80 | (0x20 if y > (P_MOD - y) % P_MOD else 0)
+    return bytes(b)
+
+
+def g1_deserialize_compressed(b):
+    """48 bytes -> ((x, y) or None, status): 0 ok, 1 malformed / not on the curve, 2 not in the r-torsion"""
+    assert len(b) == 48
+    flags = b[0] & 0xE0
+    x = int.from_bytes(bytes([b[0] & 0x1F]) + b[1:], "big")
+    if not flags & 0x80:
+        return None, 1
+    if flags & 0x40:
+        return (None, 0) if (not flags & 0x20 and x == 0) else (None, 1)
+    if x >= P_MOD:
+        return None, 1
+    rhs = (x * x * x + 4) % P_MOD
+    y = pow(rhs, (P_MOD + 1) // 4, P_MOD)
+    if y * y % P_MOD != rhs:
+        return None, 1
+    if (y > (P_MOD - y) % P_MOD) != bool(flags & 0x20):
+        y = (P_MOD - y) % P_MOD
+    acc, q, k = INF, (x, y), R_MOD          # [r]P without reducing the scalar (g1_mul works mod r)
+    while k:
+        if k & 1:
+            acc = g1_add(acc, q)
+        q = g1_add(q, q)
+        k >>= 1
+    if acc is not INF:
+        return None, 2
+    return (x, y), 0

@@ -190,6 +190,32 @@ class Context:
                                                    C.c_size_t(len(k))))
         return out
 
+    # ---- wire formats (ark-serialize compressed)
+    def g1_serialize_compressed(self, a):
+        """(n, 18) Jacobian -> (n, 48) uint8: ark-bls12-381's compressed G1 encoding (Zcash format)"""
+        a = _dev(a, 18)
+        out = torch.empty((len(a), 48), dtype=torch.uint8, device=self.device)
+        self.check(self.L.scz_g1_serialize_compressed_dev(self.h, C.c_void_p(a.data_ptr()), C.c_void_p(out.data_ptr()),
+                                                          C.c_size_t(len(a))))
+        return out
+
+    def g1_deserialize_compressed(self, b):
+        """(n, 48) uint8 -> ((n, 18) Jacobian, (n,) status: 0 ok, 1 malformed / off curve, 2 wrong subgroup)"""
+        assert b.is_cuda and b.dtype == torch.uint8 and b.is_contiguous()
+        b = b.reshape(-1, 48)
+        out, st = self.empty(len(b), 18), torch.empty(len(b), dtype=torch.uint8, device=self.device)
+        self.check(self.L.scz_g1_deserialize_compressed_dev(self.h, C.c_void_p(b.data_ptr()), C.c_void_p(out.data_ptr()),
+                                                            C.c_void_p(st.data_ptr()), C.c_size_t(len(b))))
+        return out, st
+
+    def fr_deserialize(self, b):
+        """(n, 4) int64 holding 32-byte little-endian canonical integers -> (Montgomery (n, 4), status)"""
+        b = _dev(b, 4)
+        out, st = torch.empty_like(b), torch.empty(len(b), dtype=torch.uint8, device=self.device)
+        self.check(self.L.scz_fr_deserialize_dev(self.h, C.c_void_p(b.data_ptr()), C.c_void_p(out.data_ptr()),
+                                                 C.c_void_p(st.data_ptr()), C.c_size_t(len(b))))
+        return out, st
+
     def msm_set_window(self, c):
         self.check(self.L.scz_msm_set_window(self.h, C.c_uint32(c)))
 

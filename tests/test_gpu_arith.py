@@ -105,3 +105,65 @@ def test_generator_mul(orc, ctx):
     got = ctx.to_host(ctx.g1_generator_mul(ctx.to_device(k, 4)))
     assert np.array_equal(got, packed_affine(orc.g1_gen_mul(k)))
     assert not got[0].any()
+
+
+def test_g1_compressed_wire_format(orc):
+    """scz_g1_serialize_compressed_dev / _deserialize_ against the big-int twin and the public golden vectors
+    (generator = 97f1d3a7...c6bb, -G = b7..., infinity = c0 00..00); malformed and wrong-subgroup encodings are flagged"""
+    import torch
+    import scz_b200 as scz
+    from oracle import py_twin as tw
+    ctx = scz.Context(device=0, n_parties=8)
+    rng = np.random.default_rng(31)
+    k = orc.random_fr(rng, 40)
+    aff = ctx.g1_generator_mul(ctx.to_device(k, 4))                       # random points, affine
+    jac = ctx.g1_mul(_affine_to_jac(ctx, aff), ctx.to_device(orc.random_fr(rng, 40), 4))   # non-trivial Z
+    gen = orc.g1_from_affine(orc.g1_generator())
+    g13 = orc.g1_generator()
+    neg = np.concatenate([g13[:, :6], orc.fq_sub(np.zeros((1, 6), dtype=np.uint64), g13[:, 6:12]), np.zeros((1, 1), dtype=np.uint64)], axis=1)
+    special = np.concatenate([gen, orc.g1_from_affine(neg), np.zeros((1, 18), dtype=np.uint64)])
+    special[2, 0] = 1                                                        # (1, *, 0): infinity whatever X, Y
+    allj = torch.cat([jac, ctx.to_device(special, 18)])
+    ser = ctx.g1_serialize_compressed(allj)
+    host = ser.cpu().numpy()
+    canon = orc.canon_g1(ctx.to_host(allj))
+    for i, (x, y, inf) in enumerate(canon):
+        want = tw.g1_serialize_compressed(tw.INF if inf else (x, y))
+        assert bytes(host[i]) == want, i
+    gen_hex = "97f1d3a73197d7942695638c4fa9ac0fc3688c4f9774b905a14e3a3f171bac586c55e83ff97a1aeffb3af00adb22c6bb"
+    assert bytes(host[40]).hex() == gen_hex and bytes(host[41]).hex() == "b7" + gen_hex[2:]
+    assert bytes(host[42]).hex() == "c0" + "00" * 47
+    back, st = ctx.g1_deserialize_compressed(ser)
+    assert not st.any().item()
+    assert orc.canon_g1(ctx.to_host(back)) == canon
+    # malformed inputs
+    bad = np.zeros((4, 48), dtype=np.uint8)
+    bad[1] = np.frombuffer(bytes([0xC0]) + bytes(46) + b"\x01", dtype=np.uint8)
+    bad[2] = np.frombuffer(bytes([0x9F]) + b"\xff" * 47, dtype=np.uint8)
+    x = 0
+    while True:
+        rhs = (x ** 3 + 4) % tw.P_MOD
+        y = pow(rhs, (tw.P_MOD + 1) // 4, tw.P_MOD)
+        if y * y % tw.P_MOD == rhs:
+            break
+        x += 1
+    bad[3] = np.frombuffer(tw.g1_serialize_compressed((x, y)), dtype=np.uint8)
+    _, st = ctx.g1_deserialize_compressed(torch.from_numpy(bad).to("cuda"))
+    assert st.cpu().tolist() == [1, 1, 1, 2]
+    # Fr: canonical little-endian bytes; values >= r are rejected
+    fr = orc.random_fr(rng, 50)
+    can = ctx.fr_to_canonical(ctx.to_device(fr, 4))
+    assert [orc.limbs_to_int(r) for r in ctx.to_host(can)] == orc.fr_to_ints(fr)
+    back, st = ctx.fr_deserialize(can)
+    assert np.array_equal(ctx.to_host(back), fr) and not st.any().item()
+    over = orc.ints_to_arr([tw.R_MOD, tw.R_MOD + 5, (1 << 256) - 1, tw.R_MOD - 1], 4)
+    _, st = ctx.fr_deserialize(ctx.to_device(over, 4))
+    assert st.cpu().tolist() == [1, 1, 1, 0]
+    ctx.close()
+
+
+def _affine_to_jac(ctx, aff):
+    import torch
+    one = torch.tensor(np.array([0x760900000002fffd, 0xebf4000bc40c0002, 0x5f48985753c758ba, 0x77ce585370525745,
+                                 0x5c071a97a256ec6d, 0x15f65ec3fa80e493], dtype=np.uint64).view(np.int64), device=aff.device)
+    return torch.cat([aff, one.repeat(len(aff), 1)], dim=1).contiguous()

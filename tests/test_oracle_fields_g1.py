@@ -113,3 +113,30 @@ def test_msm_ark_equals_naive_equals_twin(orc):
     S = orc.fr_from_ints([1] * n)
     want = tw.g1_mul(G, ks[0] * n % tw.R_MOD)
     assert orc.canon_g1(orc.msm(bases, S, "ark")) == [(want[0], want[1], 0)]
+
+
+def test_g1_compressed_wire_format_golden_vectors():
+    """ark-bls12-381 0.4.0 serialises G1 in the Zcash / IETF compressed form.  Public known answers: the generator is
+    97f1d3a7...c6bb (flag byte 0x80 | 0x17: its y is the smaller root), -G flips the sort bit (b7...), infinity is c0 00..00."""
+    from oracle import py_twin as tw
+    g = (tw.G1_X, tw.G1_Y)
+    gen_hex = ("97f1d3a73197d7942695638c4fa9ac0fc3688c4f9774b905a14e3a3f171bac58"
+               "6c55e83ff97a1aeffb3af00adb22c6bb")
+    assert tw.g1_serialize_compressed(g).hex() == gen_hex
+    assert tw.g1_serialize_compressed(tw.g1_neg(g)).hex() == "b7" + gen_hex[2:]
+    assert tw.g1_serialize_compressed(tw.INF).hex() == "c0" + "00" * 47
+    for pt in (g, tw.g1_neg(g), tw.g1_mul(g, 0xDEADBEEF), tw.INF):
+        back, st = tw.g1_deserialize_compressed(tw.g1_serialize_compressed(pt))
+        assert st == 0 and back == pt
+    assert tw.g1_deserialize_compressed(bytes(48))[1] == 1                                     # compression bit missing
+    assert tw.g1_deserialize_compressed(bytes([0xC0]) + bytes(46) + b"\x01")[1] == 1           # infinity with payload
+    assert tw.g1_deserialize_compressed(bytes([0x9F]) + b"\xff" * 47)[1] == 1                  # x >= p
+    # x = 4: x^3 + 4 = 68 is a square mod p? find one on-curve x whose point is outside the r-torsion (cofactor != 1)
+    x = 0
+    while True:
+        rhs = (x ** 3 + 4) % tw.P_MOD
+        y = pow(rhs, (tw.P_MOD + 1) // 4, tw.P_MOD)
+        if y * y % tw.P_MOD == rhs:
+            break
+        x += 1
+    assert tw.g1_deserialize_compressed(tw.g1_serialize_compressed((x, y)))[1] == 2            # on the curve, wrong subgroup
