@@ -255,6 +255,14 @@ int32_t scz_srs_from_device_levels(scz_ctx *ctx, size_t levels, const void *cons
                                    scz_srs **out);
 int32_t scz_srs_from_host_levels(scz_ctx *ctx, size_t levels, const void *const *levels_host, const size_t *lens,
                                  scz_srs **out);
+/* PolynomialCommitmentCub::new(g, _, s).mature() (dpoly_comm.rs:37-67, 141-150): the real SRS with trapdoor s[0..n),
+ * levels 0..n of 2^i points, built on the device (set-up) */
+int32_t scz_srs_new_dev(scz_ctx *ctx, const void *d_g_jac, const void *d_s, size_t n, scz_srs **out);
+/* to_packed (dpoly_comm.rs:164-194): PSS-pack every level over G1 in chunks of l points; returns party `party`'s SRS
+ * (levels of max(1, 2^i / l) share points) */
+int32_t scz_srs_to_packed_dev(scz_ctx *ctx, const scz_srs *srs, const scz_pp *pp, uint32_t party, scz_srs **out);
+/* copy a level (packed affine) into d_out (may be NULL to query the length) */
+int32_t scz_srs_level_dev(scz_ctx *ctx, const scz_srs *srs, size_t level, void *d_out, size_t *len);
 void scz_srs_free(scz_srs *srs);
 /* Fixed-base tables for every level: the window multiples 2^(c w) * P_j next to the points, so that all windows of a
  * scalar share one bucket set (fewer bucket additions, no Horner recombination; see csrc/srs.cu).  Same results,

@@ -542,6 +542,35 @@ class PolynomialCommitment:
         except Exception:
             pass
 
+    @classmethod
+    def _wrap(cls, ctx, handle):
+        self = cls.__new__(cls)
+        self.ctx, self.levels, self.h = ctx, [], handle
+        return self
+
+    @classmethod
+    def new(cls, ctx, g_jac, s):
+        """PolynomialCommitmentCub::new(g, _, s).mature() (dpoly_comm.rs:37-67): the real SRS for the trapdoor s"""
+        g, _ = _in(ctx, g_jac, 18)
+        sd, _ = _in(ctx, s, 4)
+        h = C.c_void_p()
+        ctx.check(ctx.L.scz_srs_new_dev(ctx.h, _vp(g), _vp(sd), C.c_size_t(len(sd)), C.byref(h)))
+        return cls._wrap(ctx, h)
+
+    def to_packed(self, pp, party):
+        """to_packed (dpoly_comm.rs:164-194): party `party`'s PSS share of this SRS"""
+        h = C.c_void_p()
+        self.ctx.check(self.ctx.L.scz_srs_to_packed_dev(self.ctx.h, self.h, pp.h, C.c_uint32(party), C.byref(h)))
+        return PolynomialCommitment._wrap(self.ctx, h)
+
+    def level(self, i):
+        """packed affine points of level i as a CUDA tensor (len, 12)"""
+        n = C.c_size_t()
+        self.ctx.check(self.ctx.L.scz_srs_level_dev(self.ctx.h, self.h, C.c_size_t(i), None, C.byref(n)))
+        out = self.ctx.empty(n.value, 12)
+        self.ctx.check(self.ctx.L.scz_srs_level_dev(self.ctx.h, self.h, C.c_size_t(i), _vp(out), C.byref(n)))
+        return out
+
     def precompute(self):
         """build the fixed-base tables of every level (scz_srs_precompute): same results, fewer bucket additions"""
         self.ctx.check(self.ctx.L.scz_srs_precompute(self.ctx.h, self.h))

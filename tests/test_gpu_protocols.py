@@ -374,3 +374,52 @@ def test_parties_mode_local_test_net(orc):
     assert sum(res[j]["comm"][0] for j in range(1, N)) == res[0]["comm"][1]
     assert sum(res[j]["comm"][1] for j in range(1, N)) == res[0]["comm"][0]
     seed_ctx.close()
+
+
+@pytest.mark.parametrize("l", [1, 2])
+def test_real_srs_and_packed_srs_end_to_end(orc, ctx_l, l):
+    """PolynomialCommitmentCub::new / to_packed (dpoly_comm.rs:37-67, 164-194) on the device, and the collaborative
+    pipeline's MEANING for N = 8 l parties: with the SRS and the polynomial both PSS-packed, the per-party MSMs unpack2
+    to l points whose sum is the plain commitment [p(s)] g (the reference's pack_unpack2_test, dmsm.rs:104-138, at the
+    protocol level), and the full c_commit protocol run by N parties hands every party a share that unpacks to it."""
+    import torch
+    import scz_b200 as scz
+    from scz_b200.api import msm_batched
+    from scz_b200.net import LocalTestNet
+    ctx = ctx_l(l)
+    N, nv = 8 * l, 5
+    rng = np.random.default_rng(560 + l)
+    s = orc.random_fr(rng, nv)
+    g = orc.g1_from_affine(orc.g1_generator())
+    osrs = orc.Srs.new(g, s)
+    srs = scz.PolynomialCommitment.new(ctx, g, s)
+    for i in range(nv + 1):
+        assert np.array_equal(ctx.to_host(srs.level(i)), osrs.level(i)[:, :12]), i      # bit-exact affine points
+    pp, opp = scz.PackedSharingParams(ctx, l), orc.pp_new(l)
+    p = orc.random_fr(rng, 1 << nv)
+    want = orc.canon_g1(orc.commit(osrs, p))
+    assert orc.canon_g1(srs.commit(p)) == want
+    # PSS-pack the polynomial in chunks of l (what a delegator does, examples/poly_comm.rs:52-55 uses random shares)
+    shares = np.stack([orc.pack_from_public(opp, p[c:c + l]) for c in range(0, len(p), l)], axis=1)   # (N, 2^nv / l, 4)
+    packed = [srs.to_packed(pp, j) for j in range(N)]
+    local = torch.cat([msm_batched(ctx, [packed[j].level(nv)], [ctx.to_device(shares[j], 4)]) for j in range(N)])
+    secrets = pp.unpack2(local, kind="g1").reshape(l, 18)
+    total = secrets[0:1].contiguous()
+    for k in range(1, l):
+        total = ctx.g1_add(total, secrets[k:k + 1].contiguous())
+    assert orc.canon_g1(ctx.to_host(total)) == want
+    # the protocol itself, N parties in one process
+    levels = [[packed[j].level(i) for i in range(nv + 1)] for j in range(N)]
+
+    def party(j, net):
+        c = scz.Context(device=0, party_id=j, n_parties=N, net=net)
+        ppj = scz.PackedSharingParams(c, l)
+        out = scz.PolynomialCommitment(c, levels[j]).c_commit(ppj, [shares[j]])
+        c.sync()
+        c.close()
+        return out
+
+    res = LocalTestNet(N, "cuda:0").simulate_network_round(party)
+    got = pp.unpack(ctx.to_device(np.concatenate(res), 18), kind="g1").reshape(l, 18)
+    for k in range(l):
+        assert orc.canon_g1(ctx.to_host(got[k:k + 1].contiguous())) == want, k
