@@ -75,20 +75,29 @@ SCZ_HD G1X g1x_neg(const G1X &p) {
     r.y = fp_neg(p.y);
     return r;
 }
+// Multiplier policy of the group law.  The throughput kernels inline every field product (MulInline); the
+// latency-bound tail kernels (bucket tree, fix-up) call ONE out-of-line copy of each (a general addition is 14
+// products: inlined it is ~90 KB of code, which, with the doubling beside it, no longer fits the instruction cache).
+struct MulInline {
+    SCZ_HD static Fq mul(const Fq &a, const Fq &b) { return fp_mul(a, b); }
+    SCZ_HD static Fq sqr(const Fq &a) { return fp_sqr(a); }
+    SCZ_HD static Fq dot2_sub(const Fq &a, const Fq &b, const Fq &c, const Fq &d) { return fp_dot2_sub(a, b, c, d); }
+};
 // dbl-2008-s-1 (a = 0)
+template <class M = MulInline>
 SCZ_HD G1X g1x_double(const G1X &p) {
     if (p.is_inf()) return p;
     Fq u = fp_dbl(p.y);
-    Fq v = fp_sqr(u);
-    Fq w = fp_mul(u, v);
-    Fq s = fp_mul(p.x, v);
-    Fq xx = fp_sqr(p.x);
+    Fq v = M::sqr(u);
+    Fq w = M::mul(u, v);
+    Fq s = M::mul(p.x, v);
+    Fq xx = M::sqr(p.x);
     Fq m = fp_add(fp_dbl(xx), xx);
     G1X r;
-    r.x = fp_sub(fp_sub(fp_sqr(m), s), s);
-    r.y = fp_dot2_sub(m, fp_sub(s, r.x), w, p.y);          // m (s - x3) - w y, one reduction
-    r.zz = fp_mul(v, p.zz);
-    r.zzz = fp_mul(w, p.zzz);
+    r.x = fp_sub(fp_sub(M::sqr(m), s), s);
+    r.y = M::dot2_sub(m, fp_sub(s, r.x), w, p.y);          // m (s - x3) - w y, one reduction
+    r.zz = M::mul(v, p.zz);
+    r.zzz = M::mul(w, p.zzz);
     return r;
 }
 // mdbl-2008-s-1: double an affine point
@@ -140,27 +149,28 @@ SCZ_HD void g1x_add_affine(G1X &acc, const G1Affine &p, bool negate) {
     g1x_add_affine(acc, p.x, y);
 }
 // add-2008-s
+template <class M = MulInline>
 SCZ_HD G1X g1x_add(const G1X &a, const G1X &b) {
     if (a.is_inf()) return b;
     if (b.is_inf()) return a;
-    Fq u1 = fp_mul(a.x, b.zz);
-    Fq u2 = fp_mul(b.x, a.zz);
-    Fq s1 = fp_mul(a.y, b.zzz);
-    Fq s2 = fp_mul(b.y, a.zzz);
+    Fq u1 = M::mul(a.x, b.zz);
+    Fq u2 = M::mul(b.x, a.zz);
+    Fq s1 = M::mul(a.y, b.zzz);
+    Fq s2 = M::mul(b.y, a.zzz);
     Fq p = fp_sub(u2, u1);
     Fq r = fp_sub(s2, s1);
     if (p.is_zero()) {
-        if (r.is_zero()) return g1x_double(a);
+        if (r.is_zero()) return g1x_double<M>(a);
         return G1X::inf();
     }
-    Fq pp = fp_sqr(p);
-    Fq ppp = fp_mul(p, pp);
-    Fq q = fp_mul(u1, pp);
+    Fq pp = M::sqr(p);
+    Fq ppp = M::mul(p, pp);
+    Fq q = M::mul(u1, pp);
     G1X o;
-    o.x = fp_sub(fp_sub(fp_sub(fp_sqr(r), ppp), q), q);
-    o.y = fp_dot2_sub(r, fp_sub(q, o.x), s1, ppp);
-    o.zz = fp_mul(fp_mul(a.zz, b.zz), pp);
-    o.zzz = fp_mul(fp_mul(a.zzz, b.zzz), ppp);
+    o.x = fp_sub(fp_sub(fp_sub(M::sqr(r), ppp), q), q);
+    o.y = M::dot2_sub(r, fp_sub(q, o.x), s1, ppp);
+    o.zz = M::mul(M::mul(a.zz, b.zz), pp);
+    o.zzz = M::mul(M::mul(a.zzz, b.zzz), ppp);
     return o;
 }
 // k * P, k = canonical little-endian 32-bit limbs (double-and-add, MSB first)

@@ -89,8 +89,17 @@ __device__ __forceinline__ int seg_by_level(const MsmSeg *segs, int K, int lvl, 
 
 // Out-of-line group law for the latency-bound tail kernels: keeps their code inside the
 // instruction cache (an inlined general add is ~5k instructions) and the build fast.
-__device__ __noinline__ void g1x_add_nl(G1X &r, const G1X &a, const G1X &b) { r = g1x_add(a, b); }
-__device__ __noinline__ void g1x_double_nl(G1X &r, const G1X &a) { r = g1x_double(a); }
+__device__ __noinline__ Fq fq_mul_nl(const Fq &a, const Fq &b) { return fp_mul(a, b); }
+__device__ __noinline__ Fq fq_dot2_sub_nl(const Fq &a, const Fq &b, const Fq &c, const Fq &d) { return fp_dot2_sub(a, b, c, d); }
+struct MulCall {
+    __device__ __forceinline__ static Fq mul(const Fq &a, const Fq &b) { return fq_mul_nl(a, b); }
+    __device__ __forceinline__ static Fq sqr(const Fq &a) { return fq_mul_nl(a, a); }
+    __device__ __forceinline__ static Fq dot2_sub(const Fq &a, const Fq &b, const Fq &c, const Fq &d) {
+        return fq_dot2_sub_nl(a, b, c, d);
+    }
+};
+__device__ __noinline__ void g1x_add_nl(G1X &r, const G1X &a, const G1X &b) { r = g1x_add<MulCall>(a, b); }
+__device__ __noinline__ void g1x_double_nl(G1X &r, const G1X &a) { r = g1x_double<MulCall>(a); }
 
 // ---- 1 + 3: recode, then count (SCATTER = false) or place (SCATTER = true)
 template <bool SCATTER>
