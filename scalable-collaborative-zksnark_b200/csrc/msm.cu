@@ -380,16 +380,52 @@ __device__ __forceinline__ G1X block_sum_g1x(G1X v, G1X *sh) {
     return v;
 }
 
+// Long chains: one WARP per bucket while the chain is short enough for 32 lanes (the few hundred low buckets that
+// collect a fixed-base table's narrow top window), the whole CTA for the really long ones (degenerate scalars).
+constexpr uint32_t FIX_WARP_MAX = 256;   // parts; beyond this the CTA sums the chain together
 __global__ void __launch_bounds__(PLN_THREADS) k_msm_fixup_heavy(uint32_t logT, const uint32_t *counts,
                                                                   const uint32_t *cursor, const void *parts,
                                                                   void *buckets, const uint32_t *heavy_list,
                                                                   const uint32_t *heavy_count) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     G1X *sh = reinterpret_cast<G1X *>(smem_raw);
-    for (uint32_t h = blockIdx.x; h < *heavy_count; h += gridDim.x) {
+    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = PLN_THREADS / 32;
+    const uint32_t total = *heavy_count;
+    // pass 1: warp per bucket
+    for (uint32_t h = blockIdx.x * nw + wid; h < total; h += gridDim.x * nw) {
         uint32_t b = heavy_list[h];
         uint32_t end = cursor[b], start = end - counts[b];
         uint32_t t0 = start >> logT, t1 = (end - 1) >> logT;
+        if (t1 - t0 > FIX_WARP_MAX) continue;
+        G1X acc = G1X::inf();
+        if (lane == 0) acc = g1x_load(parts, 2 * (size_t)t0 + 1);
+        for (uint32_t u = t0 + 1 + lane; u <= t1; u += 32) {
+            G1X v = g1x_load(parts, 2 * (size_t)u);
+            g1x_add_nl(acc, acc, v);
+        }
+        G1X *w = sh + wid * 32;
+        w[lane] = acc;
+        __syncwarp();
+        for (int stride = 16; stride > 0; stride >>= 1) {
+            if ((int)lane < stride) {
+                G1X o = w[lane + stride];
+                if (!o.is_inf()) {
+                    g1x_add_nl(acc, acc, o);
+                    w[lane] = acc;
+                }
+            }
+            __syncwarp();
+        }
+        if (lane == 0) g1x_store(buckets, b, acc);
+        __syncwarp();
+    }
+    __syncthreads();
+    // pass 2: CTA per bucket for the very long chains
+    for (uint32_t h = blockIdx.x; h < total; h += gridDim.x) {
+        uint32_t b = heavy_list[h];
+        uint32_t end = cursor[b], start = end - counts[b];
+        uint32_t t0 = start >> logT, t1 = (end - 1) >> logT;
+        if (t1 - t0 <= FIX_WARP_MAX) continue;   // uniform across the CTA
         G1X acc = G1X::inf();
         if (threadIdx.x == 0) acc = g1x_load(parts, 2 * (size_t)t0 + 1);
         for (uint32_t u = t0 + 1 + threadIdx.x; u <= t1; u += PLN_THREADS) {
@@ -576,7 +612,7 @@ int32_t msm_g1_batched(Ctx *ctx, const void *const *d_bases, const void *const *
                                                                                 cursor, d_parts.p, d_buckets.p, heavy + 1,
                                                                                 heavy);
         SCZ_LAUNCH_CHECK(ctx);
-        k_msm_fixup_heavy<<<ctx->sm_count, PLN_THREADS, PLN_THREADS * sizeof(G1X), st>>>(
+        k_msm_fixup_heavy<<<ctx->sm_count * 2, PLN_THREADS, PLN_THREADS * sizeof(G1X), st>>>(
             logT, counts, cursor, d_parts.p, d_buckets.p, heavy + 1, heavy);
         SCZ_LAUNCH_CHECK(ctx);
     }
