@@ -308,8 +308,8 @@ __global__ void __launch_bounds__(PL_THREADS) k_pointwise(const void *a, const v
 }
 
 // out[i] = num[i] / den[i] (dhyperplonk.rs:338-339).  Montgomery's trick on two levels: a thread owns
-// INV_PER_THREAD consecutive elements (prefix products in registers), a warp shares ONE Fermat inversion through
-// a shuffle scan, so an element costs ~6 products instead of ~380.  den = 0 yields 0 (arkworks would panic).
+// INV_PER_THREAD consecutive elements (prefix products in registers), a warp combines them through a shuffle scan
+// and the whole CTA (1024 elements) shares ONE Fermat inversion, so an element costs ~7 products instead of ~380.  den = 0 yields 0 (arkworks would panic).
 constexpr int INV_PER_THREAD = 4;
 __device__ __forceinline__ Fr fr_shfl(const Fr &v, int src) {
     Fr r;
@@ -342,9 +342,27 @@ __global__ void __launch_bounds__(PL_THREADS) k_div(const void *num, const void 
         Fr t = fr_shfl_up(incl, o);
         if (lane >= o) incl = fp_mul(incl, t);
     }
-    Fr total_inv = Fr::zero();
-    if (lane == 31) total_inv = fp_inv(incl);
-    total_inv = fr_shfl(total_inv, 31);
+    // one Fermat inversion per CTA: the warp totals meet in shared memory, thread 0 inverts their product and hands
+    // every warp the inverse of ITS total = inv(all) * (totals of the other warps)
+    __shared__ Fr wtot[PL_THREADS / 32], winv[PL_THREADS / 32];
+    const int wid = threadIdx.x >> 5;
+    if (lane == 31) wtot[wid] = incl;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        constexpr int NW = PL_THREADS / 32;
+        Fr pre_w[NW], acc = Fr::one();
+        for (int w = 0; w < NW; w++) {
+            pre_w[w] = acc;                      // product of the warps before w
+            acc = fp_mul(acc, wtot[w]);
+        }
+        Fr inv_all = fp_inv(acc), suf = Fr::one();
+        for (int w = NW - 1; w >= 0; w--) {
+            winv[w] = fp_mul(inv_all, fp_mul(pre_w[w], suf));
+            suf = fp_mul(suf, wtot[w]);
+        }
+    }
+    __syncthreads();
+    Fr total_inv = winv[wid];
     // inverse of this thread's product = total_inv * (product of later lanes) * (product of earlier lanes):
     // suffix products by a second scan
     Fr suf = run;
