@@ -289,6 +289,7 @@ def run_own(args):
     for ctx, _, _ in parties:
         ctx.prof_enable(True)
     launches0 = sum(c.launches for c, _, _ in parties)
+    coll0 = dict(hub.calls) if hub else {}
     stats0 = ctx0.msm_cum_stats()
     comm0 = ctx0.get_comm()
     if sampler:
@@ -305,6 +306,7 @@ def run_own(args):
         sampler.mark_end()
     ms = e0.elapsed_time(e1)
     launches = sum(c.launches for c, _, _ in parties) - launches0
+    coll = {k: (hub.calls[k] - coll0[k]) // args.steps for k in coll0} if hub else None
     stats1 = ctx0.msm_cum_stats()
     comm1 = ctx0.get_comm()
     prof = {k: ctx0.prof_read(k) for k in ctx0.KERNEL_CLASSES}
@@ -410,6 +412,7 @@ def run_own(args):
                               "launch_sequences": (stats1["sequences"] - stats0["sequences"]) // args.steps,
                               "pairs": pairs // args.steps, "bucket_adds": adds // args.steps},
             "kernel_ms_per_step": {k: v[0] / args.steps for k, v in prof.items()},
+            "nccl_collectives_per_proof_rank0": coll,
             "comm_bytes_per_proof_party0": {"upload": comm[0], "download": comm[1]},
         },
         "clocks": clocks,

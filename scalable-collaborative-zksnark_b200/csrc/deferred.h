@@ -48,7 +48,16 @@ struct Deferred {
     std::vector<PssJob> pss_jobs;
     const scz_pp *pss_pp = nullptr;
     std::vector<ColsumJob> colsum_jobs;
-    std::vector<std::function<int32_t()>> after2;      // run after the queued closures (the scatters)
+    std::vector<std::function<int32_t()>> after2;      // run after the round's scatters
+    // The leader rounds of one stage travel together: every continuation REGISTERS its gather / scatter and run()
+    // issues ONE collective per stage on the concatenated payloads (about 110 star rounds of a proof become 4).
+    struct XferReq {
+        const void *send;
+        void *recv;
+        size_t bytes, wire;
+    };
+    std::vector<XferReq> gathers, scatters;
+    std::vector<std::function<int32_t()>> after_gather;   // run once the gathered data is in place (leader-side work)
     std::vector<std::shared_ptr<DevTmp>> keep;         // temporaries that must stay alive until run() returns
 
     explicit Deferred(Ctx *c) : ctx(c) {}
@@ -68,6 +77,13 @@ struct Deferred {
     int32_t add_msm(const void *b, const void *s, size_t len, void *out, uint32_t pre_c = 0);
     void then(std::function<int32_t()> f) { after.push_back(std::move(f)); }
     void then2(std::function<int32_t()> f) { after2.push_back(std::move(f)); }
+    void then_gathered(std::function<int32_t()> f) { after_gather.push_back(std::move(f)); }
+    // worker_send_or_leader_receive_element: recv (n_parties * bytes, party-major) is only used on the leader
+    void gather(const void *send, void *recv, size_t bytes, size_t wire) { gathers.push_back(XferReq{send, recv, bytes, wire}); }
+    // worker_receive_or_leader_send_element: send (n_parties * bytes) is only used on the leader; runs after the closures
+    void scatter(const void *send, void *recv, size_t bytes, size_t wire) { scatters.push_back(XferReq{send, recv, bytes, wire}); }
+    int32_t do_gathers();    // protocols.cu
+    int32_t do_scatters();
     void add_pss(const scz_pp *pp, const void *in, uint32_t batch, void *out) {
         pss_pp = pp;
         pss_jobs.push_back(PssJob{in, out, batch, 0});

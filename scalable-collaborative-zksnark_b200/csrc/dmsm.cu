@@ -45,11 +45,11 @@ int32_t d_msm_defer(Ctx *ctx, Deferred &D, const scz_pp *pp, const void *const *
             SCZ_TRY(Dp->tmp(N * batch * PT, &recv));
             SCZ_TRY(Dp->tmp(N * batch * PT, &send));
         }
-        SCZ_TRY(net->gather(ctx, c_shares->p, recv ? recv->p : nullptr, batch * PT, wire));
+        Dp->gather(c_shares->p, recv ? recv->p : nullptr, batch * PT, wire);
         // recv is party-major [j][k]: vector k is the stride-`batch` column.  The closure (dmsm.rs:31-38) is queued:
-        // all d_msm calls of a round share one launch (deferred.h)
+        // all d_msm calls of a round share one launch, and one gather / one scatter (deferred.h)
         if (net->is_leader()) Dp->add_pss(pp, recv->p, (uint32_t)batch, send->p);
-        Dp->then2([=]() -> int32_t { return net->scatter(ctx, send ? send->p : nullptr, d_out, batch * PT, wire); });
+        Dp->scatter(send ? send->p : nullptr, d_out, batch * PT, wire);
         return SCZ_OK;
     });
     return SCZ_OK;

@@ -222,12 +222,8 @@ int32_t dhyperplonk_dev(Ctx *ctx, size_t n, const scz_hp_pk *pk, const scz_pp *p
     if (variant != HP_PERMCHECK) {
         void *coms_p = coms.p;
         auto copy_com = [&](void *dst, int k) {   // the commitments of step 1 exist once D has run their leader rounds
-            Deferred *Dp = &D;
-            D.then([=]() -> int32_t {   // queued behind the scatters that deliver the commitments (stage 2 of the round)
-                Dp->then2([=]() -> int32_t {
-                    SCZ_CUDA(ctx, cudaMemcpyAsync(dst, (char *)coms_p + k * PT, PT, cudaMemcpyDeviceToDevice, st));
-                    return SCZ_OK;
-                });
+            D.then2([=]() -> int32_t {   // after the round's scatters, which deliver the commitments of step 1
+                SCZ_CUDA(ctx, cudaMemcpyAsync(dst, (char *)coms_p + k * PT, PT, cudaMemcpyDeviceToDevice, st));
                 return SCZ_OK;
             });
         };

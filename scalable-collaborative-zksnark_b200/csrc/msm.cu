@@ -665,12 +665,18 @@ int32_t Deferred::flush_msm() {
     return rc;
 }
 int32_t Deferred::run() {
-    while (!lens.empty() || !after.empty() || !pss_jobs.empty() || !colsum_jobs.empty() || !after2.empty()) {
+    while (!lens.empty() || !after.empty() || !gathers.empty() || !after_gather.empty() || !pss_jobs.empty() ||
+           !colsum_jobs.empty() || !scatters.empty() || !after2.empty()) {
         SCZ_TRY(flush_msm());
         std::vector<std::function<int32_t()>> now;
         now.swap(after);
         for (auto &f : now) SCZ_TRY(f());
+        SCZ_TRY(do_gathers());
+        now.clear();
+        now.swap(after_gather);
+        for (auto &f : now) SCZ_TRY(f());
         SCZ_TRY(flush_closures());
+        SCZ_TRY(do_scatters());
         now.clear();
         now.swap(after2);
         for (auto &f : now) SCZ_TRY(f());

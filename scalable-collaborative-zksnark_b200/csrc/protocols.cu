@@ -104,6 +104,28 @@ int32_t pss2ss_dev(Ctx *ctx, const scz_pp *pp, const void *d_share, void *d_out)
     return SCZ_OK;
 }
 
+// k pss2ss calls on k shares in ONE leader round (c_sumcheck_product does two back to back, dsumcheck.rs:224-225):
+// d_out is [k][l].  Byte counters as for k separate rounds.
+int32_t pss2ss_many_dev(Ctx *ctx, const scz_pp *pp, const void *d_shares, size_t k, void *d_out) {
+    Net *net = ctx->net;
+    const size_t N = net->n_parties, l = pp->l;
+    if (N != pp->n) return ctx->fail(SCZ_ERR_BAD_ARG, "pss2ss: %zu parties but pp.n = %zu", N, pp->n);
+    DevTmp recv(ctx), sec(ctx), send(ctx);
+    if (net->is_leader()) {
+        SCZ_TRY(recv.alloc(N * k * 32));
+        SCZ_TRY(sec.alloc(k * l * 32));
+        SCZ_TRY(send.alloc(N * k * l * 32));
+    }
+    SCZ_TRY(net->gather(ctx, d_shares, recv.p, k * 32, k * 32));
+    if (net->is_leader()) {
+        ProfScope ps(ctx, SCZ_K_PSS);
+        SCZ_TRY(pss_apply(ctx, pp, PSS_UNPACK, 0, recv.p, N, 1, k, k, sec.p, l, 1));
+        SCZ_TRY(pss_apply(ctx, pp, PSS_PACK_SINGLE, 0, sec.p, 1, 1, 1, k * l, send.p, 1, k * l));
+    }
+    SCZ_TRY(net->scatter(ctx, send.p, d_out, k * l * 32, k * (8 + 32 * l)));
+    return SCZ_OK;
+}
+
 // ---- degree_reduce: degree_reduce.rs:29-41 ----------------------------------------------------------
 int32_t degree_reduce_dev(Ctx *ctx, const scz_pp *pp, const void *d_share, void *d_out) {
     Net *net = ctx->net;
@@ -146,16 +168,14 @@ int32_t c_sumcheck_product_dev(Ctx *ctx, const scz_pp *pp, const void *d_f, cons
     size_t n = log2_exact(len, &ok);
     if (!ok) return ctx->fail(SCZ_ERR_NOT_POW2, "c_sumcheck_product: length %zu is not a power of two", len);
     size_t l = pp->l, ll = log2_exact(l, &ok);
-    DevTmp last(ctx), f2(ctx), g2(ctx), last2(ctx);
+    DevTmp last(ctx), fg2(ctx), last2(ctx);
     SCZ_TRY(last.alloc(64));
-    SCZ_TRY(f2.alloc(l * 32));
-    SCZ_TRY(g2.alloc(l * 32));
+    SCZ_TRY(fg2.alloc(2 * l * 32));
     SCZ_TRY(last2.alloc(64));
     SCZ_TRY(sumcheck_product_rounds(ctx, d_f, d_g, len, d_challenge, d_out, last.p));   // Phase 1 :167-219
-    SCZ_TRY(pss2ss_dev(ctx, pp, last.p, f2.p));                                         // :224
-    SCZ_TRY(pss2ss_dev(ctx, pp, (char *)last.p + 32, g2.p));                            // :225
+    SCZ_TRY(pss2ss_many_dev(ctx, pp, last.p, 2, fg2.p));                                // :224-225, one round for both
     // Phase 2 :227-279 -- indexes challenge[i] with i from 0 again (:230), replicated as is
-    SCZ_TRY(sumcheck_product_rounds(ctx, f2.p, g2.p, l, d_challenge, (char *)d_out + n * 96, last2.p));
+    SCZ_TRY(sumcheck_product_rounds(ctx, fg2.p, (char *)fg2.p + l * 32, l, d_challenge, (char *)d_out + n * 96, last2.p));
     k_final_triple<<<1, 32, 0, ctx->stream>>>(last2.p, (char *)d_out + (n + ll) * 96);   // :282
     SCZ_LAUNCH_CHECK(ctx);
     return SCZ_OK;
@@ -348,9 +368,9 @@ int32_t d_commit_defer(Ctx *ctx, Deferred &D, const scz_srs *srs, const void *d_
             SCZ_TRY(Dp->tmp(N * PT, &recv));
             SCZ_TRY(Dp->tmp(N * PT, &send));
         }
-        SCZ_TRY(net->gather(ctx, loc->p, recv ? recv->p : nullptr, PT, 48));
+        Dp->gather(loc->p, recv ? recv->p : nullptr, PT, 48);
         if (net->is_leader()) Dp->add_colsum(recv->p, PT, 0, (uint32_t)N, 1, send->p, (uint32_t)N);   // sum, N copies :290-292
-        Dp->then2([=]() -> int32_t { return net->scatter(ctx, send ? send->p : nullptr, d_out, PT, 48); });
+        Dp->scatter(send ? send->p : nullptr, d_out, PT, 48);
         return SCZ_OK;
     });
     return SCZ_OK;
@@ -441,15 +461,18 @@ int32_t d_open_defer(Ctx *ctx, Deferred &D, const scz_srs *srs, const void *d_pe
             SCZ_TRY(Dp->tmp(N * payload, &recv));
             SCZ_TRY(Dp->tmp(N * 32, &lz));
         }
-        SCZ_TRY(net->gather(ctx, loc->p, recv ? recv->p : nullptr, payload, 32 + 8 + 48 * n));   // :368
-        if (!net->is_leader()) {
-            SCZ_CUDA(ctx, cudaMemsetAsync(d_value, 0, 32, ctx->stream));
+        Dp->gather(loc->p, recv ? recv->p : nullptr, payload, 32 + 8 + 48 * n);   // :368
+        Dp->then_gathered([=]() -> int32_t {
+            if (!net->is_leader()) {
+                SCZ_CUDA(ctx, cudaMemsetAsync(d_value, 0, 32, ctx->stream));
+                return SCZ_OK;
+            }
+            k_pick_fr<<<1, 32 * (uint32_t)((N + 31) / 32), 0, ctx->stream>>>(recv->p, payload, (uint32_t)N, lz->p);
+            SCZ_LAUNCH_CHECK(ctx);
+            SCZ_TRY(open_defer(ctx, *Dp, srs, lz->p, N, d_point, d_value, d_proofs));       // root_open :377 (next flush)
+            if (n) Dp->add_colsum(recv->p, payload, 32, (uint32_t)N, (uint32_t)n, (char *)d_proofs + pl * PT, 1);   // :374-376
             return SCZ_OK;
-        }
-        k_pick_fr<<<1, 32 * (uint32_t)((N + 31) / 32), 0, ctx->stream>>>(recv->p, payload, (uint32_t)N, lz->p);
-        SCZ_LAUNCH_CHECK(ctx);
-        SCZ_TRY(open_defer(ctx, *Dp, srs, lz->p, N, d_point, d_value, d_proofs));           // root_open :377 (next flush)
-        if (n) Dp->add_colsum(recv->p, payload, 32, (uint32_t)N, (uint32_t)n, (char *)d_proofs + pl * PT, 1);   // :374-376
+        });
         return SCZ_OK;
     });
     return SCZ_OK;
@@ -474,6 +497,71 @@ __global__ void __launch_bounds__(64) k_g1_colsum_multi(const Deferred::ColsumJo
     }
     G1Jac r = g1x_to_jac(acc);
     for (uint32_t k = 0; k < job.replicate; k++) g1j_store(job.out, (size_t)k * job.cols + i, r);
+}
+
+// One collective for all gathers registered in this stage.  Without a real net (leader simulator) every request is a
+// replicate launch anyway, so they go out one by one.
+int32_t Deferred::do_gathers() {
+    if (gathers.empty()) return SCZ_OK;
+    Net *net = ctx->net;
+    std::vector<XferReq> reqs;
+    reqs.swap(gathers);
+    if (!net->real() || reqs.size() == 1) {
+        for (auto &r : reqs) SCZ_TRY(net->gather(ctx, r.send, r.recv, r.bytes, r.wire));
+        return SCZ_OK;
+    }
+    const size_t N = net->n_parties;
+    size_t T = 0, wire = 0;
+    for (auto &r : reqs) T += r.bytes, wire += r.wire;
+    DevTmp sendbuf(ctx), recvbuf(ctx);
+    SCZ_TRY(sendbuf.alloc(T));
+    if (net->is_leader()) SCZ_TRY(recvbuf.alloc(N * T));
+    size_t off = 0;
+    for (auto &r : reqs) {
+        SCZ_CUDA(ctx, cudaMemcpyAsync((char *)sendbuf.p + off, r.send, r.bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+        off += r.bytes;
+    }
+    SCZ_TRY(net->gather(ctx, sendbuf.p, recvbuf.p, T, wire));
+    if (net->is_leader()) {
+        off = 0;
+        for (auto &r : reqs) {   // [party][T] -> the request's own [party][bytes]
+            SCZ_CUDA(ctx, cudaMemcpy2DAsync(r.recv, r.bytes, (const char *)recvbuf.p + off, T, r.bytes, N,
+                                            cudaMemcpyDeviceToDevice, ctx->stream));
+            off += r.bytes;
+        }
+    }
+    return SCZ_OK;
+}
+int32_t Deferred::do_scatters() {
+    if (scatters.empty()) return SCZ_OK;
+    Net *net = ctx->net;
+    std::vector<XferReq> reqs;
+    reqs.swap(scatters);
+    if (!net->real() || reqs.size() == 1) {
+        for (auto &r : reqs) SCZ_TRY(net->scatter(ctx, r.send, r.recv, r.bytes, r.wire));
+        return SCZ_OK;
+    }
+    const size_t N = net->n_parties;
+    size_t T = 0, wire = 0;
+    for (auto &r : reqs) T += r.bytes, wire += r.wire;
+    DevTmp sendbuf(ctx), recvbuf(ctx);
+    SCZ_TRY(recvbuf.alloc(T));
+    size_t off = 0;
+    if (net->is_leader()) {
+        SCZ_TRY(sendbuf.alloc(N * T));
+        for (auto &r : reqs) {   // the request's [party][bytes] -> [party][T]
+            SCZ_CUDA(ctx, cudaMemcpy2DAsync((char *)sendbuf.p + off, T, r.send, r.bytes, r.bytes, N, cudaMemcpyDeviceToDevice,
+                                            ctx->stream));
+            off += r.bytes;
+        }
+    }
+    SCZ_TRY(net->scatter(ctx, sendbuf.p, recvbuf.p, T, wire));
+    off = 0;
+    for (auto &r : reqs) {
+        SCZ_CUDA(ctx, cudaMemcpyAsync(r.recv, (const char *)recvbuf.p + off, r.bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+        off += r.bytes;
+    }
+    return SCZ_OK;
 }
 
 int32_t Deferred::flush_closures() {
