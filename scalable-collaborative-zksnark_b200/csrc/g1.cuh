@@ -197,6 +197,20 @@ SCZ_D G1Affine g1a_load(const void *base, size_t idx) {
     p.y = fp_load<FqP>(b, 1);
     return p;
 }
+// gather of a base point that will not be touched again by this SM: bypass L1 (ld.global.cg) so that the streamed
+// entry lists keep their L1 lines
+SCZ_D G1Affine g1a_load_stream(const void *base, size_t idx) {
+    G1Affine p;
+    const uint4 *q = reinterpret_cast<const uint4 *>(reinterpret_cast<const char *>(base) + idx * 96);
+    uint32_t *w = &p.x.l[0];
+#pragma unroll
+    for (int i = 0; i < 6; i++) {
+        uint4 v = __ldcg(q + i);
+        if (i == 3) w = &p.y.l[0] - 12;
+        w[4 * i] = v.x, w[4 * i + 1] = v.y, w[4 * i + 2] = v.z, w[4 * i + 3] = v.w;
+    }
+    return p;
+}
 SCZ_D void g1a_store(void *base, size_t idx, const G1Affine &p) {
     char *b = reinterpret_cast<char *>(base) + idx * 96;
     fp_store<FqP>(b, 0, p.x);

@@ -104,8 +104,7 @@ __device__ __noinline__ void g1x_double_nl(G1X &r, const G1X &a) { r = g1x_doubl
 // ---- 1 + 3: recode, then count (SCATTER = false) or place (SCATTER = true)
 template <bool SCATTER>
 __global__ void __launch_bounds__(CNT_THREADS) k_msm_recode(const MsmSeg *segs, int K, uint32_t total_points,
-                                                             uint32_t *counts, uint32_t *cursor, uint32_t *sorted,
-                                                             uint32_t *keys) {
+                                                             uint32_t *counts, uint32_t *cursor, uint2 *sorted) {
     uint32_t g = blockIdx.x * CNT_THREADS + threadIdx.x;
     if (g >= total_points) return;
     int s = K == 1 ? 0 : seg_by_point(segs, K, g);
@@ -124,8 +123,7 @@ __global__ void __launch_bounds__(CNT_THREADS) k_msm_recode(const MsmSeg *segs, 
             atomicAdd(&counts[b], 1u);
         } else {
             uint32_t pos = atomicAdd(&cursor[b], 1u);
-            sorted[pos] = ref | (d < 0 ? 0x80000000u : 0u);
-            keys[pos] = b;
+            sorted[pos] = make_uint2(ref | (d < 0 ? 0x80000000u : 0u), b);   // one 8-byte store: (point | sign, bucket)
         }
     }
 }
@@ -218,8 +216,8 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_add(uint32_t *out, const 
 #define ACC_MIN_BLOCKS 1
 #endif
 __global__ void __launch_bounds__(ACC_THREADS, ACC_MIN_BLOCKS) k_msm_accumulate(const MsmSeg *segs, int K, const uint32_t *E_ptr,
-                                                                 uint32_t logT, const uint32_t *keys,
-                                                                 const uint32_t *sorted, const uint32_t *counts,
+                                                                 uint32_t logT, const uint2 *sorted,
+                                                                 const uint32_t *counts,
                                                                  const uint32_t *cursor, void *buckets, void *parts) {
     uint32_t t = blockIdx.x * ACC_THREADS + threadIdx.x;
     const uint32_t E = __ldg(E_ptr);   // entries actually in the stream (zero digits are dropped)
@@ -227,7 +225,8 @@ __global__ void __launch_bounds__(ACC_THREADS, ACC_MIN_BLOCKS) k_msm_accumulate(
     if (lo64 >= E) return;
     uint32_t lo = (uint32_t)lo64;
     uint32_t hi = lo64 + (1u << logT) < E ? lo + (1u << logT) : E;
-    uint32_t k_first = __ldg(keys + lo), k_last = __ldg(keys + hi - 1);
+    const uint2 e_first = __ldg(sorted + lo);
+    uint32_t k_first = e_first.y, k_last = __ldg(sorted + hi - 1).y;
     bool head_piece = cursor[k_first] - counts[k_first] < lo;   // the first bucket began in an earlier chunk
     bool tail_piece = cursor[k_last] > hi;                      // the last bucket goes on in a later chunk
 
@@ -242,22 +241,25 @@ __global__ void __launch_bounds__(ACC_THREADS, ACC_MIN_BLOCKS) k_msm_accumulate(
         seg_hi = segs[s].bucket_base + segs[s].W * segs[s].nb;
         bases = segs[s].bases;
     }
-    uint32_t ent = __ldg(sorted + lo);
-    G1Affine p = g1a_load(bases, ent & 0x7fffffffu);
+    // Software pipeline, two entries deep: while entry j is added, the POINT of entry j+1 is gathered (its index
+    // arrived one iteration ago, so the gather issues at once) and the ENTRY j+2 is fetched.  Nothing on the
+    // index -> address -> point chain is ever waited for at the top of an iteration.
+    uint32_t ent = e_first.x;
+    G1Affine p = g1a_load_stream(bases, ent & 0x7fffffffu);
+    uint2 ne = lo + 1 < hi ? __ldg(sorted + lo + 1) : make_uint2(0, cur);
     for (uint32_t j = lo; j < hi; j++) {
-        // prefetch entry j+1 (key, index, point) while entry j is being added
-        uint32_t nkey = cur, nent = 0;
+        const bool more = j + 1 < hi;
+        const uint32_t nkey = more ? ne.y : cur, nent = ne.x;
         G1Affine np;
-        bool more = j + 1 < hi;
+        uint2 n2 = make_uint2(0, 0);
+        if (j + 2 < hi) n2 = __ldg(sorted + j + 2);
         if (more) {
-            nkey = __ldg(keys + j + 1);
-            nent = __ldg(sorted + j + 1);
             if (nkey >= seg_hi) {
                 int s = seg_by_bucket(segs, K, nkey);
                 seg_hi = segs[s].bucket_base + segs[s].W * segs[s].nb;
                 bases = segs[s].bases;
             }
-            np = g1a_load(bases, nent & 0x7fffffffu);
+            np = g1a_load_stream(bases, nent & 0x7fffffffu);
         }
         g1x_add_affine(acc, p, (ent >> 31) != 0);
         if (!more || nkey != cur) {   // the run of bucket `cur` ends here
@@ -272,6 +274,7 @@ __global__ void __launch_bounds__(ACC_THREADS, ACC_MIN_BLOCKS) k_msm_accumulate(
         if (more) {
             p = np;
             ent = nent;
+            ne = n2;
         }
     }
 }
@@ -282,7 +285,7 @@ __global__ void __launch_bounds__(ACC_THREADS, ACC_MIN_BLOCKS) k_msm_accumulate(
 // dense).  Long chains (the top window's few buckets, degenerate scalar distributions such as dmsm.rs:103) go
 // to a list served by whole CTAs.
 constexpr uint32_t FIX_SERIAL_MAX = 6;
-__global__ void __launch_bounds__(FIX_THREADS) k_msm_fixup(const uint32_t *E_ptr, uint32_t logT, const uint32_t *keys,
+__global__ void __launch_bounds__(FIX_THREADS) k_msm_fixup(const uint32_t *E_ptr, uint32_t logT, const uint2 *sorted,
                                                             const uint32_t *counts, const uint32_t *cursor,
                                                             const void *parts, void *buckets, uint32_t *heavy_list,
                                                             uint32_t *heavy_count) {
@@ -292,7 +295,7 @@ __global__ void __launch_bounds__(FIX_THREADS) k_msm_fixup(const uint32_t *E_ptr
     if (lo64 >= E) return;
     uint32_t lo = (uint32_t)lo64;
     uint32_t hi = lo64 + (1u << logT) < E ? lo + (1u << logT) : E;
-    uint32_t b = __ldg(keys + hi - 1);
+    uint32_t b = __ldg(sorted + hi - 1).y;
     uint32_t end = cursor[b];
     if (end <= hi) return;                      // the chunk's last bucket ends inside it
     uint32_t start = end - counts[b];
@@ -551,14 +554,13 @@ int32_t msm_g1_batched(Ctx *ctx, const void *const *d_bases, const void *const *
 
     cudaStream_t st = ctx->stream;
     uint32_t tiles = ceil_div_u32(buckets, SCAN_TILE);
-    DevTmp d_segs(ctx), d_counts(ctx), d_cursor(ctx), d_tiles(ctx), d_sorted(ctx), d_keys(ctx), d_buckets(ctx),
+    DevTmp d_segs(ctx), d_counts(ctx), d_cursor(ctx), d_tiles(ctx), d_sorted(ctx), d_buckets(ctx),
         d_parts(ctx), d_heavy(ctx), d_nodes(ctx), d_wsum(ctx);
     SCZ_TRY(d_segs.alloc(batch * sizeof(MsmSeg)));
     SCZ_TRY(d_counts.alloc(buckets * 4));
     SCZ_TRY(d_cursor.alloc(buckets * 4));
     SCZ_TRY(d_tiles.alloc((size_t)tiles * 4 + 4));
-    SCZ_TRY(d_sorted.alloc((entries ? entries : 1) * 4));
-    SCZ_TRY(d_keys.alloc((entries ? entries : 1) * 4));
+    SCZ_TRY(d_sorted.alloc((entries ? entries : 1) * sizeof(uint2)));
     SCZ_TRY(d_buckets.alloc(buckets * sizeof(G1X)));
     SCZ_TRY(d_parts.alloc(((size_t)nchunks * 2 + 2) * sizeof(G1X)));
     SCZ_TRY(d_heavy.alloc(((size_t)nchunks + 1) * 4));   // [0] = count, [1..] = list (at most one bucket per chunk)
@@ -569,8 +571,8 @@ int32_t msm_g1_batched(Ctx *ctx, const void *const *d_bases, const void *const *
     SCZ_CUDA(ctx, cudaMemsetAsync(d_heavy.p, 0, 4, st));
     const MsmSeg *sp = d_segs.as<MsmSeg>();
     int K = (int)batch;
-    uint32_t *counts = d_counts.as<uint32_t>(), *cursor = d_cursor.as<uint32_t>(), *sorted = d_sorted.as<uint32_t>();
-    uint32_t *keys = d_keys.as<uint32_t>();
+    uint32_t *counts = d_counts.as<uint32_t>(), *cursor = d_cursor.as<uint32_t>();
+    uint2 *sorted = d_sorted.as<uint2>();
     static bool attr_done = false;
     if (!attr_done) {
         cudaFuncSetAttribute(k_msm_fixup_heavy, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -582,7 +584,7 @@ int32_t msm_g1_batched(Ctx *ctx, const void *const *d_bases, const void *const *
         ProfScope ps(ctx, SCZ_K_MSM_SORT);
         if (points) {
             k_msm_recode<false><<<ceil_div_u32(points, CNT_THREADS), CNT_THREADS, 0, st>>>(
-                sp, K, (uint32_t)points, counts, nullptr, nullptr, nullptr);
+                sp, K, (uint32_t)points, counts, nullptr, nullptr);
             SCZ_LAUNCH_CHECK(ctx);
         }
         k_scan_tiles<<<tiles, SCAN_THREADS, 0, st>>>(counts, cursor, d_tiles.as<uint32_t>(), (uint32_t)buckets);
@@ -593,7 +595,7 @@ int32_t msm_g1_batched(Ctx *ctx, const void *const *d_bases, const void *const *
         SCZ_LAUNCH_CHECK(ctx);
         if (points) {
             k_msm_recode<true><<<ceil_div_u32(points, CNT_THREADS), CNT_THREADS, 0, st>>>(
-                sp, K, (uint32_t)points, nullptr, cursor, sorted, keys);
+                sp, K, (uint32_t)points, nullptr, cursor, sorted);
             SCZ_LAUNCH_CHECK(ctx);
         }
     }
@@ -603,12 +605,12 @@ int32_t msm_g1_batched(Ctx *ctx, const void *const *d_bases, const void *const *
             // bound `entries`: zero digits are dropped); chunks past that end return at once
             ProfScope ps(ctx, SCZ_K_MSM_ACCUMULATE);
             k_msm_accumulate<<<ceil_div_u32(nchunks, ACC_THREADS), ACC_THREADS, 0, st>>>(
-                sp, K, cursor + (buckets - 1), logT, keys, sorted, counts, cursor, d_buckets.p, d_parts.p);
+                sp, K, cursor + (buckets - 1), logT, sorted, counts, cursor, d_buckets.p, d_parts.p);
             SCZ_LAUNCH_CHECK(ctx);
         }
         ProfScope ps(ctx, SCZ_K_MSM_FIXUP);
         uint32_t *heavy = d_heavy.as<uint32_t>();
-        k_msm_fixup<<<ceil_div_u32(nchunks, FIX_THREADS), FIX_THREADS, 0, st>>>(cursor + (buckets - 1), logT, keys, counts,
+        k_msm_fixup<<<ceil_div_u32(nchunks, FIX_THREADS), FIX_THREADS, 0, st>>>(cursor + (buckets - 1), logT, sorted, counts,
                                                                                 cursor, d_parts.p, d_buckets.p, heavy + 1,
                                                                                 heavy);
         SCZ_LAUNCH_CHECK(ctx);
