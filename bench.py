@@ -323,7 +323,7 @@ def run_own(args):
 
     # ---- the same proof with the fixed-base tables of the SRS ignored (plain Pippenger on the level's points)
     plain_ms = None
-    if not args.no_precompute:
+    if not args.no_precompute and not args.no_plain:
         for ctx, _, _ in parties:
             ctx.msm_use_precompute(False)
         prove_all()
@@ -459,6 +459,7 @@ def main():
     ap.add_argument("--ref-steps", type=int, default=2, help="--impl reference: at most this many timed proofs")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-precompute", action="store_true", help="do not build the fixed-base tables of the SRS")
+    ap.add_argument("--no-plain", action="store_true", help="skip the extra leg that times the proof with the tables ignored")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

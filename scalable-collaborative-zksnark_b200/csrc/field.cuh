@@ -413,10 +413,137 @@ SCZ_HD Fp<P> fp_dot2_sub(const Fp<P> &a1, const Fp<P> &b1, const Fp<P> &a2, cons
     return fp_dot2(a1, b1, fp_neg(a2), b2);
 }
 
+// ---------------------------------------------------------------- squaring (Fq only)
+// Operand scanning with the symmetric half of the partial products: 66 off-diagonal products accumulated on even / odd
+// columns (so that every mad.lo.cc / madc.hi.cc pair is again one IMAD.WIDE), doubled, plus the 12 squares on the
+// diagonal, then one Montgomery reduction of the 24-limb result: 78 + 144 = 222 wide multiplies instead of 288.
+// (A squaring cannot share CIOS's short accumulator: the high products arrive early, the running sum needs all 2N limbs.)
+namespace detail {
+// t[0..2N) = a^2
+template <int N>
+SCZ_HD void sqr_wide(uint32_t *t, const uint32_t *a) {
+    uint32_t ev[2 * N], od[2 * N];   // value = ev + (od << 32); od[k] sits at limb k + 1
+#pragma unroll
+    for (int k = 0; k < 2 * N; k++) ev[k] = od[k] = 0;
+#pragma unroll
+    for (int i = 0; i < N - 1; i++) {
+        CF c{0};
+        // products a_i * a_j with i + j odd (j = i+1, i+3, ...): limb i+j is od[i+j-1]
+        {
+            bool started = false;
+            int top = 0;
+#pragma unroll
+            for (int j = i + 1; j < N; j += 2) {
+                int k = i + j - 1;
+                od[k] = started ? madc_lo_cc(c, a[i], a[j], od[k]) : mad_lo_cc(c, a[i], a[j], od[k]);
+                od[k + 1] = madc_hi_cc(c, a[i], a[j], od[k + 1]);
+                started = true;
+                top = k + 2;
+            }
+            if (started && top < 2 * N) od[top] = addc(c, od[top], 0);
+        }
+        // products with i + j even (j = i+2, i+4, ...): limb i+j is ev[i+j]
+        {
+            bool started = false;
+            int top = 0;
+#pragma unroll
+            for (int j = i + 2; j < N; j += 2) {
+                int k = i + j;
+                ev[k] = started ? madc_lo_cc(c, a[i], a[j], ev[k]) : mad_lo_cc(c, a[i], a[j], ev[k]);
+                ev[k + 1] = madc_hi_cc(c, a[i], a[j], ev[k + 1]);
+                started = true;
+                top = k + 2;
+            }
+            if (started && top < 2 * N) ev[top] = addc(c, ev[top], 0);
+        }
+    }
+    // t = ev + (od << 32)
+    {
+        CF c{0};
+        t[0] = ev[0];
+        t[1] = add_cc(c, ev[1], od[0]);
+#pragma unroll
+        for (int k = 2; k < 2 * N - 1; k++) t[k] = addc_cc(c, ev[k], od[k - 1]);
+        t[2 * N - 1] = addc(c, ev[2 * N - 1], od[2 * N - 2]);
+    }
+    // t = 2 t (the off-diagonal sum is below 2^(64N - 1))
+#pragma unroll
+    for (int k = 2 * N - 1; k > 0; k--) t[k] = (t[k] << 1) | (t[k - 1] >> 31);
+    t[0] <<= 1;
+    // + the diagonal a_i^2 at limb 2i: one carry chain over all 2N limbs
+    {
+        CF c{0};
+        t[0] = mad_lo_cc(c, a[0], a[0], t[0]);
+        t[1] = madc_hi_cc(c, a[0], a[0], t[1]);
+#pragma unroll
+        for (int i = 1; i < N; i++) {
+            t[2 * i] = madc_lo_cc(c, a[i], a[i], t[2 * i]);
+            if (i < N - 1) t[2 * i + 1] = madc_hi_cc(c, a[i], a[i], t[2 * i + 1]);
+            else t[2 * i + 1] = madc_hi(c, a[i], a[i], t[2 * i + 1]);
+        }
+    }
+}
+// one Montgomery step on the (even, odd) pair without a multiplicand row: the value is divided by 2^32
+template <class P>
+SCZ_HD void redc_row(uint32_t *even, uint32_t *odd, bool first) {
+    constexpr int N = P::N;
+    CF c{0};
+    if (!first) {
+        even[0] = add_cc(c, even[0], odd[1]);
+#pragma unroll
+        for (int j = 0; j < N - 2; j++) odd[j] = addc_cc(c, odd[j + 2], 0);   // shift right by two limbs, carry rides along
+        odd[N - 2] = addc(c, 0, 0);
+        odd[N - 1] = 0;
+    }
+    uint32_t mi = even[0] * P::INV;
+    cmad_mod<P, 1>(c, odd, mi);
+    cmad_mod<P, 0>(c, even, mi);
+    odd[N - 1] = addc(c, odd[N - 1], 0);
+}
+}   // namespace detail
+// REDC of a 2N-limb value t < p * 2^(32N): t / 2^(32N) mod p
+template <class P>
+SCZ_HD Fp<P> fp_redc_wide(const uint32_t *t) {
+    constexpr int N = P::N;
+    uint32_t even[N], odd[N];
+#pragma unroll
+    for (int k = 0; k < N; k++) {
+        even[k] = t[k];
+        odd[k] = 0;
+    }
+#pragma unroll
+    for (int i = 0; i < N; i += 2) {
+        detail::redc_row<P>(even, odd, i == 0);
+        detail::redc_row<P>(odd, even, false);
+    }
+    // low half reduced (< 2p after merging), plus the untouched high half
+    Fp<P> r;
+    CF c{0};
+    r.l[0] = add_cc(c, even[0], odd[1]);
+#pragma unroll
+    for (int i = 1; i < N - 1; i++) r.l[i] = addc_cc(c, even[i], odd[i + 1]);
+    r.l[N - 1] = addc(c, even[N - 1], 0);
+    r.l[0] = add_cc(c, r.l[0], t[N]);
+#pragma unroll
+    for (int i = 1; i < N - 1; i++) r.l[i] = addc_cc(c, r.l[i], t[N + i]);
+    r.l[N - 1] = addc(c, r.l[N - 1], t[2 * N - 1]);
+    fp_final_sub(r);   // < 2p + p/8
+    fp_final_sub(r);
+    return r;
+}
+SCZ_HD Fp<FqP> fq_sqr_sos(const Fp<FqP> &a) {
+    uint32_t t[24];
+    detail::sqr_wide<12>(t, a.l);
+    return fp_redc_wide<FqP>(t);
+}
+
 template <class P>
 SCZ_HD Fp<P> fp_sqr(const Fp<P> &a) {
     return fp_mul(a, a);
 }
+#ifndef SCZ_NO_FQ_SQR_SOS
+SCZ_HD Fp<FqP> fp_sqr(const Fp<FqP> &a) { return fq_sqr_sos(a); }   // preferred over the template for Fq
+#endif
 // Montgomery form -> canonical integer (ark-ff into_bigint)
 template <class P>
 SCZ_HD Fp<P> fp_to_canon(const Fp<P> &a) {

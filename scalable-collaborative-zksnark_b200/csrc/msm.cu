@@ -90,10 +90,11 @@ __device__ __forceinline__ int seg_by_level(const MsmSeg *segs, int K, int lvl, 
 // Out-of-line group law for the latency-bound tail kernels: keeps their code inside the
 // instruction cache (an inlined general add is ~5k instructions) and the build fast.
 __device__ __noinline__ Fq fq_mul_nl(const Fq &a, const Fq &b) { return fp_mul(a, b); }
+__device__ __noinline__ Fq fq_sqr_nl(const Fq &a) { return fp_sqr(a); }
 __device__ __noinline__ Fq fq_dot2_sub_nl(const Fq &a, const Fq &b, const Fq &c, const Fq &d) { return fp_dot2_sub(a, b, c, d); }
 struct MulCall {
     __device__ __forceinline__ static Fq mul(const Fq &a, const Fq &b) { return fq_mul_nl(a, b); }
-    __device__ __forceinline__ static Fq sqr(const Fq &a) { return fq_mul_nl(a, a); }
+    __device__ __forceinline__ static Fq sqr(const Fq &a) { return fq_sqr_nl(a); }
     __device__ __forceinline__ static Fq dot2_sub(const Fq &a, const Fq &b, const Fq &c, const Fq &d) {
         return fq_dot2_sub_nl(a, b, c, d);
     }

@@ -26,6 +26,9 @@ VEC2(emu_fr_sub, FrP, fp_sub)
 VEC2(emu_fq_mul, FqP, fp_mul)
 VEC2(emu_fq_add, FqP, fp_add)
 VEC2(emu_fq_sub, FqP, fp_sub)
+extern "C" void emu_fq_sqr_sos(const uint32_t *a, uint32_t *r, size_t n) {
+    for (size_t i = 0; i < n; i++) st<FqP>(r, i, fq_sqr_sos(ld<FqP>(a, i)));
+}
 // r = a*b - c*d with one reduction (fp_dot2_sub)
 extern "C" void emu_fq_dot2_sub(const uint32_t *a, const uint32_t *b, const uint32_t *c, const uint32_t *d, uint32_t *r, size_t n) {
     for (size_t i = 0; i < n; i++) st<FqP>(r, i, fp_dot2_sub(ld<FqP>(a, i), ld<FqP>(b, i), ld<FqP>(c, i), ld<FqP>(d, i)));

@@ -66,6 +66,20 @@ def test_fq_dot2_sub(orc, emu):
     assert np.array_equal(o1, orc.fq_sub(orc.fq_mul(m, m), orc.fq_mul(orc.fq_from_ints([1] * 4), m)))
 
 
+def test_fq_sqr_sos(orc, emu):
+    """dedicated Fq squaring (field.cuh fq_sqr_sos): symmetric product + separate Montgomery reduction"""
+    rng = np.random.default_rng(103)
+    a = np.concatenate([orc.fq_from_ints([int.from_bytes(rng.bytes(64), "little") for _ in range(4000)]),
+                        _edge(orc, tw.P_MOD, orc.fq_from_ints, 0)])
+    # raw limb patterns below p that stress the carry chains (these are Montgomery representatives of something)
+    raw = orc.ints_to_arr([tw.P_MOD - 1, tw.P_MOD - 2, (1 << 380) - 1, (1 << 380), int("ffffffff00000000" * 5 + "0fffffff00000000", 16) % tw.P_MOD,
+                           int("00000000ffffffff" * 6, 16) % tw.P_MOD, 1, 0, (1 << 381) - 1 - (1 << 200)], 6)
+    a = np.concatenate([a, raw])
+    out = np.zeros_like(a)
+    emu.emu_fq_sqr_sos(_p(a), _p(out), C.c_size_t(len(a)))
+    assert np.array_equal(out, orc.fq_mul(a, a))
+
+
 def test_fr_inv_and_canon(orc, emu):
     rng = np.random.default_rng(101)
     a = orc.random_fr(rng, 64)
