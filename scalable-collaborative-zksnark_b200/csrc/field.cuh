@@ -541,7 +541,10 @@ template <class P>
 SCZ_HD Fp<P> fp_sqr(const Fp<P> &a) {
     return fp_mul(a, a);
 }
-#ifndef SCZ_NO_FQ_SQR_SOS
+// Measured on B200 (dhyperplonk 2^20): with fq_sqr_sos in the group law the bucket kernel takes 132.9 ms instead of
+// 128.9 ms -- 66 fewer wide multiplies per squaring do not pay for the longer carry / shift chains and 14 more
+// registers -- so squarings stay fp_mul(a, a).  -DSCZ_FQ_SQR_SOS switches it on for experiments.
+#ifdef SCZ_FQ_SQR_SOS
 SCZ_HD Fp<FqP> fp_sqr(const Fp<FqP> &a) { return fq_sqr_sos(a); }   // preferred over the template for Fq
 #endif
 // Montgomery form -> canonical integer (ark-ff into_bigint)
