@@ -433,10 +433,21 @@ def run_own(args):
                      "launch_note": "per proof: the accumulate launch of the big MSM sequence; the proof's second sequence "
                                     "(192 root-opening MSMs of 8 points, < 0.05 ms) is folded into the same figures",
                      "traffic_note": (traffic or {}).get("source"),
-                     "note": "the bucket kernel is bound by the INT32 multiply pipe, not HBM: ~2.9k IMAD.WIDE per "
-                             "mixed add vs ~100 B of traffic; ncu shows sm__pipe_fmaheavy_cycles_active ~84 % "
-                             "(profiles/), see DESIGN.md 3.1"},
+                     "note": "the bucket kernel is bound by the INT32 multiply pipe, not HBM: 2736 IMAD.WIDE per "
+                             "mixed add vs ~100 B of traffic; ncu shows sm__pipe_fmaheavy_cycles_active 86 % "
+                             "(profiles/), see roofline_int_pipe and DESIGN.md 3.1"},
     }
+    # the roof that actually binds the bucket kernel: IMAD.WIDE issues once per 4 cycles per SM sub-partition
+    # (32 lanes / clk / SM); a mixed addition is 2736 of them (6 products + 2 squarings of 288, one dot2 of 432)
+    sms = torch.cuda.get_device_properties(dev).multi_processor_count
+    mhz = (clocks or {}).get("sm_mhz") or 1965
+    imad_peak = sms * 32 * mhz * 1e6
+    imad_rate = adds * 2736 / (acc_ms * 1e-3) if acc_ms > 0 else 0.0
+    line["roofline_int_pipe"] = {"kernel": "k_msm_accumulate", "bound": "INT32 multiply pipe (IMAD.WIDE)",
+                                 "achieved": imad_rate / 1e12, "peak": imad_peak / 1e12, "unit": "T wide multiplies/s",
+                                 "frac": imad_rate / imad_peak, "per_unit": 2736,
+                                 "peak_source": f"{sms} SMs x 32 lanes/clk x {mhz} MHz (issue rate measured with ncu: "
+                                                "sm__pipe_fmaheavy_cycles_active 86 % at this throughput, profiles/)"}
     if world == 1:
         line["roofline_fr_kernels"] = fr_kernel_rooflines(scz, ctx0, torch, peak)
     if world == 1 and not args.no_cpu:
