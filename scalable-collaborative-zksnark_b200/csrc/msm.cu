@@ -548,9 +548,10 @@ int32_t msm_g1_batched(Ctx *ctx, const void *const *d_bases, const void *const *
     ctx->msm_windows = windows;
     ctx->msm_cum_adds += entries, ctx->msm_cum_pairs += points, ctx->msm_cum_sequences++, ctx->msm_cum_segments += batch;
 
-    // entries per accumulate thread: 64 for big batches, less when that would leave SMs idle
-    uint32_t logT = 6;
-    while (logT > 3 && (entries >> logT) < (uint64_t)ctx->sm_count * 2 * ACC_THREADS) logT--;
+    // entries per accumulate thread: 256 for a whole proof's batch (fewer chunk boundaries = fewer pieces to fix up:
+    // 8.3 -> 1.7 ms at 375 M entries), fewer when that would leave less than ~6 waves of CTAs
+    uint32_t logT = 8;
+    while (logT > 3 && (entries >> logT) < (uint64_t)ctx->sm_count * 2 * ACC_THREADS * 6) logT--;
     uint32_t nchunks = (uint32_t)((entries + (1u << logT) - 1) >> logT);   // upper bound: zero digits shrink the stream
 
     cudaStream_t st = ctx->stream;
