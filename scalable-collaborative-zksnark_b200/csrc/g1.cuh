@@ -101,21 +101,23 @@ SCZ_HD G1X g1x_double(const G1X &p) {
     return r;
 }
 // mdbl-2008-s-1: double an affine point
+template <class M = MulInline>
 SCZ_HD G1X g1x_double_affine(const Fq &x, const Fq &y) {
     Fq u = fp_dbl(y);
-    Fq v = fp_sqr(u);
-    Fq w = fp_mul(u, v);
-    Fq s = fp_mul(x, v);
-    Fq xx = fp_sqr(x);
+    Fq v = M::sqr(u);
+    Fq w = M::mul(u, v);
+    Fq s = M::mul(x, v);
+    Fq xx = M::sqr(x);
     Fq m = fp_add(fp_dbl(xx), xx);
     G1X r;
-    r.x = fp_sub(fp_sub(fp_sqr(m), s), s);
-    r.y = fp_dot2_sub(m, fp_sub(s, r.x), w, y);
+    r.x = fp_sub(fp_sub(M::sqr(m), s), s);
+    r.y = M::dot2_sub(m, fp_sub(s, r.x), w, y);
     r.zz = v;
     r.zzz = w;
     return r;
 }
 // madd-2008-s: acc += (x2, y2) affine, not infinity
+template <class M = MulInline>
 SCZ_HD void g1x_add_affine(G1X &acc, const Fq &x2, const Fq &y2) {
     if (acc.is_inf()) {
         acc.x = x2;
@@ -124,29 +126,30 @@ SCZ_HD void g1x_add_affine(G1X &acc, const Fq &x2, const Fq &y2) {
         acc.zzz = Fq::one();
         return;
     }
-    Fq u2 = fp_mul(x2, acc.zz);
-    Fq s2 = fp_mul(y2, acc.zzz);
+    Fq u2 = M::mul(x2, acc.zz);
+    Fq s2 = M::mul(y2, acc.zzz);
     Fq p = fp_sub(u2, acc.x);
     Fq r = fp_sub(s2, acc.y);
     if (p.is_zero()) {
-        if (r.is_zero()) acc = g1x_double_affine(x2, y2);
+        if (r.is_zero()) acc = g1x_double_affine<M>(x2, y2);
         else acc = G1X::inf();
         return;
     }
-    Fq pp = fp_sqr(p);
-    Fq ppp = fp_mul(p, pp);
-    Fq q = fp_mul(acc.x, pp);
-    Fq x3 = fp_sub(fp_sub(fp_sub(fp_sqr(r), ppp), q), q);
-    Fq y3 = fp_dot2_sub(r, fp_sub(q, x3), acc.y, ppp);      // r (q - x3) - y1 ppp, one reduction
+    Fq pp = M::sqr(p);
+    Fq ppp = M::mul(p, pp);
+    Fq q = M::mul(acc.x, pp);
+    Fq x3 = fp_sub(fp_sub(fp_sub(M::sqr(r), ppp), q), q);
+    Fq y3 = M::dot2_sub(r, fp_sub(q, x3), acc.y, ppp);      // r (q - x3) - y1 ppp, one reduction
     acc.x = x3;
     acc.y = y3;
-    acc.zz = fp_mul(acc.zz, pp);
-    acc.zzz = fp_mul(acc.zzz, ppp);
+    acc.zz = M::mul(acc.zz, pp);
+    acc.zzz = M::mul(acc.zzz, ppp);
 }
+template <class M = MulInline>
 SCZ_HD void g1x_add_affine(G1X &acc, const G1Affine &p, bool negate) {
     if (p.is_inf()) return;
     Fq y = negate ? fp_neg(p.y) : p.y;
-    g1x_add_affine(acc, p.x, y);
+    g1x_add_affine<M>(acc, p.x, y);
 }
 // add-2008-s
 template <class M = MulInline>
