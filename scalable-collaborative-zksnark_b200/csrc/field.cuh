@@ -284,8 +284,10 @@ template <int N>
 SCZ_HD void mul_n(uint32_t *acc, const uint32_t *a, uint32_t bi) {
 #pragma unroll
     for (int j = 0; j < N; j += 2) {
-        acc[j] = mul_lo(a[j], bi);
-        acc[j + 1] = mul_hi(a[j], bi);
+        // one 32 x 32 -> 64 multiply (mul.wide.u32 = a single IMAD.WIDE) instead of a lo / hi pair of instructions
+        uint64_t w = (uint64_t)a[j] * bi;
+        acc[j] = (uint32_t)w;
+        acc[j + 1] = (uint32_t)(w >> 32);
     }
 }
 // acc[j],acc[j+1] += a[j]*bi over even j; leaves the carry out in CF
