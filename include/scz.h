@@ -336,6 +336,19 @@ int32_t scz_dpermcheck_dev(scz_ctx *ctx, size_t n, const scz_hp_pk *pk, const sc
                            void *d_points, size_t points_cap, void *d_values, size_t values_cap, scz_hp_item *items,
                            size_t items_cap, size_t *n_items);
 
+/* ---- local_hyperplonk (hyperplonk/src/hyperplonk.rs:15-160): the monolithic single-prover baseline ("Local HyperPlonk").
+ * Plain DEVICE tables: a_evals, b_evals, c_evals, input, q1, q2, eq: 2^n entries; m, ssigma, sid, eq_p2: 4 * 2^n;
+ * challenge n, challengep2 n + 2, alpha_beta 2 (num = m + alpha sid + beta, :106-115); commitment: levels 0 .. n+2.
+ * Returns 6 gate proofs, 6 gate commit+open entries, 6 wiring proofs, 8 wiring commits, 8 wiring opens. */
+typedef struct scz_local_pk {
+    const void *m, *a_evals, *b_evals, *c_evals, *input, *q1, *q2, *ssigma, *sid, *eq, *eq_p2, *challenge, *challengep2,
+        *alpha_beta;
+    const scz_srs *commitment;
+} scz_local_pk;
+int32_t scz_local_hyperplonk_dev(scz_ctx *ctx, size_t n, const scz_local_pk *pk, void *d_triples, size_t triples_cap,
+                                 void *d_points, size_t points_cap, void *d_values, size_t values_cap, scz_hp_item *items,
+                                 size_t items_cap, size_t *n_items);
+
 /* ---- the collaborative (PSS) permutation check, the paper's baseline: hyperplonk/src/dhyperplonk.rs:1249-1385 -----
  * c_acc_product_and_share (dacc_product.rs:66-292): masked product accumulation over N hub rounds with a moving hub.
  * shares / masks / unmask0..2 and the three outputs (v(x,0), v(x,1), v(1,x) shares) hold `len` entries each; len / N * l

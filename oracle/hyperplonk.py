@@ -354,3 +354,39 @@ def cpermcheck(n, pks, pp, mode, N, algo="ark"):
         sumcheck(vx0, vx1)
         open_(ev)
     return res
+
+
+def local_hyperplonk(n, pk, algo="ark"):
+    """hyperplonk/src/hyperplonk.rs:15-160 on explicit inputs.  pk: dict with m, a_evals, b_evals, c_evals, input, q1, q2,
+    ssigma, sid, eq, eq_p2, challenge, challengep2, alpha, beta, commitment (oracle.Srs with levels 0 .. n+2)."""
+    srs = pk["commitment"]
+    res = dict(gate_identity_proofs=[], gate_identity_commitments=[], wiring_proofs=[], wiring_commits=[], wiring_opens=[])
+    ch, ch2 = pk["challenge"], pk["challengep2"]
+    gate_tabs = [pk[k] for k in ("a_evals", "b_evals", "c_evals", "input", "q1", "q2")]
+    coms = [orc.commit(srs, t, algo) for t in gate_tabs]                                         # :55-62
+    gp = res["gate_identity_proofs"]
+    gp.append(orc.sumcheck_product(pk["eq"], pk["q1"], ch))                                      # :77
+    gp.append(orc.sumcheck_product(pk["q1"], orc.fr_add(pk["a_evals"], pk["b_evals"]), ch))      # :78-84
+    gp.append(orc.sumcheck_product(pk["eq"], pk["q2"], ch))
+    gp.append(orc.sumcheck_product(pk["a_evals"], pk["b_evals"], ch))
+    gp.append(orc.sumcheck_product(pk["q2"], pk["a_evals"], ch))
+    gp.append(orc.sumcheck_product(pk["eq"], orc.fr_sub(pk["input"], pk["c_evals"]), ch))        # :90-96
+    m = pk["m"]
+    alpha, beta = _rep(pk["alpha"], len(m)), _rep(pk["beta"], len(m))
+    num = orc.fr_add(orc.fr_add(m, orc.fr_mul(alpha, pk["sid"])), beta)                          # :106-110
+    den = orc.fr_add(orc.fr_add(m, orc.fr_mul(alpha, pk["ssigma"])), beta)                       # :111-115
+    h = orc.fr_mul(num, orc.fr_inv(den))                                                         # :116
+    vx0, vx1, v1x = orc.acc_product(h)                                                           # :118
+    for t in (pk["sid"], pk["ssigma"], h, num, den, vx0, vx1, v1x):                              # :121-136
+        res["wiring_commits"].append(orc.commit(srs, t, algo))
+        res["wiring_opens"].append(orc.open_(srs, t, ch2, algo))
+    wp = res["wiring_proofs"]
+    wp.append(orc.sumcheck_product(pk["eq_p2"], v1x, ch2))                                       # :138-145
+    wp.append(orc.sumcheck_product(pk["eq_p2"], vx0, ch2))
+    wp.append(orc.sumcheck_product(vx0, vx1, ch2))
+    wp.append(orc.sumcheck_product(pk["eq_p2"], den, ch2))
+    wp.append(orc.sumcheck_product(h, den, ch2))
+    wp.append(orc.sumcheck_product(pk["eq_p2"], num, ch2))
+    for com, t in zip(coms, gate_tabs):                                                          # :149-156
+        res["gate_identity_commitments"].append((com, orc.open_(srs, t, ch)))
+    return res

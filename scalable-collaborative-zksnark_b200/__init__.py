@@ -35,6 +35,7 @@ from .api import (  # noqa: F401
     dhyperplonk_data_parallel,
     dpermcheck,
     cpermcheck,
+    local_hyperplonk,
     c_acc_product_and_share,
     hp_table_sizes,
 )

@@ -833,6 +833,35 @@ def cpermcheck(ctx, n, tables, c_commitment, pp):
     return proof
 
 
+class LocalPk(C.Structure):
+    """scz_local_pk (include/scz.h)"""
+    _TABLES = ("m", "a_evals", "b_evals", "c_evals", "input", "q1", "q2", "ssigma", "sid", "eq", "eq_p2", "challenge",
+               "challengep2", "alpha_beta")
+    _fields_ = [(k, C.c_void_p) for k in _TABLES] + [("commitment", C.c_void_p)]
+
+
+def local_hyperplonk(ctx, n, tables, commitment):
+    """hyperplonk/src/hyperplonk.rs:15-160 ("Local HyperPlonk", the monolithic baseline) on explicit inputs.
+    tables: dict with the LocalPk._TABLES entries; commitment: PolynomialCommitment with levels 0 .. n+2."""
+    keep = {k: (_dev(tables[k], 4) if _is_dev(tables[k]) else ctx.to_device(tables[k], 4)) for k in LocalPk._TABLES}
+    cpk = LocalPk()
+    for k, t in keep.items():
+        setattr(cpk, k, t.data_ptr())
+    cpk.commitment = commitment.h
+    L = ctx.L
+    nt, npt, nv, ni = C.c_size_t(), C.c_size_t(), C.c_size_t(), C.c_size_t()
+    ctx.check(L.scz_dhyperplonk_sizes(C.c_size_t(n), C.c_size_t(1), C.c_size_t(ctx.n_parties), C.byref(nt), C.byref(npt),
+                                      C.byref(nv), C.byref(ni)))
+    tri, pts, val = ctx.empty(nt.value * 3, 4), ctx.empty(npt.value, 18), ctx.empty(nv.value, 4)
+    items = (HpItem * ni.value)()
+    cnt = C.c_size_t()
+    ctx.check(L.scz_local_hyperplonk_dev(ctx.h, C.c_size_t(n), C.byref(cpk), _vp(tri), nt, _vp(pts), npt, _vp(val), nv, items, ni,
+                                         C.byref(cnt)))
+    proof = HyperPlonkProof(ctx, tri, pts, val, list(items[: cnt.value]))
+    proof._keep = keep
+    return proof
+
+
 def dhyperplonk_data_parallel(ctx, n, pk, pp):
     """dhyperplonk.rs:573-960: pk.t['local_s'] holds the whole `s` (4 * 2^n / l entries, :603); no step-2.a exchange"""
     return dhyperplonk(ctx, n, pk, pp, "scz_dhyperplonk_data_parallel_dev")
@@ -846,5 +875,5 @@ def dpermcheck(ctx, n, pk, pp):
 __all__ = ["Context", "PackedSharingParams", "msm", "msm_batched", "d_msm", "d_msm_leader", "NetVTable",
            "fr_pointwise", "fix_variable", "acc_product_tree", "d_acc_product", "sumcheck_rounds", "sumcheck_product",
            "c_sumcheck_product", "d_sumcheck_product", "sumcheck", "c_sumcheck", "d_sumcheck", "pss2ss", "degree_reduce", "PolynomialCommitment",
-           "PackedProvingParameters", "HyperPlonkProof", "dhyperplonk", "dhyperplonk_data_parallel", "dpermcheck", "cpermcheck", "c_acc_product_and_share",
+           "PackedProvingParameters", "HyperPlonkProof", "dhyperplonk", "dhyperplonk_data_parallel", "dpermcheck", "cpermcheck", "c_acc_product_and_share", "local_hyperplonk",
            "hp_table_sizes"]

@@ -243,6 +243,78 @@ int32_t dhyperplonk_dev(Ctx *ctx, size_t n, const scz_hp_pk *pk, const scz_pp *p
     return D.run();
 }
 
+// ---- local_hyperplonk: hyperplonk/src/hyperplonk.rs:15-160, the monolithic (single-prover) baseline the reference times
+// as "Local HyperPlonk".  Same primitives, plain tables of gc = 2^n (a, b, c, input, q1, q2, eq) and 4 gc (m, ssigma, sid,
+// eq_p2) entries, one SRS with levels 0 .. n+2 (new_toy, dpoly_comm.rs:107-135).
+int32_t local_hyperplonk_dev(Ctx *ctx, size_t n, const scz_local_pk *pk, HpOut &o) {
+    if (n < 1 || n > 26) return ctx->fail(SCZ_ERR_BAD_ARG, "local_hyperplonk: n = %zu", n);
+    const size_t gc = (size_t)1 << n, g4 = gc * 4, PT = SCZ_G1_JAC_BYTES;
+    Deferred D(ctx);
+    DevTmp coms(ctx), tmp(ctx), num(ctx), den(ctx), h(ctx), tree(ctx), vx0(ctx), vx1(ctx);
+    SCZ_TRY(coms.alloc(6 * PT));
+    SCZ_TRY(tmp.alloc(gc * 32));
+    SCZ_TRY(num.alloc(g4 * 32));
+    SCZ_TRY(den.alloc(g4 * 32));
+    SCZ_TRY(h.alloc(g4 * 32));
+    SCZ_TRY(tree.alloc(2 * g4 * 32));
+    SCZ_TRY(vx0.alloc(g4 * 32));
+    SCZ_TRY(vx1.alloc(g4 * 32));
+    const void *gate_tabs[6] = {pk->a_evals, pk->b_evals, pk->c_evals, pk->input, pk->q1, pk->q2};
+    for (int k = 0; k < 6; k++) SCZ_TRY(commit_defer(ctx, D, pk->commitment, gate_tabs[k], gc, (char *)coms.p + k * PT));   // :55-62
+    auto sum = [&](uint32_t kind, const void *f, const void *g, size_t len, const void *challenge) -> int32_t {
+        size_t cnt = ilog2(len) + 1;
+        SCZ_TRY(o.reserve(cnt, 0));
+        SCZ_TRY(sumcheck_product_dev(ctx, f, g, len, challenge, o.tri_at()));
+        o.push(kind, cnt, 0, 0);
+        return SCZ_OK;
+    };
+    // gate identity (:70-96)
+    SCZ_TRY(sum(SCZ_HP_GATE_PROOF, pk->eq, pk->q1, gc, pk->challenge));
+    SCZ_TRY(fr_pointwise(ctx, 0, pk->a_evals, pk->b_evals, nullptr, tmp.p, gc));
+    SCZ_TRY(sum(SCZ_HP_GATE_PROOF, pk->q1, tmp.p, gc, pk->challenge));
+    SCZ_TRY(sum(SCZ_HP_GATE_PROOF, pk->eq, pk->q2, gc, pk->challenge));
+    SCZ_TRY(sum(SCZ_HP_GATE_PROOF, pk->a_evals, pk->b_evals, gc, pk->challenge));
+    SCZ_TRY(sum(SCZ_HP_GATE_PROOF, pk->q2, pk->a_evals, gc, pk->challenge));
+    SCZ_TRY(fr_pointwise(ctx, 1, pk->c_evals, pk->input, nullptr, tmp.p, gc));
+    SCZ_TRY(sum(SCZ_HP_GATE_PROOF, pk->eq, tmp.p, gc, pk->challenge));
+    // wire identity (:98-145)
+    SCZ_TRY(fr_pointwise(ctx, 2, pk->m, pk->sid, pk->alpha_beta, num.p, g4));       // :106-110  (alpha | beta)
+    SCZ_TRY(fr_pointwise(ctx, 2, pk->m, pk->ssigma, pk->alpha_beta, den.p, g4));    // :111-115
+    SCZ_TRY(fr_pointwise(ctx, 3, num.p, den.p, nullptr, h.p, g4));                  // :116
+    SCZ_TRY(acc_product_tree(ctx, h.p, g4, tree.p));                                // :118
+    SCZ_TRY(fr_deinterleave(ctx, tree.p, g4, vx0.p, vx1.p));
+    const void *v1x = (const char *)tree.p + g4 * 32;
+    const void *wtabs[8] = {pk->sid, pk->ssigma, h.p, num.p, den.p, vx0.p, vx1.p, v1x};   // :121-136
+    for (int k = 0; k < 8; k++) {
+        SCZ_TRY(o.reserve(0, 1));
+        SCZ_TRY(commit_defer(ctx, D, pk->commitment, wtabs[k], g4, o.pts_at()));
+        o.push(SCZ_HP_WIRING_COMMIT, 0, 1, 0);
+        SCZ_TRY(o.reserve(0, n + 2));
+        SCZ_TRY(open_defer(ctx, D, pk->commitment, wtabs[k], g4, pk->challengep2, o.val_at(), o.pts_at()));
+        o.push(SCZ_HP_WIRING_OPEN, 0, n + 2, 1);
+    }
+    SCZ_TRY(sum(SCZ_HP_WIRING_PROOF, pk->eq_p2, v1x, g4, pk->challengep2));         // :138-145
+    SCZ_TRY(sum(SCZ_HP_WIRING_PROOF, pk->eq_p2, vx0.p, g4, pk->challengep2));
+    SCZ_TRY(sum(SCZ_HP_WIRING_PROOF, vx0.p, vx1.p, g4, pk->challengep2));
+    SCZ_TRY(sum(SCZ_HP_WIRING_PROOF, pk->eq_p2, den.p, g4, pk->challengep2));
+    SCZ_TRY(sum(SCZ_HP_WIRING_PROOF, h.p, den.p, g4, pk->challengep2));
+    SCZ_TRY(sum(SCZ_HP_WIRING_PROOF, pk->eq_p2, num.p, g4, pk->challengep2));
+    // open (:149-156)
+    cudaStream_t st = ctx->stream;
+    void *coms_p = coms.p;
+    for (int k = 0; k < 6; k++) {
+        SCZ_TRY(o.reserve(0, 1 + n));
+        void *dst = o.pts_at();
+        D.then2([=]() -> int32_t {
+            SCZ_CUDA(ctx, cudaMemcpyAsync(dst, (char *)coms_p + k * PT, PT, cudaMemcpyDeviceToDevice, st));
+            return SCZ_OK;
+        });
+        SCZ_TRY(open_defer(ctx, D, pk->commitment, gate_tabs[k], gc, pk->challenge, o.val_at(), o.pts_at(1)));
+        o.push(SCZ_HP_GATE_COMMIT, 0, 1 + n, 1);
+    }
+    return D.run();
+}
+
 }   // namespace scz
 
 using namespace scz;
@@ -281,6 +353,26 @@ static int32_t hp_entry(scz_ctx *h, size_t n, const scz_hp_pk *pk, const scz_pp 
     o.tri_cap = triples_cap, o.pts_cap = points_cap, o.val_cap = values_cap, o.items_cap = items_cap;
     o.items = items;
     int32_t rc = dhyperplonk_dev(c, n, pk, pp, o, variant);
+    *n_items = o.items_n;
+    return rc;
+}
+
+int32_t scz_local_hyperplonk_dev(scz_ctx *h, size_t n, const scz_local_pk *pk, void *d_triples, size_t triples_cap, void *d_points,
+                                 size_t points_cap, void *d_values, size_t values_cap, scz_hp_item *items, size_t items_cap,
+                                 size_t *n_items) {
+    if (!h) return SCZ_ERR_BAD_ARG;
+    Ctx *c = &h->c;
+    if (!pk || !d_triples || !d_points || !d_values || !items || !n_items) return c->fail(SCZ_ERR_BAD_ARG, "local_hyperplonk: null argument");
+    const void *need[] = {pk->m, pk->a_evals, pk->b_evals, pk->c_evals, pk->input, pk->q1, pk->q2, pk->ssigma, pk->sid, pk->eq,
+                          pk->eq_p2, pk->challenge, pk->challengep2, pk->alpha_beta, pk->commitment};
+    for (const void *p : need)
+        if (!p) return c->fail(SCZ_ERR_BAD_ARG, "local_hyperplonk: a field of scz_local_pk is null");
+    HpOut o;
+    o.ctx = c;
+    o.tri = (char *)d_triples, o.pts = (char *)d_points, o.val = (char *)d_values;
+    o.tri_cap = triples_cap, o.pts_cap = points_cap, o.val_cap = values_cap, o.items_cap = items_cap;
+    o.items = items;
+    int32_t rc = local_hyperplonk_dev(c, n, pk, o);
     *n_items = o.items_n;
     return rc;
 }

@@ -173,3 +173,29 @@ def test_prover_variants_leader_mode(orc, variant):
     if not dp:
         assert got[0] == ([], []) and len(got[1][0]) == 1 + 3 + 3 * (n - 3) + 3
     ctx.close()
+
+
+def test_local_hyperplonk(orc):
+    """the monolithic baseline local_hyperplonk (hyperplonk/src/hyperplonk.rs:15-160), with and without fixed-base tables"""
+    import scz_b200 as scz
+    from oracle import hyperplonk as ohp
+    n = 5
+    rng = np.random.default_rng(680)
+    ctx = scz.Context(device=0, n_parties=8)
+    gc = 1 << n
+    pk = {k: orc.random_fr(rng, gc) for k in ("a_evals", "b_evals", "c_evals", "input", "q1", "q2", "eq")}
+    pk.update({k: orc.random_fr(rng, 4 * gc) for k in ("m", "ssigma", "sid", "eq_p2")})
+    pk.update(challenge=orc.random_fr(rng, n), challengep2=orc.random_fr(rng, n + 2), alpha=orc.random_fr(rng, 1),
+              beta=orc.random_fr(rng, 1))
+    dev, srs = _make_srs(ctx, orc, rng, [1 << i for i in range(n + 3)])
+    pk["commitment"] = srs
+    want = ohp.local_hyperplonk(n, pk)
+    tabs = {k: v for k, v in pk.items() if k not in ("commitment", "alpha", "beta")}
+    tabs["alpha_beta"] = np.concatenate([pk["alpha"], pk["beta"]])
+    for pre in (False, True):
+        pc = scz.PolynomialCommitment(ctx, dev)
+        if pre:
+            pc.precompute()
+        got = scz.local_hyperplonk(ctx, n, tabs, pc).nested()
+        _same_proof(orc, got, want, f"local pre={pre}")
+    ctx.close()
