@@ -199,3 +199,46 @@ def test_local_hyperplonk(orc):
         got = scz.local_hyperplonk(ctx, n, tabs, pc).nested()
         _same_proof(orc, got, want, f"local pre={pre}")
     ctx.close()
+
+
+def test_dhyperplonk_2p20_full_size_properties(orc):
+    """BASELINE config 5 size (2^20 constraints, l = 1, leader mode), checked through size-independent properties:
+    the proof is bit-identical with and without the fixed-base tables (different windows, bucket sets and launch
+    shapes); every gate sumcheck satisfies the verifier's round identity; the c_open values are mu_0 times the
+    evaluations of the share tables (pss2ss in leader mode, BASELINE.md 4) computed independently with fix_variable;
+    the d_commit of a slice is N times its plain commitment (the leader sums N clones, dpoly_comm.rs:290-292)."""
+    import torch
+    import scz_b200 as scz
+    from oracle import py_twin as tw
+    n, l, N = 20, 1, 8
+    ctx = scz.Context(device=0, n_parties=N)
+    pp = scz.PackedSharingParams(ctx, l)
+    pk = scz.PackedProvingParameters.new(ctx, n, l, seed=11, precompute=True)
+    proof = scz.dhyperplonk(ctx, n, pk, pp)
+    a = [x.clone() for x in (proof.triples, proof.points, proof.values)]
+    used = proof.used()
+    ctx.msm_use_precompute(False)
+    proof2 = scz.dhyperplonk(ctx, n, pk, pp)
+    assert proof2.used() == used
+    assert torch.equal(a[0][: 3 * used[0]], proof2.triples[: 3 * used[0]]) and torch.equal(a[2][: used[2]], proof2.values[: used[2]])
+    p1 = ctx.to_host(ctx.g1_to_affine(a[1][: used[1]].contiguous()))
+    p2 = ctx.to_host(ctx.g1_to_affine(proof2.points[: used[1]].contiguous()))
+    assert np.array_equal(p1, p2)                                   # same group elements, whatever the Jacobian form
+    (gp, gc), (wp, wc, wo) = proof2.nested()
+    R = tw.R_MOD
+    inv2 = pow(2, R - 2, R)
+    chi = orc.fr_to_ints(ctx.to_host(pk.t["challenge"]))
+    for proof_k in gp:
+        tri = [[orc.fr_to_ints(proof_k[i, j:j + 1])[0] for j in range(3)] for i in range(len(proof_k))]
+        for i in range(n - 1):
+            p0, p1_, p2_ = tri[i]
+            r = chi[i]
+            val = (p0 * (r - 1) * (r - 2) * inv2 - p1_ * r * (r - 2) + p2_ * r * (r - 1) * inv2) % R
+            assert val == (tri[i + 1][0] + tri[i + 1][1]) % R
+    for k, name in enumerate(("a_evals", "b_evals", "c_evals")):
+        ev = orc.fr_to_ints(ctx.to_host(scz.fix_variable(ctx, pk.t[name], pk.t["challenge"])))[0]
+        assert orc.fr_to_ints(gc[k][1][0])[0] == ev * tw.MU0 % R, name
+    plain = pk.d_commitment.commit(pk.t["I_p"])
+    eight = ctx.g1_mul(plain, ctx.to_device(orc.fr_from_ints([N]), 4))
+    assert orc.canon_g1(gc[3][0]) == orc.canon_g1(ctx.to_host(eight))
+    ctx.close()
