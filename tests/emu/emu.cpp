@@ -6,6 +6,7 @@
 #include <cstring>
 #include "../../scalable-collaborative-zksnark_b200/csrc/field.cuh"
 #include "../../scalable-collaborative-zksnark_b200/csrc/g1.cuh"
+#include "../../scalable-collaborative-zksnark_b200/csrc/fq_f64.cuh"
 #include "../../scalable-collaborative-zksnark_b200/csrc/msm_digits.cuh"
 using namespace scz;
 
@@ -26,6 +27,22 @@ VEC2(emu_fr_sub, FrP, fp_sub)
 VEC2(emu_fq_mul, FqP, fp_mul)
 VEC2(emu_fq_add, FqP, fp_add)
 VEC2(emu_fq_sub, FqP, fp_sub)
+// the FP64-pipe Fq product (fq_f64.cuh), both row-multiplier variants
+extern "C" void emu_fq_mul_f64(const uint32_t *a, const uint32_t *b, uint32_t *r, size_t n, int mchain) {
+    for (size_t i = 0; i < n; i++)
+        st<FqP>(r, i, mchain ? f64::fq_mul_f64<1>(ld<FqP>(a, i), ld<FqP>(b, i)) : f64::fq_mul_f64<0>(ld<FqP>(a, i), ld<FqP>(b, i)));
+}
+// two products in one interleaved stream (fq_mul_dual): r[2i] = a*b (integer rows), r[2i+1] = c*d (FP64 rows)
+extern "C" void emu_fq_mul_dual(const uint32_t *a, const uint32_t *b, const uint32_t *c, const uint32_t *d, uint32_t *r, size_t n,
+                                int mchain) {
+    for (size_t i = 0; i < n; i++) {
+        Fq ri, rf;
+        if (mchain) f64::fq_mul_dual<1>(ri, ld<FqP>(a, i), ld<FqP>(b, i), rf, ld<FqP>(c, i), ld<FqP>(d, i));
+        else f64::fq_mul_dual<0>(ri, ld<FqP>(a, i), ld<FqP>(b, i), rf, ld<FqP>(c, i), ld<FqP>(d, i));
+        st<FqP>(r, 2 * i, ri);
+        st<FqP>(r, 2 * i + 1, rf);
+    }
+}
 extern "C" void emu_fq_sqr_sos(const uint32_t *a, uint32_t *r, size_t n) {
     for (size_t i = 0; i < n; i++) st<FqP>(r, i, fq_sqr_sos(ld<FqP>(a, i)));
 }

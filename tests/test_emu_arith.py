@@ -66,6 +66,29 @@ def test_fq_dot2_sub(orc, emu):
     assert np.array_equal(o1, orc.fq_sub(orc.fq_mul(m, m), orc.fq_mul(orc.fq_from_ints([1] * 4), m)))
 
 
+def test_fq_mul_f64(orc, emu):
+    """Fq product on 24-bit double limbs (fq_f64.cuh): same residues as the integer multiplier, both m-chain variants"""
+    rng = np.random.default_rng(104)
+    rnd = lambda n: orc.fq_from_ints([int.from_bytes(rng.bytes(64), "little") for _ in range(n)])   # noqa: E731
+    e = _edge(orc, tw.P_MOD, orc.fq_from_ints, 0)
+    raw = orc.ints_to_arr([tw.P_MOD - 1, tw.P_MOD - 2, (1 << 380) - 1, (1 << 380), (1 << 381) - 1 - (1 << 200),
+                           int("ffffff" * 15, 16) + (0x19ffff << 360), int("800000" * 15, 16), int("7fffff" * 15, 16), 0, 1], 6)
+    e = np.concatenate([e, raw])
+    a = np.concatenate([rnd(4000), np.repeat(e, len(e), axis=0)])
+    b = np.concatenate([rnd(4000), np.tile(e, (len(e), 1))])
+    want = orc.fq_mul(a, b)
+    for mchain in (0, 1):
+        out = np.zeros_like(a)
+        emu.emu_fq_mul_f64(_p(a), _p(b), _p(out), C.c_size_t(len(a)), C.c_int(mchain))
+        assert np.array_equal(out, want), mchain
+        # the interleaved pair: (a*b on integer rows, b*a' on FP64 rows)
+        a2 = np.ascontiguousarray(a[::-1])
+        out2 = np.zeros((2 * len(a), a.shape[1]), dtype=a.dtype)
+        emu.emu_fq_mul_dual(_p(a), _p(b), _p(b), _p(a2), _p(out2), C.c_size_t(len(a)), C.c_int(mchain))
+        assert np.array_equal(out2[0::2], want), mchain
+        assert np.array_equal(out2[1::2], orc.fq_mul(b, a2)), mchain
+
+
 def test_fq_sqr_sos(orc, emu):
     """dedicated Fq squaring (field.cuh fq_sqr_sos): symmetric product + separate Montgomery reduction"""
     rng = np.random.default_rng(103)
