@@ -39,3 +39,5 @@ from .api import (  # noqa: F401
     c_acc_product_and_share,
     hp_table_sizes,
 )
+from .delegator import Delegator, read_vec_fr  # noqa: F401
+from .mpcnet import MPCNetError, MultiplexedStreamID, TorchDistMPCNet  # noqa: F401
