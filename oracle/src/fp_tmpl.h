@@ -75,36 +75,34 @@ static inline void FP(neg)(FP(t) *r, const FP(t) *a) {
 }
 static inline void FP(dbl)(FP(t) *r, const FP(t) *a) { FP(add)(r, a, a); }
 
-/* Montgomery product a*b/R mod p (CIOS). */
+/* Montgomery product a*b/R mod p: CIOS with the two inner passes fused (one sweep over j carries both the a*b_i
+ * row and the m*p row).  Valid because the top bit of both moduli is clear (Fr: 255 of 256 bits, Fq: 381 of 384),
+ * so the running sum never needs limb N + 1 -- the "no-carry" form ark-ff 0.4.2's MontBackend uses for these
+ * moduli (montgomery_backend.rs, `can_use_no_carry_mul_optimization`) [ark-recall]. */
 static inline void FP(mul)(FP(t) *r, const FP(t) *a, const FP(t) *b) {
-    uint64_t t[NL + 2];
+    uint64_t t[NL];
     memset(t, 0, sizeof t);
     for (int i = 0; i < NL; i++) {
-        unsigned __int128 c = 0;
-        for (int j = 0; j < NL; j++) {
-            c += (unsigned __int128)a->l[j] * b->l[i] + t[j];
-            t[j] = (uint64_t)c;
-            c >>= 64;
-        }
-        c += t[NL];
-        t[NL] = (uint64_t)c;
-        t[NL + 1] = (uint64_t)(c >> 64);
-        uint64_t m = t[0] * FP(INV);
-        c = (unsigned __int128)m * FP(MOD).l[0] + t[0];
-        c >>= 64;
+        const uint64_t bi = b->l[i];
+        unsigned __int128 c1 = (unsigned __int128)a->l[0] * bi + t[0];
+        const uint64_t m = (uint64_t)c1 * FP(INV);
+        unsigned __int128 c2 = (unsigned __int128)m * FP(MOD).l[0] + (uint64_t)c1;
+        c1 >>= 64;
+        c2 >>= 64;
         for (int j = 1; j < NL; j++) {
-            c += (unsigned __int128)m * FP(MOD).l[j] + t[j];
-            t[j - 1] = (uint64_t)c;
-            c >>= 64;
+            c1 += (unsigned __int128)a->l[j] * bi + t[j];
+            c2 += (unsigned __int128)m * FP(MOD).l[j] + (uint64_t)c1;
+            t[j - 1] = (uint64_t)c2;
+            c1 >>= 64;
+            c2 >>= 64;
         }
-        c += t[NL];
-        t[NL - 1] = (uint64_t)c;
-        t[NL] = t[NL + 1] + (uint64_t)(c >> 64);
+        t[NL - 1] = (uint64_t)c1 + (uint64_t)c2;
     }
-    FP(t) s;
+    /* branch-free final subtraction: keep t - p unless it borrowed */
+    FP(t) s, d;
     memcpy(s.l, t, sizeof s.l);
-    if (t[NL] || FP(geq_raw)(&s, &FP(MOD))) FP(sub_raw)(&s, &s, &FP(MOD));
-    *r = s;
+    uint64_t keep = 0 - FP(sub_raw)(&d, &s, &FP(MOD));   /* all ones when t < p */
+    for (int i = 0; i < NL; i++) r->l[i] = (s.l[i] & keep) | (d.l[i] & ~keep);
 }
 static inline void FP(sqr)(FP(t) *r, const FP(t) *a) { FP(mul)(r, a, a); }
 
