@@ -17,11 +17,12 @@ namespace scz {
 
 // The leader closure alone (dmsm.rs:31-38) on an already gathered buffer: recv is party-major
 // [party][k] (n x batch Jacobian points), send receives the same layout.  unpack2 -> sum of the l
-// secrets -> replicate -> pack_from_public is ONE fixed n x n Fr matrix (built at scz_pp_new), so the
-// closure is a single round of n^2 parallel scalar multiplications per batch entry.
+// secrets -> replicate -> pack_from_public is ONE fixed rank-one map (u, p built at scz_pp_new): n scalar
+// multiplications into S_k, n more out of it, per batch entry (pss.cu, k_pss_dmsm_multi).
 int32_t d_msm_leader(Ctx *ctx, const scz_pp *pp, const void *d_recv, size_t batch, void *d_send) {
     ProfScope ps(ctx, SCZ_K_PSS);
-    return pss_apply(ctx, pp, PSS_DMSM, 1, d_recv, pp->n, 1, batch, batch, d_send, 1, batch);
+    struct { const void *in; void *out; uint32_t batch, cta_base; } job = {d_recv, d_send, (uint32_t)batch, 0};
+    return pss_dmsm_multi(ctx, pp, &job, 1);
 }
 
 // Queues the local MSMs (dmsm.rs:19-24) on `D` and registers the leader round (:29-40) as their continuation.

@@ -97,16 +97,17 @@ __global__ void __launch_bounds__(256) k_pss_setup(uint32_t l, void *tables, voi
         for (uint32_t i = 0; i < s1; i++) acc = fp_add(acc, fp_mul(P[j * s1 + i], P[i * s1]));
         PS[j] = acc;
     }
-    // DMSM[j][i] = (sum_{a<l} PACK[j][a]) * (sum_{b<l} UNPACK2[b][i]): unpack2, sum the l secrets, replicate, pack
+    // The d_msm leader closure (dmsm.rs:31-38: unpack2, sum the l secrets, replicate, pack) is the rank-one map
+    // out_j = p_j * (sum_i u_i * in_i) with u_i = sum_{b<l} UNPACK2[b][i], p_j = sum_{a<l} PACK[j][a]: stored as u | p
     Fr *D = reinterpret_cast<Fr *>(dmsm);
-    for (uint32_t idx = threadIdx.x; idx < n * n; idx += blockDim.x) {
-        uint32_t j = idx / n, i = idx % n;
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
         Fr pj = Fr::zero(), ui = Fr::zero();
         for (uint32_t a = 0; a < l; a++) {
-            pj = fp_add(pj, P[j * s1 + a]);
+            pj = fp_add(pj, P[i * s1 + a]);
             ui = fp_add(ui, U2[a * n + i]);
         }
-        D[idx] = fp_mul(pj, ui);
+        D[i] = ui;
+        D[n + i] = pj;
     }
 }
 
@@ -160,65 +161,95 @@ __global__ void __launch_bounds__(GROUPS * 4) k_pss_apply_g1(const void *M, uint
 }
 
 // The d_msm leader closure for a LIST of gathered buffers in one launch: job q maps its party-major input
-// [party][k] (n x batch Jacobian points) through the n x n matrix M; CTA = one output point.
+// [party][k] (n x batch Jacobian points) to S_k = sum_j u_j * in(j, k), then out(o, k) = p_o * S_k: 2n scalar
+// multiplications per batch entry instead of the n^2 of the dense n x n map (the reference spends O(n log n) in
+// its FFTs over points, pss.rs:124-171 + :93-99).  Two launches; a CTA = 8 groups of 4 cooperating lanes.
 struct PssG1Job {
     const void *in;
     void *out;
     uint32_t batch, cta_base;
 };
-__global__ void __launch_bounds__(32) k_pss_dmsm_multi(const void *M, uint32_t n, const PssG1Job *jobs, uint32_t njobs) {
+// PHASE 1: CTA (entry e, chunk c) sums u_j * in(j, e) over its 8 parties j = 8c .. 8c+7 into partial[e][c].
+// PHASE 2: CTA (e, c) adds the n / 8 partials of its entry (S_e) and writes out(o, e) = p_o * S_e, o = 8c .. 8c+7.
+// Every scalar multiplication of a phase runs at the same time: the closure costs two scalar-multiplication
+// latencies whatever l is.
+template <int PHASE>
+__global__ void __launch_bounds__(32) k_pss_dmsm_multi(const void *UP, uint32_t n, const PssG1Job *jobs, uint32_t njobs,
+                                                        void *partial) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int GROUPS = 8;
     G1Jac *tab = reinterpret_cast<G1Jac *>(smem_raw);          // [GROUPS][16]
     G1Jac *res = tab + GROUPS * 16;                             // [GROUPS]
+    const uint32_t C = n / GROUPS, e = blockIdx.x / C, c = blockIdx.x % C;
     uint32_t lo = 0, hi = njobs - 1;
     while (lo < hi) {
         uint32_t mid = (lo + hi + 1) >> 1;
-        if (jobs[mid].cta_base <= blockIdx.x) lo = mid;
+        if (jobs[mid].cta_base <= e) lo = mid;
         else hi = mid - 1;
     }
     const PssG1Job job = jobs[lo];
-    uint32_t rel = blockIdx.x - job.cta_base;
-    uint32_t b = rel / n, o = rel % n;                          // batch entry, output party
+    const uint32_t b = e - job.cta_base;                        // batch entry of this job
     const Coop g;
     const int gi = threadIdx.x >> 2;
-    G1Jac acc = g1j_inf();
-    for (uint32_t j = gi; j < n; j += GROUPS) {
-        G1Jac p = g1j_load(job.in, (size_t)j * job.batch + b);
-        Fr k = fp_to_canon(fp_load<FrP>(M, (size_t)o * n + j));
-        if (p.z.is_zero() || k.is_zero()) continue;
-        G1Jac t = coop_mul_bits(g, p, k.l, tab + gi * 16);
-        coop_add(g, acc, t);
-    }
-    if (g.role == 0) res[gi] = acc;
-    __syncwarp();
-    for (int stride = GROUPS / 2; stride > 0; stride >>= 1) {
-        if (gi < stride) {
-            G1Jac o2 = res[gi + stride];
-            coop_add(g, acc, o2);
+    if (PHASE == 1) {
+        const uint32_t j = c * GROUPS + gi;
+        G1Jac acc = g1j_inf();
+        {
+            G1Jac p = g1j_load(job.in, (size_t)j * job.batch + b);
+            Fr k = fp_to_canon(fp_load<FrP>(UP, j));
+            if (!p.z.is_zero() && !k.is_zero()) acc = coop_mul_bits(g, p, k.l, tab + gi * 16);
         }
+        if (g.role == 0) res[gi] = acc;
         __syncwarp();
-        if (gi < stride && g.role == 0) res[gi] = acc;
+        for (int stride = GROUPS / 2; stride > 0; stride >>= 1) {
+            if (gi < stride) {
+                G1Jac o2 = res[gi + stride];
+                coop_add(g, acc, o2);
+            }
+            __syncwarp();
+            if (gi < stride && g.role == 0) res[gi] = acc;
+            __syncwarp();
+        }
+        if (threadIdx.x == 0) g1j_store(partial, (size_t)e * C + c, acc);
+    } else {
+        G1Jac S = g1j_load(partial, (size_t)e * C);
+        for (uint32_t q = 1; q < C; q++) {
+            G1Jac t = g1j_load(partial, (size_t)e * C + q);
+            coop_add(g, S, t);
+        }
+        // every lane takes S from ONE shared-memory copy: with S read per lane straight from global memory the
+        // products below came out wrong on sm_100a / nvcc 12.9 (memcheck and synccheck clean, the loaded value itself
+        // correct) -- the cooperative routines want their replicated operand bit-identical AND identically placed
+        if (g.role == 0) res[gi] = S;
         __syncwarp();
+        S = res[0];
+        const uint32_t o = c * GROUPS + gi;
+        Fr k = fp_to_canon(fp_load<FrP>(UP, (size_t)n + o));
+        G1Jac t = g1j_inf();
+        if (!S.z.is_zero() && !k.is_zero()) t = coop_mul_bits(g, S, k.l, tab + gi * 16);
+        if (g.role == 0) g1j_store(job.out, (size_t)o * job.batch + b, t);
     }
-    if (threadIdx.x == 0) g1j_store(job.out, (size_t)o * job.batch + b, acc);
 }
-// jobs: host array of (in, out, batch, -) ; cta_base is filled here
+// jobs: host array of (in, out, batch, -) ; cta_base (first entry of the job) is filled here
 int32_t pss_dmsm_multi(Ctx *ctx, const scz_pp *pp, const void *jobs_host, size_t njobs) {
     if (!njobs) return SCZ_OK;
     std::vector<PssG1Job> jobs(njobs);
     memcpy(jobs.data(), jobs_host, njobs * sizeof(PssG1Job));
-    uint32_t ctas = 0;
+    uint32_t entries = 0;
     for (auto &j : jobs) {
-        j.cta_base = ctas;
-        ctas += j.batch * (uint32_t)pp->n;
+        j.cta_base = entries;
+        entries += j.batch;
     }
-    if (!ctas) return SCZ_OK;
-    DevTmp d(ctx);
+    if (!entries) return SCZ_OK;
+    const uint32_t C = (uint32_t)pp->n / 8;
+    DevTmp d(ctx), partial(ctx);
     SCZ_TRY(d.alloc(njobs * sizeof(PssG1Job)));
+    SCZ_TRY(partial.alloc((size_t)entries * C * sizeof(G1Jac)));
     SCZ_TRY(ctx->h2d_staged(d.p, jobs.data(), njobs * sizeof(PssG1Job)));
     constexpr size_t SH8 = 8 * 17 * sizeof(G1Jac);
-    k_pss_dmsm_multi<<<ctas, 32, SH8, ctx->stream>>>(pp->d_dmsm, (uint32_t)pp->n, d.as<PssG1Job>(), (uint32_t)njobs);
+    k_pss_dmsm_multi<1><<<entries * C, 32, SH8, ctx->stream>>>(pp->d_dmsm, (uint32_t)pp->n, d.as<PssG1Job>(), (uint32_t)njobs, partial.p);
+    SCZ_LAUNCH_CHECK(ctx);
+    k_pss_dmsm_multi<2><<<entries * C, 32, SH8, ctx->stream>>>(pp->d_dmsm, (uint32_t)pp->n, d.as<PssG1Job>(), (uint32_t)njobs, partial.p);
     SCZ_LAUNCH_CHECK(ctx);
     return SCZ_OK;
 }
@@ -248,9 +279,7 @@ int32_t pss_apply(Ctx *ctx, const scz_pp *pp, PssMap map, int kind, const void *
             M = pp->d_unpack2, mcols = (uint32_t)pp->n, rows = (uint32_t)pp->l;
             break;
         default:
-            len_in = pp->n;
-            M = pp->d_dmsm, mcols = (uint32_t)pp->n, rows = (uint32_t)pp->n;
-            break;
+            return ctx->fail(SCZ_ERR_BAD_ARG, "pss: the d_msm closure runs through pss_dmsm_multi");
     }
     if (kind == 0) {
         k_pss_apply_fr<<<ceil_div_u32(batch * rows, 128), 128, 0, ctx->stream>>>(M, mcols, rows, (uint32_t)len_in, d_in,
@@ -292,7 +321,7 @@ int32_t scz_pp_new(scz_ctx *h, size_t l, scz_pp **out) {
     pp->device = c->device;
     size_t n = pp->n;
     char *blk = nullptr;
-    size_t total = (n * 2 * l + n + 2 * l * n + n * n) * 32;
+    size_t total = (n * 2 * l + n + 2 * l * n + 2 * n) * 32;
     cudaError_t e = cudaMalloc(&blk, total);
     if (e != cudaSuccess) {
         delete pp;

@@ -10,7 +10,7 @@ struct scz_pp {
     void *d_pack_single;  // n      : pack_single(s)[j] = PS[j] * s
     void *d_unpack;       // l x n
     void *d_unpack2;      // l x n
-    void *d_dmsm;         // n x n : the whole d_msm leader closure, pack([sum_l unpack2(.)] * l)  (dmsm.rs:31-38)
+    void *d_dmsm;         // u[n] | p[n] : the d_msm leader closure pack([sum_l unpack2(.)] * l) (dmsm.rs:31-38) is out_j = p_j * sum_i u_i in_i
 };
 
 namespace scz {
@@ -24,7 +24,7 @@ enum PssMap { PSS_PACK = 0, PSS_PACK_SINGLE = 1, PSS_UNPACK = 2, PSS_UNPACK2 = 3
 int32_t pss_apply(Ctx *ctx, const scz_pp *pp, PssMap map, int kind, const void *d_in, size_t len_in, size_t in_bstride,
                   size_t in_jstride, size_t batch, void *d_out, size_t out_bstride, size_t out_ostride);
 
-// the d_msm leader closure on a list of gathered buffers (Deferred::PssJob array) in one launch
+// the d_msm leader closure on a list of gathered buffers (Deferred::PssJob array: in, out, batch, -) in one launch
 int32_t pss_dmsm_multi(Ctx *ctx, const scz_pp *pp, const void *jobs_host, size_t njobs);
 
 }   // namespace scz

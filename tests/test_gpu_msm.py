@@ -167,10 +167,11 @@ def test_config2_msm_2p20_trapdoor_and_linearity(orc, ctx):
     assert st["bucket_adds"] == n * st["windows"]
 
 
-@pytest.mark.parametrize("l", [1, 2])
+@pytest.mark.parametrize("l", [1, 2, 4, 8])
 def test_d_msm_leader_closure_parties_mode(orc, ctx, l):
     """dmsm.rs:31-38 with N real parties: per batch entry unpack2 -> sum of the l secrets -> [sum; l] -> pack.
-    The device folds the closure into one n x n matrix; the oracle runs the FFT pairs step by step."""
+    The device runs the closure as the rank-one map it is (n scalar multiplications into the sum, n out of it, in
+    two launches); the oracle runs the FFT pairs step by step."""
     import scz_b200 as scz
     rng = np.random.default_rng(310 + l)
     pp = scz.PackedSharingParams(ctx, l)

@@ -1,5 +1,5 @@
 """dev tool: time dhyperplonk (leader mode, one GPU) at circuit size 2^n with the per-kernel-class device timers.
-usage: python tools/hp_time.py [n] [reps]"""
+usage: python tools/hp_time.py [n] [reps] [pre|plain] [l]"""
 import os
 import sys
 import time
@@ -11,11 +11,12 @@ import scz_b200 as scz  # noqa: E402
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 20
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
-ctx = scz.Context(device=0, n_parties=8)
-pp = scz.PackedSharingParams(ctx, 1)
+l = int(sys.argv[4]) if len(sys.argv) > 4 else 1
+ctx = scz.Context(device=0, n_parties=8 * l)
+pp = scz.PackedSharingParams(ctx, l)
 t0 = time.time()
 pre = (sys.argv[3] if len(sys.argv) > 3 else 'pre') == 'pre'
-pk = scz.PackedProvingParameters.new(ctx, n, 1, seed=1, precompute=pre)
+pk = scz.PackedProvingParameters.new(ctx, n, l, seed=1, precompute=pre)
 ctx.sync()
 print(f"setup {time.time() - t0:.2f} s, {torch.cuda.memory_allocated() / 2**30:.2f} GiB", flush=True)
 for r in range(reps):
