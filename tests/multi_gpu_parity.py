@@ -2,9 +2,10 @@
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node W --master-addr 127.0.0.1 --master-port P tests/multi_gpu_parity.py
 
-The 8 parties of an l = 1 run are spread over the W ranks (8 / W per GPU, HybridNet over NCCL); every party proves a
-2^5-constraint circuit with dhyperplonk and cpermcheck on seeded inputs, rank 0 re-runs the oracle's 8-party
-restatement and compares every party's outputs bit for bit (canonical affine for points)."""
+The N = 8 l parties of a run (l = SCZ_PARITY_L, default 1) are spread over the W ranks (N / W per GPU, HybridNet over
+NCCL); every party proves a 2^SCZ_PARITY_NV-constraint circuit (default 2^5) with dhyperplonk on seeded inputs, rank 0
+re-runs the oracle's N-party restatement and compares every party's outputs bit for bit (canonical affine for
+points)."""
 import os
 import sys
 
@@ -21,7 +22,8 @@ from scz_b200.net import HybridNet  # noqa: E402
 from tests.gpu_util import oracle_affine  # noqa: E402
 from tests.test_gpu_hyperplonk import _same_proof, _tables_for_product  # noqa: E402
 
-N, L_PACK, NV = 8, 1, 5
+L_PACK = int(os.environ.get("SCZ_PARITY_L", "1"))
+N, NV = 8 * L_PACK, int(os.environ.get("SCZ_PARITY_NV", "5"))
 
 
 def all_inputs():
@@ -77,7 +79,7 @@ def main():
         flat = [x for per_rank in gathered for x in per_rank]
         for j in range(N):
             _same_proof(orc, flat[j], want[j], f"party {j} (rank {j // P})")
-        print(f"MULTI_GPU_PARITY_OK world={world} parties_per_gpu={P} collectives={hub.calls}", flush=True)
+        print(f"MULTI_GPU_PARITY_OK world={world} l={L_PACK} parties={N} log2_constraints={NV} parties_per_gpu={P} collectives={hub.calls}", flush=True)
     dist.barrier()
     seed_ctx.close()
     dist.destroy_process_group()
