@@ -236,6 +236,12 @@ void scz_ctx_destroy(scz_ctx *h) {
     c->prof_clear();
     for (cudaEvent_t e : c->prof_pool) cudaEventDestroy(e);
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+    if (c->msm_stream) {
+        cudaStreamSynchronize(c->msm_stream);
+        cudaStreamDestroy(c->msm_stream);
+        cudaEventDestroy(c->msm_fork);
+        cudaEventDestroy(c->msm_join);
+    }
     delete c->net;
     delete h;
 }

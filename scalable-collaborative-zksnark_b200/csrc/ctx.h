@@ -18,6 +18,8 @@ struct Ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
+    cudaStream_t msm_stream = nullptr;         // optional lowest-priority stream of the MSM launch sequences (msm.cu, flush_msm)
+    cudaEvent_t msm_fork = nullptr, msm_join = nullptr;
     int sm_count = 148;
     std::string err;
     // pinned host staging for small results

@@ -31,6 +31,7 @@
 // The accumulate kernel is bound by the integer multiply pipe (a mixed add is ~2.9k
 // IMAD.WIDE for ~104 B of HBM traffic), see DESIGN.md.
 #include <algorithm>
+#include <cstdlib>
 #include <vector>
 
 #include "deferred.h"
@@ -661,9 +662,32 @@ int32_t Deferred::add_msm(const void *b, const void *s, size_t len, void *out, u
     points += len;
     return SCZ_OK;
 }
+// With SCZ_MSM_STREAM=1 the launch sequence runs on a second, lowest-priority stream of the ctx, fenced by events on
+// both sides: for ONE proof nothing changes (the main stream waits for the sequence), but when several provers share
+// a GPU (proofs in flight on different ctxs) the short protocol kernels of one prover are dispatched ahead of the
+// bucket kernel's queued CTAs of another instead of waiting for its whole grid to drain.
 int32_t Deferred::flush_msm() {
     if (lens.empty()) return SCZ_OK;
+    static const bool side = [] { const char *e = getenv("SCZ_MSM_STREAM"); return e && e[0] == '1'; }();
+    cudaStream_t main_stream = ctx->stream;
+    if (side) {
+        if (!ctx->msm_stream) {
+            int least = 0, greatest = 0;
+            SCZ_CUDA(ctx, cudaDeviceGetStreamPriorityRange(&least, &greatest));
+            SCZ_CUDA(ctx, cudaStreamCreateWithPriority(&ctx->msm_stream, cudaStreamNonBlocking, least));
+            SCZ_CUDA(ctx, cudaEventCreateWithFlags(&ctx->msm_fork, cudaEventDisableTiming));
+            SCZ_CUDA(ctx, cudaEventCreateWithFlags(&ctx->msm_join, cudaEventDisableTiming));
+        }
+        SCZ_CUDA(ctx, cudaEventRecord(ctx->msm_fork, main_stream));
+        SCZ_CUDA(ctx, cudaStreamWaitEvent(ctx->msm_stream, ctx->msm_fork, 0));
+        ctx->stream = ctx->msm_stream;
+    }
     int32_t rc = msm_g1_batched(ctx, bases.data(), scalars.data(), lens.data(), lens.size(), nullptr, outs.data(), pre.data());
+    if (side) {
+        ctx->stream = main_stream;
+        SCZ_CUDA(ctx, cudaEventRecord(ctx->msm_join, ctx->msm_stream));
+        SCZ_CUDA(ctx, cudaStreamWaitEvent(main_stream, ctx->msm_join, 0));
+    }
     bases.clear(), scalars.clear(), lens.clear(), outs.clear(), pre.clear();
     entries = points = 0;
     return rc;

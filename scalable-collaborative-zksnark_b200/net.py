@@ -294,12 +294,22 @@ class _LocalParty:
 
 class HybridNet:
     """Fewer GPUs than parties: every rank hosts `per_rank` parties (one host thread and one ctx each, all on the
-    rank's GPU and on the same CUDA stream), party id = rank * per_rank + local index; party 0 is the leader.
+    rank's GPU), party id = rank * per_rank + local index; party 0 is the leader.
     A collective is a host barrier among the local parties, ONE torch.distributed collective per rank issued by
     local party 0 on the concatenated payloads, and a second host barrier.  With per_rank = 1 this is
-    TorchDistNet; with world = 1 it is LocalTestNet."""
+    TorchDistNet; with world = 1 it is LocalTestNet.
+
+    By default all hosted parties' ctxs share the caller's CUDA stream.  SCZ_PARTY_STREAMS=1 gives every hosted party
+    its OWN high-priority stream (`party_stream`); the host barriers then order the ENQUEUEING and CUDA events order
+    the EXECUTION across the parties' streams: every party fences its stream before local party 0 touches its buffers
+    (`ready`), waits for party 0's work (`done`), and the owner of a source buffer waits for the readers (`copied`).
+    Measured on 2 GPUs x 4 parties: bit-exact, but SLOWER than the shared stream (806 vs 714 ms per round of 8
+    proofs) -- the star rounds keep the parties of one proof in the same phase, so there is nothing to overlap and
+    four concurrent MSM sequences only contend; independent proofs are where separate streams pay (bench.py,
+    `pipelined`).  The fences are exercised either way (they are no-ops on one stream)."""
 
     def __init__(self, device, per_rank, group=None):
+        import os
         import threading
         self.device = torch.device(device)
         self.per_rank = per_rank
@@ -312,23 +322,90 @@ class HybridNet:
         self.slots = [None] * per_rank
         self.stage = None
         self.calls = {"gather": 0, "scatter": 0, "all_gather": 0, "sync": 0}
+        self.cuda = self.device.type == "cuda"
+        self.streams = None
+        if self.cuda:
+            self.ev_ready = [torch.cuda.Event() for _ in range(per_rank)]
+            self.ev_copied = [torch.cuda.Event() for _ in range(per_rank)]
+            self.ev_done = torch.cuda.Event()
+            if per_rank > 1 and os.environ.get("SCZ_PARTY_STREAMS", "0") == "1":
+                self.streams = [torch.cuda.Stream(device=self.device, priority=-1) for _ in range(per_rank)]
 
     def party(self, local_index):
         return _HybridParty(self, local_index)
 
+    def party_stream(self, p):
+        """the CUDA stream of local party p (None: the caller's current stream)"""
+        return self.streams[p] if self.streams else None
+
+    def adopt(self, p, ctx):
+        """bind a ctx that was created outside run_parties to local party p's stream"""
+        if self.streams:
+            with torch.cuda.stream(self.streams[p]):
+                ctx.use_torch_stream()
+
     def _buf(self, nbytes):
         return torch.empty(nbytes, dtype=torch.uint8, device=self.device)
 
+    # -- stream fences of a collective (no-ops on CPU)
+    def _on(self, stream):
+        """torch ops of a callback run on the ctx's own stream, whatever the calling thread's current stream is"""
+        import contextlib
+        if self.cuda and stream:
+            return torch.cuda.stream(torch.cuda.ExternalStream(int(stream), device=self.device))
+        return contextlib.nullcontext()
+
+    def _ready(self, p):
+        if self.cuda:
+            self.ev_ready[p].record()
+
+    def _wait_ready(self):
+        if self.cuda:
+            cur = torch.cuda.current_stream()
+            for e in self.ev_ready:
+                cur.wait_event(e)
+
+    def _done(self):
+        if self.cuda:
+            self.ev_done.record()
+
+    def _wait_done(self):
+        if self.cuda:
+            torch.cuda.current_stream().wait_event(self.ev_done)
+
+    def _copied(self, p):
+        if self.cuda:
+            self.ev_copied[p].record()
+
+    def _wait_copied(self):
+        if self.cuda:
+            cur = torch.cuda.current_stream()
+            for e in self.ev_copied:
+                cur.wait_event(e)
+
     def run_parties(self, fn):
-        """fn(party_id, local_index, net) on one thread per hosted party; returns the results by local index"""
+        """fn(party_id, local_index, net) on one thread per hosted party; returns the results by local index.
+        With party streams the call still behaves like work enqueued on the caller's current stream: the party
+        streams start after what the caller enqueued before, and the caller's stream continues after all of them."""
         import threading
         out, err = [None] * self.per_rank, [None] * self.per_rank
+        start = end = None
+        if self.streams:
+            start = torch.cuda.Event()
+            start.record()
+            end = [torch.cuda.Event() for _ in range(self.per_rank)]
 
         def body(p):
             try:
-                if self.device.type == "cuda":
+                if self.cuda:
                     torch.cuda.set_device(self.device)
-                out[p] = fn(self.rank * self.per_rank + p, p, self.party(p))
+                if self.streams:
+                    with torch.cuda.stream(self.streams[p]):
+                        self.streams[p].wait_event(start)
+                        out[p] = fn(self.rank * self.per_rank + p, p, self.party(p))
+                        end[p].record()
+                else:
+                    out[p] = fn(self.rank * self.per_rank + p, p, self.party(p))
             except BaseException as e:   # noqa: BLE001
                 err[p] = e
                 self.barrier.abort()
@@ -346,6 +423,10 @@ class HybridNet:
         for e in err:
             if e is not None:
                 raise e
+        if self.streams:
+            cur = torch.cuda.current_stream()
+            for e in end:
+                cur.wait_event(e)
         return out
 
 
@@ -362,27 +443,32 @@ class _HybridParty:
         def _gather_to(user, root, d_send, d_recv, nbytes, wire, stream):
             # the root party lives on rank root // P as local party root % P; local party 0 of every rank drives
             try:
-                rr, rp = root // P, root % P
-                hub.slots[p] = d_send
-                if hub.rank == rr and p == rp:
-                    hub.root_recv = d_recv
-                hub.barrier.wait()
-                if p == 0:
-                    hub.calls["gather"] += 1
-                    if W == 1:
-                        recv = _tensor(hub.root_recv, nbytes * hub.n, dev).view(P, nbytes)
-                        for q in range(P):
-                            recv[q].copy_(_tensor(hub.slots[q], nbytes, dev))
-                    else:
-                        loc = hub._buf(P * nbytes).view(P, nbytes)
-                        for q in range(P):
-                            loc[q].copy_(_tensor(hub.slots[q], nbytes, dev))
-                        if hub.rank == rr:
-                            recv = _tensor(hub.root_recv, nbytes * hub.n, dev).view(W, P * nbytes)
-                            dist.gather(loc.view(-1), list(recv.unbind(0)), dst=rr, group=hub.group)
+                with hub._on(stream):
+                    rr, rp = root // P, root % P
+                    hub.slots[p] = d_send
+                    if hub.rank == rr and p == rp:
+                        hub.root_recv = d_recv
+                    hub._ready(p)
+                    hub.barrier.wait()
+                    if p == 0:
+                        hub._wait_ready()
+                        hub.calls["gather"] += 1
+                        if W == 1:
+                            recv = _tensor(hub.root_recv, nbytes * hub.n, dev).view(P, nbytes)
+                            for q in range(P):
+                                recv[q].copy_(_tensor(hub.slots[q], nbytes, dev))
                         else:
-                            dist.gather(loc.view(-1), None, dst=rr, group=hub.group)
-                hub.barrier.wait()
+                            loc = hub._buf(P * nbytes).view(P, nbytes)
+                            for q in range(P):
+                                loc[q].copy_(_tensor(hub.slots[q], nbytes, dev))
+                            if hub.rank == rr:
+                                recv = _tensor(hub.root_recv, nbytes * hub.n, dev).view(W, P * nbytes)
+                                dist.gather(loc.view(-1), list(recv.unbind(0)), dst=rr, group=hub.group)
+                            else:
+                                dist.gather(loc.view(-1), None, dst=rr, group=hub.group)
+                        hub._done()
+                    hub.barrier.wait()
+                    hub._wait_done()    # the root's buffer is filled, every send buffer may be reused
                 return 0
             except Exception as e:
                 print(f"[scz hybrid net] gather failed: {e!r}", flush=True)
@@ -390,25 +476,32 @@ class _HybridParty:
 
         def _scatter_from(user, root, d_send, d_recv, nbytes, wire, stream):
             try:
-                rr, rp = root // P, root % P
-                if hub.rank == rr and p == rp:
-                    hub.root_send = d_send
-                hub.barrier.wait()
-                if p == 0:
-                    if W == 1:
-                        hub.stage = _tensor(hub.root_send, nbytes * hub.n, dev).view(P, nbytes)
-                    else:
-                        hub.calls["scatter"] += 1
-                        loc = hub._buf(P * nbytes)
-                        if hub.rank == rr:
-                            send = _tensor(hub.root_send, nbytes * hub.n, dev).view(W, P * nbytes)
-                            dist.scatter(loc, list(send.unbind(0)), src=rr, group=hub.group)
+                with hub._on(stream):
+                    rr, rp = root // P, root % P
+                    if hub.rank == rr and p == rp:
+                        hub.root_send = d_send
+                    hub._ready(p)
+                    hub.barrier.wait()
+                    if p == 0:
+                        hub._wait_ready()
+                        if W == 1:
+                            hub.stage = _tensor(hub.root_send, nbytes * hub.n, dev).view(P, nbytes)
                         else:
-                            dist.scatter(loc, None, src=rr, group=hub.group)
-                        hub.stage = loc.view(P, nbytes)
-                hub.barrier.wait()
-                _tensor(d_recv, nbytes, dev).copy_(hub.stage[p])
-                hub.barrier.wait()
+                            hub.calls["scatter"] += 1
+                            loc = hub._buf(P * nbytes)
+                            if hub.rank == rr:
+                                send = _tensor(hub.root_send, nbytes * hub.n, dev).view(W, P * nbytes)
+                                dist.scatter(loc, list(send.unbind(0)), src=rr, group=hub.group)
+                            else:
+                                dist.scatter(loc, None, src=rr, group=hub.group)
+                            hub.stage = loc.view(P, nbytes)
+                        hub._done()
+                    hub.barrier.wait()
+                    hub._wait_done()
+                    _tensor(d_recv, nbytes, dev).copy_(hub.stage[p])
+                    hub._copied(p)
+                    hub.barrier.wait()
+                    hub._wait_copied()  # the staging buffer / the root's send buffer is free again
                 return 0
             except Exception as e:
                 print(f"[scz hybrid net] scatter failed: {e!r}", flush=True)
@@ -422,24 +515,31 @@ class _HybridParty:
 
         def _all_gather(user, d_send, d_recv, nbytes, wire, stream):
             try:
-                hub.slots[p] = d_send
-                hub.barrier.wait()
-                if p == 0:
-                    hub.calls["all_gather"] += 1
-                    full = _tensor(d_recv, nbytes * hub.n, dev)
-                    if W == 1:
-                        for q in range(P):
-                            full.view(P, nbytes)[q].copy_(_tensor(hub.slots[q], nbytes, dev))
-                    else:
-                        loc = hub._buf(P * nbytes).view(P, nbytes)
-                        for q in range(P):
-                            loc[q].copy_(_tensor(hub.slots[q], nbytes, dev))
-                        dist.all_gather_into_tensor(full, loc.view(-1), group=hub.group)
-                    hub.stage = full
-                hub.barrier.wait()
-                if p != 0:
-                    _tensor(d_recv, nbytes * hub.n, dev).copy_(hub.stage)
-                hub.barrier.wait()
+                with hub._on(stream):
+                    hub.slots[p] = d_send
+                    hub._ready(p)
+                    hub.barrier.wait()
+                    if p == 0:
+                        hub._wait_ready()
+                        hub.calls["all_gather"] += 1
+                        full = _tensor(d_recv, nbytes * hub.n, dev)
+                        if W == 1:
+                            for q in range(P):
+                                full.view(P, nbytes)[q].copy_(_tensor(hub.slots[q], nbytes, dev))
+                        else:
+                            loc = hub._buf(P * nbytes).view(P, nbytes)
+                            for q in range(P):
+                                loc[q].copy_(_tensor(hub.slots[q], nbytes, dev))
+                            dist.all_gather_into_tensor(full, loc.view(-1), group=hub.group)
+                        hub.stage = full
+                        hub._done()
+                    hub.barrier.wait()
+                    hub._wait_done()
+                    if p != 0:
+                        _tensor(d_recv, nbytes * hub.n, dev).copy_(hub.stage)
+                    hub._copied(p)
+                    hub.barrier.wait()
+                    hub._wait_copied()  # party 0's buffer has been read by everybody
                 return 0
             except Exception as e:
                 print(f"[scz hybrid net] all_gather failed: {e!r}", flush=True)
@@ -447,11 +547,17 @@ class _HybridParty:
 
         def _sync(user, stream):
             try:
-                hub.barrier.wait()
-                if p == 0 and W > 1:
-                    hub.calls["sync"] += 1
-                    dist.barrier(group=hub.group)
-                hub.barrier.wait()
+                with hub._on(stream):
+                    hub._ready(p)
+                    hub.barrier.wait()
+                    if p == 0:
+                        hub._wait_ready()
+                        if W > 1:
+                            hub.calls["sync"] += 1
+                            dist.barrier(group=hub.group)
+                        hub._done()
+                    hub.barrier.wait()
+                    hub._wait_done()
                 return 0
             except Exception:
                 return 1

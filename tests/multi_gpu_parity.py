@@ -9,6 +9,8 @@ points)."""
 import os
 import sys
 
+os.environ.setdefault("SCZ_MSM_STREAM", "1")   # exercise the side-stream MSM path too
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import numpy as np  # noqa: E402
