@@ -18,8 +18,7 @@ roofline fraction of the Pippenger bucket kernel) are measured inside the same s
 and `roofline`.  One JSON line on stdout (rank 0).
 """
 import os as _os
-if int(_os.environ.get("WORLD_SIZE", "1")) == 1:   # only the N = 1 `pipelined` leg has independent provers to overlap
-    _os.environ.setdefault("SCZ_MSM_STREAM", "1")  # MSM launch sequences on the ctx's low-priority stream (csrc/msm.cu)
+_os.environ.setdefault("SCZ_MSM_STREAM", "1")   # MSM launch sequences on the ctx's low-priority stream (csrc/msm.cu)
 import argparse
 import json
 import math
@@ -295,6 +294,9 @@ def run_own(args):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+    # everything below runs on ONE high-priority stream: the provers' short protocol kernels must outrank the MSM
+    # launch sequences, which libscz puts on a lowest-priority stream of each ctx (SCZ_MSM_STREAM, csrc/msm.cu)
+    torch.cuda.set_stream(torch.cuda.Stream(device=dev, priority=-1))
     assert world in (1, 2, 4, 8), "the 8 parties of l=1 spread over 1, 2, 4 or 8 GPUs"
     P = 1 if world == 1 else N_PARTIES // world          # parties hosted by this rank
     n = args.logn

@@ -60,7 +60,10 @@ struct Deferred {
     std::vector<std::function<int32_t()>> after_gather;   // run once the gathered data is in place (leader-side work)
     std::vector<std::shared_ptr<DevTmp>> keep;         // temporaries that must stay alive until run() returns
 
+    bool early_pending = false;                        // a sequence started by flush_early() has not been joined yet
+
     explicit Deferred(Ctx *c) : ctx(c) {}
+    ~Deferred();
     Deferred(const Deferred &) = delete;
     Deferred &operator=(const Deferred &) = delete;
 
@@ -92,6 +95,9 @@ struct Deferred {
         colsum_jobs.push_back(ColsumJob{in, out, stride, off, parties, cols, replicate, 0});
     }
     int32_t flush_msm();
+    int32_t flush_early();      // start the sequence of what is queued now, without waiting for it (SCZ_MSM_STREAM=1 only)
+    int32_t join_early();
+    int32_t flush_msm_on_side(bool wait);
     int32_t flush_closures();   // protocols.cu
     int32_t run();
 };

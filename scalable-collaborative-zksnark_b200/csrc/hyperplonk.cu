@@ -6,6 +6,7 @@
 // through the host-side collectives of a real net; in leader mode the whole proof is one stream of launches.
 // Outputs are written straight into three device arenas (triples, points, values); `items` tells the host which
 // slice is which entry of the reference's return tuple (:567-570), in the reference's push order.
+#include <cstdlib>
 #include <vector>
 
 #include "net.h"
@@ -69,6 +70,12 @@ int32_t dhyperplonk_dev(Ctx *ctx, size_t n, const scz_hp_pk *pk, const scz_pp *p
     const size_t nc = ilog2(share_len) + ll + 1;   // triples of a c_sumcheck_product on 2^n/l shares
     cudaStream_t st = ctx->stream;
     Deferred D(ctx);   // every MSM of the proof is queued here and runs in (at most a few) batched launch sequences
+    // early starts of the queued MSM work under the rest of the protocol phase (deferred.h, SCZ_MSM_STREAM=1 only);
+    // SCZ_MSM_EARLY is a dev knob: bit 0 after step 1, bit 1 after 2.d, bit 2 after the commits / openings of 2.e.
+    // Measured at 2^20 (profiles/r1_pipelined.txt): one early start at the last point is best (167.6 ms per proof vs
+    // 173.2 without); more starts cost more in per-sequence overhead than they hide (171.4 / 174.0 ms with two / three)
+    static const unsigned early_mask = [] { const char *e = getenv("SCZ_MSM_EARLY"); return e ? (unsigned)strtoul(e, nullptr, 0) : 4u; }();
+    auto early = [&](unsigned bit) -> int32_t { return (early_mask >> bit) & 1 ? D.flush_early() : SCZ_OK; };
 
     // ---- Step 1: commit (:196-217).  The six commitments leave with the openings at the very end (:518-553).
     DevTmp coms(ctx);
@@ -80,6 +87,7 @@ int32_t dhyperplonk_dev(Ctx *ctx, size_t n, const scz_hp_pk *pk, const scz_pp *p
         const void *slc[3] = {pk->I_p, pk->S1_p, pk->S2_p};
         for (int k = 0; k < 3; k++)   // :213-215
             SCZ_TRY(d_commit_defer(ctx, D, pk->d_commitment, slc[k], slice_len, (char *)coms.p + (3 + k) * PT));
+        SCZ_TRY(early(0));
     }
 
     // ---- Step 3: gate identity (:222-260): six collaborative product sumchecks on 2^n/l shares
@@ -152,6 +160,7 @@ int32_t dhyperplonk_dev(Ctx *ctx, size_t n, const scz_hp_pk *pk, const scz_pp *p
     SCZ_TRY(c_open(SCZ_HP_WIRING_OPEN, pk->V, v_len, pk->challenge_r1, 0));                  // 2.d :306-320
     SCZ_TRY(c_open(SCZ_HP_WIRING_OPEN, pk->V, v_len, pk->challenge_r2, 0));
     SCZ_TRY(d_open(SCZ_HP_WIRING_OPEN, pk->local_s_p, hl, r2, n + 2, 0));
+    SCZ_TRY(early(1));   // the two openings of V are a third of the proof's MSM work
 
     // 2.e (:324-342): num, den, h = num / den, product tree of h
     DevTmp num(ctx), den(ctx), h_p(ctx), subtree(ctx), vx0(ctx), vx1(ctx), ltree(ctx);
@@ -173,6 +182,7 @@ int32_t dhyperplonk_dev(Ctx *ctx, size_t n, const scz_hp_pk *pk, const scz_pp *p
         for (int k = 0; k < 8; k++) SCZ_TRY(d_commit(tabs[k], hl));                         // :363-380
         for (int k = 0; k < 5; k++) SCZ_TRY(d_open(SCZ_HP_WIRING_OPEN, tabs[k], hl, r2, n + 2, 0));   // :383-407
     }
+    SCZ_TRY(early(2));   // ~3/4 of the proof's MSM work has been queued by now
     SCZ_TRY(d_sum(den.p, pk->eq_r2_p, hl, r2));                                             // 2.e.1 :411-413
     SCZ_TRY(d_sum(h_p.p, den.p, hl, r2));
     SCZ_TRY(d_sum(num.p, pk->eq_r2_p, hl, r2));

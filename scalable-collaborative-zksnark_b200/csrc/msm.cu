@@ -662,32 +662,61 @@ int32_t Deferred::add_msm(const void *b, const void *s, size_t len, void *out, u
     points += len;
     return SCZ_OK;
 }
-// With SCZ_MSM_STREAM=1 the launch sequence runs on a second, lowest-priority stream of the ctx, fenced by events on
-// both sides: for ONE proof nothing changes (the main stream waits for the sequence), but when several provers share
-// a GPU (proofs in flight on different ctxs) the short protocol kernels of one prover are dispatched ahead of the
-// bucket kernel's queued CTAs of another instead of waiting for its whole grid to drain.
-int32_t Deferred::flush_msm() {
-    if (lens.empty()) return SCZ_OK;
+// With SCZ_MSM_STREAM=1 the launch sequences run on a second, lowest-priority stream of the ctx, fenced by events on
+// both sides (the host gives the ctx's main stream a higher priority).  Two things follow:
+//  * flush_early(): the schedule (hyperplonk.cu) starts the sequence of everything queued so far while its own
+//    protocol phase is still running -- the latency-bound short kernels of the remaining sumchecks / folds are
+//    dispatched ahead of the bucket kernel's queued CTAs and hide under it; run() joins before anything reads a
+//    result.  Inputs of queued MSMs are immutable until run() anyway (that is what deferring them relies on).
+//  * when several provers share a GPU (proofs in flight on different ctxs) one prover's protocol kernels overlap
+//    another's bucket kernel instead of waiting for its whole grid to drain.
+static bool msm_side_stream() {
     static const bool side = [] { const char *e = getenv("SCZ_MSM_STREAM"); return e && e[0] == '1'; }();
+    return side;
+}
+static int32_t msm_stream_ready(Ctx *ctx) {
+    if (ctx->msm_stream) return SCZ_OK;
+    int least = 0, greatest = 0;
+    SCZ_CUDA(ctx, cudaDeviceGetStreamPriorityRange(&least, &greatest));
+    SCZ_CUDA(ctx, cudaStreamCreateWithPriority(&ctx->msm_stream, cudaStreamNonBlocking, least));
+    SCZ_CUDA(ctx, cudaEventCreateWithFlags(&ctx->msm_fork, cudaEventDisableTiming));
+    SCZ_CUDA(ctx, cudaEventCreateWithFlags(&ctx->msm_join, cudaEventDisableTiming));
+    return SCZ_OK;
+}
+int32_t Deferred::join_early() {
+    if (!early_pending) return SCZ_OK;
+    early_pending = false;
+    SCZ_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->msm_join, 0));
+    return SCZ_OK;
+}
+Deferred::~Deferred() {
+    if (early_pending) cudaStreamWaitEvent(ctx->stream, ctx->msm_join, 0);   // error path: `keep` is freed on the main stream
+}
+int32_t Deferred::flush_msm_on_side(bool wait) {
     cudaStream_t main_stream = ctx->stream;
-    if (side) {
-        if (!ctx->msm_stream) {
-            int least = 0, greatest = 0;
-            SCZ_CUDA(ctx, cudaDeviceGetStreamPriorityRange(&least, &greatest));
-            SCZ_CUDA(ctx, cudaStreamCreateWithPriority(&ctx->msm_stream, cudaStreamNonBlocking, least));
-            SCZ_CUDA(ctx, cudaEventCreateWithFlags(&ctx->msm_fork, cudaEventDisableTiming));
-            SCZ_CUDA(ctx, cudaEventCreateWithFlags(&ctx->msm_join, cudaEventDisableTiming));
-        }
-        SCZ_CUDA(ctx, cudaEventRecord(ctx->msm_fork, main_stream));
-        SCZ_CUDA(ctx, cudaStreamWaitEvent(ctx->msm_stream, ctx->msm_fork, 0));
-        ctx->stream = ctx->msm_stream;
-    }
+    SCZ_TRY(msm_stream_ready(ctx));
+    SCZ_CUDA(ctx, cudaEventRecord(ctx->msm_fork, main_stream));
+    SCZ_CUDA(ctx, cudaStreamWaitEvent(ctx->msm_stream, ctx->msm_fork, 0));
+    ctx->stream = ctx->msm_stream;
     int32_t rc = msm_g1_batched(ctx, bases.data(), scalars.data(), lens.data(), lens.size(), nullptr, outs.data(), pre.data());
-    if (side) {
-        ctx->stream = main_stream;
-        SCZ_CUDA(ctx, cudaEventRecord(ctx->msm_join, ctx->msm_stream));
-        SCZ_CUDA(ctx, cudaStreamWaitEvent(main_stream, ctx->msm_join, 0));
-    }
+    ctx->stream = main_stream;
+    bases.clear(), scalars.clear(), lens.clear(), outs.clear(), pre.clear();
+    entries = points = 0;
+    SCZ_CUDA(ctx, cudaEventRecord(ctx->msm_join, ctx->msm_stream));
+    if (wait) SCZ_CUDA(ctx, cudaStreamWaitEvent(main_stream, ctx->msm_join, 0));
+    else early_pending = true;
+    return rc;
+}
+int32_t Deferred::flush_early() {
+    if (!msm_side_stream() || lens.empty()) return SCZ_OK;
+    SCZ_TRY(join_early());
+    return flush_msm_on_side(false);
+}
+int32_t Deferred::flush_msm() {
+    SCZ_TRY(join_early());
+    if (lens.empty()) return SCZ_OK;
+    if (msm_side_stream()) return flush_msm_on_side(true);
+    int32_t rc = msm_g1_batched(ctx, bases.data(), scalars.data(), lens.data(), lens.size(), nullptr, outs.data(), pre.data());
     bases.clear(), scalars.clear(), lens.clear(), outs.clear(), pre.clear();
     entries = points = 0;
     return rc;

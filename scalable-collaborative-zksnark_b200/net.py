@@ -390,6 +390,7 @@ class HybridNet:
         import threading
         out, err = [None] * self.per_rank, [None] * self.per_rank
         start = end = None
+        caller = torch.cuda.current_stream() if self.cuda else None   # a new thread would start on the default stream
         if self.streams:
             start = torch.cuda.Event()
             start.record()
@@ -404,6 +405,9 @@ class HybridNet:
                         self.streams[p].wait_event(start)
                         out[p] = fn(self.rank * self.per_rank + p, p, self.party(p))
                         end[p].record()
+                elif self.cuda:
+                    with torch.cuda.stream(caller):
+                        out[p] = fn(self.rank * self.per_rank + p, p, self.party(p))
                 else:
                     out[p] = fn(self.rank * self.per_rank + p, p, self.party(p))
             except BaseException as e:   # noqa: BLE001

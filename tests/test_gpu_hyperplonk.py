@@ -1,10 +1,14 @@
 """-m gpu: the collaborative HyperPlonk prover (`dhyperplonk`, hyperplonk/src/dhyperplonk.rs:159-571) through the
 C ABI (scz_dhyperplonk_dev), entry by entry against the oracle's restatement (oracle/hyperplonk.py): leader mode on
 one ctx and parties mode (N = 8 ctxs on one GPU under LocalTestNet)."""
+import os
+
 import numpy as np
 import pytest
 
 from tests.gpu_util import oracle_affine
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 pytestmark = pytest.mark.gpu
 
@@ -242,3 +246,43 @@ def test_dhyperplonk_2p20_full_size_properties(orc):
     eight = ctx.g1_mul(plain, ctx.to_device(orc.fr_from_ints([N]), 4))
     assert orc.canon_g1(gc[3][0]) == orc.canon_g1(ctx.to_host(eight))
     ctx.close()
+
+
+def test_msm_side_stream_same_proof(tmp_path):
+    """SCZ_MSM_STREAM=1 (MSM launch sequences on the ctx's low-priority stream, the first one started early under the
+    rest of the protocol phase: csrc/msm.cu, Deferred::flush_early) must not change a single byte of the proof.
+    The switch is read once per process, so both settings run in fresh interpreters on a high-priority stream."""
+    import subprocess
+    import sys
+    code = r"""
+import sys, numpy as np, torch
+sys.path.insert(0, %r)
+import scz_b200 as scz
+torch.cuda.set_stream(torch.cuda.Stream(priority=-1))
+ctx = scz.Context(device=0, n_parties=8)
+pp = scz.PackedSharingParams(ctx, 1)
+out = {}
+for n in (6, 12, 16):
+    pk = scz.PackedProvingParameters.new(ctx, n, 1, seed=7, precompute=(n == 16))
+    for rep in range(2):
+        proof = scz.dhyperplonk(ctx, n, pk, pp)
+        used = proof.used()
+        out[f"t{n}_{rep}"] = ctx.to_host(proof.triples[: used[0]].contiguous())
+        out[f"p{n}_{rep}"] = ctx.to_host(ctx.g1_to_affine(proof.points[: used[1]].contiguous()))
+        out[f"v{n}_{rep}"] = ctx.to_host(proof.values[: used[2]].contiguous())
+np.savez(sys.argv[1], **out)
+""" % ROOT
+    files = []
+    for flag in ("0", "1"):
+        f = str(tmp_path / f"proof_{flag}.npz")
+        env = dict(os.environ, SCZ_MSM_STREAM=flag)
+        r = subprocess.run([sys.executable, "-c", code, f], env=env, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+        files.append(np.load(f))
+    a, b = files
+    assert sorted(a.files) == sorted(b.files) and len(a.files) == 18
+    for k in a.files:
+        assert np.array_equal(a[k], b[k]), k
+    for n in (6, 12, 16):   # and a proof repeats itself
+        for kind in "tpv":
+            assert np.array_equal(b[f"{kind}{n}_0"], b[f"{kind}{n}_1"]), (kind, n)
