@@ -542,6 +542,11 @@ def run_own(args):
                               "launch_sequences": (stats1["sequences"] - stats0["sequences"]) // args.steps,
                               "pairs": pairs // args.steps, "bucket_adds": adds // args.steps},
             "kernel_ms_per_step": {k: v[0] / args.steps for k, v in prof.items()},
+            "kernel_ms_note": ("event brackets per kernel class on the stream the class runs on; with SCZ_MSM_STREAM=1 the first MSM "
+                               "sequence runs UNDER the rest of the protocol phase, so the sumcheck / open_fold brackets include the "
+                               "time their kernels wait for SM slots and the classes add up to more than ms_per_step"
+                               if os.environ.get("SCZ_MSM_STREAM") == "1" else "event brackets per kernel class, one stream"),
+            "msm_side_stream": os.environ.get("SCZ_MSM_STREAM") == "1",
             "nccl_collectives_per_proof_rank0": coll,
             "comm_bytes_per_proof_party0": {"upload": comm[0], "download": comm[1]},
         },
