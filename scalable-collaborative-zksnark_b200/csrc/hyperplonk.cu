@@ -7,6 +7,7 @@
 // Outputs are written straight into three device arenas (triples, points, values); `items` tells the host which
 // slice is which entry of the reference's return tuple (:567-570), in the reference's push order.
 #include <cstdlib>
+#include <functional>
 #include <vector>
 
 #include "net.h"
@@ -90,23 +91,32 @@ int32_t dhyperplonk_dev(Ctx *ctx, size_t n, const scz_hp_pk *pk, const scz_pp *p
         SCZ_TRY(early(0));
     }
 
-    // ---- Step 3: gate identity (:222-260): six collaborative product sumchecks on 2^n/l shares
+    // ---- Step 3: gate identity (:222-260): six collaborative product sumchecks on 2^n/l shares.
+    // Sumchecks feed no MSM: their output slots are claimed here, in the reference's push order, but the kernels (and
+    // the pss2ss rounds inside) are issued after the early MSM start below, where they hide under the bucket kernel
+    // instead of delaying it (`later`; every party defers the same calls, so the collectives still pair up).
+    std::vector<std::function<int32_t()>> later;
+    DevTmp tmp(ctx), sv(ctx);
     if (variant != HP_PERMCHECK) {
-        DevTmp tmp(ctx);
         SCZ_TRY(tmp.alloc(share_len * 32));
         auto c_sum = [&](const void *f, const void *g) -> int32_t {
             SCZ_TRY(o.reserve(nc, 0));
-            SCZ_TRY(c_sumcheck_product_dev(ctx, pp, f, g, share_len, pk->challenge, o.tri_at()));
+            void *dst = o.tri_at();
             o.push(SCZ_HP_GATE_PROOF, nc, 0, 0);
+            later.push_back([=]() -> int32_t { return c_sumcheck_product_dev(ctx, pp, f, g, share_len, pk->challenge, dst); });
             return SCZ_OK;
         };
+        auto pointwise = [&](int mode, const void *a, const void *b) {
+            void *dst = tmp.p;
+            later.push_back([=]() -> int32_t { return fr_pointwise(ctx, mode, a, b, nullptr, dst, share_len); });
+        };
         SCZ_TRY(c_sum(pk->eq, pk->S1));                                                     // :230-231
-        SCZ_TRY(fr_pointwise(ctx, 0, pk->a_evals, pk->b_evals, nullptr, tmp.p, share_len));  // sum_ab :233-238
+        pointwise(0, pk->a_evals, pk->b_evals);                                             // sum_ab :233-238
         SCZ_TRY(c_sum(pk->S1, tmp.p));                                                      // :240-241
         SCZ_TRY(c_sum(pk->eq, pk->S2));                                                     // :243-244
         SCZ_TRY(c_sum(pk->a_evals, pk->b_evals));                                           // :245-246
         SCZ_TRY(c_sum(pk->S2, pk->a_evals));                                                // :247-248
-        SCZ_TRY(fr_pointwise(ctx, 1, pk->c_evals, pk->I, nullptr, tmp.p, share_len));        // -c + I :251-256
+        pointwise(1, pk->c_evals, pk->I);                                                   // -c + I :251-256
         SCZ_TRY(c_sum(pk->eq, tmp.p));                                                      // :258-259
     }
 
@@ -143,7 +153,6 @@ int32_t dhyperplonk_dev(Ctx *ctx, size_t n, const scz_hp_pk *pk, const scz_pp *p
     {
         // 2.a (:270-294): N hub rounds in which hub i sends its local_s to everybody = one all-gather;
         // s = local_s^(0) | ... | local_s^(N-1).  The leader simulator repeats the own vector N times (:289-293).
-        DevTmp sv(ctx);
         SCZ_TRY(sv.alloc(v_len * 32));
         if (variant == HP_DATA_PARALLEL)   // s drawn locally (:603): no exchange
             SCZ_CUDA(ctx, cudaMemcpyAsync(sv.p, pk->local_s, v_len * 32, cudaMemcpyDeviceToDevice, st));
@@ -153,8 +162,10 @@ int32_t dhyperplonk_dev(Ctx *ctx, size_t n, const scz_hp_pk *pk, const scz_pp *p
         {                                                                                    // 2.c :304
             size_t cnt = ilog2(v_len) + ll + 1;
             SCZ_TRY(o.reserve(cnt, 0));
-            SCZ_TRY(c_sumcheck_product_dev(ctx, pp, sv.p, pk->V, v_len, pk->challenge_r1, o.tri_at()));
+            void *dst = o.tri_at();
+            const void *svp = sv.p;
             o.push(SCZ_HP_WIRING_PROOF, cnt, 0, 0);
+            later.push_back([=]() -> int32_t { return c_sumcheck_product_dev(ctx, pp, svp, pk->V, v_len, pk->challenge_r1, dst); });
         }
     }
     SCZ_TRY(c_open(SCZ_HP_WIRING_OPEN, pk->V, v_len, pk->challenge_r1, 0));                  // 2.d :306-320
@@ -183,6 +194,7 @@ int32_t dhyperplonk_dev(Ctx *ctx, size_t n, const scz_hp_pk *pk, const scz_pp *p
         for (int k = 0; k < 5; k++) SCZ_TRY(d_open(SCZ_HP_WIRING_OPEN, tabs[k], hl, r2, n + 2, 0));   // :383-407
     }
     SCZ_TRY(early(2));   // ~3/4 of the proof's MSM work has been queued by now
+    for (auto &f : later) SCZ_TRY(f());   // the gate-identity sumchecks and the sumcheck of 2.c
     SCZ_TRY(d_sum(den.p, pk->eq_r2_p, hl, r2));                                             // 2.e.1 :411-413
     SCZ_TRY(d_sum(h_p.p, den.p, hl, r2));
     SCZ_TRY(d_sum(num.p, pk->eq_r2_p, hl, r2));
