@@ -7,6 +7,8 @@
 #include "../../scalable-collaborative-zksnark_b200/csrc/field.cuh"
 #include "../../scalable-collaborative-zksnark_b200/csrc/g1.cuh"
 #include "../../scalable-collaborative-zksnark_b200/csrc/fq_f64.cuh"
+#include "../../scalable-collaborative-zksnark_b200/csrc/g1_batch_affine.cuh"
+#include <vector>
 #include "../../scalable-collaborative-zksnark_b200/csrc/msm_digits.cuh"
 using namespace scz;
 
@@ -98,4 +100,24 @@ extern "C" uint32_t emu_msm_digits(const uint32_t *k, size_t n, uint32_t c, int3
         if (carry) return 0xffffffffu;   // must never happen
     }
     return W;
+}
+
+// n affine additions out[i] = p[i] + q[i] with ONE inversion per `batch` additions (g1_batch_affine.cuh); packed affine
+// rows of 24 words, all-zero = infinity
+extern "C" void emu_g1_batch_affine_add(const uint32_t *p, const uint32_t *q, uint32_t *out, size_t n, size_t batch) {
+    std::vector<G1Affine> P(n), Q(n), R(n);
+    for (size_t i = 0; i < n; i++) {
+        P[i].x = ld<FqP>(p, 2 * i), P[i].y = ld<FqP>(p, 2 * i + 1);
+        Q[i].x = ld<FqP>(q, 2 * i), Q[i].y = ld<FqP>(q, 2 * i + 1);
+    }
+    std::vector<Fq> prefix(batch);
+    for (size_t lo = 0; lo < n; lo += batch) {
+        int m = (int)(n - lo < batch ? n - lo : batch);
+        Fq total = g1a_batch_phase1(&P[lo], &Q[lo], m, prefix.data());
+        g1a_batch_phase2(&P[lo], &Q[lo], m, prefix.data(), fp_inv(total), &R[lo]);
+    }
+    for (size_t i = 0; i < n; i++) {
+        st<FqP>(out, 2 * i, R[i].x);
+        st<FqP>(out, 2 * i + 1, R[i].y);
+    }
 }

@@ -180,3 +180,31 @@ def test_msm_digits_recompose(orc, emu, c):
     assert digits.max() <= half and digits.min() > -half - (1 if c == 1 else 0)
     for i, kv in enumerate(ks):
         assert sum(int(d) << (c * w) for w, d in enumerate(digits[i])) == kv
+
+
+def test_g1_batch_affine_add(orc, emu):
+    """affine additions with one shared inversion per batch (g1_batch_affine.cuh, the round-2 bucket kernel's group
+    law): every exceptional case in the same batch as ordinary additions"""
+    from tests.gpu_util import oracle_affine, packed_affine
+    rng = np.random.default_rng(105)
+    n = 96
+    pa, qa = orc.random_g1(rng, n), orc.random_g1(rng, n)
+    inf = np.zeros((1, 13), dtype=np.uint64)
+    inf[0, 12] = 1
+    neg = qa.copy()
+    neg[:, 6:12] = orc.fq_sub(np.zeros((n, 6), dtype=np.uint64), qa[:, 6:12])      # -Q
+    qa[5], pa[9] = pa[5], inf[0]            # P + P, inf + Q
+    qa[13] = inf[0]                         # P + inf
+    pa[20], qa[20] = inf[0], inf[0]         # inf + inf
+    pa[31] = neg[31]                        # (-Q) + Q = inf
+    qa[40], qa[41] = pa[40], pa[41]         # two doublings next to each other
+    pa[95] = neg[95]                        # last of its batch
+    qa[64] = pa[64]                         # first of a batch of 32
+    p, q = packed_affine(pa), packed_affine(qa)
+    want = orc.canon_g1(orc.g1_add(orc.g1_from_affine(pa), orc.g1_from_affine(qa)))
+    for batch in (1, 7, 32, 96, 200):
+        out = np.zeros_like(p)
+        emu.emu_g1_batch_affine_add(_p(p), _p(q), _p(out), C.c_size_t(n), C.c_size_t(batch))
+        got = orc.canon_g1(orc.g1_from_affine(oracle_affine(out)))
+        assert got == want, batch
+    assert want[31] == (0, 0, 1) and want[20] == (0, 0, 1) and want[95] == (0, 0, 1)
