@@ -202,7 +202,9 @@ def run_reference(args):
     dt = sum(cpu_hyperplonk(n, pk, threads) for _ in range(steps))
     value = (1 << n) * steps / dt
     sample = (f"each step = one leader-mode dhyperplonk proof at 2^{n} constraints (bounded sample of the 2^{args.logn} "
-              f"workload: the CPU path needs minutes per proof there), oracle C restatement of the arkworks path, MSM windows on "
+              f"workload: the CPU path needs minutes per proof there; its constraints/s still grow with the size -- 2.1 k / 3.6 k / "
+              f"4.3 k / 5.7 k at 2^13 / 2^15 / 2^16 / 2^18 on 8 threads of the authoring box -- so a small sample understates it), "
+              f"oracle C restatement of the arkworks path, MSM windows on "
               f"{threads} host threads (arkworks `parallel`, which the reference leaves off); everything else single-threaded "
               f"like the reference")
     line = {
@@ -603,7 +605,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
     ap.add_argument("--logn", type=int, default=20, help="log2 of the circuit size (BASELINE: 20)")
-    ap.add_argument("--ref-logn", type=int, default=15, help="--impl reference: circuit size of the bounded CPU sample")
+    ap.add_argument("--ref-logn", type=int, default=18, help="--impl reference: circuit size of the bounded CPU sample")
     ap.add_argument("--ref-steps", type=int, default=2, help="--impl reference: at most this many timed proofs")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-precompute", action="store_true", help="do not build the fixed-base tables of the SRS")
