@@ -11,11 +11,14 @@ what the reference's "Distributed HyperPlonk" timer covers (:194-561) -- ~800 MS
 ~150 product sumchecks, the PST opening folds, 2^19 field inversions, the product tree and ~150 leader rounds.
   N = 1      leader mode (the reference's build without `comm`): ONE party's whole prover on one GPU
   N = 2,4,8  the 8 parties spread over the N GPUs (8/N per GPU), the reference's star rounds over NCCL
-`value` = constraints proved per second summed over the parties that ran (every party of an l = 1 run works on
-full-size share tables: 8 GPUs give 8 provers' worth of work per unit time, not a shorter proof), so per-GPU
-work is fixed as N grows ("weak").  The d_msm figures BASELINE.json's metric also names (G1 adds/s, HBM
-roofline fraction of the Pippenger bucket kernel) are measured inside the same step and reported in `d_msm`
-and `roofline`.  One JSON line on stdout (rank 0).
+`value` = 2^n / t(one proof) at EVERY N (the circuit size over the "Distributed HyperPlonk" timer).
+The 8 parties of an l = 1 run jointly prove ONE circuit and each works on full-size share tables, so 8 GPUs give
+privacy and 8 provers' worth of work per unit time, not a shorter proof: that party-summed work rate is reported
+beside it as `value_party_aggregate`, never as `value`.  Per-GPU work is fixed from N = 1 (one party) to N = 8 (one
+party per GPU): "weak".  The d_msm figures BASELINE.json's metric also names (G1 adds/s, HBM roofline fraction of
+the Pippenger bucket kernel) are measured inside the same step and reported in `d_msm` and `roofline`.  For N > 1
+an untimed leg after the measurement proves a 2^10 circuit over the same live NCCL net and compares every party's
+proof with the oracle's 8-party run (`parity_check`).  One JSON line on stdout (rank 0).
 """
 import os as _os
 _os.environ.setdefault("SCZ_MSM_STREAM", "1")   # MSM launch sequences on the ctx's low-priority stream (csrc/msm.cu)
@@ -194,24 +197,25 @@ def run_reference(args):
     from oracle import oracle as orc
     orc.lib()
     threads = os.cpu_count() or 1
-    n = args.ref_logn
+    n = args.ref_logn or args.logn
     pk = cpu_hyperplonk_inputs(n, 11)
     for _ in range(min(args.warmup, 1)):
         cpu_hyperplonk(min(n, 10), cpu_hyperplonk_inputs(min(n, 10), 12), threads)
     steps = max(1, min(args.steps, args.ref_steps))
     dt = sum(cpu_hyperplonk(n, pk, threads) for _ in range(steps))
     value = (1 << n) * steps / dt
-    sample = (f"each step = one leader-mode dhyperplonk proof at 2^{n} constraints (bounded sample of the 2^{args.logn} "
-              f"workload: the CPU path needs minutes per proof there; its constraints/s still grow with the size -- 2.1 k / 3.6 k / "
-              f"4.3 k / 5.7 k at 2^13 / 2^15 / 2^16 / 2^18 on 8 threads of the authoring box -- so a small sample understates it), "
-              f"oracle C restatement of the arkworks path, MSM windows on "
-              f"{threads} host threads (arkworks `parallel`, which the reference leaves off); everything else single-threaded "
-              f"like the reference")
+    same = n == args.logn
+    sample = (f"each step = one leader-mode dhyperplonk proof at 2^{n} constraints "
+              + ("(the own arm's config, whole proof) " if same else f"(bounded sample of the 2^{args.logn} workload) ")
+              + f"-- {steps} timed proof(s): a proof takes about a minute of CPU time at 2^20; oracle C restatement of the "
+              f"arkworks path, MSM windows on {threads} host threads (arkworks `parallel`, which the reference leaves "
+              f"off); everything else single-threaded like the reference")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": dt / steps * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": DTYPE, "data": "synthetic",
-        "config": {"workload": f"dhyperplonk 2^{args.logn} constraints, l=1, N=8, leader mode", "sample_log2_constraints": n},
+        "config": {"workload": f"dhyperplonk 2^{args.logn} constraints, l=1, N=8, leader mode (one party's prover)",
+                   "log2_constraints": n, "same_config_as_own_arm": same},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -285,7 +289,7 @@ def run_own(args):
     import torch
     import torch.distributed as dist
     import scz_b200 as scz
-    from scz_b200.net import HybridNet
+    from scz_b200.net import HybridNet, NativeNcclNet
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -308,7 +312,10 @@ def run_own(args):
         sampler.start()
 
     # ---- setup (untimed, like PackedProvingParameters::new in the reference's bench binary)
-    hub = HybridNet(dev, P) if world > 1 else None
+    # N > 1: the star rounds are issued by libscz itself (NCCL hub, csrc/nccl_net.cu); SCZ_BENCH_NET=python routes them
+    # through the torch.distributed callbacks of net.py instead (same proofs, for A/B measurements)
+    net_kind = os.environ.get("SCZ_BENCH_NET", "native")
+    hub = (NativeNcclNet(dev, P) if net_kind == "native" else HybridNet(dev, P)) if world > 1 else None
     parties = []
     for p in range(P):
         pid = rank * P + p
@@ -371,7 +378,7 @@ def run_own(args):
         dist.all_reduce(t[1:2], op=dist.ReduceOp.SUM)
         ms, launches = float(t[0]), int(t[1])
     parties_total = 1 if world == 1 else N_PARTIES
-    value = parties_total * (1 << n) * args.steps / (ms * 1e-3)
+    value = (1 << n) * args.steps / (ms * 1e-3)          # 2^n / t(proof): the parties prove ONE circuit together
 
     # ---- the same proof with the fixed-base tables of the SRS ignored (plain Pippenger on the level's points)
     plain_ms = None
@@ -444,7 +451,7 @@ def run_own(args):
         t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t[0])
-    e2e_value = parties_total * (1 << n) * e2e_steps / e2e_s
+    e2e_value = (1 << n) * e2e_steps / e2e_s
     comm = ((comm1[0] - comm0[0]) // args.steps, (comm1[1] - comm0[1]) // args.steps)
 
     # ---- N = 1 only: TWO independent provers in flight on the same GPU (a proving service's steady state).  Each has
@@ -506,9 +513,21 @@ def run_own(args):
         ctxB.close()
         ctxA.use_torch_stream()
 
+    # ---- N > 1: untimed parity leg -- a 2^10 proof by the same 8 parties over the live NCCL net, every party's output
+    #      bit for bit against the oracle's 8-party run (rank 0 checks; tests/parity_util.py)
+    parity = None
+    if world > 1 and not args.no_parity:
+        from tests.parity_util import nccl_parity_check
+        try:
+            parity = nccl_parity_check(local_rank, nv=args.parity_logn, l=1, net_kind=net_kind)
+        except Exception as e:   # noqa: BLE001 - reported in the JSON line
+            parity = {"result": f"ERROR: {e!r}"[:400]}
+
     if rank != 0:
         for ctx, _, _ in parties:
             ctx.close()
+        if hub:
+            hub.close()
         if world > 1:
             dist.destroy_process_group()
         return
@@ -532,11 +551,13 @@ def run_own(args):
             "workload": f"dhyperplonk 2^{n} constraints, l=1, N=8, " + ("leader mode (one party's prover)" if world == 1 else
                                                                           f"8 parties on {world} GPUs ({P} per GPU), star rounds over NCCL"),
             "log2_constraints": n, "parties_per_gpu": P,
-            "value_counts": "2^n constraints per party per proof, summed over the parties that ran",
+            "value_counts": "2^n / t(one proof), BASELINE.md 3 -- at N > 1 the 8 parties prove ONE circuit together; "
+                            "the party-summed work rate is value_party_aggregate",
+            "value_party_aggregate": parties_total * value,
             "proofs_per_s": args.steps / (ms * 1e-3),
             "srs_fixed_base_tables": (not args.no_precompute) and "window multiples of every SRS level beside the points "
                                      "(csrc/srs.cu), 12.4 GB per party, built at set-up like the SRS itself",
-            "value_plain_srs": parties_total * (1 << n) / (plain_ms * 1e-3) if plain_ms else None,
+            "value_plain_srs": (1 << n) / (plain_ms * 1e-3) if plain_ms else None,
             "ms_per_step_plain_srs": plain_ms,
             "l2": "one proof streams > 1.2 GB of tables and bases and ~4 GB of MSM temporaries: nothing survives in "
                   "the 126 MB L2 from one step to the next (inputs larger than L2)",
@@ -550,9 +571,14 @@ def run_own(args):
                                if os.environ.get("SCZ_MSM_STREAM") == "1" else "event brackets per kernel class, one stream"),
             "msm_side_stream": os.environ.get("SCZ_MSM_STREAM") == "1",
             "nccl_collectives_per_proof_rank0": coll,
+            "net": (net_kind + (": libscz's NCCL hub (grouped ncclSend/ncclRecv + ncclAllGather on the ctx stream, no host "
+                                "callback)" if net_kind == "native" else ": torch.distributed callbacks (net.py)")) if world > 1
+                   else "leader simulator (serializing_net.rs:144-264)",
             "comm_bytes_per_proof_party0": {"upload": comm[0], "download": comm[1]},
         },
         "clocks": clocks,
+        "parity_check": (parity or {}).get("result") if world > 1 else None,
+        "parity_check_detail": parity,
         "pipelined": pipelined,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d * parties_total,
                 "d2h_bytes_per_step": d2h * parties_total, "steps": e2e_steps, "ms_per_step": e2e_s / e2e_steps * 1e3,
@@ -593,6 +619,8 @@ def run_own(args):
         line["cpu_baseline"] = cpu_baseline_leg()
     for ctx, _, _ in parties:
         ctx.close()
+    if hub:
+        hub.close()
     if world > 1:
         dist.destroy_process_group()
     print(json.dumps(line), flush=True)
@@ -605,11 +633,14 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
     ap.add_argument("--logn", type=int, default=20, help="log2 of the circuit size (BASELINE: 20)")
-    ap.add_argument("--ref-logn", type=int, default=18, help="--impl reference: circuit size of the bounded CPU sample")
-    ap.add_argument("--ref-steps", type=int, default=2, help="--impl reference: at most this many timed proofs")
+    ap.add_argument("--ref-logn", type=int, default=0, help="--impl reference: circuit size of the CPU run (0 = --logn: "
+                                                            "the same config as the own arm, about a minute per proof)")
+    ap.add_argument("--ref-steps", type=int, default=1, help="--impl reference: at most this many timed proofs")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-precompute", action="store_true", help="do not build the fixed-base tables of the SRS")
     ap.add_argument("--no-plain", action="store_true", help="skip the extra leg that times the proof with the tables ignored")
+    ap.add_argument("--no-parity", action="store_true", help="N > 1: skip the untimed parity leg against the oracle")
+    ap.add_argument("--parity-logn", type=int, default=10, help="N > 1: circuit size of the parity leg")
     ap.add_argument("--no-pipelined", action="store_true", help="skip the extra N = 1 leg with two provers in flight")
     args = ap.parse_args()
     if args.impl == "reference":

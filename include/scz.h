@@ -115,6 +115,47 @@ int32_t scz_prof_enable(scz_ctx *ctx, int32_t on);
 int32_t scz_prof_read(scz_ctx *ctx, int32_t kernel_class, double *ms_total, uint64_t *brackets);
 /* MPCNet::get_comm (mpc-net/src/lib.rs:59): (upload, download) in the reference's serialised bytes */
 int32_t scz_ctx_get_comm(const scz_ctx *ctx, uint64_t *upload, uint64_t *download);
+/* Sticky status bits of work already EXECUTED on the ctx stream; synchronises the stream, returns and clears them.
+ * SCZ_STATUS_DIV_BY_ZERO: a field division (`num / den`, hyperplonk/src/dhyperplonk.rs:338-339) met den = 0 --
+ * arkworks panics there ("division by zero" in Field::div); the kernel writes 0 for that element, sets this bit,
+ * and the Rust shim panics when it sees it. */
+#define SCZ_STATUS_DIV_BY_ZERO 1u
+int32_t scz_ctx_take_status(scz_ctx *ctx, uint32_t *bits);
+
+/* ---- native data plane: NCCL over NVLink in place of the reference's TCP star (mpc-net/src/multi.rs:98-266) ----
+ * One process per GPU ("rank"), `parties_per_rank` MPC parties hosted by each rank (1 on an 8-GPU box at l = 1; 8 l / W
+ * on W GPUs), party id = rank * parties_per_rank + local index, party 0 = the leader (MPCNet::is_leader).  A hub owns
+ * the rank's ncclComm_t; every hosted party gets its own ctx (one host thread per party, like the reference's one task
+ * per party, multi.rs:345-348).  A star round (worker_send_or_leader_receive / worker_receive_or_leader_send,
+ * mpc-net/src/lib.rs:64-256) is ONE grouped ncclSend / ncclRecv per rank on the concatenated payloads of its parties,
+ * issued on the ctx stream of the rank's local party 0 -- no host copy, no serialisation, no Python; the hub rounds of
+ * dhyperplonk.rs:271-294 are one ncclAllGather.  Local parties meet at a host barrier and are fenced by CUDA events.
+ * The unique id is NCCL's (128 bytes): rank 0 creates it and the host hands it to the other ranks by whatever
+ * channel it has (the reference's address file, MPI, torch.distributed ...). */
+#define SCZ_NCCL_UID_BYTES 128
+typedef struct scz_nccl_hub scz_nccl_hub;
+int32_t scz_nccl_unique_id(void *uid128);
+int32_t scz_nccl_hub_create(int32_t device, uint32_t rank, uint32_t nranks, uint32_t parties_per_rank, const void *uid128,
+                            scz_nccl_hub **out);
+void scz_nccl_hub_destroy(scz_nccl_hub *hub);
+/* unblocks every party waiting at the hub's host barrier with SCZ_ERR_NET (a party thread failed) */
+void scz_nccl_hub_abort(scz_nccl_hub *hub);
+/* NCCL collectives issued so far by this rank: [gather, scatter, all_gather, sync] */
+int32_t scz_nccl_hub_calls(const scz_nccl_hub *hub, uint64_t out4[4]);
+/* the ctx of local party `local_index` (MPCNetConnection::init_from_path + listen + connect_to_all, multi.rs:109-266) */
+int32_t scz_ctx_create_on_hub(scz_nccl_hub *hub, uint32_t local_index, scz_ctx **out);
+/* one party per rank: hub + ctx in one call (the hub dies with the ctx) */
+int32_t scz_ctx_create_nccl(int32_t device, uint32_t rank, uint32_t nranks, const void *uid128, scz_ctx **out);
+
+/* The star collectives themselves on DEVICE buffers, for hosts that move their own elements (MPCNet's
+ * worker_send_or_leader_receive :64, worker_receive_or_leader_send :165 and their dynamic_ variants :111, :211, sync
+ * :275): whatever net the ctx was created with (leader simulator, callbacks, NCCL hub).  Asynchronous on the ctx stream.
+ * gather: party `root` receives n_parties * bytes (party-major) in d_recv; scatter: party `root`'s d_send holds
+ * n_parties * bytes and party j receives slice j in d_recv.  Byte counters advance by `bytes` per message. */
+int32_t scz_net_gather(scz_ctx *ctx, uint32_t root, const void *d_send, void *d_recv, size_t bytes);
+int32_t scz_net_scatter(scz_ctx *ctx, uint32_t root, const void *d_send, void *d_recv, size_t bytes);
+int32_t scz_net_all_gather(scz_ctx *ctx, const void *d_send, void *d_recv, size_t bytes);
+int32_t scz_net_sync(scz_ctx *ctx);
 
 /* ---- device memory ---------------------------------------------------------------------- */
 int32_t scz_dev_alloc(scz_ctx *ctx, size_t bytes, void **d_ptr);

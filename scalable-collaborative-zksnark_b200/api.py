@@ -51,11 +51,16 @@ class Context:
         self.device = torch.device("cuda", device)
         self.net = net
         self._vt = None
-        if net is not None:
-            self._vt = net.vtable()
         h = C.c_void_p()
-        rc = self.L.scz_ctx_create(C.c_int32(device), C.c_uint32(party_id), C.c_uint32(n_parties),
-                                   C.byref(self._vt) if self._vt is not None else None, C.byref(h))
+        if net is not None and hasattr(net, "native_create"):
+            # libscz's own NCCL hub (csrc/nccl_net.cu): the collectives never come back to Python
+            assert (party_id, n_parties) == (net.rank, net.n_parties), "party id / count are the hub's"
+            rc = net.native_create(self.L, h)
+        else:
+            if net is not None:
+                self._vt = net.vtable()
+            rc = self.L.scz_ctx_create(C.c_int32(device), C.c_uint32(party_id), C.c_uint32(n_parties),
+                                       C.byref(self._vt) if self._vt is not None else None, C.byref(h))
         if rc != 0:
             raise SczError(rc, "scz_ctx_create failed")
         self.h = h
@@ -85,6 +90,17 @@ class Context:
 
     def sync(self):
         self.check(self.L.scz_ctx_sync(self.h))
+
+    def take_status(self):
+        """sticky SCZ_STATUS_* bits of the work executed so far (synchronises); bit 0: a division met a zero denominator"""
+        bits = C.c_uint32()
+        self.check(self.L.scz_ctx_take_status(self.h, C.byref(bits)))
+        return bits.value
+
+    def raise_on_status(self):
+        """what the Rust shim does after a prover call: arkworks panics on `a / 0` (dhyperplonk.rs:338-339)"""
+        if self.take_status() & 1:
+            raise ZeroDivisionError("field division by zero (arkworks panics here: hyperplonk/src/dhyperplonk.rs:338-339)")
 
     @property
     def launches(self):
@@ -396,6 +412,8 @@ def fr_pointwise(ctx, mode, a, b, k=None):
     m = {"add": 0, "rsub": 1, "axpb": 2, "div": 3}[mode]
     ctx.check(ctx.L.scz_fr_pointwise_dev(ctx.h, C.c_int32(m), _vp(ad), _vp(bd), _vp(kd) if kd is not None else None,
                                          _vp(out), C.c_size_t(len(ad))))
+    if host and m == 3:   # host path: synchronous anyway, so the reference's panic on a zero denominator surfaces here
+        ctx.raise_on_status()
     return _out(ctx, out, host)
 
 
@@ -750,8 +768,10 @@ class HyperPlonkProof:
         return t, p, v
 
     def to_host(self):
-        """device -> host copy of the written part of the three arenas (numpy, synchronous)"""
+        """device -> host copy of the written part of the three arenas (numpy, synchronous); raises ZeroDivisionError
+        when the proof divided by zero (the reference panics, dhyperplonk.rs:338-339)"""
         t, p, v = self.used()
+        self.ctx.raise_on_status()
         return (self.ctx.to_host(self.triples[: 3 * t]), self.ctx.to_host(self.points[:p]), self.ctx.to_host(self.values[:v]))
 
     def nested(self):

@@ -332,6 +332,7 @@ extern "C" {
 int32_t scz_c_acc_product_and_share_dev(scz_ctx *h, const scz_pp *pp, const void *d_shares, const void *d_masks,
                                         const void *d_unmask0, const void *d_unmask1, const void *d_unmask2, size_t len,
                                         void *d_share0, void *d_share1, void *d_share2) {
+    scz::DeviceGuard dg__(h);
     if (!h) return SCZ_ERR_BAD_ARG;
     if (!pp || !d_shares || !d_masks || !d_unmask0 || !d_unmask1 || !d_unmask2 || !d_share0 || !d_share1 || !d_share2)
         return h->c.fail(SCZ_ERR_BAD_ARG, "c_acc_product_and_share: null argument");
@@ -342,6 +343,7 @@ int32_t scz_c_acc_product_and_share_dev(scz_ctx *h, const scz_pp *pp, const void
 int32_t scz_cpermcheck_dev(scz_ctx *h, size_t n, const scz_cperm_pk *pk, const scz_pp *pp, void *d_triples, size_t triples_cap,
                            void *d_points, size_t points_cap, void *d_values, size_t values_cap, scz_hp_item *items,
                            size_t items_cap, size_t *n_items) {
+    scz::DeviceGuard dg__(h);
     if (!h) return SCZ_ERR_BAD_ARG;
     Ctx *c = &h->c;
     if (!pk || !pp || !d_triples || !d_points || !d_values || !items || !n_items)

@@ -198,11 +198,17 @@ int32_t scz_ctx_create(int32_t device, uint32_t party_id, uint32_t n_parties, co
     scz_ctx *h = new scz_ctx();
     Ctx *c = &h->c;
     c->device = device;
+    DeviceGuard dg(h);   // the caller's current device is restored on return
     if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
         delete h;
         return SCZ_ERR_CUDA;
     }
     c->own_stream = true;
+    if (cudaMalloc(&c->d_status, sizeof(uint32_t)) != cudaSuccess || cudaMemset(c->d_status, 0, sizeof(uint32_t)) != cudaSuccess) {
+        cudaStreamDestroy(c->stream);
+        delete h;
+        return SCZ_ERR_CUDA;
+    }
     cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
     {   // keep freed temporaries cached in the pool instead of returning them to the driver
         cudaMemPool_t pool;
@@ -229,6 +235,7 @@ void scz_ctx_destroy(scz_ctx *h) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     if (c->pinned) cudaFreeHost(c->pinned);
+    if (c->d_status) cudaFree(c->d_status);
     for (auto &st : c->stage) {
         if (st.p) cudaFreeHost(st.p);
         if (st.ev) cudaEventDestroy(st.ev);
@@ -247,6 +254,7 @@ void scz_ctx_destroy(scz_ctx *h) {
 }
 const char *scz_last_error(const scz_ctx *h) { return h ? h->c.err.c_str() : "null ctx"; }
 int32_t scz_ctx_set_stream(scz_ctx *h, void *s) {
+    scz::DeviceGuard dg__(h);
     if (!h) return SCZ_ERR_BAD_ARG;
     Ctx *c = &h->c;
     SCZ_CUDA(c, cudaSetDevice(c->device));
@@ -257,6 +265,7 @@ int32_t scz_ctx_set_stream(scz_ctx *h, void *s) {
     return SCZ_OK;
 }
 int32_t scz_ctx_own_stream(scz_ctx *h) {
+    scz::DeviceGuard dg__(h);
     if (!h) return SCZ_ERR_BAD_ARG;
     Ctx *c = &h->c;
     if (c->own_stream) return SCZ_OK;
@@ -267,11 +276,13 @@ int32_t scz_ctx_own_stream(scz_ctx *h) {
     return SCZ_OK;
 }
 int32_t scz_ctx_sync(scz_ctx *h) {
+    scz::DeviceGuard dg__(h);
     if (!h) return SCZ_ERR_BAD_ARG;
     SCZ_CUDA(&h->c, cudaStreamSynchronize(h->c.stream));
     return SCZ_OK;
 }
 int32_t scz_prof_enable(scz_ctx *h, int32_t on) {
+    scz::DeviceGuard dg__(h);
     if (!h) return SCZ_ERR_BAD_ARG;
     SCZ_CUDA(&h->c, cudaStreamSynchronize(h->c.stream));
     h->c.prof_clear();
@@ -279,6 +290,7 @@ int32_t scz_prof_enable(scz_ctx *h, int32_t on) {
     return SCZ_OK;
 }
 int32_t scz_prof_read(scz_ctx *h, int32_t kernel_class, double *ms_total, uint64_t *brackets) {
+    scz::DeviceGuard dg__(h);
     if (!h) return SCZ_ERR_BAD_ARG;
     Ctx *c = &h->c;
     SCZ_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -296,13 +308,26 @@ int32_t scz_prof_read(scz_ctx *h, int32_t kernel_class, double *ms_total, uint64
     return SCZ_OK;
 }
 uint64_t scz_ctx_launch_count(const scz_ctx *h) { return h ? h->c.launches : 0; }
+int32_t scz_ctx_take_status(scz_ctx *h, uint32_t *bits) {
+    scz::DeviceGuard dg__(h);
+    if (!h || !bits) return SCZ_ERR_BAD_ARG;
+    Ctx *c = &h->c;
+    uint32_t v = 0;
+    SCZ_CUDA(c, cudaMemcpyAsync(&v, c->d_status, sizeof v, cudaMemcpyDeviceToHost, c->stream));
+    SCZ_CUDA(c, cudaMemsetAsync(c->d_status, 0, sizeof v, c->stream));
+    SCZ_CUDA(c, cudaStreamSynchronize(c->stream));
+    *bits = v;
+    return SCZ_OK;
+}
 int32_t scz_ctx_get_comm(const scz_ctx *h, uint64_t *up, uint64_t *down) {
+    scz::DeviceGuard dg__(h);
     if (!h) return SCZ_ERR_BAD_ARG;
     if (up) *up = h->c.net->upload;
     if (down) *down = h->c.net->download;
     return SCZ_OK;
 }
 int32_t scz_dev_alloc(scz_ctx *h, size_t bytes, void **p) {
+    scz::DeviceGuard dg__(h);
     if (!h || !p) return SCZ_ERR_BAD_ARG;
     SCZ_CUDA(&h->c, cudaSetDevice(h->c.device));
     cudaError_t e = cudaMalloc(p, bytes ? bytes : 1);
@@ -313,29 +338,34 @@ int32_t scz_dev_alloc(scz_ctx *h, size_t bytes, void **p) {
     return SCZ_OK;
 }
 int32_t scz_dev_free(scz_ctx *h, void *p) {
+    scz::DeviceGuard dg__(h);
     if (!h) return SCZ_ERR_BAD_ARG;
     SCZ_CUDA(&h->c, cudaStreamSynchronize(h->c.stream));
     SCZ_CUDA(&h->c, cudaFree(p));
     return SCZ_OK;
 }
 int32_t scz_h2d(scz_ctx *h, void *d, const void *s, size_t bytes) {
+    scz::DeviceGuard dg__(h);
     if (!h) return SCZ_ERR_BAD_ARG;
     SCZ_CUDA(&h->c, cudaMemcpyAsync(d, s, bytes, cudaMemcpyHostToDevice, h->c.stream));
     SCZ_CUDA(&h->c, cudaStreamSynchronize(h->c.stream));
     return SCZ_OK;
 }
 int32_t scz_d2h(scz_ctx *h, void *d, const void *s, size_t bytes) {
+    scz::DeviceGuard dg__(h);
     if (!h) return SCZ_ERR_BAD_ARG;
     SCZ_CUDA(&h->c, cudaMemcpyAsync(d, s, bytes, cudaMemcpyDeviceToHost, h->c.stream));
     SCZ_CUDA(&h->c, cudaStreamSynchronize(h->c.stream));
     return SCZ_OK;
 }
 int32_t scz_host_alloc(scz_ctx *h, size_t bytes, void **p) {
+    scz::DeviceGuard dg__(h);
     if (!h || !p) return SCZ_ERR_BAD_ARG;
     SCZ_CUDA(&h->c, cudaMallocHost(p, bytes ? bytes : 1));
     return SCZ_OK;
 }
 int32_t scz_host_free(scz_ctx *h, void *p) {
+    scz::DeviceGuard dg__(h);
     if (!h) return SCZ_ERR_BAD_ARG;
     SCZ_CUDA(&h->c, cudaFreeHost(p));
     return SCZ_OK;

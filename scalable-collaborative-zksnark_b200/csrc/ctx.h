@@ -27,6 +27,10 @@ struct Ctx {
     size_t pinned_cap = 0;
     Net *net = nullptr;
     uint64_t launches = 0;   // kernels launched by this ctx (bench.py reports it as gpu_launches)
+    // cudaFuncSetAttribute is per device: every ctx raises the dynamic shared memory limits it needs once (no
+    // process-wide flags -- a process may drive several devices and several party threads)
+    bool attr_msm = false, attr_pss = false;
+    uint32_t *d_status = nullptr;   // sticky SCZ_STATUS_* bits set by kernels (scz_ctx_take_status)
     uint32_t msm_window_override = 0;
     bool msm_no_precompute = false;   // ignore fixed-base tables (for A/B measurements)
     uint64_t msm_bucket_adds = 0, msm_buckets = 0, msm_windows = 0;   // statistics of the last MSM sequence
@@ -121,3 +125,24 @@ static inline uint32_t ceil_div_u32(size_t a, size_t b) { return (uint32_t)((a +
 struct scz_ctx {
     scz::Ctx c;
 };
+
+namespace scz {
+// Every ABI entry point runs on the ctx's device whatever the calling thread's current device is (the reference's
+// party tasks hop OS threads, mpc-net/src/multi.rs:345-348), and leaves the caller's device as it found it.
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(const scz_ctx *h) {
+        if (!h) return;
+        int cur = -1;
+        if (cudaGetDevice(&cur) == cudaSuccess && cur != h->c.device) {
+            prev = cur;
+            cudaSetDevice(h->c.device);
+        }
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+    DeviceGuard(const DeviceGuard &) = delete;
+    DeviceGuard &operator=(const DeviceGuard &) = delete;
+};
+}   // namespace scz

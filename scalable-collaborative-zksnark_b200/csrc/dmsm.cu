@@ -71,12 +71,14 @@ extern "C" {
 
 int32_t scz_d_msm_dev(scz_ctx *h, const scz_pp *pp, const void *const *d_bases, const void *const *d_scalars,
                       const size_t *lens, size_t batch, void *d_out) {
+    scz::DeviceGuard dg__(h);
     if (!h) return SCZ_ERR_BAD_ARG;
     if (batch && (!d_bases || !d_scalars || !lens || !d_out)) return h->c.fail(SCZ_ERR_BAD_ARG, "d_msm: null argument");
     return d_msm_dev(&h->c, pp, d_bases, d_scalars, lens, batch, d_out);
 }
 
 int32_t scz_d_msm_leader_dev(scz_ctx *h, const scz_pp *pp, const void *d_gathered, size_t batch, void *d_to_scatter) {
+    scz::DeviceGuard dg__(h);
     if (!h || !pp) return SCZ_ERR_BAD_ARG;
     if (batch && (!d_gathered || !d_to_scatter)) return h->c.fail(SCZ_ERR_BAD_ARG, "d_msm_leader: null argument");
     if (!batch) return SCZ_OK;
@@ -85,6 +87,7 @@ int32_t scz_d_msm_leader_dev(scz_ctx *h, const scz_pp *pp, const void *d_gathere
 
 int32_t scz_d_msm(scz_ctx *h, const scz_pp *pp, const void *const *bases, const size_t *bases_lens,
                   const void *const *scalars, const size_t *scalars_lens, size_t batch, void *out_jac) {
+    scz::DeviceGuard dg__(h);
     if (!h) return SCZ_ERR_BAD_ARG;
     Ctx *c = &h->c;
     if (batch && (!bases || !scalars || !bases_lens || !scalars_lens || !out_jac))

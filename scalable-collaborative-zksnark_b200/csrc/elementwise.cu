@@ -111,6 +111,7 @@ using namespace scz;
 extern "C" {
 
 int32_t scz_fr_vec_op_dev(scz_ctx *h, int32_t op, const void *a, const void *b, void *out, size_t n) {
+    scz::DeviceGuard dg__(h);
     CHECK_ARGS(h, a && b && out && op >= 0 && op <= 2);
     if (!n) return SCZ_OK;
     Ctx *c = &h->c;
@@ -122,6 +123,7 @@ int32_t scz_fr_vec_op_dev(scz_ctx *h, int32_t op, const void *a, const void *b, 
     return SCZ_OK;
 }
 int32_t scz_fq_vec_op_dev(scz_ctx *h, int32_t op, const void *a, const void *b, void *out, size_t n) {
+    scz::DeviceGuard dg__(h);
     CHECK_ARGS(h, a && b && out && op >= 0 && op <= 2);
     if (!n) return SCZ_OK;
     Ctx *c = &h->c;
@@ -148,6 +150,7 @@ int32_t scz_fr_to_canonical_dev(scz_ctx *h, const void *a, void *out, size_t n) 
 int32_t scz_fr_from_canonical_dev(scz_ctx *h, const void *a, void *out, size_t n) { return fr_unary(h, 2, a, out, n); }
 
 int32_t scz_g1_add_affine_dev(scz_ctx *h, const void *acc, const void *aff, const uint8_t *neg, void *out, size_t n) {
+    scz::DeviceGuard dg__(h);
     CHECK_ARGS(h, acc && aff && out);
     if (!n) return SCZ_OK;
     Ctx *c = &h->c;
@@ -156,6 +159,7 @@ int32_t scz_g1_add_affine_dev(scz_ctx *h, const void *acc, const void *aff, cons
     return SCZ_OK;
 }
 int32_t scz_g1_vec_op_dev(scz_ctx *h, int32_t op, const void *a, const void *b, void *out, size_t n) {
+    scz::DeviceGuard dg__(h);
     CHECK_ARGS(h, a && out && (op == 1 || (op == 0 && b)));
     if (!n) return SCZ_OK;
     Ctx *c = &h->c;
@@ -165,6 +169,7 @@ int32_t scz_g1_vec_op_dev(scz_ctx *h, int32_t op, const void *a, const void *b, 
     return SCZ_OK;
 }
 int32_t scz_g1_mul_fr_dev(scz_ctx *h, const void *a, const void *k, void *out, size_t n) {
+    scz::DeviceGuard dg__(h);
     CHECK_ARGS(h, a && k && out);
     if (!n) return SCZ_OK;
     Ctx *c = &h->c;
@@ -173,6 +178,7 @@ int32_t scz_g1_mul_fr_dev(scz_ctx *h, const void *a, const void *k, void *out, s
     return SCZ_OK;
 }
 int32_t scz_g1_to_affine_dev(scz_ctx *h, const void *a, void *out, size_t n) {
+    scz::DeviceGuard dg__(h);
     CHECK_ARGS(h, a && out);
     if (!n) return SCZ_OK;
     Ctx *c = &h->c;
@@ -181,6 +187,7 @@ int32_t scz_g1_to_affine_dev(scz_ctx *h, const void *a, void *out, size_t n) {
     return SCZ_OK;
 }
 int32_t scz_g1_generator_mul_dev(scz_ctx *h, const void *k, void *out, size_t n) {
+    scz::DeviceGuard dg__(h);
     CHECK_ARGS(h, k && out);
     if (!n) return SCZ_OK;
     Ctx *c = &h->c;
@@ -189,6 +196,7 @@ int32_t scz_g1_generator_mul_dev(scz_ctx *h, const void *k, void *out, size_t n)
     return SCZ_OK;
 }
 int32_t scz_g1_apply_inf_mask_dev(scz_ctx *h, void *bases, const uint8_t *mask, size_t n) {
+    scz::DeviceGuard dg__(h);
     CHECK_ARGS(h, bases && mask);
     if (!n) return SCZ_OK;
     Ctx *c = &h->c;

@@ -127,7 +127,14 @@ __device__ __forceinline__ G1Jac g1x_to_jac_nl(const G1X &p) { return g1x_to_jac
 // acc = k * P for a canonical 256-bit scalar k (little-endian 32-bit limbs), 4-bit fixed windows.
 // tab: 16 Jacobian slots private to the group (shared or global memory); every lane of the group writes the
 // same values.  ~64 * (4 doublings + 1 addition) = 1.1k product levels instead of ~4k serial products.
-__device__ __forceinline__ G1Jac coop_mul_bits(const Coop &g, const G1Jac &p, const uint32_t (&k)[8], G1Jac *tab) {
+// The operand is taken from ONE copy in the group's (otherwise unused) slot 0: the cooperative routines rely on the
+// group's lanes holding a bit-identical operand, and a value each lane loaded by itself from global memory was seen
+// to break that on sm_100a / nvcc 12.9 in k_pss_dmsm_multi<2> (pss.cu; root cause not isolated, memcheck / synccheck
+// clean), so every entry point goes through the same canonicalisation (tests/test_gpu_msm.py::test_d_msm_closure_*).
+__device__ __forceinline__ G1Jac coop_mul_bits(const Coop &g, const G1Jac &p_in, const uint32_t (&k)[8], G1Jac *tab) {
+    if (g.role == 0) tab[0] = p_in;
+    __syncwarp(g.mask);
+    const G1Jac p = tab[0];
     G1Jac t = p;
     tab[1] = t;
     for (int j = 2; j < 16; j++) {

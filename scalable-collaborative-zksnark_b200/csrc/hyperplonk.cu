@@ -382,6 +382,7 @@ static int32_t hp_entry(scz_ctx *h, size_t n, const scz_hp_pk *pk, const scz_pp 
 int32_t scz_local_hyperplonk_dev(scz_ctx *h, size_t n, const scz_local_pk *pk, void *d_triples, size_t triples_cap, void *d_points,
                                  size_t points_cap, void *d_values, size_t values_cap, scz_hp_item *items, size_t items_cap,
                                  size_t *n_items) {
+    scz::DeviceGuard dg__(h);
     if (!h) return SCZ_ERR_BAD_ARG;
     Ctx *c = &h->c;
     if (!pk || !d_triples || !d_points || !d_values || !items || !n_items) return c->fail(SCZ_ERR_BAD_ARG, "local_hyperplonk: null argument");
@@ -402,18 +403,21 @@ int32_t scz_local_hyperplonk_dev(scz_ctx *h, size_t n, const scz_local_pk *pk, v
 int32_t scz_dhyperplonk_dev(scz_ctx *h, size_t n, const scz_hp_pk *pk, const scz_pp *pp, void *d_triples, size_t triples_cap,
                             void *d_points, size_t points_cap, void *d_values, size_t values_cap, scz_hp_item *items,
                             size_t items_cap, size_t *n_items) {
+    scz::DeviceGuard dg__(h);
     return hp_entry(h, n, pk, pp, d_triples, triples_cap, d_points, points_cap, d_values, values_cap, items, items_cap, n_items,
                     HP_FULL);
 }
 int32_t scz_dhyperplonk_data_parallel_dev(scz_ctx *h, size_t n, const scz_hp_pk *pk, const scz_pp *pp, void *d_triples,
                                           size_t triples_cap, void *d_points, size_t points_cap, void *d_values,
                                           size_t values_cap, scz_hp_item *items, size_t items_cap, size_t *n_items) {
+    scz::DeviceGuard dg__(h);
     return hp_entry(h, n, pk, pp, d_triples, triples_cap, d_points, points_cap, d_values, values_cap, items, items_cap, n_items,
                     HP_DATA_PARALLEL);
 }
 int32_t scz_dpermcheck_dev(scz_ctx *h, size_t n, const scz_hp_pk *pk, const scz_pp *pp, void *d_triples, size_t triples_cap,
                            void *d_points, size_t points_cap, void *d_values, size_t values_cap, scz_hp_item *items,
                            size_t items_cap, size_t *n_items) {
+    scz::DeviceGuard dg__(h);
     return hp_entry(h, n, pk, pp, d_triples, triples_cap, d_points, points_cap, d_values, values_cap, items, items_cap, n_items,
                     HP_PERMCHECK);
 }

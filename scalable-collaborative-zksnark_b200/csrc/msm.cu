@@ -576,12 +576,12 @@ int32_t msm_g1_batched(Ctx *ctx, const void *const *d_bases, const void *const *
     int K = (int)batch;
     uint32_t *counts = d_counts.as<uint32_t>(), *cursor = d_cursor.as<uint32_t>();
     uint2 *sorted = d_sorted.as<uint2>();
-    static bool attr_done = false;
-    if (!attr_done) {
-        cudaFuncSetAttribute(k_msm_fixup_heavy, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)(PLN_THREADS * sizeof(G1X)));
-        cudaFuncSetAttribute(k_msm_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(FIN_THREADS * sizeof(G1Jac)));
-        attr_done = true;
+    if (!ctx->attr_msm) {   // per device, so per ctx
+        SCZ_CUDA(ctx, cudaFuncSetAttribute(k_msm_fixup_heavy, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)(PLN_THREADS * sizeof(G1X))));
+        SCZ_CUDA(ctx, cudaFuncSetAttribute(k_msm_finish, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)(FIN_THREADS * sizeof(G1Jac))));
+        ctx->attr_msm = true;
     }
     {
         ProfScope ps(ctx, SCZ_K_MSM_SORT);
@@ -749,6 +749,7 @@ extern "C" {
 
 int32_t scz_msm_g1_batched_dev(scz_ctx *h, const void *const *d_bases, const void *const *d_scalars, const size_t *lens,
                                size_t batch, void *d_out) {
+    scz::DeviceGuard dg__(h);
     if (!h) return SCZ_ERR_BAD_ARG;
     if (batch && (!d_bases || !d_scalars || !lens || !d_out)) return h->c.fail(SCZ_ERR_BAD_ARG, "msm: null argument");
     return msm_g1_batched(&h->c, d_bases, d_scalars, lens, batch, d_out);
@@ -756,6 +757,7 @@ int32_t scz_msm_g1_batched_dev(scz_ctx *h, const void *const *d_bases, const voi
 
 int32_t scz_msm_g1(scz_ctx *h, const void *bases, const uint8_t *inf_mask, size_t bases_len, const void *scalars,
                    size_t scalars_len, void *out_jac) {
+    scz::DeviceGuard dg__(h);
     if (!h) return SCZ_ERR_BAD_ARG;
     Ctx *c = &h->c;
     if (!out_jac) return c->fail(SCZ_ERR_BAD_ARG, "msm: null output");
@@ -784,16 +786,19 @@ int32_t scz_msm_g1(scz_ctx *h, const void *bases, const uint8_t *inf_mask, size_
 }
 
 int32_t scz_msm_set_window(scz_ctx *h, uint32_t cbits) {
+    scz::DeviceGuard dg__(h);
     if (!h || cbits > 20) return SCZ_ERR_BAD_ARG;
     h->c.msm_window_override = cbits;
     return SCZ_OK;
 }
 int32_t scz_msm_use_precompute(scz_ctx *h, int32_t on) {
+    scz::DeviceGuard dg__(h);
     if (!h) return SCZ_ERR_BAD_ARG;
     h->c.msm_no_precompute = on == 0;
     return SCZ_OK;
 }
 int32_t scz_msm_cum_stats(const scz_ctx *h, uint64_t *adds, uint64_t *pairs, uint64_t *sequences, uint64_t *segments) {
+    scz::DeviceGuard dg__(h);
     if (!h) return SCZ_ERR_BAD_ARG;
     if (adds) *adds = h->c.msm_cum_adds;
     if (pairs) *pairs = h->c.msm_cum_pairs;
@@ -802,6 +807,7 @@ int32_t scz_msm_cum_stats(const scz_ctx *h, uint64_t *adds, uint64_t *pairs, uin
     return SCZ_OK;
 }
 int32_t scz_msm_last_stats(const scz_ctx *h, uint64_t *adds, uint64_t *buckets, uint64_t *windows) {
+    scz::DeviceGuard dg__(h);
     if (!h) return SCZ_ERR_BAD_ARG;
     if (adds) *adds = h->c.msm_bucket_adds;
     if (buckets) *buckets = h->c.msm_buckets;

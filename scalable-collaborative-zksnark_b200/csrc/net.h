@@ -17,6 +17,13 @@ struct Net {
     uint32_t n_parties = 1, party_id = 0;
     uint64_t upload = 0, download = 0;
     bool is_leader() const { return party_id == 0; }
+    // a leader -> everybody message of `wire` serialised bytes per party that carries no data on this path (the
+    // (F::zero(), vec![]) workers get from d_open, dpoly_comm.rs:382-391): counted like the reference counts it
+    // (serializing_net.rs:210 / mpc-net/src/multi.rs:378-417), nothing moves
+    void count_scatter(size_t wire) {
+        if (is_leader()) upload += wire * (n_parties - 1);
+        else download += wire;
+    }
     virtual ~Net() {}
     // d_recv: n_parties * bytes on the leader (ignored elsewhere)
     virtual int32_t gather(Ctx *ctx, const void *d_send, void *d_recv, size_t bytes, size_t wire) = 0;

@@ -323,7 +323,7 @@ __device__ __forceinline__ Fr fr_shfl_up(const Fr &v, int d) {
     for (int i = 0; i < 8; i++) r.l[i] = __shfl_up_sync(0xffffffffu, v.l[i], d);
     return r;
 }
-__global__ void __launch_bounds__(PL_THREADS) k_div(const void *num, const void *den, void *out, size_t n) {
+__global__ void __launch_bounds__(PL_THREADS) k_div(const void *num, const void *den, void *out, size_t n, uint32_t *status) {
     size_t base = ((size_t)blockIdx.x * PL_THREADS + threadIdx.x) * INV_PER_THREAD;
     int lane = threadIdx.x & 31;
     Fr d[INV_PER_THREAD], pre[INV_PER_THREAD];
@@ -383,6 +383,7 @@ __global__ void __launch_bounds__(PL_THREADS) k_div(const void *num, const void 
         inv_run = fp_mul(inv_run, d[j]);
         if (base + j < n) {
             Fr dn = fp_load_rw<FrP>(den, base + j);
+            if (dn.is_zero()) atomicOr(status, SCZ_STATUS_DIV_BY_ZERO);   // arkworks panics here; the host reads the bit
             Fr r = dn.is_zero() ? Fr::zero() : fp_mul(fp_load_rw<FrP>(num, base + j), inv_j);
             fp_store<FrP>(out, base + j, r);
         }
@@ -569,7 +570,7 @@ int32_t fr_pointwise(Ctx *c, int32_t mode, const void *d_a, const void *d_b, con
     if (mode == 0) k_pointwise<0><<<g, PL_THREADS, 0, c->stream>>>(d_a, d_b, d_k, d_out, n);
     else if (mode == 1) k_pointwise<1><<<g, PL_THREADS, 0, c->stream>>>(d_a, d_b, d_k, d_out, n);
     else if (mode == 2) k_pointwise<2><<<g, PL_THREADS, 0, c->stream>>>(d_a, d_b, d_k, d_out, n);
-    else k_div<<<ceil_div_u32(n, (size_t)PL_THREADS * INV_PER_THREAD), PL_THREADS, 0, c->stream>>>(d_a, d_b, d_out, n);
+    else k_div<<<ceil_div_u32(n, (size_t)PL_THREADS * INV_PER_THREAD), PL_THREADS, 0, c->stream>>>(d_a, d_b, d_out, n, c->d_status);
     SCZ_LAUNCH_CHECK(c);
     return SCZ_OK;
 }
@@ -598,32 +599,38 @@ extern "C" {
 
 int32_t scz_sumcheck_product_rounds_dev(scz_ctx *h, const void *d_f, const void *d_g, size_t len, const void *d_challenge,
                                         void *d_out_triples, void *d_last_fg) {
+    scz::DeviceGuard dg__(h);
     if (!h) return SCZ_ERR_BAD_ARG;
     if (!d_f || !d_g || !d_last_fg || (len > 1 && (!d_challenge || !d_out_triples)))
         return h->c.fail(SCZ_ERR_BAD_ARG, "sumcheck: null argument");
     return sumcheck_product_rounds(&h->c, d_f, d_g, len, d_challenge, d_out_triples, d_last_fg);
 }
 int32_t scz_open_fold_dev(scz_ctx *h, const void *d_peval, size_t len, const void *d_point, void *d_q, void *d_value) {
+    scz::DeviceGuard dg__(h);
     if (!h) return SCZ_ERR_BAD_ARG;
     if (!d_peval || !d_value || (len > 1 && (!d_point || !d_q))) return h->c.fail(SCZ_ERR_BAD_ARG, "open_fold: null argument");
     return open_fold_rounds(&h->c, d_peval, len, d_point, d_q, d_value);
 }
 int32_t scz_fix_variable_dev(scz_ctx *h, const void *d_evals, size_t len, const void *d_points, size_t npoints, void *d_out) {
+    scz::DeviceGuard dg__(h);
     if (!h) return SCZ_ERR_BAD_ARG;
     if (!d_evals || !d_out || (npoints && !d_points)) return h->c.fail(SCZ_ERR_BAD_ARG, "fix_variable: null argument");
     return fix_variable_rounds(&h->c, d_evals, len, d_points, npoints, d_out);
 }
 int32_t scz_acc_product_dev(scz_ctx *h, const void *d_x, size_t m, void *d_tree) {
+    scz::DeviceGuard dg__(h);
     if (!h) return SCZ_ERR_BAD_ARG;
     if (!d_x || !d_tree) return h->c.fail(SCZ_ERR_BAD_ARG, "acc_product: null argument");
     return acc_product_tree(&h->c, d_x, m, d_tree);
 }
 int32_t scz_fr_pointwise_dev(scz_ctx *h, int32_t mode, const void *d_a, const void *d_b, const void *d_k, void *d_out,
                              size_t n) {
+    scz::DeviceGuard dg__(h);
     if (!h) return SCZ_ERR_BAD_ARG;
     return fr_pointwise(&h->c, mode, d_a, d_b, d_k, d_out, n);
 }
 int32_t scz_fr_deinterleave_dev(scz_ctx *h, const void *d_in, size_t n_pairs, void *d_even, void *d_odd) {
+    scz::DeviceGuard dg__(h);
     if (!h) return SCZ_ERR_BAD_ARG;
     return fr_deinterleave(&h->c, d_in, n_pairs, d_even, d_odd);
 }

@@ -463,6 +463,9 @@ int32_t d_open_defer(Ctx *ctx, Deferred &D, const scz_srs *srs, const void *d_pe
         }
         Dp->gather(loc->p, recv ? recv->p : nullptr, payload, 32 + 8 + 48 * n);   // :368
         Dp->then_gathered([=]() -> int32_t {
+            // the scatter half of leader_compute_element: the leader keeps (value, proofs), every worker is sent
+            // (F::zero(), vec![]) = 32 + 8 serialised bytes (:382-391); only the byte counters see it here
+            net->count_scatter(32 + 8);
             if (!net->is_leader()) {
                 SCZ_CUDA(ctx, cudaMemsetAsync(d_value, 0, 32, ctx->stream));
                 return SCZ_OK;
@@ -628,6 +631,7 @@ using namespace scz;
 extern "C" {
 
 int32_t scz_srs_from_device_levels(scz_ctx *h, size_t levels, const void *const *d_levels, const size_t *lens, scz_srs **out) {
+    scz::DeviceGuard dg__(h);
     NEED(h, out && (levels == 0 || (d_levels && lens)), "srs");
     scz_srs *s = new scz_srs();
     s->device = h->c.device;
@@ -639,6 +643,7 @@ int32_t scz_srs_from_device_levels(scz_ctx *h, size_t levels, const void *const 
     return SCZ_OK;
 }
 int32_t scz_srs_from_host_levels(scz_ctx *h, size_t levels, const void *const *levels_host, const size_t *lens, scz_srs **out) {
+    scz::DeviceGuard dg__(h);
     NEED(h, out && (levels == 0 || (levels_host && lens)), "srs");
     Ctx *c = &h->c;
     scz_srs *s = new scz_srs();
@@ -674,69 +679,84 @@ int32_t scz_srs_info(const scz_srs *s, size_t *levels) {
 }
 
 int32_t scz_pss2ss_dev(scz_ctx *h, const scz_pp *pp, const void *d_share, void *d_out) {
+    scz::DeviceGuard dg__(h);
     NEED(h, pp && d_share && d_out, "pss2ss");
     return pss2ss_dev(&h->c, pp, d_share, d_out);
 }
 int32_t scz_degree_reduce_dev(scz_ctx *h, const scz_pp *pp, const void *d_share, void *d_out) {
+    scz::DeviceGuard dg__(h);
     NEED(h, pp && d_share && d_out, "degree_reduce");
     return degree_reduce_dev(&h->c, pp, d_share, d_out);
 }
 int32_t scz_sumcheck_product_dev(scz_ctx *h, const void *d_f, const void *d_g, size_t len, const void *d_challenge,
                                  void *d_out) {
+    scz::DeviceGuard dg__(h);
     NEED(h, d_f && d_g && d_out && (len <= 1 || d_challenge), "sumcheck_product");
     return sumcheck_product_dev(&h->c, d_f, d_g, len, d_challenge, d_out);
 }
 int32_t scz_c_sumcheck_product_dev(scz_ctx *h, const scz_pp *pp, const void *d_f, const void *d_g, size_t len,
                                    const void *d_challenge, void *d_out) {
+    scz::DeviceGuard dg__(h);
     NEED(h, pp && d_f && d_g && d_out && d_challenge, "c_sumcheck_product");
     return c_sumcheck_product_dev(&h->c, pp, d_f, d_g, len, d_challenge, d_out);
 }
 int32_t scz_d_sumcheck_product_dev(scz_ctx *h, const void *d_f, const void *d_g, size_t len, const void *d_challenge,
                                    void *d_out, size_t *count) {
+    scz::DeviceGuard dg__(h);
     NEED(h, d_f && d_g && d_challenge && (d_out || h->c.net->party_id != 0), "d_sumcheck_product");
     return d_sumcheck_product_dev(&h->c, d_f, d_g, len, d_challenge, d_out, count);
 }
 int32_t scz_sumcheck_dev(scz_ctx *h, const void *d_f, size_t len, const void *d_challenge, void *d_out) {
+    scz::DeviceGuard dg__(h);
     NEED(h, d_f && d_out && (len <= 1 || d_challenge), "sumcheck");
     return sumcheck_dev(&h->c, d_f, len, d_challenge, d_out);
 }
 int32_t scz_c_sumcheck_dev(scz_ctx *h, const scz_pp *pp, const void *d_f, size_t len, const void *d_challenge, void *d_out) {
+    scz::DeviceGuard dg__(h);
     NEED(h, pp && d_f && d_out && d_challenge, "c_sumcheck");
     return c_sumcheck_dev(&h->c, pp, d_f, len, d_challenge, d_out);
 }
 int32_t scz_d_sumcheck_dev(scz_ctx *h, const void *d_f, size_t len, const void *d_challenge, void *d_out, size_t *count) {
+    scz::DeviceGuard dg__(h);
     NEED(h, d_f && d_challenge && (d_out || h->c.net->party_id != 0), "d_sumcheck");
     return d_sumcheck_dev(&h->c, d_f, len, d_challenge, d_out, count);
 }
 int32_t scz_d_acc_product_dev(scz_ctx *h, const void *d_x, size_t m, void *d_subtree, void *d_leader_tree) {
+    scz::DeviceGuard dg__(h);
     NEED(h, d_x && d_subtree && (d_leader_tree || h->c.net->party_id != 0), "d_acc_product");
     return d_acc_product_dev(&h->c, d_x, m, d_subtree, d_leader_tree);
 }
 int32_t scz_commit_dev(scz_ctx *h, const scz_srs *srs, const void *d_peval, size_t len, void *d_out) {
+    scz::DeviceGuard dg__(h);
     NEED(h, srs && d_peval && d_out, "commit");
     return commit_dev(&h->c, srs, d_peval, len, d_out);
 }
 int32_t scz_c_commit_dev(scz_ctx *h, const scz_srs *srs, const scz_pp *pp, const void *const *d_pevals, const size_t *lens,
                          size_t batch, void *d_out) {
+    scz::DeviceGuard dg__(h);
     NEED(h, srs && pp && (batch == 0 || (d_pevals && lens && d_out)), "c_commit");
     return c_commit_dev(&h->c, srs, pp, d_pevals, lens, batch, d_out);
 }
 int32_t scz_d_commit_dev(scz_ctx *h, const scz_srs *srs, const void *d_peval, size_t len, void *d_out) {
+    scz::DeviceGuard dg__(h);
     NEED(h, srs && d_peval && d_out, "d_commit");
     return d_commit_dev(&h->c, srs, d_peval, len, d_out);
 }
 int32_t scz_open_dev(scz_ctx *h, const scz_srs *srs, const void *d_peval, size_t len, const void *d_point, void *d_value,
                      void *d_proofs) {
+    scz::DeviceGuard dg__(h);
     NEED(h, srs && d_peval && d_value && (len <= 1 || (d_point && d_proofs)), "open");
     return open_dev(&h->c, srs, d_peval, len, d_point, d_value, d_proofs);
 }
 int32_t scz_c_open_dev(scz_ctx *h, const scz_srs *srs, const scz_pp *pp, const void *d_peval, size_t len,
                        const void *d_point, void *d_value, void *d_proofs) {
+    scz::DeviceGuard dg__(h);
     NEED(h, srs && pp && d_peval && d_value && d_point && d_proofs, "c_open");
     return c_open_dev(&h->c, srs, pp, d_peval, len, d_point, d_value, d_proofs);
 }
 int32_t scz_d_open_dev(scz_ctx *h, const scz_srs *srs, const void *d_peval, size_t len, const void *d_point, size_t npoint,
                        void *d_value, void *d_proofs, size_t *count) {
+    scz::DeviceGuard dg__(h);
     NEED(h, srs && d_peval && d_value && d_point && (d_proofs || h->c.net->party_id != 0), "d_open");
     return d_open_dev(&h->c, srs, d_peval, len, d_point, npoint, d_value, d_proofs, count);
 }

@@ -285,11 +285,10 @@ int32_t pss_apply(Ctx *ctx, const scz_pp *pp, PssMap map, int kind, const void *
         k_pss_apply_fr<<<ceil_div_u32(batch * rows, 128), 128, 0, ctx->stream>>>(M, mcols, rows, (uint32_t)len_in, d_in,
                                                                                  in_b, in_j, batch, d_out, out_b, out_o);
     } else {
-        static bool attr_done = false;
         constexpr size_t SH8 = 8 * 17 * sizeof(G1Jac), SH32 = 32 * 17 * sizeof(G1Jac);
-        if (!attr_done) {
-            cudaFuncSetAttribute(k_pss_apply_g1<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SH32);
-            attr_done = true;
+        if (!ctx->attr_pss) {   // per device, so per ctx (78 KB of dynamic shared memory is above the 48 KB default)
+            SCZ_CUDA(ctx, cudaFuncSetAttribute(k_pss_apply_g1<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SH32));
+            ctx->attr_pss = true;
         }
         if (len_in <= 8)
             k_pss_apply_g1<8><<<(uint32_t)(batch * rows), 32, SH8, ctx->stream>>>(M, mcols, rows, (uint32_t)len_in, d_in,
@@ -309,6 +308,7 @@ using namespace scz;
 extern "C" {
 
 int32_t scz_pp_new(scz_ctx *h, size_t l, scz_pp **out) {
+    scz::DeviceGuard dg__(h);
     if (!h || !out) return SCZ_ERR_BAD_ARG;
     Ctx *c = &h->c;
     *out = nullptr;
@@ -365,19 +365,23 @@ int32_t scz_pp_info(const scz_pp *pp, size_t *t, size_t *l, size_t *n) {
 static size_t esz(int kind) { return kind == 0 ? SCZ_FR_BYTES : SCZ_G1_JAC_BYTES; }
 int32_t scz_pss_pack_from_public_dev(scz_ctx *h, const scz_pp *pp, int32_t kind, const void *in, size_t len_in,
                                      size_t batch, void *out) {
+    scz::DeviceGuard dg__(h);
     if (!h || !pp) return SCZ_ERR_BAD_ARG;
     (void)esz;
     return pss_apply(&h->c, pp, PSS_PACK, kind, in, len_in, len_in, 1, batch, out, pp->n, 1);
 }
 int32_t scz_pss_pack_single_dev(scz_ctx *h, const scz_pp *pp, int32_t kind, const void *in, size_t batch, void *out) {
+    scz::DeviceGuard dg__(h);
     if (!h || !pp) return SCZ_ERR_BAD_ARG;
     return pss_apply(&h->c, pp, PSS_PACK_SINGLE, kind, in, 1, 1, 1, batch, out, pp->n, 1);
 }
 int32_t scz_pss_unpack_dev(scz_ctx *h, const scz_pp *pp, int32_t kind, const void *in, size_t batch, void *out) {
+    scz::DeviceGuard dg__(h);
     if (!h || !pp) return SCZ_ERR_BAD_ARG;
     return pss_apply(&h->c, pp, PSS_UNPACK, kind, in, pp->n, pp->n, 1, batch, out, pp->l, 1);
 }
 int32_t scz_pss_unpack2_dev(scz_ctx *h, const scz_pp *pp, int32_t kind, const void *in, size_t batch, void *out) {
+    scz::DeviceGuard dg__(h);
     if (!h || !pp) return SCZ_ERR_BAD_ARG;
     return pss_apply(&h->c, pp, PSS_UNPACK2, kind, in, pp->n, pp->n, 1, batch, out, pp->l, 1);
 }

@@ -123,6 +123,7 @@ using namespace scz;
 extern "C" {
 
 int32_t scz_g1_serialize_compressed_dev(scz_ctx *h, const void *d_jac, void *d_bytes, size_t n) {
+    scz::DeviceGuard dg__(h);
     if (!h) return SCZ_ERR_BAD_ARG;
     if (n && (!d_jac || !d_bytes)) return h->c.fail(SCZ_ERR_BAD_ARG, "g1_serialize: null argument");
     if (!n) return SCZ_OK;
@@ -131,6 +132,7 @@ int32_t scz_g1_serialize_compressed_dev(scz_ctx *h, const void *d_jac, void *d_b
     return SCZ_OK;
 }
 int32_t scz_g1_deserialize_compressed_dev(scz_ctx *h, const void *d_bytes, void *d_jac, uint8_t *d_status, size_t n) {
+    scz::DeviceGuard dg__(h);
     if (!h) return SCZ_ERR_BAD_ARG;
     if (n && (!d_jac || !d_bytes || !d_status)) return h->c.fail(SCZ_ERR_BAD_ARG, "g1_deserialize: null argument");
     if (!n) return SCZ_OK;
@@ -139,6 +141,7 @@ int32_t scz_g1_deserialize_compressed_dev(scz_ctx *h, const void *d_bytes, void 
     return SCZ_OK;
 }
 int32_t scz_fr_deserialize_dev(scz_ctx *h, const void *d_bytes, void *d_out, uint8_t *d_status, size_t n) {
+    scz::DeviceGuard dg__(h);
     if (!h) return SCZ_ERR_BAD_ARG;
     if (n && (!d_out || !d_bytes || !d_status)) return h->c.fail(SCZ_ERR_BAD_ARG, "fr_deserialize: null argument");
     if (!n) return SCZ_OK;

@@ -117,6 +117,7 @@ using namespace scz;
 extern "C" {
 
 int32_t scz_srs_precompute(scz_ctx *h, scz_srs *srs) {
+    scz::DeviceGuard dg__(h);
     if (!h) return SCZ_ERR_BAD_ARG;
     if (!srs) return h->c.fail(SCZ_ERR_BAD_ARG, "srs_precompute: null srs");
     return srs_precompute(&h->c, srs);
@@ -172,6 +173,7 @@ __global__ void __launch_bounds__(128) k_affine_to_jac_padded(const void *aff, u
 extern "C" {
 
 int32_t scz_srs_new_dev(scz_ctx *h, const void *d_g_jac, const void *d_s, size_t n, scz_srs **out) {
+    scz::DeviceGuard dg__(h);
     if (!h) return SCZ_ERR_BAD_ARG;
     Ctx *c = &h->c;
     if (!d_g_jac || (n && !d_s) || !out || n > 26) return c->fail(SCZ_ERR_BAD_ARG, "srs_new: bad argument");
@@ -216,6 +218,7 @@ int32_t scz_srs_new_dev(scz_ctx *h, const void *d_g_jac, const void *d_s, size_t
 }
 
 int32_t scz_srs_to_packed_dev(scz_ctx *h, const scz_srs *srs, const scz_pp *pp, uint32_t party, scz_srs **out) {
+    scz::DeviceGuard dg__(h);
     if (!h) return SCZ_ERR_BAD_ARG;
     Ctx *c = &h->c;
     if (!srs || !pp || !out || party >= pp->n) return c->fail(SCZ_ERR_BAD_ARG, "srs_to_packed: bad argument");
@@ -259,6 +262,7 @@ int32_t scz_srs_to_packed_dev(scz_ctx *h, const scz_srs *srs, const scz_pp *pp, 
 
 // copy one level to a caller buffer (packed affine)
 int32_t scz_srs_level_dev(scz_ctx *h, const scz_srs *srs, size_t level, void *d_out, size_t *len) {
+    scz::DeviceGuard dg__(h);
     if (!h) return SCZ_ERR_BAD_ARG;
     if (!srs || level >= srs->level.size()) return h->c.fail(SCZ_ERR_LEVEL_OOB, "srs_level: level %zu", level);
     if (len) *len = srs->len[level];

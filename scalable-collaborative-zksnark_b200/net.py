@@ -30,6 +30,17 @@ def _tensor(ptr, nbytes, device):
     return torch.frombuffer(buf, dtype=torch.uint8)
 
 
+def _on_stream(device, stream):
+    """Context manager: torch ops inside run on the CUDA stream libscz passed to the callback (ctx->stream), whatever the
+    calling thread's current torch stream is -- the collectives must be ordered after the kernels that produced
+    d_send and before the ones that consume d_recv, and those run on ctx->stream (which differs from torch's current
+    stream after scz_ctx_own_stream or inside a `with torch.cuda.stream(..)` block)."""
+    import contextlib
+    if device.type == "cuda" and stream:
+        return torch.cuda.stream(torch.cuda.ExternalStream(int(stream), device=device))
+    return contextlib.nullcontext()
+
+
 class TorchDistNet:
     """gather / scatter / all_gather / sync of the MPCSerializeNet seam on a torch.distributed group."""
 
@@ -89,9 +100,10 @@ class TorchDistNet:
 
         def _gather_to(user, root, d_send, d_recv, nbytes, wire, stream):
             try:
-                send = _tensor(d_send, nbytes, dev)
-                recv = _tensor(d_recv, nbytes * self.n_parties, dev) if self.rank == root else None
-                self.gather_to_t(root, send, recv)
+                with _on_stream(dev, stream):
+                    send = _tensor(d_send, nbytes, dev)
+                    recv = _tensor(d_recv, nbytes * self.n_parties, dev) if self.rank == root else None
+                    self.gather_to_t(root, send, recv)
                 return 0
             except Exception as e:
                 print(f"[scz net] gather_to failed: {e!r}", flush=True)
@@ -99,9 +111,10 @@ class TorchDistNet:
 
         def _scatter_from(user, root, d_send, d_recv, nbytes, wire, stream):
             try:
-                recv = _tensor(d_recv, nbytes, dev)
-                send = _tensor(d_send, nbytes * self.n_parties, dev) if self.rank == root else None
-                self.scatter_from_t(root, send, recv)
+                with _on_stream(dev, stream):
+                    recv = _tensor(d_recv, nbytes, dev)
+                    send = _tensor(d_send, nbytes * self.n_parties, dev) if self.rank == root else None
+                    self.scatter_from_t(root, send, recv)
                 return 0
             except Exception as e:
                 print(f"[scz net] scatter_from failed: {e!r}", flush=True)
@@ -109,9 +122,10 @@ class TorchDistNet:
 
         def _gather(user, d_send, d_recv, nbytes, wire, stream):
             try:
-                send = _tensor(d_send, nbytes, dev)
-                recv = _tensor(d_recv, nbytes * self.n_parties, dev) if self.rank == 0 else None
-                self.gather_t(send, recv)
+                with _on_stream(dev, stream):
+                    send = _tensor(d_send, nbytes, dev)
+                    recv = _tensor(d_recv, nbytes * self.n_parties, dev) if self.rank == 0 else None
+                    self.gather_t(send, recv)
                 return 0
             except Exception as e:   # never let an exception cross the C boundary
                 print(f"[scz net] gather failed: {e!r}", flush=True)
@@ -119,9 +133,10 @@ class TorchDistNet:
 
         def _scatter(user, d_send, d_recv, nbytes, wire, stream):
             try:
-                recv = _tensor(d_recv, nbytes, dev)
-                send = _tensor(d_send, nbytes * self.n_parties, dev) if self.rank == 0 else None
-                self.scatter_t(send, recv)
+                with _on_stream(dev, stream):
+                    recv = _tensor(d_recv, nbytes, dev)
+                    send = _tensor(d_send, nbytes * self.n_parties, dev) if self.rank == 0 else None
+                    self.scatter_t(send, recv)
                 return 0
             except Exception as e:
                 print(f"[scz net] scatter failed: {e!r}", flush=True)
@@ -129,7 +144,8 @@ class TorchDistNet:
 
         def _all_gather(user, d_send, d_recv, nbytes, wire, stream):
             try:
-                self.all_gather_t(_tensor(d_send, nbytes, dev), _tensor(d_recv, nbytes * self.n_parties, dev))
+                with _on_stream(dev, stream):
+                    self.all_gather_t(_tensor(d_send, nbytes, dev), _tensor(d_recv, nbytes * self.n_parties, dev))
                 return 0
             except Exception as e:
                 print(f"[scz net] all_gather failed: {e!r}", flush=True)
@@ -137,7 +153,8 @@ class TorchDistNet:
 
         def _sync(user, stream):
             try:
-                self.sync_t()
+                with _on_stream(dev, stream):
+                    self.sync_t()
                 return 0
             except Exception as e:
                 print(f"[scz net] sync failed: {e!r}", flush=True)
@@ -168,6 +185,9 @@ class LocalTestNet:
         self.barrier = threading.Barrier(n_parties)
         self.slots = [None] * n_parties
         self.leader_send = None
+        cuda = self.device.type == "cuda"
+        self.ev_ready = [torch.cuda.Event() if cuda else None for _ in range(n_parties)]
+        self.ev_copied = [torch.cuda.Event() if cuda else None for _ in range(n_parties)]
 
     def party(self, party_id):
         return _LocalParty(self, party_id)
@@ -199,48 +219,89 @@ class LocalTestNet:
 
 
 class _LocalParty:
+    """One party of a LocalTestNet.  The torch copies of a callback run on the stream libscz passed in (ctx->stream);
+    parties whose ctxs sit on different streams are fenced with events: a sender's `ready` event is recorded before the
+    host barrier and waited for by every reader, a reader's `copied` event is waited for by everybody after the second
+    barrier (so send buffers and stream-ordered temporaries are not reused under a pending copy).  On one shared
+    stream the fences are no-ops."""
+
     def __init__(self, hub, party_id):
         self.hub, self.rank, self.n_parties = hub, party_id, hub.n
         self._keep = None
 
     def vtable(self):
         hub, me, dev = self.hub, self.rank, self.hub.device
+        cuda = dev.type == "cuda"
 
-        def _gather(user, d_send, d_recv, nbytes, wire, stream):
+        def ready():
+            if cuda:
+                hub.ev_ready[me].record()
+
+        def wait_ready(who):
+            if cuda:
+                cur = torch.cuda.current_stream()
+                for j in who:
+                    cur.wait_event(hub.ev_ready[j])
+
+        def copied_then_wait():
+            if cuda:
+                hub.ev_copied[me].record()
+            hub.barrier.wait()
+            if cuda:
+                cur = torch.cuda.current_stream()
+                for e in hub.ev_copied:
+                    cur.wait_event(e)
+
+        def _gather_to(user, root, d_send, d_recv, nbytes, wire, stream):
             try:
-                hub.slots[me] = d_send
-                hub.barrier.wait()
-                if me == 0:
-                    recv = _tensor(d_recv, nbytes * hub.n, dev).view(hub.n, nbytes)
-                    for j in range(hub.n):
-                        recv[j].copy_(_tensor(hub.slots[j], nbytes, dev))
-                hub.barrier.wait()
+                with _on_stream(dev, stream):
+                    hub.slots[me] = d_send
+                    ready()
+                    hub.barrier.wait()
+                    if me == root:
+                        wait_ready(range(hub.n))
+                        recv = _tensor(d_recv, nbytes * hub.n, dev).view(hub.n, nbytes)
+                        for j in range(hub.n):
+                            recv[j].copy_(_tensor(hub.slots[j], nbytes, dev))
+                    copied_then_wait()
                 return 0
             except Exception as e:
                 print(f"[scz local net] gather failed: {e!r}", flush=True)
                 return 1
 
-        def _scatter(user, d_send, d_recv, nbytes, wire, stream):
+        def _scatter_from(user, root, d_send, d_recv, nbytes, wire, stream):
             try:
-                if me == 0:
-                    hub.leader_send = d_send
-                hub.barrier.wait()
-                src = _tensor(hub.leader_send, nbytes * hub.n, dev).view(hub.n, nbytes)
-                _tensor(d_recv, nbytes, dev).copy_(src[me])
-                hub.barrier.wait()
+                with _on_stream(dev, stream):
+                    if me == root:
+                        hub.leader_send = d_send
+                    ready()
+                    hub.barrier.wait()
+                    wait_ready([root])
+                    src = _tensor(hub.leader_send, nbytes * hub.n, dev).view(hub.n, nbytes)
+                    _tensor(d_recv, nbytes, dev).copy_(src[me])
+                    copied_then_wait()
                 return 0
             except Exception as e:
                 print(f"[scz local net] scatter failed: {e!r}", flush=True)
                 return 1
 
+        def _gather(user, d_send, d_recv, nbytes, wire, stream):
+            return _gather_to(user, 0, d_send, d_recv, nbytes, wire, stream)
+
+        def _scatter(user, d_send, d_recv, nbytes, wire, stream):
+            return _scatter_from(user, 0, d_send, d_recv, nbytes, wire, stream)
+
         def _all_gather(user, d_send, d_recv, nbytes, wire, stream):
             try:
-                hub.slots[me] = d_send
-                hub.barrier.wait()
-                recv = _tensor(d_recv, nbytes * hub.n, dev).view(hub.n, nbytes)
-                for j in range(hub.n):
-                    recv[j].copy_(_tensor(hub.slots[j], nbytes, dev))
-                hub.barrier.wait()
+                with _on_stream(dev, stream):
+                    hub.slots[me] = d_send
+                    ready()
+                    hub.barrier.wait()
+                    wait_ready(range(hub.n))
+                    recv = _tensor(d_recv, nbytes * hub.n, dev).view(hub.n, nbytes)
+                    for j in range(hub.n):
+                        recv[j].copy_(_tensor(hub.slots[j], nbytes, dev))
+                    copied_then_wait()
                 return 0
             except Exception as e:
                 print(f"[scz local net] all_gather failed: {e!r}", flush=True)
@@ -251,33 +312,6 @@ class _LocalParty:
                 hub.barrier.wait()
                 return 0
             except Exception:
-                return 1
-
-        def _gather_to(user, root, d_send, d_recv, nbytes, wire, stream):
-            try:
-                hub.slots[me] = d_send
-                hub.barrier.wait()
-                if me == root:
-                    recv = _tensor(d_recv, nbytes * hub.n, dev).view(hub.n, nbytes)
-                    for j in range(hub.n):
-                        recv[j].copy_(_tensor(hub.slots[j], nbytes, dev))
-                hub.barrier.wait()
-                return 0
-            except Exception as e:
-                print(f"[scz local net] gather_to failed: {e!r}", flush=True)
-                return 1
-
-        def _scatter_from(user, root, d_send, d_recv, nbytes, wire, stream):
-            try:
-                if me == root:
-                    hub.leader_send = d_send
-                hub.barrier.wait()
-                src = _tensor(hub.leader_send, nbytes * hub.n, dev).view(hub.n, nbytes)
-                _tensor(d_recv, nbytes, dev).copy_(src[me])
-                hub.barrier.wait()
-                return 0
-            except Exception as e:
-                print(f"[scz local net] scatter_from failed: {e!r}", flush=True)
                 return 1
 
         vt = NetVTable()
@@ -333,6 +367,9 @@ class HybridNet:
 
     def party(self, local_index):
         return _HybridParty(self, local_index)
+
+    def close(self):
+        pass
 
     def party_stream(self, p):
         """the CUDA stream of local party p (None: the caller's current stream)"""
@@ -413,6 +450,8 @@ class HybridNet:
             except BaseException as e:   # noqa: BLE001
                 err[p] = e
                 self.barrier.abort()
+                if hasattr(self, "abort"):
+                    self.abort()         # native hub: release the parties waiting at its host barrier
         if self.per_rank == 1:
             body(0)
         else:
@@ -576,3 +615,74 @@ class _HybridParty:
         vt.scatter_from = NetVTable._ROOTED(_scatter_from)
         self._keep = vt
         return vt
+
+
+class NativeNcclNet(HybridNet):
+    """The same party layout as HybridNet with the data plane inside libscz (csrc/nccl_net.cu, include/scz.h "native
+    data plane"): this class only creates the hub -- NCCL's unique id travels from rank 0 through torch.distributed, the
+    channel a Python host happens to have; a Rust host would use its own -- and hands out parties whose ctxs are made
+    by scz_ctx_create_on_hub.  No collective of a proof ever calls back into Python."""
+
+    def __init__(self, device, per_rank, group=None):
+        import os
+        os.environ.setdefault("SCZ_PARTY_STREAMS", "0")
+        super().__init__(device, per_rank, group)
+        self.streams = None
+        from .binding import lib
+        self.L = lib()
+        uid = torch.zeros(128, dtype=torch.uint8)
+        if self.world > 1:
+            if self.rank == 0:
+                buf = (C.c_uint8 * 128)()
+                rc = self.L.scz_nccl_unique_id(buf)
+                if rc != 0:
+                    raise RuntimeError(f"scz_nccl_unique_id failed ({rc})")
+                uid = torch.tensor(list(buf), dtype=torch.uint8)
+            t = uid.to(self.device) if dist.get_backend(group) == "nccl" else uid
+            dist.broadcast(t, src=0, group=group)
+            uid = t.cpu()
+        raw = (C.c_uint8 * 128)(*uid.tolist())
+        hub = C.c_void_p()
+        rc = self.L.scz_nccl_hub_create(C.c_int32(self.device.index or 0), C.c_uint32(self.rank), C.c_uint32(self.world),
+                                        C.c_uint32(per_rank), raw, C.byref(hub))
+        if rc != 0:
+            raise RuntimeError(f"scz_nccl_hub_create failed ({rc})")
+        self.hub = hub
+        self._ctxs = 0
+
+    @property
+    def calls(self):
+        out = (C.c_uint64 * 4)()
+        if getattr(self, "hub", None):
+            self.L.scz_nccl_hub_calls(self.hub, out)
+        return {"gather": int(out[0]), "scatter": int(out[1]), "all_gather": int(out[2]), "sync": int(out[3])}
+
+    @calls.setter
+    def calls(self, _):   # HybridNet.__init__ assigns its own counter dict; the hub counts in C
+        pass
+
+    def party(self, local_index):
+        return _NativeParty(self, local_index)
+
+    def adopt(self, p, ctx):
+        pass
+
+    def abort(self):
+        self.L.scz_nccl_hub_abort(self.hub)
+
+    def close(self):
+        """after every ctx created on the hub has been closed"""
+        if getattr(self, "hub", None):
+            self.L.scz_nccl_hub_destroy.restype = None
+            self.L.scz_nccl_hub_destroy(self.hub)
+            self.hub = None
+
+
+class _NativeParty:
+    def __init__(self, hub, p):
+        self.hub, self.p = hub, p
+        self.rank = hub.rank * hub.per_rank + p      # party id
+        self.n_parties = hub.n
+
+    def native_create(self, L, out_handle):
+        return L.scz_ctx_create_on_hub(self.hub.hub, C.c_uint32(self.p), C.byref(out_handle))

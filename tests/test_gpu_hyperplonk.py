@@ -51,11 +51,16 @@ def _same_proof(orc, got, want, who):
         assert len(proofs) == len(oproofs) and orc.canon_g1(proofs) == orc.canon_g1(oproofs), (who, k)
 
 
-@pytest.mark.parametrize("n,l,pre", [(4, 1, False), (6, 1, False), (6, 2, False), (6, 1, True), (7, 2, True)])
+# n >= 12: every sumcheck / fold starts in the multi-CTA kernels, the product tree reaches k_tree_level, the MSM batch
+# mixes 2^0 .. 2^(n+2)-point segments with wide windows and 256-entry accumulate chunks -- the sizes at which the
+# prover's integration (not only the per-kernel tests) is compared entry by entry with the oracle.
+@pytest.mark.parametrize("n,l,pre", [(4, 1, False), (6, 1, False), (6, 2, False), (6, 1, True), (7, 2, True),
+                                     (12, 1, False), (12, 2, True), (14, 1, True), (14, 2, True), (16, 1, True)])
 def test_dhyperplonk_leader_mode(orc, n, l, pre):
     import scz_b200 as scz
     from oracle import hyperplonk as ohp
     N = 8 * l
+    orc.set_msm_threads(os.cpu_count() or 1)   # the oracle's MSM windows over all host threads (same group elements)
     rng = np.random.default_rng(600 + 10 * n + l)
     ctx = scz.Context(device=0, n_parties=N)
     pp, opp = scz.PackedSharingParams(ctx, l), orc.pp_new(l)
@@ -116,11 +121,14 @@ def test_dhyperplonk_generated_parameters_round_identities(orc):
     ctx.close()
 
 
-def test_dhyperplonk_parties_mode(orc):
-    """N = 8 parties (l = 1) on one GPU under LocalTestNet; every party's proof against the oracle's 8-party run."""
+@pytest.mark.parametrize("net_kind", ["local", "native_hub"])
+def test_dhyperplonk_parties_mode(orc, net_kind):
+    """N = 8 parties (l = 1) on one GPU; every party's proof against the oracle's 8-party run.  "local": LocalTestNet
+    (Python callbacks); "native_hub": libscz's own hub (csrc/nccl_net.cu) with world = 1 and 8 parties per rank -- the
+    host barrier, the event fences and the device copies of the native data plane, everything but NCCL itself."""
     import scz_b200 as scz
     from oracle import hyperplonk as ohp
-    from scz_b200.net import LocalTestNet
+    from scz_b200.net import LocalTestNet, NativeNcclNet
     n, l, N = 5, 1, 8
     rng = np.random.default_rng(640)
     opp = orc.pp_new(l)
@@ -145,11 +153,57 @@ def test_dhyperplonk_parties_mode(orc):
         c.close()
         return got, comm
 
-    res = LocalTestNet(N, "cuda:0").simulate_network_round(party)
+    if net_kind == "local":
+        res = LocalTestNet(N, "cuda:0").simulate_network_round(party)
+    else:
+        import torch
+        hub = NativeNcclNet(torch.device("cuda", 0), N)
+        res = hub.run_parties(lambda pid, p, net: party(pid, net))
+        assert hub.calls["gather"] > 0 and hub.calls["all_gather"] == 1
+        hub.close()
     for j in range(N):
         _same_proof(orc, res[j][0], want[j], f"party {j}")
     (gp, gc), (wp, wc, wo) = res[3][0]
     assert all(len(t) == 0 for t in wp[1:]) and len(wp) == 1 + 3 + 3 * (n - 3)     # workers: empty d_ proofs, no leader tail
+    assert all(res[j][1] == res[1][1] for j in range(2, N)) and res[0][1][1] > res[1][1][1]   # byte counters by role
+    seed_ctx.close()
+
+
+@pytest.mark.parametrize("variant", ["data_parallel", "permcheck"])
+def test_prover_variants_parties_mode(orc, variant):
+    """dhyperplonk_data_parallel / dpermcheck with N = 8 real parties (LocalTestNet): every party's output against the
+    oracle's 8-party run of the same variant"""
+    import scz_b200 as scz
+    from oracle import hyperplonk as ohp
+    from scz_b200.net import LocalTestNet
+    n, l, N = 5, 1, 8
+    rng = np.random.default_rng(670)
+    opp = orc.pp_new(l)
+    seed_ctx = scz.Context(device=0, n_parties=N)
+    csz, dsz = ohp.srs_level_sizes(n, l, N)
+    dp = variant == "data_parallel"
+    opks, srs_dev = [], []
+    for j in range(N):
+        cdev, csrs = _make_srs(seed_ctx, orc, rng, csz)
+        ddev, dsrs = _make_srs(seed_ctx, orc, rng, dsz)
+        opks.append(ohp.random_pk(rng, n, l, N, csrs, dsrs, shared=opks[0] if opks else None, data_parallel=dp))
+        srs_dev.append((cdev, ddev))
+    want = ohp.dhyperplonk(n, opks, opp, orc.PARTIES, N, variant=variant)
+    fn = scz.dhyperplonk_data_parallel if dp else scz.dpermcheck
+
+    def party(j, net):
+        c = scz.Context(device=0, party_id=j, n_parties=N, net=net)
+        pp = scz.PackedSharingParams(c, l)
+        pk = scz.PackedProvingParameters(c, n, l, _tables_for_product(opks[j]), scz.PolynomialCommitment(c, srs_dev[j][0]),
+                                         scz.PolynomialCommitment(c, srs_dev[j][1]), data_parallel=dp)
+        got = fn(c, n, pk, pp).nested()
+        c.sync()
+        c.close()
+        return got
+
+    res = LocalTestNet(N, "cuda:0").simulate_network_round(party)
+    for j in range(N):
+        _same_proof(orc, res[j], want[j], f"{variant} party {j}")
     seed_ctx.close()
 
 
