@@ -156,6 +156,11 @@ int32_t scz_net_gather(scz_ctx *ctx, uint32_t root, const void *d_send, void *d_
 int32_t scz_net_scatter(scz_ctx *ctx, uint32_t root, const void *d_send, void *d_recv, size_t bytes);
 int32_t scz_net_all_gather(scz_ctx *ctx, const void *d_send, void *d_recv, size_t bytes);
 int32_t scz_net_sync(scz_ctx *ctx);
+/* MPCNet::send_to / recv_from (mpc-net/src/lib.rs:55-61) as ncclSend / ncclRecv of `bytes` on the ctx stream: NCCL ctxs
+ * with one party per rank only (the peer is the rank); the two sides must agree on `bytes` (the shim sends an 8-byte
+ * length first, like the reference's length-delimited frames, mpc-net/src/multi.rs:29-35) */
+int32_t scz_net_send(scz_ctx *ctx, uint32_t peer, const void *d_buf, size_t bytes);
+int32_t scz_net_recv(scz_ctx *ctx, uint32_t peer, void *d_buf, size_t bytes);
 
 /* ---- device memory ---------------------------------------------------------------------- */
 int32_t scz_dev_alloc(scz_ctx *ctx, size_t bytes, void **d_ptr);
@@ -228,6 +233,13 @@ int32_t scz_msm_g1(scz_ctx *ctx, const void *bases, const uint8_t *inf_mask, siz
                    size_t scalars_len, void *out_jac);
 /* window override for experiments: 0 = automatic */
 int32_t scz_msm_set_window(scz_ctx *ctx, uint32_t c);
+/* Bucket accumulation variant (csrc/msm_affine.cu).  mode 0: automatic -- batched-affine additions (one shared field
+ * inversion per tree level) inside the aligned single-bucket blocks of big sorted entry streams, XYZZ mixed additions
+ * for the rest; 1: always; 2: never.  levels: affine tree levels, 0 = automatic; slab_entries: entries processed per
+ * pass, 0 = from the free device memory.  The group elements are the same in every mode (tests/test_gpu_msm.py). */
+int32_t scz_msm_set_affine(scz_ctx *ctx, uint32_t mode, uint32_t levels, uint64_t slab_entries);
+/* launch sequences of this ctx whose bucket accumulation took the batched-affine path */
+int32_t scz_msm_affine_sequences(const scz_ctx *ctx, uint64_t *sequences);
 /* statistics of the last MSM launch sequence: total (point, window) pairs = bucket additions, buckets, windows */
 int32_t scz_msm_last_stats(const scz_ctx *ctx, uint64_t *bucket_adds, uint64_t *buckets, uint64_t *windows);
 /* cumulative since scz_ctx_create: bucket additions, (base, scalar) pairs, launch sequences, MSMs (segments) */

@@ -235,6 +235,15 @@ class Context:
     def msm_set_window(self, c):
         self.check(self.L.scz_msm_set_window(self.h, C.c_uint32(c)))
 
+    def msm_set_affine(self, mode=0, levels=0, slab_entries=0):
+        """bucket accumulation variant (scz_msm_set_affine): mode 0 automatic, 1 always batched-affine, 2 never"""
+        self.check(self.L.scz_msm_set_affine(self.h, C.c_uint32(mode), C.c_uint32(levels), C.c_uint64(slab_entries)))
+
+    def msm_affine_sequences(self):
+        n = C.c_uint64()
+        self.check(self.L.scz_msm_affine_sequences(self.h, C.byref(n)))
+        return n.value
+
     def msm_last_stats(self):
         a, b, w = C.c_uint64(), C.c_uint64(), C.c_uint64()
         self.check(self.L.scz_msm_last_stats(self.h, C.byref(a), C.byref(b), C.byref(w)))

@@ -1,5 +1,6 @@
 // Context, device memory, and the two network back-ends.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "ctx.h"
@@ -95,6 +96,8 @@ static int32_t replicate(Ctx *ctx, void *d_recv, const void *d_send, size_t byte
         SCZ_CUDA(ctx, cudaMemcpyAsync((char *)d_recv + (size_t)j * bytes, d_send, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
     return SCZ_OK;
 }
+
+int32_t Net::ctx_fail_p2p(Ctx *ctx) { return ctx->fail(SCZ_ERR_NET, "this net has no point-to-point transport"); }
 
 // ------------------------------------------------------------------ leader simulator
 // serializing_net.rs:147-167: the leader "receives" n_parties clones of its own message
@@ -226,6 +229,9 @@ int32_t scz_ctx_create(int32_t device, uint32_t party_id, uint32_t n_parties, co
     }
     c->net->n_parties = n_parties;
     c->net->party_id = party_id;
+    if (const char *e = getenv("SCZ_MSM_AFFINE"))   // A/B switch for measurements: 0 = XYZZ only, 1 = always batched-affine
+        c->msm_affine_mode = e[0] == '0' ? 2 : (e[0] == '1' ? 1 : 0);
+    if (const char *e = getenv("SCZ_MSM_AFFINE_LEVELS")) c->msm_affine_levels = (uint32_t)atoi(e);
     *out = h;
     return SCZ_OK;
 }

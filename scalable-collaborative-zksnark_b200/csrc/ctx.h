@@ -33,6 +33,11 @@ struct Ctx {
     uint32_t *d_status = nullptr;   // sticky SCZ_STATUS_* bits set by kernels (scz_ctx_take_status)
     uint32_t msm_window_override = 0;
     bool msm_no_precompute = false;   // ignore fixed-base tables (for A/B measurements)
+    // batched-affine bucket accumulation (msm_affine.cu): 0 = automatic (big sequences with long bucket runs), 1 = always,
+    // 2 = never; levels / slab entries: 0 = automatic
+    uint32_t msm_affine_mode = 0, msm_affine_levels = 0;
+    uint64_t msm_affine_slab = 0;
+    uint64_t msm_cum_affine_sequences = 0;
     uint64_t msm_bucket_adds = 0, msm_buckets = 0, msm_windows = 0;   // statistics of the last MSM sequence
     uint64_t msm_cum_adds = 0, msm_cum_pairs = 0, msm_cum_sequences = 0, msm_cum_segments = 0;   // since ctx creation
     // optional per-kernel-class device timing (scz_prof_*): CUDA events recorded on `stream` around the launches

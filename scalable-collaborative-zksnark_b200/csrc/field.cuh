@@ -590,6 +590,85 @@ SCZ_HD Fp<P> fp_inv(const Fp<P> &a) {
     return acc;
 }
 
+// Inverse by the binary extended Euclidean algorithm (shifts, additions, subtractions: no multiplier), for the places
+// where ONE inversion sits on the critical path of a whole launch sequence (the top of the batched-affine product
+// tree, msm_affine.cu): a Fermat chain is ~570 dependent Montgomery products (~0.6 ms on one thread), this is ~760
+// halving / subtraction steps of 12-limb integer arithmetic (~0.1 ms).  a in Montgomery form, a != 0; 0 -> 0.
+//   invariants: x1 * v == u, x2 * v == w (mod p), v = the stored integer a R; ends with u == 1 or w == 1
+//   result a^-1 R = (v^-1) * R^2 = montmul(montmul(v^-1, R^2), R^2)
+template <class P>
+SCZ_HD Fp<P> fp_inv_bingcd(const Fp<P> &a) {
+    constexpr int N = P::N;
+    if (a.is_zero()) return a;
+    uint32_t u[N], w[N], x1[N], x2[N];
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+        u[i] = a.l[i];
+        w[i] = P::mod(i);
+        x1[i] = i == 0 ? 1u : 0u;
+        x2[i] = 0;
+    }
+    auto is_one = [](const uint32_t *t) {
+        uint32_t acc = t[0] ^ 1u;
+#pragma unroll
+        for (int i = 1; i < N; i++) acc |= t[i];
+        return acc == 0;
+    };
+    auto halve = [](uint32_t *t, uint32_t *x) {   // t even: t /= 2, x /= 2 (mod p)
+#pragma unroll
+        for (int i = 0; i < N - 1; i++) t[i] = (t[i] >> 1) | (t[i + 1] << 31);
+        t[N - 1] >>= 1;
+        uint32_t m = 0u - (x[0] & 1u);            // odd: add p first (x + p < 2^(32 N): p < 2^(32 N - 1))
+        CF c{0};
+        x[0] = add_cc(c, x[0], P::mod(0) & m);
+#pragma unroll
+        for (int i = 1; i < N - 1; i++) x[i] = addc_cc(c, x[i], P::mod(i) & m);
+        x[N - 1] = addc(c, x[N - 1], P::mod(N - 1) & m);
+#pragma unroll
+        for (int i = 0; i < N - 1; i++) x[i] = (x[i] >> 1) | (x[i + 1] << 31);
+        x[N - 1] >>= 1;
+    };
+    auto sub_mod = [](uint32_t *x, const uint32_t *y) {   // x = x - y mod p, x, y < p
+        CF c{0};
+        x[0] = sub_cc(c, x[0], y[0]);
+#pragma unroll
+        for (int i = 1; i < N; i++) x[i] = subc_cc(c, x[i], y[i]);
+        uint32_t m = borrow_mask(c);
+        x[0] = add_cc(c, x[0], P::mod(0) & m);
+#pragma unroll
+        for (int i = 1; i < N - 1; i++) x[i] = addc_cc(c, x[i], P::mod(i) & m);
+        x[N - 1] = addc(c, x[N - 1], P::mod(N - 1) & m);
+    };
+    while (!is_one(u) && !is_one(w)) {
+        while (!(u[0] & 1u)) halve(u, x1);
+        while (!(w[0] & 1u)) halve(w, x2);
+        // u >= w ?
+        uint32_t t[N];
+        CF c{0};
+        t[0] = sub_cc(c, u[0], w[0]);
+#pragma unroll
+        for (int i = 1; i < N; i++) t[i] = subc_cc(c, u[i], w[i]);
+        uint32_t lt = borrow_mask(c);
+        if (!lt) {
+#pragma unroll
+            for (int i = 0; i < N; i++) u[i] = t[i];
+            sub_mod(x1, x2);
+        } else {
+            CF c2{0};
+            w[0] = sub_cc(c2, w[0], u[0]);
+#pragma unroll
+            for (int i = 1; i < N; i++) w[i] = subc_cc(c2, w[i], u[i]);
+            sub_mod(x2, x1);
+        }
+    }
+    Fp<P> r;
+    const bool from_u = is_one(u);
+#pragma unroll
+    for (int i = 0; i < N; i++) r.l[i] = from_u ? x1[i] : x2[i];
+    r = fp_mul(r, Fp<P>::rsquared());
+    return fp_mul(r, Fp<P>::rsquared());
+}
+
 using Fr = Fp<FrP>;
 using Fq = Fp<FqP>;
 

@@ -60,15 +60,6 @@ __device__ __forceinline__ int seg_by_point(const MsmSeg *segs, int K, uint32_t 
     }
     return lo;
 }
-__device__ __forceinline__ int seg_by_bucket(const MsmSeg *segs, int K, uint32_t b) {
-    int lo = 0, hi = K - 1;
-    while (lo < hi) {
-        int mid = (lo + hi + 1) >> 1;
-        if (__ldg(&segs[mid].bucket_base) <= b) lo = mid;
-        else hi = mid - 1;
-    }
-    return lo;
-}
 __device__ __forceinline__ int seg_by_window(const MsmSeg *segs, int K, uint32_t w) {
     int lo = 0, hi = K - 1;
     while (lo < hi) {
@@ -607,9 +598,27 @@ int32_t msm_g1_batched(Ctx *ctx, const void *const *d_bases, const void *const *
             // after the scatter cursor[last bucket] = entries really in the stream (the host only knows the
             // bound `entries`: zero digits are dropped); chunks past that end return at once
             ProfScope ps(ctx, SCZ_K_MSM_ACCUMULATE);
-            k_msm_accumulate<<<ceil_div_u32(nchunks, ACC_THREADS), ACC_THREADS, 0, st>>>(
-                sp, K, cursor + (buckets - 1), logT, sorted, counts, cursor, d_buckets.p, d_parts.p);
-            SCZ_LAUNCH_CHECK(ctx);
+            // long bucket runs in a big stream: affine additions with a shared inversion inside the aligned pure blocks
+            // of the stream, XYZZ for what is left (msm_affine.cu); otherwise XYZZ for every entry
+            uint32_t aff_levels = 0;
+            if (ctx->msm_affine_mode != 2) {
+                double avg_run = (double)entries / (double)std::max<uint64_t>(1, buckets);
+                uint32_t want = ctx->msm_affine_levels;
+                if (!want)
+                    while (want < 6 && (double)(2u << want) <= avg_run && (entries >> (want + 1)) >= (1ull << 21)) want++;
+                want = std::min(want, logT);
+                if (ctx->msm_affine_mode == 1) aff_levels = std::max(1u, want);
+                else if (want >= 2 && entries >= (1ull << 24)) aff_levels = want;
+            }
+            if (aff_levels) {
+                ctx->msm_cum_affine_sequences++;
+                SCZ_TRY(msm_accumulate_affine(ctx, sp, K, cursor + (buckets - 1), entries, logT, sorted, counts, cursor,
+                                              d_buckets.p, d_parts.p, aff_levels));
+            } else {
+                k_msm_accumulate<<<ceil_div_u32(nchunks, ACC_THREADS), ACC_THREADS, 0, st>>>(
+                    sp, K, cursor + (buckets - 1), logT, sorted, counts, cursor, d_buckets.p, d_parts.p);
+                SCZ_LAUNCH_CHECK(ctx);
+            }
         }
         ProfScope ps(ctx, SCZ_K_MSM_FIXUP);
         uint32_t *heavy = d_heavy.as<uint32_t>();
@@ -789,6 +798,18 @@ int32_t scz_msm_set_window(scz_ctx *h, uint32_t cbits) {
     scz::DeviceGuard dg__(h);
     if (!h || cbits > 20) return SCZ_ERR_BAD_ARG;
     h->c.msm_window_override = cbits;
+    return SCZ_OK;
+}
+int32_t scz_msm_set_affine(scz_ctx *h, uint32_t mode, uint32_t levels, uint64_t slab_entries) {
+    if (!h || mode > 2 || levels > 8) return SCZ_ERR_BAD_ARG;
+    h->c.msm_affine_mode = mode;
+    h->c.msm_affine_levels = levels;
+    h->c.msm_affine_slab = slab_entries;
+    return SCZ_OK;
+}
+int32_t scz_msm_affine_sequences(const scz_ctx *h, uint64_t *sequences) {
+    if (!h || !sequences) return SCZ_ERR_BAD_ARG;
+    *sequences = h->c.msm_cum_affine_sequences;
     return SCZ_OK;
 }
 int32_t scz_msm_use_precompute(scz_ctx *h, int32_t on) {

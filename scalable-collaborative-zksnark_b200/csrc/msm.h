@@ -29,6 +29,26 @@ struct MsmSeg {
     void *out;             // where this segment's result goes (one Jacobian point); null: slot `k` of d_out_jac
 };
 
+#if defined(__CUDACC__)
+// the segment whose bucket range holds global bucket id `b`
+__device__ __forceinline__ int seg_by_bucket(const MsmSeg *segs, int K, uint32_t b) {
+    int lo = 0, hi = K - 1;
+    while (lo < hi) {
+        int mid = (lo + hi + 1) >> 1;
+        if (__ldg(&segs[mid].bucket_base) <= b) lo = mid;
+        else hi = mid - 1;
+    }
+    return lo;
+}
+#endif
+
+// Batched-affine bucket accumulation (msm_affine.cu): replaces the k_msm_accumulate launch of a sequence.  Same
+// contract: whole buckets to `buckets` (XYZZ), pieces cut by the 2^logT-entry chunk boundaries to `parts`.
+// levels = affine tree levels (1 .. logT).  entries = host-side upper bound of the stream length, *E_ptr the real one.
+int32_t msm_accumulate_affine(Ctx *ctx, const MsmSeg *d_segs, int nseg, const uint32_t *E_ptr, uint64_t entries,
+                              uint32_t logT, const uint2 *sorted, const uint32_t *counts, const uint32_t *cursor,
+                              void *buckets, void *parts, uint32_t levels);
+
 // d_out: batch Jacobian points (144 B each).  Asynchronous on ctx->stream.
 // d_outs (optional, host array of `batch` device pointers) sends each result to its own address instead.
 // pre_c (optional, host array): per segment the window of a fixed-base table passed as its bases, 0 = plain bases.

@@ -260,6 +260,21 @@ struct NcclNet : Net {
         HUB_BARRIER(ctx);
         return wait_done(ctx);
     }
+    // MPCNet::send_to / recv_from as ncclSend / ncclRecv on the ctx stream (one party per rank: the peer IS the rank)
+    int32_t send_to(Ctx *ctx, uint32_t peer, const void *d_buf, size_t bytes) override {
+        if (hub->per_rank != 1 || peer >= n_parties || peer == party_id || hub->world < 2)
+            return ctx->fail(SCZ_ERR_BAD_ARG, "net send_to: needs one party per rank and a peer other than self");
+        upload += bytes;
+        SCZ_NCCL(ctx, ncclSend(d_buf, bytes, ncclUint8, (int)peer, hub->comm, ctx->stream));
+        return SCZ_OK;
+    }
+    int32_t recv_from(Ctx *ctx, uint32_t peer, void *d_buf, size_t bytes) override {
+        if (hub->per_rank != 1 || peer >= n_parties || peer == party_id || hub->world < 2)
+            return ctx->fail(SCZ_ERR_BAD_ARG, "net recv_from: needs one party per rank and a peer other than self");
+        download += bytes;
+        SCZ_NCCL(ctx, ncclRecv(d_buf, bytes, ncclUint8, (int)peer, hub->comm, ctx->stream));
+        return SCZ_OK;
+    }
     bool real() const override { return true; }
     ~NcclNet() override {
         if (hub) {
@@ -400,6 +415,16 @@ int32_t scz_net_all_gather(scz_ctx *h, const void *d_send, void *d_recv, size_t 
     scz::DeviceGuard dg__(h);
     if (!h || !d_send || !d_recv) return SCZ_ERR_BAD_ARG;
     return h->c.net->all_gather(&h->c, d_send, d_recv, bytes, bytes);
+}
+int32_t scz_net_send(scz_ctx *h, uint32_t peer, const void *d_buf, size_t bytes) {
+    scz::DeviceGuard dg__(h);
+    if (!h || (bytes && !d_buf)) return SCZ_ERR_BAD_ARG;
+    return h->c.net->send_to(&h->c, peer, d_buf, bytes);
+}
+int32_t scz_net_recv(scz_ctx *h, uint32_t peer, void *d_buf, size_t bytes) {
+    scz::DeviceGuard dg__(h);
+    if (!h || (bytes && !d_buf)) return SCZ_ERR_BAD_ARG;
+    return h->c.net->recv_from(&h->c, peer, d_buf, bytes);
 }
 int32_t scz_net_sync(scz_ctx *h) {
     scz::DeviceGuard dg__(h);

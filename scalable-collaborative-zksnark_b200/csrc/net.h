@@ -37,6 +37,11 @@ struct Net {
     virtual int32_t scatter_from(Ctx *ctx, uint32_t root, const void *d_send, void *d_recv, size_t bytes, size_t wire,
                                  bool *got) = 0;
     virtual int32_t sync(Ctx *ctx) = 0;
+    // point-to-point bytes between two parties (MPCNet::send_to / recv_from, mpc-net/src/lib.rs:55-61): only nets that
+    // have a peer-to-peer transport implement them
+    virtual int32_t send_to(Ctx *ctx, uint32_t, const void *, size_t) { return ctx_fail_p2p(ctx); }
+    virtual int32_t recv_from(Ctx *ctx, uint32_t, void *, size_t) { return ctx_fail_p2p(ctx); }
+    static int32_t ctx_fail_p2p(Ctx *ctx);
     // true when non-leaders receive real data on scatter (false in the leader simulator: there are none)
     virtual bool real() const = 0;
 };

@@ -52,6 +52,12 @@ extern "C" void emu_fq_sqr_sos(const uint32_t *a, uint32_t *r, size_t n) {
 extern "C" void emu_fq_dot2_sub(const uint32_t *a, const uint32_t *b, const uint32_t *c, const uint32_t *d, uint32_t *r, size_t n) {
     for (size_t i = 0; i < n; i++) st<FqP>(r, i, fp_dot2_sub(ld<FqP>(a, i), ld<FqP>(b, i), ld<FqP>(c, i), ld<FqP>(d, i)));
 }
+extern "C" void emu_fq_inv_bingcd(const uint32_t *a, uint32_t *r, size_t n) {
+    for (size_t i = 0; i < n; i++) st<FqP>(r, i, fp_inv_bingcd(ld<FqP>(a, i)));
+}
+extern "C" void emu_fr_inv_bingcd(const uint32_t *a, uint32_t *r, size_t n) {
+    for (size_t i = 0; i < n; i++) st<FrP>(r, i, fp_inv_bingcd(ld<FrP>(a, i)));
+}
 extern "C" void emu_fr_inv(const uint32_t *a, uint32_t *r, size_t n) {
     for (size_t i = 0; i < n; i++) st<FrP>(r, i, fp_inv(ld<FrP>(a, i)));
 }

@@ -208,3 +208,22 @@ def test_g1_batch_affine_add(orc, emu):
         got = orc.canon_g1(orc.g1_from_affine(oracle_affine(out)))
         assert got == want, batch
     assert want[31] == (0, 0, 1) and want[20] == (0, 0, 1) and want[95] == (0, 0, 1)
+
+
+def test_inverse_by_binary_gcd(orc, emu):
+    """field.cuh fp_inv_bingcd (the one inversion at the top of the batched-affine product tree, msm_affine.cu):
+    a * inv(a) == 1 in Montgomery form for random and edge values of Fq and Fr, and equality with the oracle's Fr inverse"""
+    rng = np.random.default_rng(140)
+    fq = np.concatenate([orc.fq_from_ints([int.from_bytes(rng.bytes(64), "little") for _ in range(300)]),
+                         orc.fq_from_ints([1, 2, 3, tw.P_MOD - 1, tw.P_MOD - 2, (tw.P_MOD - 1) // 2, (1 << 380) + 5, 1 << 64])])
+    out = np.zeros_like(fq)
+    emu.emu_fq_inv_bingcd(_p(fq), _p(out), C.c_size_t(len(fq)))
+    one = orc.fq_from_ints([1])
+    assert np.array_equal(orc.fq_mul(fq, out), np.repeat(one, len(fq), axis=0))
+    z = np.zeros((1, 6), dtype=np.uint64)
+    emu.emu_fq_inv_bingcd(_p(z), _p(out[:1]), C.c_size_t(1))
+    assert not out[:1].any()
+    fr = np.concatenate([orc.random_fr(rng, 300), orc.fr_from_ints([1, 2, tw.R_MOD - 1, (tw.R_MOD + 1) // 2])])
+    out = np.zeros_like(fr)
+    emu.emu_fr_inv_bingcd(_p(fr), _p(out), C.c_size_t(len(fr)))
+    assert np.array_equal(out, orc.fr_inv(fr))

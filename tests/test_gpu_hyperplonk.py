@@ -282,6 +282,18 @@ def test_dhyperplonk_2p20_full_size_properties(orc):
     p1 = ctx.to_host(ctx.g1_to_affine(a[1][: used[1]].contiguous()))
     p2 = ctx.to_host(ctx.g1_to_affine(proof2.points[: used[1]].contiguous()))
     assert np.array_equal(p1, p2)                                   # same group elements, whatever the Jacobian form
+    # and a third time with the batched-affine bucket accumulation switched off (XYZZ mixed additions for every
+    # entry, csrc/msm.cu k_msm_accumulate): the first two runs took the affine path for their big sequence
+    assert ctx.msm_affine_sequences() >= 2
+    ctx.msm_use_precompute(True)
+    ctx.msm_set_affine(2)
+    seq0 = ctx.msm_affine_sequences()
+    proof3 = scz.dhyperplonk(ctx, n, pk, pp)
+    assert ctx.msm_affine_sequences() == seq0
+    p3 = ctx.to_host(ctx.g1_to_affine(proof3.points[: used[1]].contiguous()))
+    assert np.array_equal(p1, p3) and torch.equal(a[0][: 3 * used[0]], proof3.triples[: 3 * used[0]])
+    ctx.msm_set_affine(0)
+    ctx.msm_use_precompute(False)
     (gp, gc), (wp, wc, wo) = proof2.nested()
     R = tw.R_MOD
     inv2 = pow(2, R - 2, R)

@@ -13,11 +13,23 @@ from tests.gpu_util import fr_dot, packed_affine
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(scope="module")
-def ctx():
+# every test of this file runs with both bucket accumulation variants: "xyzz" = mixed additions only (the path small
+# sequences take by default), "affine" = the batched-affine levels forced on (csrc/msm_affine.cu: 3 levels, slabs of
+# 4096 entries so that several slabs and cut runs occur even in small inputs)
+@pytest.fixture(scope="module", params=["xyzz", "affine"])
+def ctx(request):
     import scz_b200 as scz
     c = scz.Context(device=0, n_parties=8)
+    if request.param == "affine":
+        c.msm_set_affine(1, 3, 4096)
+    else:
+        c.msm_set_affine(2)
+    c.variant = request.param
     yield c
+    if request.param == "affine":
+        assert c.msm_affine_sequences() > 0
+    else:
+        assert c.msm_affine_sequences() == 0
     c.close()
 
 
@@ -165,6 +177,27 @@ def test_config2_msm_2p20_trapdoor_and_linearity(orc, ctx):
     assert orc.canon_g1(ctx.to_host(ctx.g1_add(r1, r2))) == orc.canon_g1(ctx.to_host(r12))
     st = ctx.msm_last_stats()
     assert st["bucket_adds"] == n * st["windows"]
+    if ctx.variant == "affine":   # deep trees, one slab and the automatic choice: all the same point
+        for levels, slab in ((6, 0), (1, 1 << 20), (0, 0)):
+            ctx.msm_set_affine(1, levels, slab)
+            assert orc.canon_g1(ctx.to_host(scz.msm(ctx, bases, d1))) == [(exp[0], exp[1], 0)], (levels, slab)
+        # 8-bit windows: runs of ~8 k entries per bucket, 6 affine levels, every chunk boundary cuts a run
+        ctx.msm_set_window(8)
+        ctx.msm_set_affine(1, 6, 1 << 22)
+        try:
+            assert orc.canon_g1(ctx.to_host(scz.msm(ctx, bases, d1))) == [(exp[0], exp[1], 0)]
+            # all scalars equal to one (dmsm.rs:103): ONE bucket holds the whole stream, every addition inside the
+            # affine levels is of distinct points; then the same point 2^20 times: every addition is a doubling
+            ones = ctx.to_device(np.repeat(orc.fr_from_ints([1]), n, axis=0), 4)
+            ksum = orc.fr_to_ints(fr_dot(orc, k, np.repeat(orc.fr_from_ints([1]), n, axis=0)))[0]
+            e1 = tw.g1_mul(G, ksum)
+            assert orc.canon_g1(ctx.to_host(scz.msm(ctx, bases, ones))) == [(e1[0], e1[1], 0)]
+            same = bases[:1].repeat(n, 1).contiguous()
+            e2 = tw.g1_mul(G, orc.fr_to_ints(k[:1])[0] * n % tw.R_MOD)
+            assert orc.canon_g1(ctx.to_host(scz.msm(ctx, same, ones))) == [(e2[0], e2[1], 0)]
+        finally:
+            ctx.msm_set_window(0)
+            ctx.msm_set_affine(1, 3, 4096)
 
 
 @pytest.mark.parametrize("l", [1, 2, 4, 8])

@@ -128,15 +128,24 @@ def test_pointwise_maps(orc, ctx):
     assert np.array_equal(scz.fr_pointwise(ctx, "rsub", a, b), orc.fr_sub(b, a))
     want = orc.fr_add(orc.fr_add(a, orc.fr_mul(np.repeat(k[0:1], n, axis=0), b)), np.repeat(k[1:2], n, axis=0))
     assert np.array_equal(scz.fr_pointwise(ctx, "axpb", a, b, k), want)
-    b[7] = 0
-    b[4096] = 0
     b[n - 1] = orc.fr_from_ints([1])[0]
     inv = orc.fr_inv(b)
-    inv[7] = 0
-    inv[4096] = 0
     assert np.array_equal(scz.fr_pointwise(ctx, "div", a, b), orc.fr_mul(a, inv))
     for m in (1, 3, 127, 128, 129, 1025):
         assert np.array_equal(scz.fr_pointwise(ctx, "div", a[:m], b[:m]), orc.fr_mul(a[:m], inv[:m])), m
+    # a zero denominator: arkworks panics (dhyperplonk.rs:338-339).  The device path writes 0 for that element, keeps
+    # the rest of the batch right and raises the ctx's sticky SCZ_STATUS_DIV_BY_ZERO bit; the host path raises.
+    assert ctx.take_status() == 0
+    b[7] = 0
+    b[4096] = 0
+    inv[7] = 0
+    inv[4096] = 0
+    with pytest.raises(ZeroDivisionError):
+        scz.fr_pointwise(ctx, "div", a, b)
+    assert ctx.take_status() == 0                      # taken (and cleared) by the failed call
+    got = scz.fr_pointwise(ctx, "div", ctx.to_device(a, 4), ctx.to_device(b, 4))
+    assert np.array_equal(ctx.to_host(got), orc.fr_mul(a, inv))
+    assert ctx.take_status() == 1 and ctx.take_status() == 0
 
 
 # ------------------------------------------------------------------------------------------- leader mode
