@@ -283,6 +283,143 @@ def fr_kernel_rooflines(scz, ctx, torch, peak):
     return res
 
 
+
+# ------------------------------------------------------------------------------------------ BASELINE configs 2, 3, 4
+def timed_collective(torch, dist, world, dev, run_all, reps, warm=2):
+    """device time per call of `run_all` (every hosted party of every rank makes the call once): CUDA events around
+    `reps` calls on this rank's stream, barriers on both sides, max over ranks"""
+    for _ in range(warm):
+        run_all()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(reps):
+        run_all()
+    b.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ms = a.elapsed_time(b) / reps
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t[0])
+    return ms
+
+
+def config2_d_msm(scz, ctx, pp, pk, torch, peak, imad_peak, with_cpu):
+    """BASELINE config 2: leader-mode d_msm (dmsm.rs:9-43), one MSM of 2^20 G1 bases, l = 1, on one GPU.  The bases are
+    call arguments of d_msm, so the plain Pippenger path runs (level 20 of the SRS serves as 2^20 random points);
+    c_commit's variant with the level's fixed-base table is timed beside it."""
+    import numpy as np
+    n = 1 << 20
+    bases = pk.c_commitment.level(20)
+    scalars = pk.t["a_evals"]
+    assert len(bases) == n and len(scalars) == n
+    out = {}
+    for name, fn in (("d_msm (plain bases)", lambda: scz.d_msm(ctx, pp, [bases], [scalars])),
+                     ("c_commit (fixed-base table of the SRS level)", lambda: pk.c_commitment.c_commit(pp, [scalars]))):
+        ms = timed_collective(torch, None, 1, ctx.device, fn, reps=5)
+        a0 = ctx.msm_cum_stats()["bucket_adds"]
+        ctx.prof_enable(True)
+        fn()
+        acc_ms = ctx.prof_read("msm_accumulate")[0]
+        ctx.prof_enable(False)
+        adds = ctx.msm_cum_stats()["bucket_adds"] - a0
+        out[name] = {"ms": ms, "pairs_per_s": n / (ms * 1e-3), "bucket_adds": adds, "g1_adds_per_s": adds / (ms * 1e-3),
+                     "bucket_kernel_ms": acc_ms, "bucket_kernel_adds_per_s": adds / (acc_ms * 1e-3) if acc_ms else None,
+                     "bucket_kernel_hbm_frac": adds * ALG_BYTES_PER_ADD / (acc_ms * 1e-3) / 1e9 / peak if acc_ms else None,
+                     "bucket_kernel_alg_bytes_per_add": ALG_BYTES_PER_ADD}
+    res = {"workload": "BASELINE config 2: d_msm G1 2^20 bases, l=1, leader mode, 1 GPU (dmsm.rs:9-43; examples/msm.rs:17-101)",
+           "gpu": out}
+    if with_cpu:
+        from oracle import oracle as orc
+        rng = np.random.default_rng(5)
+        m = 1 << 18                                           # bounded sample: a quarter of the size, all host threads
+        pool = orc.random_g1(rng, 1024)
+        b = np.tile(pool, (m // 1024, 1))
+        sc = orc.random_fr(rng, m)
+        thr = os.cpu_count() or 1
+        t0 = time.perf_counter()
+        orc.msm(b, sc, "ark", threads=thr)
+        dt = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        orc.msm(b[: m // 4], sc[: m // 4], "ark", threads=1)
+        dt1 = time.perf_counter() - t0
+        res["cpu_port"] = {"pairs_per_s_all_threads": m / dt, "threads": thr, "pairs_per_s_one_thread": (m // 4) / dt1,
+                           "sample": f"arkworks-style signed-digit Pippenger (oracle port) on 2^18 pairs with {thr} threads and on "
+                                     "2^16 pairs with 1 thread (the reference runs G::msm on one thread per party)"}
+    return res
+
+
+def config34(scz, torch, dist, world, dev, parties, run_each, peak, n):
+    """BASELINE configs 3 and 4 on the live net (N parties over `world` GPUs): d_sumcheck_product on 2 x 2^(n-3) plain
+    slices per party (20 variables in total at n = 20, N = 8: dsumcheck.rs:359-512, examples/sumcheck.rs:94-265) and
+    c_commit + c_open of one 2^n-share table per party (dpoly_comm.rs:244-267, 401-464; examples/poly_comm.rs:36-201)."""
+    res = {}
+    m = 1 << (n - 3)
+    ms = timed_collective(torch, dist, world, dev,
+                          lambda: run_each(lambda ctx, pp, pk: scz.d_sumcheck_product(ctx, pk.t["I_p"], pk.t["S1_p"], pk.t["challenge"])), reps=10)
+    alg = (m - 1) * 192
+    res["config3_d_sumcheck_product"] = {
+        "workload": f"BASELINE config 3: d_sumcheck_product, {n} variables in total, N=8 parties on {world} GPU(s), 2 x 2^{n - 3} "
+                    f"Fr per party, {n} challenges, one gather of {n - 3 + 1} triples (96 B each) to the leader + 3 leader rounds",
+        "ms_per_call": ms, "constraints_per_s": (1 << n) / (ms * 1e-3), "alg_bytes_per_party": alg,
+        "hbm_frac_per_gpu": alg * (len(parties)) / (ms * 1e-3) / 1e9 / peak,
+        "note": "latency-bound at this size: 17 rounds of halving tables (the last 9 inside one CTA) + the gather; the HBM fraction "
+                "only says how far from a bandwidth problem a 4 MiB table is"}
+    ms_c = timed_collective(torch, dist, world, dev,
+                            lambda: run_each(lambda ctx, pp, pk: pk.c_commitment.c_commit(pp, [pk.t["a_evals"]])), reps=5)
+    ms_o = timed_collective(torch, dist, world, dev,
+                            lambda: run_each(lambda ctx, pp, pk: pk.c_commitment.c_open(pp, pk.t["a_evals"], pk.t["challenge"])), reps=5)
+    res["config4_dpoly_comm"] = {
+        "workload": f"BASELINE config 4: c_commit and c_open of one 2^{n}-share table per party, l=1, N=8 parties on {world} GPU(s) "
+                    "(one d_msm of 2^20 points; 20 fold rounds + one batched d_msm of 2^20 - 1 points + pss2ss)",
+        "c_commit_ms": ms_c, "c_open_ms": ms_o, "c_commit_coeffs_per_s": (1 << n) / (ms_c * 1e-3),
+        "c_open_coeffs_per_s": (1 << n) / (ms_o * 1e-3)}
+    return res
+
+
+def config34_cpu(n):
+    """the oracle port of configs 3 and 4 on the host (bounded samples), rank 0 only"""
+    import numpy as np
+    from oracle import oracle as orc
+    orc.lib()
+    rng = np.random.default_rng(6)
+    thr = os.cpu_count() or 1
+    out = {}
+    m = 1 << (n - 3)
+    f = [orc.random_fr(rng, m) for _ in range(N_PARTIES)]
+    g = [orc.random_fr(rng, m) for _ in range(N_PARTIES)]
+    ch = orc.random_fr(rng, n)
+    t0 = time.perf_counter()
+    orc.d_sumcheck_product(orc.PARTIES, N_PARTIES, f, g, ch)
+    dt = time.perf_counter() - t0
+    out["config3_d_sumcheck_product"] = {"s_all_8_parties_one_thread": dt, "s_per_party": dt / N_PARTIES,
+                                         "constraints_per_s_one_party_per_core": (1 << n) / (dt / N_PARTIES),
+                                         "sample": "oracle port, the 8 parties' local rounds run one after the other on one thread; "
+                                                   "the reference runs them on 8 machines, so the per-party time is the comparable figure"}
+    ns = min(n, 18)                                             # bounded sample of config 4
+    pool = orc.random_g1(rng, 1024)
+    levels = [np.tile(pool, (((1 << i) + 1023) // 1024, 1))[: 1 << i].copy() for i in range(ns + 1)]
+    srs = orc.Srs.from_levels(levels)
+    p = orc.random_fr(rng, 1 << ns)
+    u = orc.random_fr(rng, ns)
+    orc.set_msm_threads(thr)
+    t0 = time.perf_counter()
+    orc.c_commit([srs], orc.pp_new(1), orc.LEADER_SIM, [[p]])
+    dc = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    orc.c_open([srs], orc.pp_new(1), orc.LEADER_SIM, [p], u)
+    do = time.perf_counter() - t0
+    orc.set_msm_threads(1)
+    out["config4_dpoly_comm"] = {"c_commit_coeffs_per_s": (1 << ns) / dc, "c_open_coeffs_per_s": (1 << ns) / do, "threads": thr,
+                                 "sample": f"oracle port, leader mode, 2^{ns} shares (bounded sample), MSM windows on {thr} threads"}
+    return out
+
+
 # ------------------------------------------------------------------------------------------ own arm
 def run_own(args):
     import numpy as np  # noqa: F401
@@ -454,6 +591,17 @@ def run_own(args):
     e2e_value = (1 << n) * e2e_steps / e2e_s
     comm = ((comm1[0] - comm0[0]) // args.steps, (comm1[1] - comm0[1]) // args.steps)
 
+    # ---- BASELINE configs 3 and 4 as stand-alone calls on the same net (every N); config 2 at N = 1 below
+    def run_each(fn):
+        if P == 1:
+            c_, pp_, pk_ = parties[0]
+            return [fn(c_, pp_, pk_)]
+        return hub.run_parties(lambda pid, p, net: fn(*parties[p]))
+    peak_early, _ = hbm_peak()
+    standalone = None
+    if not args.no_standalone and n >= 6:
+        standalone = config34(scz, torch, dist, world, dev, parties, run_each, peak_early, n)
+
     # ---- N = 1 only: TWO independent provers in flight on the same GPU (a proving service's steady state).  Each has
     #      its own ctx, high-priority stream and host thread; the MSM launch sequences run on the ctxs' low-priority
     #      streams (SCZ_MSM_STREAM), so one prover's short protocol kernels are dispatched ahead of the other's queued
@@ -613,6 +761,14 @@ def run_own(args):
                                  "frac": imad_rate / imad_peak, "per_unit": 2736,
                                  "peak_source": f"{sms} SMs x 32 lanes/clk x {mhz} MHz (issue rate measured with ncu: "
                                                 "sm__pipe_fmaheavy_cycles_active 86 % at this throughput, profiles/)"}
+    if standalone:
+        line.update(standalone)
+        if not args.no_cpu and world in (1, 8):
+            cpu34 = config34_cpu(n)
+            for k in cpu34:
+                line[k]["cpu_port"] = cpu34[k]
+    if world == 1 and not args.no_standalone and n == 20 and not args.no_precompute:
+        line["config2_d_msm"] = config2_d_msm(scz, ctx0, parties[0][1], parties[0][2], torch, peak, imad_peak, not args.no_cpu)
     if world == 1:
         line["roofline_fr_kernels"] = fr_kernel_rooflines(scz, ctx0, torch, peak)
     if world == 1 and not args.no_cpu:
@@ -639,6 +795,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-precompute", action="store_true", help="do not build the fixed-base tables of the SRS")
     ap.add_argument("--no-plain", action="store_true", help="skip the extra leg that times the proof with the tables ignored")
+    ap.add_argument("--no-standalone", action="store_true", help="skip the stand-alone legs of BASELINE configs 2, 3, 4")
     ap.add_argument("--no-parity", action="store_true", help="N > 1: skip the untimed parity leg against the oracle")
     ap.add_argument("--parity-logn", type=int, default=10, help="N > 1: circuit size of the parity leg")
     ap.add_argument("--no-pipelined", action="store_true", help="skip the extra N = 1 leg with two provers in flight")

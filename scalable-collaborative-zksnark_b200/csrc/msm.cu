@@ -605,7 +605,7 @@ int32_t msm_g1_batched(Ctx *ctx, const void *const *d_bases, const void *const *
                 double avg_run = (double)entries / (double)std::max<uint64_t>(1, buckets);
                 uint32_t want = ctx->msm_affine_levels;
                 if (!want)
-                    while (want < 6 && (double)(2u << want) <= avg_run && (entries >> (want + 1)) >= (1ull << 21)) want++;
+                    while (want < 6 && (double)(4u << want) <= avg_run && (entries >> (want + 1)) >= (1ull << 21)) want++;
                 want = std::min(want, logT);
                 if (ctx->msm_affine_mode == 1) aff_levels = std::max(1u, want);
                 else if (want >= 2 && entries >= (1ull << 24)) aff_levels = want;

@@ -258,7 +258,10 @@ __global__ void __launch_bounds__(BA_THREADS) k_ba_tree_down(const void *V, uint
 //      The loop is split: a light phase in which every lane walks on its own (run boundaries, first blocks of a run,
 //      identity blocks) until it holds an addition that must really be done, then ONE mixed addition for all lanes of
 //      the warp that have one -- the expensive code always runs with as many lanes as there is work.
-__global__ void __launch_bounds__(BA_ACC_THREADS) k_ba_accumulate(const MsmSeg *segs, int nseg, const uint32_t *E_ptr,
+#ifndef BA_ACC_MIN_BLOCKS
+#define BA_ACC_MIN_BLOCKS 3   // 170 registers: three CTAs per SM hide the walk's dependent loads (measured: -1.4 ms per 2^20 proof)
+#endif
+__global__ void __launch_bounds__(BA_ACC_THREADS, BA_ACC_MIN_BLOCKS) k_ba_accumulate(const MsmSeg *segs, int nseg, const uint32_t *E_ptr,
                                                                    uint32_t logT, const uint2 *sorted, const uint32_t *counts,
                                                                    const uint32_t *cursor, const uint8_t *lvl,
                                                                    uint32_t slab_base, uint32_t slab_len, BaLevels L,
@@ -327,16 +330,21 @@ __global__ void __launch_bounds__(BA_ACC_THREADS) k_ba_accumulate(const MsmSeg *
 }
 
 // ------------------------------------------------------------------ host side
+// The slab size must not depend on how much memory happens to be free at the moment (a size that changes from one
+// sequence to the next makes the stream-ordered pool re-map memory: 80 ms stalls were measured): a third of the
+// DEVICE's memory, the same for every sequence; when several parties share the device and the pool cannot give that
+// much, the caller halves the slab and tries again.
 static size_t ba_budget_bytes(Ctx *ctx) {
-    size_t free_b = 0, total_b = 0;
-    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) {
-        cudaGetLastError();
-        return (size_t)8 << 30;
-    }
-    // memory held by the stream-ordered pool counts as used here although it is reusable: be generous, but leave room
-    // for the other parties that may share the device (each on its own stream)
-    size_t b = std::max(free_b / 3, (size_t)4 << 30);
-    return std::min(b, (size_t)48 << 30);
+    static size_t total = [] {
+        size_t free_b = 0, total_b = 0;
+        if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) {
+            cudaGetLastError();
+            total_b = (size_t)32 << 30;
+        }
+        return total_b;
+    }();
+    (void)ctx;
+    return std::min(total / 3, (size_t)64 << 30);
 }
 
 namespace {
@@ -419,8 +427,20 @@ int32_t msm_accumulate_affine(Ctx *ctx, const MsmSeg *sp, int nseg, const uint32
     slab = std::max<uint64_t>(T, slab / T * T);
     slab = std::min<uint64_t>(slab, entries_up);
     if (slab >= (1ull << 32)) slab = (1ull << 32) - T;
-    BaHalf half[1];
-    SCZ_TRY(half[0].alloc(ctx, slab, levels));
+    // as few slabs as the budget allows, all of the same length
+    {
+        const uint64_t nslabs = (entries_up + slab - 1) / slab;
+        slab = ((entries_up + nslabs - 1) / nslabs + T - 1) / T * T;
+    }
+    std::unique_ptr<BaHalf> slab_mem;
+    while (true) {
+        slab_mem.reset(new BaHalf());
+        if (slab_mem->alloc(ctx, slab, levels) == SCZ_OK) break;
+        slab_mem.reset();                      // frees what it got (stream-ordered)
+        if (slab <= (1ull << 22)) return ctx->fail(SCZ_ERR_NOMEM, "msm affine: no memory for a slab of %llu entries", (unsigned long long)slab);
+        slab = (slab / 2 + T - 1) / T * T;     // another party's sequence holds the pool: work in smaller passes
+    }
+    BaHalf *half = slab_mem.get();
 
     for (uint64_t base = 0; base < entries_up; base += slab) {
         const uint64_t slab_len = std::min<uint64_t>(slab, entries_up - base);
