@@ -159,7 +159,7 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------ CPU arms
-def cpu_hyperplonk_inputs(n, seed):
+def cpu_hyperplonk_inputs(n, seed, l=1):
     """oracle pk at circuit size 2^n: random tables; SRS levels tile a pool of 1024 random G1 points (group-law
     cost does not depend on the values; drawing 2^(n+3) independent points on the CPU would take minutes)"""
     import numpy as np
@@ -170,19 +170,19 @@ def cpu_hyperplonk_inputs(n, seed):
 
     def level(m):
         return np.tile(pool, ((m + 1023) // 1024, 1))[:m].copy()
-    csz, dsz = ohp.srs_level_sizes(n, 1, N_PARTIES)
+    csz, dsz = ohp.srs_level_sizes(n, l, 8 * l)
     srs_c = orc.Srs.from_levels([level(m) for m in csz])
     srs_d = orc.Srs.from_levels([level(m) for m in dsz])
-    return ohp.random_pk(rng, n, 1, N_PARTIES, srs_c, srs_d)
+    return ohp.random_pk(rng, n, l, 8 * l, srs_c, srs_d)
 
 
-def cpu_hyperplonk(n, pk, threads):
+def cpu_hyperplonk(n, pk, threads, l=1):
     """one leader-mode proof with the oracle's restatement of dhyperplonk (oracle/hyperplonk.py)"""
     from oracle import hyperplonk as ohp
     from oracle import oracle as orc
     orc.set_msm_threads(threads)
     t0 = time.perf_counter()
-    ohp.dhyperplonk(n, [pk], orc.pp_new(1), orc.LEADER_SIM, N_PARTIES)
+    ohp.dhyperplonk(n, [pk], orc.pp_new(l), orc.LEADER_SIM, 8 * l)
     dt = time.perf_counter() - t0
     orc.set_msm_threads(1)
     return dt
@@ -198,11 +198,12 @@ def run_reference(args):
     orc.lib()
     threads = os.cpu_count() or 1
     n = args.ref_logn or args.logn
-    pk = cpu_hyperplonk_inputs(n, 11)
+    l = args.l
+    pk = cpu_hyperplonk_inputs(n, 11, l)
     for _ in range(min(args.warmup, 1)):
-        cpu_hyperplonk(min(n, 10), cpu_hyperplonk_inputs(min(n, 10), 12), threads)
+        cpu_hyperplonk(min(n, 10), cpu_hyperplonk_inputs(min(n, 10), 12, l), threads, l)
     steps = max(1, min(args.steps, args.ref_steps))
-    dt = sum(cpu_hyperplonk(n, pk, threads) for _ in range(steps))
+    dt = sum(cpu_hyperplonk(n, pk, threads, l) for _ in range(steps))
     value = (1 << n) * steps / dt
     same = n == args.logn
     sample = (f"each step = one leader-mode dhyperplonk proof at 2^{n} constraints "
@@ -214,7 +215,8 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": dt / steps * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": DTYPE, "data": "synthetic",
-        "config": {"workload": f"dhyperplonk 2^{args.logn} constraints, l=1, N=8, leader mode (one party's prover)",
+        "config": {"workload": f"dhyperplonk 2^{args.logn} constraints, l={args.l}, N={8 * args.l}, leader mode (one party's prover)",
+                   "packing_factor_l": args.l,
                    "log2_constraints": n, "same_config_as_own_arm": same},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -223,65 +225,69 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
-def cpu_baseline_leg(n=14):
+def cpu_baseline_leg(n=14, l=1):
     """own arm, N = 1: the oracle port on ONE thread (what the reference does per party: ark `parallel` is off)"""
     from oracle import oracle as orc
     orc.lib()
-    pk = cpu_hyperplonk_inputs(n, 12)
-    dt = cpu_hyperplonk(n, pk, 1)
+    pk = cpu_hyperplonk_inputs(n, 12, l)
+    dt = cpu_hyperplonk(n, pk, 1, l)
     return {"value": (1 << n) / dt, "unit": UNIT, "cores": 1, "kind": "port",
-            "sample": f"one leader-mode dhyperplonk proof at 2^{n} constraints (l=1, N=8), 1 thread, {dt:.1f} s of CPU work; "
+            "sample": f"one leader-mode dhyperplonk proof at 2^{n} constraints (l={l}, N={8 * l}), 1 thread, {dt:.1f} s of CPU work; "
                       f"oracle C restatement of the arkworks path (portable C field arithmetic, no assembly backend)"}
 
 
 def fr_kernel_rooflines(scz, ctx, torch, peak):
-    """the HBM-side kernels of the path, each timed alone on a 2^22-entry table (128 MiB > L2) with CUDA events:
-    algorithmic bytes / time against the measured HBM peak"""
-    n = 1 << 22
+    """the HBM-side kernels of the path, each timed alone with CUDA events on tables larger than L2: algorithmic bytes
+    (the UNFUSED per-round figures) / time against the measured HBM peak.  Two sizes: 2^22 entries
+    (128 MiB; a whole call is ~0.1-0.6 ms there, of which ~0.1 ms is the host issuing its ~15 launches and stream-ordered
+    allocations -- the calls are launch-bound as much as bandwidth-bound) and 2^24 entries (512 MiB), where the
+    kernels themselves dominate."""
+    C = __import__("ctypes")
+    vp = lambda t: C.c_void_p(t.data_ptr())   # noqa: E731
     g = torch.Generator(device=ctx.device).manual_seed(7)
 
     def rand_fr(m):
         t = torch.randint(-2**63, 2**63 - 1, (m, 4), dtype=torch.int64, device=ctx.device, generator=g)
         t[:, 3] &= (1 << 62) - 1
         return t
-    f, h, ch = rand_fr(n), rand_fr(n), rand_fr(24)
-    C = __import__("ctypes")
-    vp = lambda t: C.c_void_p(t.data_ptr())   # noqa: E731
-    q, val = ctx.empty(n, 4), ctx.empty(1, 4)
-    out3, last = ctx.empty(3 * 24, 4), ctx.empty(2, 4)
-    cases = {
-        # first round only would need a private entry point; the whole call is the geometric series 2 * first round
-        "open_fold (dpoly_comm.rs:309-323), all 22 rounds": (
-            lambda: ctx.check(ctx.L.scz_open_fold_dev(ctx.h, vp(f), C.c_size_t(n), vp(ch), vp(q), vp(val))), (n - 1) * 128),
-        "product sumcheck rounds (dsumcheck.rs:37-85), all 22 rounds": (
-            lambda: ctx.check(ctx.L.scz_sumcheck_product_rounds_dev(ctx.h, vp(f), vp(h), C.c_size_t(n), vp(ch), vp(out3), vp(last))),
-            (n - 1) * 192),
-        "single-MLE sumcheck (dsumcheck.rs:6-26), all 22 rounds": (
-            lambda: ctx.check(ctx.L.scz_sumcheck_dev(ctx.h, vp(f), C.c_size_t(n), vp(ch), vp(out3))), (n - 1) * 96),
-        "pointwise a + k0*b + k1 (dhyperplonk.rs:326-337)": (
-            lambda: ctx.check(ctx.L.scz_fr_pointwise_dev(ctx.h, 2, vp(f), vp(h), vp(ch), vp(q), C.c_size_t(n))), n * 96),
-        "division num/den, batched inversion (dhyperplonk.rs:339)": (
-            lambda: ctx.check(ctx.L.scz_fr_pointwise_dev(ctx.h, 3, vp(f), vp(h), None, vp(q), C.c_size_t(n))), n * 96),
-        "fix_variable, 2 variables (mle.rs:88-104)": (
-            lambda: ctx.check(ctx.L.scz_fix_variable_dev(ctx.h, vp(f), C.c_size_t(n), vp(ch), C.c_size_t(2), vp(q))),
-            (n // 2) * 96 + (n // 4) * 96),
-    }
     res = []
-    for name, (fn, nbytes) in cases.items():
-        for _ in range(3):
-            fn()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        torch.cuda.synchronize()
-        e0.record()
-        for _ in range(5):
-            fn()
-        e1.record()
-        torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / 5
-        gbs = nbytes / (ms * 1e-3) / 1e9
-        res.append({"kernel": name, "table_entries": n, "alg_bytes": nbytes, "ms": ms, "achieved_gbs": gbs, "frac_of_hbm_peak": gbs / peak})
+    for logn in (22, 24):
+        n = 1 << logn
+        f, h, ch = rand_fr(n), rand_fr(n), rand_fr(26)
+        q, val = ctx.empty(n, 4), ctx.empty(1, 4)
+        out3, last = ctx.empty(3 * 26, 4), ctx.empty(2, 4)
+        cases = {
+            f"open_fold (dpoly_comm.rs:309-323), all {logn} rounds": (
+                lambda: ctx.check(ctx.L.scz_open_fold_dev(ctx.h, vp(f), C.c_size_t(n), vp(ch), vp(q), vp(val))), (n - 1) * 128),
+            f"product sumcheck rounds (dsumcheck.rs:37-85), all {logn} rounds": (
+                lambda: ctx.check(ctx.L.scz_sumcheck_product_rounds_dev(ctx.h, vp(f), vp(h), C.c_size_t(n), vp(ch), vp(out3), vp(last))),
+                (n - 1) * 192),
+            f"single-MLE sumcheck (dsumcheck.rs:6-26), all {logn} rounds": (
+                lambda: ctx.check(ctx.L.scz_sumcheck_dev(ctx.h, vp(f), C.c_size_t(n), vp(ch), vp(out3))), (n - 1) * 96),
+            "pointwise a + k0*b + k1 (dhyperplonk.rs:326-337)": (
+                lambda: ctx.check(ctx.L.scz_fr_pointwise_dev(ctx.h, 2, vp(f), vp(h), vp(ch), vp(q), C.c_size_t(n))), n * 96),
+            "division num/den, one shared inversion (dhyperplonk.rs:339)": (
+                lambda: ctx.check(ctx.L.scz_fr_pointwise_dev(ctx.h, 3, vp(f), vp(h), None, vp(q), C.c_size_t(n))), n * 96),
+            "fix_variable, 2 variables (mle.rs:88-104)": (
+                lambda: ctx.check(ctx.L.scz_fix_variable_dev(ctx.h, vp(f), C.c_size_t(n), vp(ch), C.c_size_t(2), vp(q))),
+                (n // 2) * 96 + (n // 4) * 96),
+        }
+        for name, (fn, nbytes) in cases.items():
+            for _ in range(3):
+                fn()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(5):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / 5
+            gbs = nbytes / (ms * 1e-3) / 1e9
+            res.append({"kernel": name, "table_entries": n, "alg_bytes": nbytes, "ms": ms, "achieved_gbs": gbs,
+                        "frac_of_hbm_peak": gbs / peak})
+        del f, h, q
     return res
-
 
 
 # ------------------------------------------------------------------------------------------ BASELINE configs 2, 3, 4
@@ -440,7 +446,9 @@ def run_own(args):
     # everything below runs on ONE high-priority stream: the provers' short protocol kernels must outrank the MSM
     # launch sequences, which libscz puts on a lowest-priority stream of each ctx (SCZ_MSM_STREAM, csrc/msm.cu)
     torch.cuda.set_stream(torch.cuda.Stream(device=dev, priority=-1))
-    assert world in (1, 2, 4, 8), "the 8 parties of l=1 spread over 1, 2, 4 or 8 GPUs"
+    assert world in (1, 2, 4, 8), "the 8 l parties spread over 1, 2, 4 or 8 GPUs"
+    L_PACK = args.l                                      # packing factor l: N = 8 l parties, each holds 1 / l of every table
+    N_PARTIES = 8 * L_PACK
     P = 1 if world == 1 else N_PARTIES // world          # parties hosted by this rank
     n = args.logn
 
@@ -460,8 +468,8 @@ def run_own(args):
                           net=hub.party(p) if hub else None)
         if hub:
             hub.adopt(p, ctx)   # parties that share a GPU run on their own streams (net.py, HybridNet)
-        pp = scz.PackedSharingParams(ctx, 1)
-        pk = scz.PackedProvingParameters.new(ctx, n, 1, seed=1 + pid, shared_seed=0, precompute=not args.no_precompute)
+        pp = scz.PackedSharingParams(ctx, L_PACK)
+        pk = scz.PackedProvingParameters.new(ctx, n, L_PACK, seed=1 + pid, shared_seed=0, precompute=not args.no_precompute)
         parties.append((ctx, pp, pk))
     torch.cuda.synchronize()
 
@@ -546,7 +554,7 @@ def run_own(args):
     host_tabs, alt = [], []
     for ctx, pp, pk in parties:
         host_tabs.append({name: torch.empty(t.shape, dtype=torch.int64).pin_memory().copy_(t) for name, t in pk.t.items()})
-        alt.append(scz.PackedProvingParameters(ctx, n, 1, {k: v.clone() for k, v in pk.t.items()}, pk.c_commitment,
+        alt.append(scz.PackedProvingParameters(ctx, n, L_PACK, {k: v.clone() for k, v in pk.t.items()}, pk.c_commitment,
                                                pk.d_commitment))
     h2d = sum(t.numel() * 8 for t in host_tabs[0].values())
 
@@ -599,7 +607,7 @@ def run_own(args):
         return hub.run_parties(lambda pid, p, net: fn(*parties[p]))
     peak_early, _ = hbm_peak()
     standalone = None
-    if not args.no_standalone and n >= 6:
+    if not args.no_standalone and n >= 6 and L_PACK == 1:
         standalone = config34(scz, torch, dist, world, dev, parties, run_each, peak_early, n)
 
     # ---- N = 1 only: TWO independent provers in flight on the same GPU (a proving service's steady state).  Each has
@@ -607,7 +615,7 @@ def run_own(args):
     #      streams (SCZ_MSM_STREAM), so one prover's short protocol kernels are dispatched ahead of the other's queued
     #      bucket-kernel CTAs.  Reported beside `value` (which stays one proof at a time), never instead of it.
     pipelined = None
-    if world == 1 and not args.no_pipelined and os.environ.get("SCZ_MSM_STREAM") == "1":
+    if world == 1 and L_PACK == 1 and not args.no_pipelined and os.environ.get("SCZ_MSM_STREAM") == "1":
         ctxA, ppA, pkA = parties[0]
         sA, sB = torch.cuda.Stream(priority=-1), torch.cuda.Stream(priority=-1)
         with torch.cuda.stream(sA):
@@ -667,7 +675,7 @@ def run_own(args):
     if world > 1 and not args.no_parity:
         from tests.parity_util import nccl_parity_check
         try:
-            parity = nccl_parity_check(local_rank, nv=args.parity_logn, l=1, net_kind=net_kind)
+            parity = nccl_parity_check(local_rank, nv=args.parity_logn, l=L_PACK, net_kind=net_kind)
         except Exception as e:   # noqa: BLE001 - reported in the JSON line
             parity = {"result": f"ERROR: {e!r}"[:400]}
 
@@ -696,9 +704,10 @@ def run_own(args):
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": DTYPE, "data": "synthetic",
         "config": {
-            "workload": f"dhyperplonk 2^{n} constraints, l=1, N=8, " + ("leader mode (one party's prover)" if world == 1 else
-                                                                          f"8 parties on {world} GPUs ({P} per GPU), star rounds over NCCL"),
-            "log2_constraints": n, "parties_per_gpu": P,
+            "workload": f"dhyperplonk 2^{n} constraints, l={L_PACK}, N={N_PARTIES}, " + (
+                "leader mode (one party's prover)" if world == 1 else
+                f"{N_PARTIES} parties on {world} GPUs ({P} per GPU), star rounds over NCCL"),
+            "log2_constraints": n, "parties_per_gpu": P, "packing_factor_l": L_PACK,
             "value_counts": "2^n / t(one proof), BASELINE.md 3 -- at N > 1 the 8 parties prove ONE circuit together; "
                             "the party-summed work rate is value_party_aggregate",
             "value_party_aggregate": parties_total * value,
@@ -772,7 +781,7 @@ def run_own(args):
     if world == 1:
         line["roofline_fr_kernels"] = fr_kernel_rooflines(scz, ctx0, torch, peak)
     if world == 1 and not args.no_cpu:
-        line["cpu_baseline"] = cpu_baseline_leg()
+        line["cpu_baseline"] = cpu_baseline_leg(l=L_PACK)
     for ctx, _, _ in parties:
         ctx.close()
     if hub:
@@ -789,6 +798,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
     ap.add_argument("--logn", type=int, default=20, help="log2 of the circuit size (BASELINE: 20)")
+    ap.add_argument("--l", type=int, default=1, help="packing factor l (N = 8 l parties; BASELINE: 1).  l > 1 is SURVEY 8(f)3: "
+                                                     "every party holds 1 / l of each table, 8 l / gpus parties share a GPU")
     ap.add_argument("--ref-logn", type=int, default=0, help="--impl reference: circuit size of the CPU run (0 = --logn: "
                                                             "the same config as the own arm, about a minute per proof)")
     ap.add_argument("--ref-steps", type=int, default=1, help="--impl reference: at most this many timed proofs")

@@ -1,5 +1,6 @@
 // Context, device memory, and the two network back-ends.
 #include <stdarg.h>
+#include <atomic>
 #include <stdlib.h>
 #include <string.h>
 
@@ -7,6 +8,9 @@
 #include "net.h"
 
 namespace scz {
+
+static std::atomic<int> g_live_ctx[64];
+int ctx_live_on_device(int device) { return device >= 0 && device < 64 ? g_live_ctx[device].load() : 1; }
 
 int32_t Ctx::fail(int32_t code, const char *fmt, ...) {
     char buf[512];
@@ -229,6 +233,7 @@ int32_t scz_ctx_create(int32_t device, uint32_t party_id, uint32_t n_parties, co
     }
     c->net->n_parties = n_parties;
     c->net->party_id = party_id;
+    if (device < 64) g_live_ctx[device]++;
     if (const char *e = getenv("SCZ_MSM_AFFINE"))   // A/B switch for measurements: 0 = XYZZ only, 1 = always batched-affine
         c->msm_affine_mode = e[0] == '0' ? 2 : (e[0] == '1' ? 1 : 0);
     if (const char *e = getenv("SCZ_MSM_AFFINE_LEVELS")) c->msm_affine_levels = (uint32_t)atoi(e);
@@ -246,6 +251,8 @@ void scz_ctx_destroy(scz_ctx *h) {
         if (st.p) cudaFreeHost(st.p);
         if (st.ev) cudaEventDestroy(st.ev);
     }
+    c->msm_affine_ws.reset();
+    if (c->device < 64) g_live_ctx[c->device]--;
     c->prof_clear();
     for (cudaEvent_t e : c->prof_pool) cudaEventDestroy(e);
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);

@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <memory>
 #include <string>
 #include <vector>
 
@@ -38,6 +39,11 @@ struct Ctx {
     uint32_t msm_affine_mode = 0, msm_affine_levels = 0;
     uint64_t msm_affine_slab = 0;
     uint64_t msm_cum_affine_sequences = 0;
+    // the level arrays of the batched-affine accumulation: allocated once per ctx and kept (grow-only).  Per-sequence
+    // stream-ordered allocations of tens of GB made the pool re-map memory when proofs are enqueued back to back
+    // (254 instead of 122 ms per proof measured), so this workspace is NOT a DevTmp.
+    std::shared_ptr<void> msm_affine_ws;
+    uint64_t msm_affine_ws_limit = UINT64_MAX;   // slab entries above which an allocation failed on this device
     uint64_t msm_bucket_adds = 0, msm_buckets = 0, msm_windows = 0;   // statistics of the last MSM sequence
     uint64_t msm_cum_adds = 0, msm_cum_pairs = 0, msm_cum_sequences = 0, msm_cum_segments = 0;   // since ctx creation
     // optional per-kernel-class device timing (scz_prof_*): CUDA events recorded on `stream` around the launches
@@ -73,26 +79,32 @@ struct Ctx {
 // Stream-ordered temporary from the device's CUDA memory pool (cudaMallocAsync): freed in
 // stream order when the object dies, so kernels already queued keep their memory and
 // steady-state calls never hit the allocator's slow path (release threshold = unlimited).
+// `persistent`: a plain cudaMalloc that lives until the object dies (workspaces kept across calls).
 struct DevTmp {
     Ctx *c;
     void *p = nullptr;
-    explicit DevTmp(Ctx *ctx) : c(ctx) {}
+    bool persistent = false;
+    explicit DevTmp(Ctx *ctx, bool keep = false) : c(ctx), persistent(keep) {}
     DevTmp(const DevTmp &) = delete;
     DevTmp &operator=(const DevTmp &) = delete;
     int32_t alloc(size_t bytes) {
-        cudaError_t e = cudaMallocAsync(&p, bytes ? bytes : 256, c->stream);
+        cudaError_t e = persistent ? cudaMalloc(&p, bytes ? bytes : 256) : cudaMallocAsync(&p, bytes ? bytes : 256, c->stream);
         if (e != cudaSuccess) {
             p = nullptr;
             cudaGetLastError();
-            return c->fail(SCZ_ERR_NOMEM, "cudaMallocAsync(%zu): %s", bytes, cudaGetErrorString(e));
+            return c->fail(SCZ_ERR_NOMEM, "%s(%zu): %s", persistent ? "cudaMalloc" : "cudaMallocAsync", bytes, cudaGetErrorString(e));
         }
         return SCZ_OK;
     }
     template <class T> T *as() const { return reinterpret_cast<T *>(p); }
     ~DevTmp() {
-        if (p) cudaFreeAsync(p, c->stream);
+        if (!p) return;
+        if (persistent) cudaFree(p);
+        else cudaFreeAsync(p, c->stream);
     }
 };
+// live ctxs on a device (several parties may share one GPU: workspaces are sized accordingly)
+int ctx_live_on_device(int device);
 
 #define SCZ_CUDA(ctx, expr)                                   \
     do {                                                      \

@@ -13,6 +13,7 @@
 //     phase 1  denominator d = x2 - x1 of every pure pair (2 y1 for a doubling, 1 when no inverse is needed),
 //              per-thread running products to scratch, thread totals to the product tree
 //     tree     fan-in-32 prefix products up, ONE field inversion at the top, inverses of the thread totals down
+//              (batch_inv.cuh)
 //     phase 2  walks each thread's pairs backwards (1 / d_j = I * prefix_{j-1}, I *= d_j), slope, sum -> R[k+1]
 // No compaction, no per-level scan, fixed index arithmetic: a bucket of 58 entries decomposes into ~5 maximal pure
 // blocks; the ~52 additions inside them are affine, the ~5 between them (and everything a chunk boundary cuts) go
@@ -24,6 +25,7 @@
 #include <memory>
 #include <vector>
 
+#include "batch_inv.cuh"
 #include "g1_batch_affine.cuh"
 #include "msm.h"
 
@@ -31,8 +33,6 @@ namespace scz {
 
 constexpr int BA_THREADS = 128;
 constexpr int BA_B = 8;          // pairs per thread in phase 1 / 2 (strided by the CTA: coalesced across lanes)
-constexpr int BA_F = 32;         // fan-in of the product tree (contiguous per thread)
-constexpr int BA_TOP = 32;       // the tree stops at <= this many values: one thread finishes them
 constexpr int BA_MAX_LEVELS = 8;
 constexpr int BA_ACC_THREADS = 128;
 
@@ -212,47 +212,6 @@ __global__ void __launch_bounds__(BA_THREADS) k_ba_phase2(const MsmSeg *segs, in
     if (it.k == 0) ba_phase2_cta<true>(segs, nseg, sorted, it, blockIdx.x);
     else ba_phase2_cta<false>(segs, nseg, sorted, it, blockIdx.x);
 }
-// ---- product tree over the thread totals: thread g owns values [g F, (g + 1) F)
-__global__ void __launch_bounds__(BA_THREADS) k_ba_tree_up(const void *V, uint32_t n, void *pfx, void *tot, uint32_t ngroups) {
-    uint32_t g = blockIdx.x * BA_THREADS + threadIdx.x;
-    if (g >= ngroups) return;
-    uint32_t lo = g * BA_F, hi = min(n, lo + BA_F);
-    Fq run = Fq::one();
-    for (uint32_t e = lo; e < hi; e++) {
-        run = fp_mul(run, fp_load_rw<FqP>(V, e));
-        fp_store<FqP>(pfx, e, run);
-    }
-    fp_store<FqP>(tot, g, run);
-}
-// one thread: inverses of n <= BA_TOP values with one inversion (binary extended Euclid: ~6x shorter than a Fermat chain)
-__global__ void k_ba_tree_top(const void *V, uint32_t n, void *inv) {
-    if (threadIdx.x || blockIdx.x) return;
-    Fq pre[BA_TOP];
-    Fq run = Fq::one();
-    for (uint32_t e = 0; e < n; e++) {
-        pre[e] = run;
-        run = fp_mul(run, fp_load_rw<FqP>(V, e));
-    }
-    Fq I = fp_inv_bingcd(run);
-    for (uint32_t e = n; e-- > 0;) {
-        fp_store<FqP>(inv, e, fp_mul(I, pre[e]));
-        I = fp_mul(I, fp_load_rw<FqP>(V, e));
-    }
-}
-// pfx: in = inclusive prefix products of V inside each group, out = the inverse of every value
-__global__ void __launch_bounds__(BA_THREADS) k_ba_tree_down(const void *V, uint32_t n, void *pfx, const void *inv_parent,
-                                                              uint32_t ngroups) {
-    uint32_t g = blockIdx.x * BA_THREADS + threadIdx.x;
-    if (g >= ngroups) return;
-    uint32_t lo = g * BA_F, hi = min(n, lo + BA_F);
-    Fq I = fp_load_rw<FqP>(inv_parent, g);
-    for (uint32_t e = hi; e-- > lo;) {
-        Fq inv_e = e > lo ? fp_mul(I, fp_load_rw<FqP>(pfx, e - 1)) : I;
-        if (e > lo) I = fp_mul(I, fp_load_rw<FqP>(V, e));
-        fp_store<FqP>(pfx, e, inv_e);
-    }
-}
-
 // ---- the XYZZ pass over what the affine levels left: same chunks, same outputs as k_msm_accumulate, but the walk
 //      steps from one maximal pure block to the next (lvl[] gives its size, R[m] its sum) instead of entry by entry.
 //      The loop is split: a light phase in which every lane walks on its own (run boundaries, first blocks of a run,
@@ -330,10 +289,8 @@ __global__ void __launch_bounds__(BA_ACC_THREADS, BA_ACC_MIN_BLOCKS) k_ba_accumu
 }
 
 // ------------------------------------------------------------------ host side
-// The slab size must not depend on how much memory happens to be free at the moment (a size that changes from one
-// sequence to the next makes the stream-ordered pool re-map memory: 80 ms stalls were measured): a third of the
-// DEVICE's memory, the same for every sequence; when several parties share the device and the pool cannot give that
-// much, the caller halves the slab and tries again.
+// The slab (entries worked on per pass) is sized from the DEVICE's memory and the number of ctxs that share the device,
+// never from what happens to be free: the workspace is allocated once per ctx and kept.
 static size_t ba_budget_bytes(Ctx *ctx) {
     static size_t total = [] {
         size_t free_b = 0, total_b = 0;
@@ -343,40 +300,34 @@ static size_t ba_budget_bytes(Ctx *ctx) {
         }
         return total_b;
     }();
-    (void)ctx;
-    return std::min(total / 3, (size_t)64 << 30);
+    const int live = std::max(1, ctx_live_on_device(ctx->device));
+    return std::min((size_t)((double)total * 0.45 / live), (size_t)64 << 30);
 }
 
 namespace {
 // the arrays of one slab: its levels, scratch and product tree
 struct BaHalf {
     uint32_t base = 0, len = 0;
+    uint64_t cap = 0;
+    uint32_t levels = 0;
     std::unique_ptr<DevTmp> lvl, pre, R[BA_MAX_LEVELS + 1];
-    std::vector<std::unique_ptr<DevTmp>> V, P;
+    InvTree<FqP> tree;   // values = the thread totals of phase 1, inverses = what phase 2 starts from (batch_inv.cuh)
     BaLevels L;
-    int32_t alloc(Ctx *ctx, uint64_t cap, uint32_t levels) {
-        lvl.reset(new DevTmp(ctx));
-        pre.reset(new DevTmp(ctx));
+    int32_t alloc(Ctx *ctx, uint64_t cap_, uint32_t levels_) {
+        cap = cap_, levels = levels_;
+        lvl.reset(new DevTmp(ctx, true));
+        pre.reset(new DevTmp(ctx, true));
         SCZ_TRY(lvl->alloc(cap));
         SCZ_TRY(pre->alloc((cap >> 1) * sizeof(Fq)));
         for (uint32_t m = 0; m <= BA_MAX_LEVELS; m++) {
             L.R[m] = nullptr;
             if (m >= 1 && m <= levels) {
-                R[m].reset(new DevTmp(ctx));
+                R[m].reset(new DevTmp(ctx, true));
                 SCZ_TRY(R[m]->alloc((cap >> m) * sizeof(G1Affine)));
                 L.R[m] = R[m]->p;
             }
         }
-        // product tree: V[0] = the thread totals of phase 1 (at most the level-0 thread count), V[l + 1] = group totals
-        uint64_t n = (((cap >> 1) + BA_THREADS * BA_B - 1) / (BA_THREADS * BA_B)) * BA_THREADS;
-        while (true) {
-            V.emplace_back(new DevTmp(ctx));
-            P.emplace_back(new DevTmp(ctx));
-            SCZ_TRY(V.back()->alloc(n * sizeof(Fq)));
-            SCZ_TRY(P.back()->alloc(n * sizeof(Fq)));
-            if (n <= BA_TOP) break;
-            n = (n + BA_F - 1) / BA_F;
-        }
+        SCZ_TRY(tree.alloc(ctx, (((cap >> 1) + BA_THREADS * BA_B - 1) / (BA_THREADS * BA_B)) * BA_THREADS, true));
         return SCZ_OK;
     }
     BaItem item(uint32_t k) const {
@@ -384,34 +335,12 @@ struct BaHalf {
         it.lvl = lvl->as<uint8_t>();
         it.slab_base = base, it.k = k, it.npairs = len >> (k + 1);
         it.Rk = k ? L.R[k] : nullptr;
-        it.pre = pre->p, it.tot = V[0]->p, it.inv_tot = P[0]->p, it.Rk1 = L.R[k + 1];
+        it.pre = pre->p, it.tot = tree.values(), it.inv_tot = tree.inverses(), it.Rk1 = L.R[k + 1];
         return it;
     }
 };
 uint32_t ba_ctas(const BaItem &it) { return ceil_div_u32(it.npairs, BA_THREADS * BA_B); }
 
-// the product tree of one item: prefix products up, one inversion, inverses down; leaves P[0] = 1 / V[0]
-int32_t ba_tree(Ctx *ctx, BaHalf &h, const BaItem &it) {
-    cudaStream_t st = ctx->stream;
-    std::vector<uint32_t> n;
-    n.push_back(ba_ctas(it) * BA_THREADS);
-    size_t lv = 0;
-    while (n[lv] > BA_TOP) {
-        uint32_t groups = (n[lv] + BA_F - 1) / BA_F;
-        k_ba_tree_up<<<ceil_div_u32(groups, BA_THREADS), BA_THREADS, 0, st>>>(h.V[lv]->p, n[lv], h.P[lv]->p, h.V[lv + 1]->p, groups);
-        SCZ_LAUNCH_CHECK(ctx);
-        n.push_back(groups);
-        lv++;
-    }
-    k_ba_tree_top<<<1, 32, 0, st>>>(h.V[lv]->p, n[lv], h.P[lv]->p);
-    SCZ_LAUNCH_CHECK(ctx);
-    while (lv-- > 0) {
-        uint32_t groups = n[lv + 1];
-        k_ba_tree_down<<<ceil_div_u32(groups, BA_THREADS), BA_THREADS, 0, st>>>(h.V[lv]->p, n[lv], h.P[lv]->p, h.P[lv + 1]->p, groups);
-        SCZ_LAUNCH_CHECK(ctx);
-    }
-    return SCZ_OK;
-}
 }   // namespace
 
 int32_t msm_accumulate_affine(Ctx *ctx, const MsmSeg *sp, int nseg, const uint32_t *E_ptr, uint64_t entries, uint32_t logT,
@@ -432,16 +361,29 @@ int32_t msm_accumulate_affine(Ctx *ctx, const MsmSeg *sp, int nseg, const uint32
         const uint64_t nslabs = (entries_up + slab - 1) / slab;
         slab = ((entries_up + nslabs - 1) / nslabs + T - 1) / T * T;
     }
-    std::unique_ptr<BaHalf> slab_mem;
-    while (true) {
-        slab_mem.reset(new BaHalf());
-        if (slab_mem->alloc(ctx, slab, levels) == SCZ_OK) break;
-        slab_mem.reset();                      // frees what it got (stream-ordered)
-        if (slab <= (1ull << 22)) return ctx->fail(SCZ_ERR_NOMEM, "msm affine: no memory for a slab of %llu entries", (unsigned long long)slab);
-        slab = (slab / 2 + T - 1) / T * T;     // another party's sequence holds the pool: work in smaller passes
+    // the ctx's workspace: kept across sequences, replaced only when a bigger one is needed
+    if (slab > ctx->msm_affine_ws_limit) {
+        const uint64_t lim = std::max<uint64_t>(T, ctx->msm_affine_ws_limit / T * T);
+        const uint64_t nslabs = (entries_up + lim - 1) / lim;
+        slab = std::min(lim, ((entries_up + nslabs - 1) / nslabs + T - 1) / T * T);
     }
-    BaHalf *half = slab_mem.get();
-
+    BaHalf *half = static_cast<BaHalf *>(ctx->msm_affine_ws.get());
+    if (!half || half->levels < levels || half->cap < slab) {
+        SCZ_CUDA(ctx, cudaStreamSynchronize(st));
+        ctx->msm_affine_ws.reset();
+        while (true) {
+            std::shared_ptr<BaHalf> ws(new BaHalf());
+            if (ws->alloc(ctx, slab, std::max(levels, 4u)) == SCZ_OK) {
+                ctx->msm_affine_ws = ws;
+                half = ws.get();
+                break;
+            }
+            ws.reset();
+            if (slab <= (1ull << 20)) return ctx->fail(SCZ_ERR_NOMEM, "msm affine: no memory for a slab of %llu entries", (unsigned long long)slab);
+            slab = (slab / 2 + T - 1) / T * T;     // other parties hold the device's memory: work in smaller passes
+            ctx->msm_affine_ws_limit = slab;
+        }
+    }
     for (uint64_t base = 0; base < entries_up; base += slab) {
         const uint64_t slab_len = std::min<uint64_t>(slab, entries_up - base);
         BaHalf &h0 = half[0];
@@ -454,7 +396,7 @@ int32_t msm_accumulate_affine(Ctx *ctx, const MsmSeg *sp, int nseg, const uint32
             const BaItem it = h0.item(k);
             k_ba_phase1<<<ba_ctas(it), BA_THREADS, 0, st>>>(sp, nseg, sorted, it);
             SCZ_LAUNCH_CHECK(ctx);
-            SCZ_TRY(ba_tree(ctx, h0, it));
+            SCZ_TRY(h0.tree.run(ctx, ba_ctas(it) * BA_THREADS));
             k_ba_phase2<<<ba_ctas(it), BA_THREADS, 0, st>>>(sp, nseg, sorted, it);
             SCZ_LAUNCH_CHECK(ctx);
         }

@@ -14,6 +14,7 @@
 // SAME round's three sums: one pass reads (f_lo, f_hi, g_lo, g_hi) = 128 B per pair and writes the folded
 // pair = 64 B, five Fr products in between.  a*(1-r) + b*r is computed as a + r*(b - a): the same field
 // element with one product instead of two.
+#include "batch_inv.cuh"
 #include "ctx.h"
 #include "field.cuh"
 
@@ -203,6 +204,85 @@ __global__ void __launch_bounds__(PL_THREADS) k_sum_round(const void *f_in, void
         *ticket = 0;
     }
 }
+// R rounds of the single-MLE sumcheck in ONE pass (every challenge is known up-front, dsumcheck.rs:151): a thread
+// holds the 2^R entries i + m w (w = len >> R) that fold into entry i, adds them to the (lo, hi) sums of each of the R
+// rounds as it folds them down.  Traffic per folded entry: 2^R * 32 B read + 32 B written instead of 96 B per pair per
+// round (R = 3: 288 B instead of 672 B), and a third of the launches -- this chain of halving passes is bandwidth- and
+// launch-bound, not compute-bound (one product per pair).
+template <int R>
+__global__ void __launch_bounds__(PL_THREADS) k_sum_rounds(const void *f_in, void *f_out, uint32_t w, const void *challenge,
+                                                            Fr *partial, uint32_t *ticket, Fr2 *out) {
+    constexpr int M = 1 << R, NV = 2 * R;
+    __shared__ Fr sh[NV * PL_THREADS / 32];
+    __shared__ bool last;
+    Fr r[R], s[NV];
+#pragma unroll
+    for (int t = 0; t < R; t++) r[t] = fp_load<FrP>(challenge, t);
+#pragma unroll
+    for (int k = 0; k < NV; k++) s[k] = Fr::zero();
+    for (uint32_t i = blockIdx.x * PL_THREADS + threadIdx.x; i < w; i += gridDim.x * PL_THREADS) {
+        Fr v[M];
+#pragma unroll
+        for (int m = 0; m < M; m++) v[m] = fp_load_rw<FrP>(f_in, (size_t)m * w + i);
+#pragma unroll
+        for (int t = 0; t < R; t++) {
+            constexpr int dummy = 0;
+            (void)dummy;
+            const int half = M >> (t + 1);
+#pragma unroll
+            for (int m = 0; m < M / 2; m++) {
+                if (m < half) {
+                    s[2 * t] = fp_add(s[2 * t], v[m]);
+                    s[2 * t + 1] = fp_add(s[2 * t + 1], v[m + half]);
+                    v[m] = fp_add(v[m], fp_mul(r[t], fp_sub(v[m + half], v[m])));
+                }
+            }
+        }
+        fp_store<FrP>(f_out, i, v[0]);
+    }
+    // block-wide sums of the NV accumulators
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < NV; k++) {
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) s[k] = fp_add(s[k], fr_shfl_down(s[k], d));
+        if (lane == 0) sh[k * (PL_THREADS / 32) + wid] = s[k];
+    }
+    __syncthreads();
+    if (threadIdx.x < NV) {
+        Fr acc = sh[threadIdx.x * (PL_THREADS / 32)];
+        for (int q = 1; q < PL_THREADS / 32; q++) acc = fp_add(acc, sh[threadIdx.x * (PL_THREADS / 32) + q]);
+        fp_store<FrP>(partial, (size_t)blockIdx.x * NV + threadIdx.x, acc);
+        __threadfence();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    // the last CTA adds the partials: warp k sums accumulator k
+    if (wid < NV) {
+        Fr acc = Fr::zero();
+        for (uint32_t b = lane; b < gridDim.x; b += 32) {
+            const uint4 *p = reinterpret_cast<const uint4 *>(reinterpret_cast<const char *>(partial) + ((size_t)b * NV + wid) * 32);
+            Fr t;
+#pragma unroll
+            for (int q = 0; q < 2; q++) {
+                uint4 x = __ldcg(p + q);   // written by other CTAs: read through L2
+                t.l[4 * q] = x.x, t.l[4 * q + 1] = x.y, t.l[4 * q + 2] = x.z, t.l[4 * q + 3] = x.w;
+            }
+            acc = fp_add(acc, t);
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) acc = fp_add(acc, fr_shfl_down(acc, d));
+        if (lane == 0) {
+            Fr *o = reinterpret_cast<Fr *>(out);   // round t: (sum lo, sum hi) = accumulators 2t, 2t + 1
+            o[wid] = acc;
+        }
+    }
+    if (threadIdx.x == 0) *ticket = 0;
+}
+
 // all remaining rounds (h <= TAIL_PAIRS) in one CTA, in place on f
 __global__ void __launch_bounds__(PL_THREADS) k_sum_tail(void *f, uint32_t h, const void *challenge, Fr2 *out) {
     __shared__ Fr sh[3 * PL_THREADS / 32];
@@ -307,86 +387,48 @@ __global__ void __launch_bounds__(PL_THREADS) k_pointwise(const void *a, const v
     fp_store<FrP>(out, i, r);
 }
 
-// out[i] = num[i] / den[i] (dhyperplonk.rs:338-339).  Montgomery's trick on two levels: a thread owns
-// INV_PER_THREAD consecutive elements (prefix products in registers), a warp combines them through a shuffle scan
-// and the whole CTA (1024 elements) shares ONE Fermat inversion, so an element costs ~7 products instead of ~380.  den = 0 yields 0 (arkworks would panic).
-constexpr int INV_PER_THREAD = 4;
-__device__ __forceinline__ Fr fr_shfl(const Fr &v, int src) {
-    Fr r;
-#pragma unroll
-    for (int i = 0; i < 8; i++) r.l[i] = __shfl_sync(0xffffffffu, v.l[i], src);
-    return r;
-}
-__device__ __forceinline__ Fr fr_shfl_up(const Fr &v, int d) {
-    Fr r;
-#pragma unroll
-    for (int i = 0; i < 8; i++) r.l[i] = __shfl_up_sync(0xffffffffu, v.l[i], d);
-    return r;
-}
-__global__ void __launch_bounds__(PL_THREADS) k_div(const void *num, const void *den, void *out, size_t n, uint32_t *status) {
-    size_t base = ((size_t)blockIdx.x * PL_THREADS + threadIdx.x) * INV_PER_THREAD;
-    int lane = threadIdx.x & 31;
-    Fr d[INV_PER_THREAD], pre[INV_PER_THREAD];
+// out[i] = num[i] / den[i] (dhyperplonk.rs:338-339) with ONE field inversion for the whole table (Montgomery's trick as
+// a device-wide product tree, batch_inv.cuh): phase 1 writes per-thread running products of the denominators and the
+// thread totals, the tree turns the totals into their inverses, phase 2 walks each thread's elements backwards.  Four
+// products per element, 192 B of traffic against 96 B algorithmic; the earlier version ran one 255-bit Fermat chain per
+// 1024 elements on a single lane of each CTA, which serialised the kernel (3.6 ms for 2^22 elements, now ~0.2 ms).
+// den = 0: arkworks panics (Field::div); here the element comes out 0, the rest of the batch stays right and the ctx's
+// SCZ_STATUS_DIV_BY_ZERO bit is raised.
+constexpr int DIV_THREADS = 256;
+constexpr int DIV_PER = 4;      // elements per thread, strided by the CTA (coalesced)
+__global__ void __launch_bounds__(DIV_THREADS) k_div_phase1(const void *den, size_t n, void *pre, void *tot, uint32_t *status) {
+    const size_t cta_base = (size_t)blockIdx.x * (DIV_THREADS * DIV_PER);
     Fr run = Fr::one();
+    bool zero = false;
 #pragma unroll
-    for (int j = 0; j < INV_PER_THREAD; j++) {
-        d[j] = base + j < n ? fp_load_rw<FrP>(den, base + j) : Fr::one();
-        if (d[j].is_zero()) d[j] = Fr::one();   // keeps the batch invertible; fixed up below
-        pre[j] = run;                            // product of the thread's earlier elements
-        run = fp_mul(run, d[j]);
-    }
-    // inclusive warp scan of the thread products
-    Fr incl = run;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        Fr t = fr_shfl_up(incl, o);
-        if (lane >= o) incl = fp_mul(incl, t);
-    }
-    // one Fermat inversion per CTA: the warp totals meet in shared memory, thread 0 inverts their product and hands
-    // every warp the inverse of ITS total = inv(all) * (totals of the other warps)
-    __shared__ Fr wtot[PL_THREADS / 32], winv[PL_THREADS / 32];
-    const int wid = threadIdx.x >> 5;
-    if (lane == 31) wtot[wid] = incl;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        constexpr int NW = PL_THREADS / 32;
-        Fr pre_w[NW], acc = Fr::one();
-        for (int w = 0; w < NW; w++) {
-            pre_w[w] = acc;                      // product of the warps before w
-            acc = fp_mul(acc, wtot[w]);
-        }
-        Fr inv_all = fp_inv(acc), suf = Fr::one();
-        for (int w = NW - 1; w >= 0; w--) {
-            winv[w] = fp_mul(inv_all, fp_mul(pre_w[w], suf));
-            suf = fp_mul(suf, wtot[w]);
+    for (int j = 0; j < DIV_PER; j++) {
+        size_t e = cta_base + (size_t)j * DIV_THREADS + threadIdx.x;
+        if (e < n) {
+            Fr d = fp_load_rw<FrP>(den, e);
+            if (d.is_zero()) zero = true;                  // keeps the batch invertible; the element is fixed up in phase 2
+            else run = fp_mul(run, d);
+            fp_store<FrP>(pre, e, run);
         }
     }
-    __syncthreads();
-    Fr total_inv = winv[wid];
-    // inverse of this thread's product = total_inv * (product of later lanes) * (product of earlier lanes):
-    // suffix products by a second scan
-    Fr suf = run;
+    fp_store<FrP>(tot, (size_t)blockIdx.x * DIV_THREADS + threadIdx.x, run);
+    if (zero) atomicOr(status, SCZ_STATUS_DIV_BY_ZERO);
+}
+__global__ void __launch_bounds__(DIV_THREADS) k_div_phase2(const void *num, const void *den, size_t n, const void *pre,
+                                                             const void *inv_tot, void *out) {
+    const size_t cta_base = (size_t)blockIdx.x * (DIV_THREADS * DIV_PER);
+    Fr I = fp_load_rw<FrP>(inv_tot, (size_t)blockIdx.x * DIV_THREADS + threadIdx.x);
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        Fr t = fr_shfl_down(suf, o);
-        if (lane + o < 32) suf = fp_mul(suf, t);
-    }
-    Fr excl_pre = fr_shfl_up(incl, 1);          // product of lanes < lane
-    Fr excl_suf = fr_shfl_down(suf, 1);         // product of lanes > lane
-    Fr inv_run = total_inv;
-    if (lane > 0) inv_run = fp_mul(inv_run, excl_pre);
-    if (lane < 31) inv_run = fp_mul(inv_run, excl_suf);
-    // walk back through the thread's own elements
-#pragma unroll
-    for (int j = INV_PER_THREAD - 1; j >= 0; j--) {
-        Fr inv_j = fp_mul(inv_run, pre[j]);
-        inv_run = fp_mul(inv_run, d[j]);
-        if (base + j < n) {
-            Fr dn = fp_load_rw<FrP>(den, base + j);
-            if (dn.is_zero()) atomicOr(status, SCZ_STATUS_DIV_BY_ZERO);   // arkworks panics here; the host reads the bit
-            Fr r = dn.is_zero() ? Fr::zero() : fp_mul(fp_load_rw<FrP>(num, base + j), inv_j);
-            fp_store<FrP>(out, base + j, r);
+    for (int j = DIV_PER - 1; j >= 0; j--) {
+        size_t e = cta_base + (size_t)j * DIV_THREADS + threadIdx.x;
+        if (e >= n) continue;
+        Fr d = fp_load_rw<FrP>(den, e);
+        if (d.is_zero()) {
+            fp_store<FrP>(out, e, Fr::zero());
+            continue;
         }
+        Fr dinv = j ? fp_mul(I, fp_load_rw<FrP>(pre, e - DIV_THREADS)) : I;
+        if (j) I = fp_mul(I, d);
+        fp_store<FrP>(out, e, fp_mul(fp_load_rw<FrP>(num, e), dinv));
     }
 }
 
@@ -463,18 +505,24 @@ int32_t sumcheck_rounds(Ctx *ctx, const void *d_f, size_t len, const void *d_cha
     size_t h = len / 2, round = 0;
     DevTmp tf(ctx), partial(ctx), ticket(ctx);
     SCZ_TRY(tf.alloc((h > TAIL_PAIRS ? h : len) * 32));
-    SCZ_TRY(partial.alloc((size_t)grid_for(ctx, h) * sizeof(Fr3)));
+    SCZ_TRY(partial.alloc((size_t)grid_for(ctx, h) * 6 * sizeof(Fr)));
     SCZ_TRY(ticket.alloc(4));
     SCZ_CUDA(ctx, cudaMemsetAsync(ticket.p, 0, 4, st));
     const void *fi = d_f;
     while (h > TAIL_PAIRS) {
-        k_sum_round<<<grid_for(ctx, h), PL_THREADS, 0, st>>>(fi, tf.p, (uint32_t)h, (const char *)d_challenge + round * 32,
-                                                             partial.as<Fr3>(), ticket.as<uint32_t>(),
-                                                             reinterpret_cast<Fr2 *>(d_out) + round);
+        // up to three rounds per pass while more than TAIL_PAIRS pairs remain afterwards
+        int R = 1;
+        while (R < 3 && (h >> R) > TAIL_PAIRS) R++;
+        const uint32_t w = (uint32_t)((2 * h) >> R);
+        const void *ch = (const char *)d_challenge + round * 32;
+        Fr2 *o = reinterpret_cast<Fr2 *>(d_out) + round;
+        if (R == 3) k_sum_rounds<3><<<grid_for(ctx, w), PL_THREADS, 0, st>>>(fi, tf.p, w, ch, partial.as<Fr>(), ticket.as<uint32_t>(), o);
+        else if (R == 2) k_sum_rounds<2><<<grid_for(ctx, w), PL_THREADS, 0, st>>>(fi, tf.p, w, ch, partial.as<Fr>(), ticket.as<uint32_t>(), o);
+        else k_sum_round<<<grid_for(ctx, h), PL_THREADS, 0, st>>>(fi, tf.p, (uint32_t)h, ch, partial.as<Fr3>(), ticket.as<uint32_t>(), o);
         SCZ_LAUNCH_CHECK(ctx);
         fi = tf.p;
-        h >>= 1;
-        round++;
+        h >>= R;
+        round += R;
     }
     if (fi == d_f) SCZ_CUDA(ctx, cudaMemcpyAsync(tf.p, d_f, len * 32, cudaMemcpyDeviceToDevice, st));
     k_sum_tail<<<1, PL_THREADS, 0, st>>>(tf.p, (uint32_t)h, (const char *)d_challenge + round * 32,
@@ -570,7 +618,17 @@ int32_t fr_pointwise(Ctx *c, int32_t mode, const void *d_a, const void *d_b, con
     if (mode == 0) k_pointwise<0><<<g, PL_THREADS, 0, c->stream>>>(d_a, d_b, d_k, d_out, n);
     else if (mode == 1) k_pointwise<1><<<g, PL_THREADS, 0, c->stream>>>(d_a, d_b, d_k, d_out, n);
     else if (mode == 2) k_pointwise<2><<<g, PL_THREADS, 0, c->stream>>>(d_a, d_b, d_k, d_out, n);
-    else k_div<<<ceil_div_u32(n, (size_t)PL_THREADS * INV_PER_THREAD), PL_THREADS, 0, c->stream>>>(d_a, d_b, d_out, n, c->d_status);
+    else {
+        const uint32_t grid = ceil_div_u32(n, (size_t)DIV_THREADS * DIV_PER);
+        DevTmp pre(c);
+        InvTree<FrP> tree;
+        SCZ_TRY(pre.alloc(n * sizeof(Fr)));
+        SCZ_TRY(tree.alloc(c, (uint64_t)grid * DIV_THREADS));
+        k_div_phase1<<<grid, DIV_THREADS, 0, c->stream>>>(d_b, n, pre.p, tree.values(), c->d_status);
+        SCZ_LAUNCH_CHECK(c);
+        SCZ_TRY(tree.run(c, grid * DIV_THREADS));
+        k_div_phase2<<<grid, DIV_THREADS, 0, c->stream>>>(d_a, d_b, n, pre.p, tree.inverses(), d_out);
+    }
     SCZ_LAUNCH_CHECK(c);
     return SCZ_OK;
 }
