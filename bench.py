@@ -222,7 +222,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit_line(line)
 
 
 def cpu_baseline_leg(n=14, l=1):
@@ -788,17 +788,44 @@ def run_own(args):
         hub.close()
     if world > 1:
         dist.destroy_process_group()
-    print(json.dumps(line), flush=True)
+    emit_line(line)
+
+
+class _StdoutToStderr:
+    """Everything but the final JSON line goes to stderr, C libraries included (NCCL prints its version banner to fd 1
+    when NCCL_DEBUG=VERSION): fd 1 is pointed at fd 2 for the whole run, `emit` writes to the real stdout."""
+
+    def __init__(self):
+        sys.stdout.flush()
+        self.real = os.dup(1)
+        os.dup2(2, 1)
+
+    def emit(self, text):
+        sys.stdout.flush()
+        os.write(self.real, (text + "\n").encode())
+
+
+_OUT = None
+
+
+def emit_line(line):
+    text = json.dumps(line)
+    if _OUT is not None:
+        _OUT.emit(text)
+    else:
+        print(text, flush=True)
 
 
 def main():
+    global _OUT
+    _OUT = _StdoutToStderr()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
     ap.add_argument("--logn", type=int, default=20, help="log2 of the circuit size (BASELINE: 20)")
-    ap.add_argument("--l", type=int, default=1, help="packing factor l (N = 8 l parties; BASELINE: 1).  l > 1 is SURVEY 8(f)3: "
+    ap.add_argument("--pack", dest="l", type=int, default=1, help="packing factor l (N = 8 l parties; BASELINE: 1).  l > 1 is SURVEY 8(f)3: "
                                                      "every party holds 1 / l of each table, 8 l / gpus parties share a GPU")
     ap.add_argument("--ref-logn", type=int, default=0, help="--impl reference: circuit size of the CPU run (0 = --logn: "
                                                             "the same config as the own arm, about a minute per proof)")
