@@ -32,7 +32,10 @@
 namespace scz {
 
 constexpr int BA_THREADS = 128;
-constexpr int BA_B = 8;          // pairs per thread in phase 1 / 2 (strided by the CTA: coalesced across lanes)
+#ifndef BA_B_PAIRS
+#define BA_B_PAIRS 32   // measured per 2^20 proof: 8 -> 122.2, 16 -> 120.5, 32 -> 119.7 ms of accumulation (the product tree shrinks)
+#endif
+constexpr int BA_B = BA_B_PAIRS;   // pairs per thread in phase 1 / 2 (strided by the CTA: coalesced across lanes)
 constexpr int BA_MAX_LEVELS = 8;
 constexpr int BA_ACC_THREADS = 128;
 
@@ -44,12 +47,14 @@ struct BaLevels {
 struct SegCursor {
     uint32_t lo = 1, hi = 0;
     const void *bases = nullptr;
+    bool wide = false;   // the segment's bases are a fixed-base table: 128 B records (g1.cuh)
     __device__ __forceinline__ const void *get(const MsmSeg *segs, int nseg, uint32_t key) {
         if (key < lo || key >= hi) {
             int s = nseg == 1 ? 0 : seg_by_bucket(segs, nseg, key);
             lo = __ldg(&segs[s].bucket_base);
             hi = lo + __ldg(&segs[s].W) * __ldg(&segs[s].nb);
             bases = segs[s].bases;
+            wide = __ldg(&segs[s].pre) != 0;
         }
         return bases;
     }
@@ -82,7 +87,8 @@ __device__ __forceinline__ G1Affine ba_point(const MsmSeg *segs, int nseg, SegCu
                                              uint32_t slab_base, uint32_t k, uint32_t rel, const void *Rk) {
     if (L0) {
         uint2 e = __ldg(sorted + (size_t)slab_base + rel);
-        G1Affine p = g1a_load_stream(sc.get(segs, nseg, e.y), e.x & 0x7fffffffu);
+        const void *bases = sc.get(segs, nseg, e.y);
+        G1Affine p = g1a_gather(bases, e.x & 0x7fffffffu, sc.wide);
         if (e.x >> 31) p.y = fp_neg(p.y);
         return p;
     }
@@ -97,7 +103,8 @@ __device__ __forceinline__ Fq ba_point_x(const MsmSeg *segs, int nseg, SegCursor
                                          uint32_t k, uint32_t rel, const void *Rk) {
     if (L0) {
         uint2 e = __ldg(sorted + (size_t)slab_base + rel);
-        const char *b = reinterpret_cast<const char *>(sc.get(segs, nseg, e.y)) + (size_t)(e.x & 0x7fffffffu) * 96;
+        const char *b = reinterpret_cast<const char *>(sc.get(segs, nseg, e.y));
+        b += (size_t)(e.x & 0x7fffffffu) * (sc.wide ? G1A_WIDE : (size_t)96);
         Fq x;
         const uint4 *q = reinterpret_cast<const uint4 *>(b);
 #pragma unroll
@@ -196,7 +203,7 @@ __device__ __forceinline__ void ba_phase2_cta(const MsmSeg *segs, int nseg, cons
             ba_add_slow(P, Q, dinv, r);
         } else {
             Fq lam = fp_mul(fp_sub(Q.y, P.y), dinv);
-            r.x = fp_sub(fp_sub(fp_sqr(lam), P.x), Q.x);
+            r.x = fp_sub(fp_sub(fp_sqr(lam), P.x), Q.x);   // (a dedicated squaring, fq_sqr_sos, measured slower: +1.5 ms per proof)
             r.y = fp_sub(fp_mul(lam, fp_sub(P.x, r.x)), P.y);
         }
         if (j) I = fp_mul(I, d);                                                // 1 / (d_0 ... d_{j-1})
@@ -208,7 +215,10 @@ __global__ void __launch_bounds__(BA_THREADS) k_ba_phase1(const MsmSeg *segs, in
     if (it.k == 0) ba_phase1_cta<true>(segs, nseg, sorted, it, blockIdx.x);
     else ba_phase1_cta<false>(segs, nseg, sorted, it, blockIdx.x);
 }
-__global__ void __launch_bounds__(BA_THREADS) k_ba_phase2(const MsmSeg *segs, int nseg, const uint2 *sorted, BaItem it) {
+#ifndef BA_P2_MIN_BLOCKS
+#define BA_P2_MIN_BLOCKS 1
+#endif
+__global__ void __launch_bounds__(BA_THREADS, BA_P2_MIN_BLOCKS) k_ba_phase2(const MsmSeg *segs, int nseg, const uint2 *sorted, BaItem it) {
     if (it.k == 0) ba_phase2_cta<true>(segs, nseg, sorted, it, blockIdx.x);
     else ba_phase2_cta<false>(segs, nseg, sorted, it, blockIdx.x);
 }
@@ -267,7 +277,8 @@ __global__ void __launch_bounds__(BA_ACC_THREADS, BA_ACC_MIN_BLOCKS) k_ba_accumu
                 cur = e.y;
             }
             if (m == 0) {
-                p = g1a_load_stream(sc.get(segs, nseg, e.y), e.x & 0x7fffffffu);
+                const void *bases = sc.get(segs, nseg, e.y);
+                p = g1a_gather(bases, e.x & 0x7fffffffu, sc.wide);
                 if (e.x >> 31) p.y = fp_neg(p.y);
             } else {
                 const char *b = reinterpret_cast<const char *>(L.R[m]) + (size_t)((i - slab_base) >> m) * 96;
