@@ -228,7 +228,6 @@ __global__ void __launch_bounds__(ACC_THREADS, ACC_MIN_BLOCKS) k_msm_accumulate(
     // segment of the current run (bases pointer); re-resolved when the bucket id leaves its range
     uint32_t seg_hi = 0;
     const void *bases = nullptr;
-    bool wide = false;   // fixed-base tables hold 128 B records (g1.cuh)
     uint32_t cur = k_first;
     bool first_run = true;
     G1X acc = G1X::inf();
@@ -236,13 +235,12 @@ __global__ void __launch_bounds__(ACC_THREADS, ACC_MIN_BLOCKS) k_msm_accumulate(
         int s = K == 1 ? 0 : seg_by_bucket(segs, K, cur);
         seg_hi = segs[s].bucket_base + segs[s].W * segs[s].nb;
         bases = segs[s].bases;
-        wide = segs[s].pre != 0;
     }
     // Software pipeline, two entries deep: while entry j is added, the POINT of entry j+1 is gathered (its index
     // arrived one iteration ago, so the gather issues at once) and the ENTRY j+2 is fetched.  Nothing on the
     // index -> address -> point chain is ever waited for at the top of an iteration.
     uint32_t ent = e_first.x;
-    G1Affine p = g1a_gather(bases, ent & 0x7fffffffu, wide);
+    G1Affine p = g1a_load_stream(bases, ent & 0x7fffffffu);
     uint2 ne = lo + 1 < hi ? __ldg(sorted + lo + 1) : make_uint2(0, cur);
     for (uint32_t j = lo; j < hi; j++) {
         const bool more = j + 1 < hi;
@@ -255,9 +253,8 @@ __global__ void __launch_bounds__(ACC_THREADS, ACC_MIN_BLOCKS) k_msm_accumulate(
                 int s = seg_by_bucket(segs, K, nkey);
                 seg_hi = segs[s].bucket_base + segs[s].W * segs[s].nb;
                 bases = segs[s].bases;
-                wide = segs[s].pre != 0;
             }
-            np = g1a_gather(bases, nent & 0x7fffffffu, wide);
+            np = g1a_load_stream(bases, nent & 0x7fffffffu);
         }
         g1x_add_affine(acc, p, (ent >> 31) != 0);   // fully inlined: out-of-line products cost 60 % here (measured)
         if (!more || nkey != cur) {   // the run of bucket `cur` ends here

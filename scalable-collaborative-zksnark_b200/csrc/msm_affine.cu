@@ -47,14 +47,12 @@ struct BaLevels {
 struct SegCursor {
     uint32_t lo = 1, hi = 0;
     const void *bases = nullptr;
-    bool wide = false;   // the segment's bases are a fixed-base table: 128 B records (g1.cuh)
     __device__ __forceinline__ const void *get(const MsmSeg *segs, int nseg, uint32_t key) {
         if (key < lo || key >= hi) {
             int s = nseg == 1 ? 0 : seg_by_bucket(segs, nseg, key);
             lo = __ldg(&segs[s].bucket_base);
             hi = lo + __ldg(&segs[s].W) * __ldg(&segs[s].nb);
             bases = segs[s].bases;
-            wide = __ldg(&segs[s].pre) != 0;
         }
         return bases;
     }
@@ -87,8 +85,7 @@ __device__ __forceinline__ G1Affine ba_point(const MsmSeg *segs, int nseg, SegCu
                                              uint32_t slab_base, uint32_t k, uint32_t rel, const void *Rk) {
     if (L0) {
         uint2 e = __ldg(sorted + (size_t)slab_base + rel);
-        const void *bases = sc.get(segs, nseg, e.y);
-        G1Affine p = g1a_gather(bases, e.x & 0x7fffffffu, sc.wide);
+        G1Affine p = g1a_load_stream(sc.get(segs, nseg, e.y), e.x & 0x7fffffffu);
         if (e.x >> 31) p.y = fp_neg(p.y);
         return p;
     }
@@ -103,8 +100,7 @@ __device__ __forceinline__ Fq ba_point_x(const MsmSeg *segs, int nseg, SegCursor
                                          uint32_t k, uint32_t rel, const void *Rk) {
     if (L0) {
         uint2 e = __ldg(sorted + (size_t)slab_base + rel);
-        const char *b = reinterpret_cast<const char *>(sc.get(segs, nseg, e.y));
-        b += (size_t)(e.x & 0x7fffffffu) * (sc.wide ? G1A_WIDE : (size_t)96);
+        const char *b = reinterpret_cast<const char *>(sc.get(segs, nseg, e.y)) + (size_t)(e.x & 0x7fffffffu) * 96;
         Fq x;
         const uint4 *q = reinterpret_cast<const uint4 *>(b);
 #pragma unroll
@@ -277,8 +273,7 @@ __global__ void __launch_bounds__(BA_ACC_THREADS, BA_ACC_MIN_BLOCKS) k_ba_accumu
                 cur = e.y;
             }
             if (m == 0) {
-                const void *bases = sc.get(segs, nseg, e.y);
-                p = g1a_gather(bases, e.x & 0x7fffffffu, sc.wide);
+                p = g1a_load_stream(sc.get(segs, nseg, e.y), e.x & 0x7fffffffu);
                 if (e.x >> 31) p.y = fp_neg(p.y);
             } else {
                 const char *b = reinterpret_cast<const char *>(L.R[m]) + (size_t)((i - slab_base) >> m) * 96;
