@@ -21,6 +21,8 @@
 // keeps the contract of k_msm_accumulate (whole buckets -> buckets[], pieces -> parts[], fixed up by k_msm_fixup*).
 // Every exceptional case (identity operands, P + P, P + (-P)) is handled by g1a_batch_denominator's case analysis.
 // The stream is processed in slabs so that the level arrays (96 B per entry) stay inside a memory budget.
+#include <stdlib.h>
+
 #include <algorithm>
 #include <memory>
 #include <vector>
@@ -207,6 +209,9 @@ __device__ __forceinline__ void ba_phase2_cta(const MsmSeg *segs, int nseg, cons
     }
 }
 
+// (measured, not kept: level-0 phase 2 with its two gathered operands staged per thread in shared memory by cp.async,
+// two pairs deep, four CTAs per SM -- 121.0 instead of 119.5 ms of accumulation per 2^20 proof.  The level-0 kernels are
+// bound by the DRAM rate of random 96 B gathers (ncu: 2.6 - 3.9 TB/s of 128 B line fills), not by exposed latency.)
 __global__ void __launch_bounds__(BA_THREADS) k_ba_phase1(const MsmSeg *segs, int nseg, const uint2 *sorted, BaItem it) {
     if (it.k == 0) ba_phase1_cta<true>(segs, nseg, sorted, it, blockIdx.x);
     else ba_phase1_cta<false>(segs, nseg, sorted, it, blockIdx.x);
@@ -218,6 +223,9 @@ __global__ void __launch_bounds__(BA_THREADS, BA_P2_MIN_BLOCKS) k_ba_phase2(cons
     if (it.k == 0) ba_phase2_cta<true>(segs, nseg, sorted, it, blockIdx.x);
     else ba_phase2_cta<false>(segs, nseg, sorted, it, blockIdx.x);
 }
+// (measured, not kept: phase 2 of one slab half and phase 1 of the other in ONE grid with the two kinds of CTA interleaved,
+// so that the memory-bound and the pipe-bound phase share every SM: 134 instead of 127 ms -- phase 2 needs its occupancy)
+
 // ---- the XYZZ pass over what the affine levels left: same chunks, same outputs as k_msm_accumulate, but the walk
 //      steps from one maximal pure block to the next (lvl[] gives its size, R[m] its sum) instead of entry by entry.
 //      The loop is split: a light phase in which every lane walks on its own (run boundaries, first blocks of a run,
