@@ -502,10 +502,15 @@ def run_own(args):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
+    marks = []
     for _ in range(args.steps):
         proofs = prove_all()
+        m = torch.cuda.Event(enable_timing=True)
+        m.record()                      # an event per step: no synchronisation, the steps stay back to back
+        marks.append(m)
     e1.record()
     barrier()
+    step_ms = [round((marks[i - 1] if i else e0).elapsed_time(marks[i]), 2) for i in range(len(marks))]
     if sampler:
         sampler.mark_end()
     ms = e0.elapsed_time(e1)
@@ -694,9 +699,13 @@ def run_own(args):
     pairs = stats1["pairs"] - stats0["pairs"]
     msm_ms = sum(prof[k][0] for k in ("msm_sort", "msm_accumulate", "msm_fixup", "msm_reduce", "msm_finish"))
     achieved = adds * ALG_BYTES_PER_ADD / (acc_ms * 1e-3) / 1e9 if acc_ms > 0 else 0.0
+    affine_ran = ctx0.msm_affine_sequences() > 0
+    acc_kernel = ("bucket accumulation: k_ba_levels / k_ba_phase1 / k_inv_tree_* / k_ba_phase2 / k_ba_accumulate (csrc/msm_affine.cu)"
+                  if affine_ran else "k_msm_accumulate")
     traffic = None
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))["k_msm_accumulate"]
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))[
+            "msm_accumulate_affine" if affine_ran else "k_msm_accumulate"]
     except Exception:
         pass
     line = {
@@ -712,6 +721,7 @@ def run_own(args):
                             "the party-summed work rate is value_party_aggregate",
             "value_party_aggregate": parties_total * value,
             "proofs_per_s": args.steps / (ms * 1e-3),
+            "ms_each_step_rank0": step_ms,
             "srs_fixed_base_tables": (not args.no_precompute) and "window multiples of every SRS level beside the points "
                                      "(csrc/srs.cu), 12.4 GB per party, built at set-up like the SRS itself",
             "value_plain_srs": (1 << n) / (plain_ms * 1e-3) if plain_ms else None,
@@ -749,27 +759,36 @@ def run_own(args):
                   "note": "bucket additions of the proof's MSMs (party 0) over the device time of the MSM kernels / of "
                           "k_msm_accumulate alone, inside the timed region"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": (traffic or {}).get("dram_bytes"), "kernel": "k_msm_accumulate", "peak_source": peak_src,
+                     "traffic": (traffic or {}).get("dram_bytes"), "kernel": acc_kernel, "peak_source": peak_src,
                      "launch_ms": acc_ms / args.steps, "launches": acc_n,
                      "units_per_launch": adds / args.steps, "alg_bytes_per_unit": ALG_BYTES_PER_ADD,
-                     "launch_note": "per proof: the accumulate launch of the big MSM sequence; the proof's second sequence "
-                                    "(192 root-opening MSMs of 8 points, < 0.05 ms) is folded into the same figures",
+                     "launch_note": "per proof: the bucket accumulation of the proof's MSM sequences (event brackets around the whole "
+                                    "accumulation stage of every sequence: with the batched-affine path that is k_ba_levels, 4 x "
+                                    "(k_ba_phase1, k_inv_tree_*, k_ba_phase2) and k_ba_accumulate); the sequence of 192 root-opening MSMs "
+                                    "of 8 points (< 0.05 ms) is folded into the same figures",
                      "traffic_note": (traffic or {}).get("source"),
-                     "note": "the bucket kernel is bound by the INT32 multiply pipe, not HBM: 2736 IMAD.WIDE per "
-                             "mixed add vs ~100 B of traffic; ncu shows sm__pipe_fmaheavy_cycles_active 86 % "
-                             "(profiles/), see roofline_int_pipe and DESIGN.md 3.1"},
+                     "note": "achieved = ALGORITHMIC bytes (100 B per bucket addition, SURVEY 8d) / time, as the contract defines it.  The "
+                             "accumulation is not one HBM-bound kernel: its upper levels and the XYZZ leftovers are bound by the INT32 multiply "
+                             "pipe (ncu: 89 % / 64 %), its level 0 by the DRAM rate of random 96 B gathers (2.6 - 3.9 TB/s of line fills, "
+                             "40 - 60 % of the HBM peak); the measured DRAM traffic (`traffic`) is ~7x the algorithmic figure because the "
+                             "batched-affine levels trade multiplies for bytes (profiles/r2_ncu_ba_*.txt, DESIGN.md 3.1)"},
     }
-    # the roof that actually binds the bucket kernel: IMAD.WIDE issues once per 4 cycles per SM sub-partition
-    # (32 lanes / clk / SM); a mixed addition is 2736 of them (6 products + 2 squarings of 288, one dot2 of 432)
+    # the other roof of the accumulation: IMAD.WIDE issues once per 4 cycles per SM sub-partition (32 lanes / clk / SM).  An
+    # XYZZ mixed addition is 2736 of them (9.5 products of 288); with the batched-affine levels a bucket addition costs
+    # 0.88 x 6.1 products (affine, shared inversion) + 0.10 x 9.5 products (XYZZ leftovers) = 1823 on average (4 levels,
+    # runs of ~58 entries; 1 / 58 of the entries start a bucket and cost nothing)
     sms = torch.cuda.get_device_properties(dev).multi_processor_count
     mhz = (clocks or {}).get("sm_mhz") or 1965
     imad_peak = sms * 32 * mhz * 1e6
-    imad_rate = adds * 2736 / (acc_ms * 1e-3) if acc_ms > 0 else 0.0
-    line["roofline_int_pipe"] = {"kernel": "k_msm_accumulate", "bound": "INT32 multiply pipe (IMAD.WIDE)",
+    per_unit = 1823 if affine_ran else 2736
+    imad_rate = adds * per_unit / (acc_ms * 1e-3) if acc_ms > 0 else 0.0
+    line["roofline_int_pipe"] = {"kernel": acc_kernel, "bound": "INT32 multiply pipe (IMAD.WIDE)",
                                  "achieved": imad_rate / 1e12, "peak": imad_peak / 1e12, "unit": "T wide multiplies/s",
-                                 "frac": imad_rate / imad_peak, "per_unit": 2736,
+                                 "frac": imad_rate / imad_peak, "per_unit": per_unit,
+                                 "per_unit_note": "estimated mix for the batched-affine path (see comment in bench.py); 2736 = one XYZZ "
+                                                  "mixed addition when the affine levels are off (SCZ_MSM_AFFINE=0)",
                                  "peak_source": f"{sms} SMs x 32 lanes/clk x {mhz} MHz (issue rate measured with ncu: "
-                                                "sm__pipe_fmaheavy_cycles_active 86 % at this throughput, profiles/)"}
+                                                "sm__pipe_fmaheavy_cycles_active 86 % for the XYZZ kernel at 2.85 G adds/s, profiles/)"}
     if standalone:
         line.update(standalone)
         if not args.no_cpu and world in (1, 8):

@@ -102,9 +102,9 @@ uint64_t scz_ctx_launch_count(const scz_ctx *ctx);
  * mpc-net/src/utils/timer.rs:25-197, are the host-side analogue).  scz_prof_read synchronises the stream
  * and returns the summed device time and the number of brackets of that class since scz_prof_enable. */
 #define SCZ_K_MSM_SORT 0        /* digit recode, histogram, scan, scatter */
-#define SCZ_K_MSM_ACCUMULATE 1  /* Pippenger bucket accumulation (the dominant kernel) */
+#define SCZ_K_MSM_ACCUMULATE 1  /* Pippenger bucket accumulation (the dominant stage): batched-affine levels + XYZZ, or XYZZ alone */
 #define SCZ_K_MSM_FIXUP 2       /* buckets cut by chunk boundaries */
-#define SCZ_K_MSM_REDUCE 3      /* bucket reduction: chunks + bit planes */
+#define SCZ_K_MSM_REDUCE 3      /* bucket reduction: fan-in-8 tree (k_msm_tree) */
 #define SCZ_K_MSM_FINISH 4      /* window recombination, Horner chain */
 #define SCZ_K_PSS 5             /* PSS maps of the leader closures */
 #define SCZ_K_SUMCHECK 6        /* fused fold + product-sum rounds */
@@ -218,7 +218,8 @@ int32_t scz_fix_variable_dev(scz_ctx *ctx, const void *d_evals, size_t len, cons
 /* acc_product's table (dacc_product.rs:30-39 = :374-381): d_tree has 2m entries: x | products level by level | 0 */
 int32_t scz_acc_product_dev(scz_ctx *ctx, const void *d_x, size_t m, void *d_tree);
 /* point-wise maps of dhyperplonk.rs:233-238, 251-256, 326-339.  mode 0: a + b; 1: b - a; 2: a + k[0]*b + k[1]
- * (d_k: two Fr on the device); 3: a / b with one shared inversion per warp (b = 0 -> 0; arkworks would panic) */
+ * (d_k: two Fr on the device); 3: a / b with ONE shared inversion per call (b = 0 -> 0 and SCZ_STATUS_DIV_BY_ZERO is raised:
+ * arkworks panics there) */
 int32_t scz_fr_pointwise_dev(scz_ctx *ctx, int32_t mode, const void *d_a, const void *d_b, const void *d_k, void *d_out,
                              size_t n);
 /* even[i] = in[2i], odd[i] = in[2i+1]: v(x,0) and v(x,1) of the product tree (dhyperplonk.rs:349-359) */

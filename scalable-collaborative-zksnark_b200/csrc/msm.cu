@@ -13,23 +13,21 @@
 //   3 scatter    digits recomputed; (bucket id, point index | sign) written to the bucket's
 //                slot: a counting sort whose within-bucket order is irrelevant because
 //                group addition commutes (the result is bit-exact regardless)
-//   4 accumulate the sorted entry stream is cut into equal chunks of T entries, one
-//                thread per chunk: perfectly balanced whatever the digit distribution
-//                (the all-ones scalars of dmsm.rs:103 included).  A thread mixed-adds
-//                (XYZZ += affine, 96 B gathered per entry with 128-bit loads, next point
-//                prefetched during the current add) run by run; runs that are whole
-//                buckets go straight to the bucket array, the first / last run of a
-//                chunk may be a piece of a bucket shared with the neighbours
+//   4 accumulate the sorted entry stream is cut into equal chunks of T entries, one thread per chunk: perfectly
+//                balanced whatever the digit distribution (the all-ones scalars of dmsm.rs:103 included).  Big streams
+//                with long bucket runs take the batched-affine path (msm_affine.cu: affine additions with one shared
+//                inversion per tree level inside the aligned single-bucket blocks of the stream, XYZZ mixed additions
+//                for what is left); small ones the plain XYZZ kernel below (XYZZ += affine per entry, 96 B gathered
+//                with 128-bit loads, next point prefetched during the current add).  Either way runs that are whole
+//                buckets go straight to the bucket array, the first / last run of a chunk may be a piece of a bucket
+//                shared with the neighbours
 //   5 fix-up     pieces of buckets that straddle chunk boundaries are summed
-//   6 chunks     bucket reduction, level 1: one thread per L = 8 consecutive buckets:
-//                S_q = sum B, R_q = sum j*B_j (running sums)
-//   7 planes     level 2: sum_k k*B_k = sum_q R_q + L*sum_q q*S_q + sum_q S_q with
-//                sum_q q*S_q = sum_b 2^b * (sum of S_q over q with bit b set): one CTA per
-//                (window, bit plane), plain tree sums, no doublings
-//   8 finish     per segment: windows recombine their planes in parallel, then one
-//                Horner chain over the windows, XYZZ -> Jacobian
-// The accumulate kernel is bound by the integer multiply pipe (a mixed add is ~2.9k
-// IMAD.WIDE for ~104 B of HBM traffic), see DESIGN.md.
+//   6 tree       bucket reduction sum_j (j + 1) B_j per window as a tree of fan-in 8: a node keeps S = sum B and
+//                T = sum (j - base) B; two general additions per bucket at level 0, three per node above
+//   7 finish     per segment: one Horner chain over the window sums (groups of 4 cooperating lanes), XYZZ -> Jacobian;
+//                with a fixed-base table there is ONE window sum and no chain
+// The XYZZ kernel is bound by the integer multiply pipe (a mixed add is 2 736 IMAD.WIDE for ~104 B of HBM traffic), the
+// affine levels by the same pipe (upper levels) and by the DRAM rate of random gathers (level 0), see DESIGN.md 3.1.
 #include <algorithm>
 #include <cstdlib>
 #include <vector>

@@ -6,7 +6,7 @@
 #include <cstring>
 #include "../../scalable-collaborative-zksnark_b200/csrc/field.cuh"
 #include "../../scalable-collaborative-zksnark_b200/csrc/g1.cuh"
-#include "../../scalable-collaborative-zksnark_b200/csrc/fq_f64.cuh"
+#include "../../tools/ubench/fq_f64.cuh"
 #include "../../scalable-collaborative-zksnark_b200/csrc/g1_batch_affine.cuh"
 #include <vector>
 #include "../../scalable-collaborative-zksnark_b200/csrc/msm_digits.cuh"

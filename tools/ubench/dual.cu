@@ -5,7 +5,7 @@
 #include <cstdlib>
 #include <cuda_runtime.h>
 #include "../../scalable-collaborative-zksnark_b200/csrc/field.cuh"
-#include "../../scalable-collaborative-zksnark_b200/csrc/fq_f64.cuh"
+#include "fq_f64.cuh"
 using namespace scz;
 
 // MODE 0: I only, 1: F only, 2: I then F (source order), 3: dual (interleaved rows), 4: two I, 5: two F

@@ -15,7 +15,7 @@
 #pragma once
 #include <math.h>
 
-#include "field.cuh"
+#include "../../scalable-collaborative-zksnark_b200/csrc/field.cuh"
 
 namespace scz {
 namespace f64 {

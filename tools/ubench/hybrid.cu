@@ -1,5 +1,5 @@
 // dev micro-benchmark: the bucket kernel's inner loop (XYZZ += affine, gathered points) with some of the Fq products
-// of the mixed add moved to the FP64 pipe (csrc/fq_f64.cuh).  Prints G1 mixed adds/s per policy and checks that every
+// of the mixed add moved to the FP64 pipe (tools/ubench/fq_f64.cuh).  Prints G1 mixed adds/s per policy and checks that every
 // policy produces the same points.
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -Xptxas -v -o hybrid hybrid.cu
 #include <cstdio>
@@ -7,7 +7,7 @@
 #include <vector>
 #include <cuda_runtime.h>
 #include "../../scalable-collaborative-zksnark_b200/csrc/g1.cuh"
-#include "../../scalable-collaborative-zksnark_b200/csrc/fq_f64.cuh"
+#include "fq_f64.cuh"
 using namespace scz;
 
 // MASK bit k: product k runs on the FP64 pipe.  0 u2, 1 s2, 2 pp, 3 ppp, 4 q, 5 rr, 6 zz', 7 zzz'
