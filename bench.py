@@ -486,12 +486,16 @@ def run_own(args):
             dist.barrier()
             torch.cuda.synchronize()
 
+    # the per-class event brackets are on during the warm-up too: the first profiled proof creates ~2 600 CUDA events
+    # (0.4 s measured inside the first timed step when they were only switched on after the warm-up)
+    for ctx, _, _ in parties:
+        ctx.prof_enable(True)
     for _ in range(args.warmup):
         prove_all()
     barrier()
     ctx0 = parties[0][0]
     for ctx, _, _ in parties:
-        ctx.prof_enable(True)
+        ctx.prof_enable(True)          # clears the warm-up's records, keeps the event pool
     launches0 = sum(c.launches for c, _, _ in parties)
     coll0 = dict(hub.calls) if hub else {}
     stats0 = ctx0.msm_cum_stats()
@@ -602,6 +606,28 @@ def run_own(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t[0])
     e2e_value = (1 << n) * e2e_steps / e2e_s
+
+    # one proof with nothing overlapped: host tables -> HBM, prove, proof -> host, strictly one after the other (the latency of
+    # a single request with the proving key resident; `e2e.value` above is the steady state of a stream of requests)
+    def single(p):
+        ctx, pp, pk = parties[p]
+        t0 = time.perf_counter()
+        pk.upload(host_tabs[p])
+        torch.cuda.current_stream().synchronize()
+        proof = scz.dhyperplonk(ctx, n, pk, pp)
+        proof.to_host()
+        return time.perf_counter() - t0
+
+    def single_all():
+        if P == 1:
+            return [single(0)]
+        return hub.run_parties(lambda pid, p, net: single(p))
+    barrier()
+    single_s = max(max(single_all()) for _ in range(3))
+    if world > 1:
+        t = torch.tensor([single_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        single_s = float(t[0])
     comm = ((comm1[0] - comm0[0]) // args.steps, (comm1[1] - comm0[1]) // args.steps)
 
     # ---- BASELINE configs 3 and 4 as stand-alone calls on the same net (every N); config 2 at N = 1 below
@@ -749,6 +775,7 @@ def run_own(args):
         "pipelined": pipelined,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d * parties_total,
                 "d2h_bytes_per_step": d2h * parties_total, "steps": e2e_steps, "ms_per_step": e2e_s / e2e_steps * 1e3,
+                "single_proof_ms_no_overlap": single_s * 1e3,
                 "api": "PackedProvingParameters.upload (pinned host tables -> HBM, on a copy stream, double-buffered so that the "
                        "copy of proof i+1 overlaps proof i) + scz_dhyperplonk_dev + proof -> host"},
         "gpu_launches": launches,

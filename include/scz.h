@@ -50,6 +50,8 @@ extern "C" {
 #define SCZ_G1_AFFINE_BYTES 96
 #define SCZ_G1_JAC_BYTES 144
 #define SCZ_TRIPLE_BYTES 96
+#define SCZ_G2_AFFINE_BYTES 192 /* x | y, each Fq2 = c0 | c1 (ark-ff Fp2); the identity is all zero */
+#define SCZ_G2_JAC_BYTES 288    /* X | Y | Z = ark-ec Projective<g2::Config> */
 
 typedef struct scz_ctx scz_ctx;
 typedef struct scz_pp scz_pp;   /* PackedSharingParams<Fr>, secret-sharing/src/pss.rs:17-33 */
@@ -276,6 +278,19 @@ int32_t scz_d_msm_leader_dev(scz_ctx *ctx, const scz_pp *pp, const void *d_gathe
                              void *d_to_scatter);
 int32_t scz_d_msm(scz_ctx *ctx, const scz_pp *pp, const void *const *bases, const size_t *bases_lens,
                   const void *const *scalars, const size_t *scalars_lens, size_t batch, void *out_jac);
+
+/* ---- the same over G2 (`d_msm` is generic over `G: CurveGroup`, dmsm.rs:9-15; BASELINE names "d_msm over G1/G2"; the
+ * reference itself only ever instantiates G1).  Affine bases 192 B, results Jacobian 288 B (SCZ_G2_*).  Same semantics as the
+ * G1 entry points; a plain, untuned Pippenger that shares the G1 path's digit recoding and counting sort (csrc/msm_g2.cu). */
+int32_t scz_msm_g2_batched_dev(scz_ctx *ctx, const void *const *d_bases, const void *const *d_scalars, const size_t *lens,
+                               size_t batch, void *d_out_jac);
+int32_t scz_msm_g2(scz_ctx *ctx, const void *bases, const uint8_t *inf_mask, size_t bases_len, const void *scalars,
+                   size_t scalars_len, void *out_jac);
+int32_t scz_d_msm_g2_dev(scz_ctx *ctx, const scz_pp *pp, const void *const *d_bases, const void *const *d_scalars,
+                         const size_t *lens, size_t batch, void *d_out_jac);
+int32_t scz_d_msm_g2_leader_dev(scz_ctx *ctx, const scz_pp *pp, const void *d_gathered, size_t batch, void *d_to_scatter);
+/* unit operations on Jacobian G2 points for the parity tests: op 0 out = a + b, 1 out = 2 a, 2 out = k * a (d_b: Fr) */
+int32_t scz_g2_vec_op_dev(scz_ctx *ctx, int32_t op, const void *d_a_jac, const void *d_b, void *d_out_jac, size_t n);
 
 /* ---- re-sharing rounds -------------------------------------------------------------------------------- */
 /* pss2ss (unpack.rs:72-97): one share in, Vec<F> of length l out (gather, leader unpack + pack_single, scatter) */

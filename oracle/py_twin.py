@@ -240,3 +240,54 @@ def g1_deserialize_compressed(b):
     if acc is not INF:
         return None, 2
     return (x, y), 0
+
+
+# ---------------------------------------------------------------- G2 (for d_msm over G2; Fq2 = Fq[u] / (u^2 + 1))
+# public constants of BLS12-381: the G2 generator, curve y^2 = x^3 + 4 (1 + u)
+G2_X = (0x024aa2b2f08f0a91260805272dc51051c6e47ad4fa403b02b4510b647ae3d1770bac0326a805bbefd48056c8c121bdb8,
+        0x13e02b6052719f607dacd3a088274f65596bd0d09920b61ab5da61bbdc7f5049334cf11213945d57e5ac7d055d042b7e)
+G2_Y = (0x0ce5d527727d6e118cc9cdc6da2e351aadfd9baa8cbdd3a76d429a695160d12c923ac9cc3baca289e193548608b82801,
+        0x0606c4a02ea734cc32acd2b02bc28b99cb3e287e85a763af267492ab572e99ab3f370d275cec1da1aaa9075ff05f79be)
+G2_B = (4, 4)
+
+
+def f2_add(a, b): return ((a[0] + b[0]) % P_MOD, (a[1] + b[1]) % P_MOD)
+def f2_sub(a, b): return ((a[0] - b[0]) % P_MOD, (a[1] - b[1]) % P_MOD)
+def f2_mul(a, b): return ((a[0] * b[0] - a[1] * b[1]) % P_MOD, (a[0] * b[1] + a[1] * b[0]) % P_MOD)
+
+
+def f2_inv(a):
+    n = pow((a[0] * a[0] + a[1] * a[1]) % P_MOD, P_MOD - 2, P_MOD)
+    return (a[0] * n % P_MOD, -a[1] * n % P_MOD)
+
+
+def g2_on_curve(p):
+    if p is None:
+        return True
+    x, y = p
+    return f2_mul(y, y) == f2_add(f2_mul(f2_mul(x, x), x), G2_B)
+
+
+def g2_add(p, q):
+    """affine addition over Fq2; None is the identity"""
+    if p is None:
+        return q
+    if q is None:
+        return p
+    if p[0] == q[0]:
+        if f2_add(p[1], q[1]) == (0, 0):
+            return None
+        lam = f2_mul(f2_mul((3, 0), f2_mul(p[0], p[0])), f2_inv(f2_add(p[1], p[1])))
+    else:
+        lam = f2_mul(f2_sub(q[1], p[1]), f2_inv(f2_sub(q[0], p[0])))
+    x3 = f2_sub(f2_sub(f2_mul(lam, lam), p[0]), q[0])
+    return (x3, f2_sub(f2_mul(lam, f2_sub(p[0], x3)), p[1]))
+
+
+def g2_mul(p, k):
+    acc = None
+    for bit in bin(k % R_MOD)[2:] if k % R_MOD else "":
+        acc = g2_add(acc, acc)
+        if bit == "1":
+            acc = g2_add(acc, p)
+    return acc

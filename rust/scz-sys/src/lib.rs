@@ -21,6 +21,8 @@ pub const SCZ_FR_BYTES: usize = 32;
 pub const SCZ_G1_AFFINE_BYTES: usize = 96;
 pub const SCZ_G1_JAC_BYTES: usize = 144;
 pub const SCZ_TRIPLE_BYTES: usize = 96;
+pub const SCZ_G2_AFFINE_BYTES: usize = 192; // x | y, each Fq2 = c0 | c1
+pub const SCZ_G2_JAC_BYTES: usize = 288; // X | Y | Z = Projective<g2::Config>
 pub const SCZ_NCCL_UID_BYTES: usize = 128;
 pub const SCZ_STATUS_DIV_BY_ZERO: u32 = 1;
 

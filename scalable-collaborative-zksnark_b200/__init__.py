@@ -38,6 +38,13 @@ from .api import (  # noqa: F401
     local_hyperplonk,
     c_acc_product_and_share,
     hp_table_sizes,
+    msm_g2,
+    msm_g2_batched,
+    d_msm_g2,
+    d_msm_g2_leader,
+    g2_op,
+    g2_affine_to_jac,
+    G2_GENERATOR_AFFINE,
 )
 from .delegator import Delegator, read_vec_fr  # noqa: F401
 from .mpcnet import MPCNetError, MultiplexedStreamID, TorchDistMPCNet  # noqa: F401

@@ -260,6 +260,93 @@ class Context:
         return {"bucket_adds": a.value, "pairs": p.value, "sequences": q.value, "segments": g.value}
 
 
+# ---------------------------------------------------------------------------- G2 (d_msm is generic over CurveGroup, dmsm.rs:9-15)
+G2_AFF_LIMBS, G2_JAC_LIMBS = 24, 36
+# the BLS12-381 G2 generator, affine x | y with Fq2 = c0 | c1, Montgomery limbs (public constant)
+G2_GENERATOR_AFFINE = np.array([[
+    0xf5f28fa202940a10, 0xb3f5fb2687b4961a, 0xa1a893b53e2ae580, 0x9894999d1a3caee9, 0x6f67b7631863366b, 0x058191924350bcd7,
+    0xa5a9c0759e23f606, 0xaaa0c59dbccd60c3, 0x3bb17e18e2867806, 0x1b1ab6cc8541b367, 0xc2b6ed0ef2158547, 0x11922a097360edf3,
+    0x4c730af860494c4a, 0x597cfa1f5e369c5a, 0xe7e6856caa0a635a, 0xbbefb5e96e0d495f, 0x07d3a975f0ef25a2, 0x0083fd8e7e80dae5,
+    0xadc0fc92df64b05d, 0x18aa270a2b1461dc, 0x86adac6a3be4eba0, 0x79495c4ec93da33a, 0xe7175850a43ccaed, 0x0b2bc2a163de1bf2]],
+    dtype=np.uint64)
+_FQ_ONE = np.array([0x760900000002fffd, 0xebf4000bc40c0002, 0x5f48985753c758ba, 0x77ce585370525745, 0x5c071a97a256ec6d,
+                    0x15f65ec3fa80e493], dtype=np.uint64)
+
+
+def g2_affine_to_jac(aff):
+    """(n, 24) affine -> (n, 36) Jacobian with Z = 1 (identity rows, all zero, become (1, 1, 0))"""
+    a = _host(aff, G2_AFF_LIMBS)
+    out = np.zeros((len(a), G2_JAC_LIMBS), dtype=np.uint64)
+    out[:, :24] = a
+    out[:, 24:30] = _FQ_ONE
+    inf = ~a.any(axis=1)
+    out[inf, 0:6] = _FQ_ONE
+    out[inf, 12:18] = _FQ_ONE
+    out[inf, 24:30] = 0
+    return out
+
+
+def g2_op(ctx, op, a, b=None):
+    """element-wise on Jacobian G2 points (device tensors (n, 36)): 'add' a + b, 'double' 2 a, 'mul' b * a with b Fr (n, 4)"""
+    a = _dev(a, G2_JAC_LIMBS)
+    out = torch.empty_like(a)
+    code = {"add": 0, "double": 1, "mul": 2}[op]
+    bp = None if b is None else _vp(_dev(b, G2_JAC_LIMBS if code == 0 else 4))
+    ctx.check(ctx.L.scz_g2_vec_op_dev(ctx.h, C.c_int32(code), _vp(a), bp, _vp(out), C.c_size_t(len(a))))
+    return out
+
+
+def msm_g2(ctx, bases, scalars, inf_mask=None):
+    """G2::msm(bases, scalars).  numpy: host path (scz_msm_g2; bases (n, 24) affine); torch: device path.  -> (1, 36) Jacobian"""
+    if _is_dev(bases):
+        return msm_g2_batched(ctx, [bases], [scalars])
+    b, s = _host(bases, G2_AFF_LIMBS), _host(scalars, 4)
+    out = np.zeros((1, G2_JAC_LIMBS), dtype=np.uint64)
+    mask = None if inf_mask is None else np.ascontiguousarray(inf_mask, dtype=np.uint8)
+    ctx.check(ctx.L.scz_msm_g2(ctx.h, b.ctypes.data_as(C.c_void_p), None if mask is None else mask.ctypes.data_as(C.c_void_p),
+                               C.c_size_t(len(b)), s.ctypes.data_as(C.c_void_p), C.c_size_t(len(s)), out.ctypes.data_as(C.c_void_p)))
+    return out
+
+
+def msm_g2_batched(ctx, bases_list, scalars_list):
+    k = len(bases_list)
+    bl = [_dev(b, G2_AFF_LIMBS) for b in bases_list]
+    sl = [_dev(s_, 4) for s_ in scalars_list]
+    for b, s_ in zip(bl, sl):
+        if len(b) != len(s_):
+            raise SczError(-2, f"msm_g2: {len(b)} bases vs {len(s_)} scalars")
+    out = ctx.empty(max(k, 1), G2_JAC_LIMBS)
+    lens = (C.c_size_t * k)(*[len(b) for b in bl])
+    ctx.check(ctx.L.scz_msm_g2_batched_dev(ctx.h, _ptr_array([b.data_ptr() for b in bl]), _ptr_array([s_.data_ptr() for s_ in sl]),
+                                           lens, C.c_size_t(k), _vp(out)))
+    return out[:k]
+
+
+def d_msm_g2(ctx, pp, bases, scalars):
+    """d_msm over G2 (dmsm.rs:9-43): device tensors, bases[k] (m_k, 24) affine, scalars[k] (m_k, 4) -> (batch, 36) Jacobian"""
+    assert len(bases) == len(scalars)                                       # dmsm.rs:16
+    k = len(bases)
+    bl = [_dev(b, G2_AFF_LIMBS) for b in bases]
+    sl = [_dev(s_, 4) for s_ in scalars]
+    for b, s_ in zip(bl, sl):
+        if len(b) != len(s_):
+            raise SczError(-2, f"d_msm_g2: {len(b)} bases vs {len(s_)} scalars")   # G::msm(..).unwrap(), dmsm.rs:23
+    out = ctx.empty(max(k, 1), G2_JAC_LIMBS)
+    lens = (C.c_size_t * k)(*[len(b) for b in bl])
+    ctx.check(ctx.L.scz_d_msm_g2_dev(ctx.h, pp.h, _ptr_array([b.data_ptr() for b in bl]), _ptr_array([s_.data_ptr() for s_ in sl]),
+                                     lens, C.c_size_t(k), _vp(out)))
+    return out[:k]
+
+
+def d_msm_g2_leader(ctx, pp, gathered):
+    """the leader closure (dmsm.rs:31-38) over G2 on a gathered buffer (n_parties, batch, 36) -> same shape"""
+    g = ctx.to_device(np.ascontiguousarray(gathered, dtype=np.uint64).reshape(-1, G2_JAC_LIMBS), G2_JAC_LIMBS) if not _is_dev(gathered) else gathered
+    n, batch = gathered.shape[0], gathered.shape[1]
+    out = torch.empty_like(g)
+    ctx.check(ctx.L.scz_d_msm_g2_leader_dev(ctx.h, pp.h, _vp(g), C.c_size_t(batch), _vp(out)))
+    return ctx.to_host(out).reshape(n, batch, G2_JAC_LIMBS)
+
+
 # ---------------------------------------------------------------------------- MSM
 def msm(ctx, bases, scalars, inf_mask=None):
     """G1::msm(bases, scalars) (ark-ec VariableBaseMSM; dmsm.rs:23).  Raises SczError
@@ -902,6 +989,7 @@ def dpermcheck(ctx, n, pk, pp):
 
 
 __all__ = ["Context", "PackedSharingParams", "msm", "msm_batched", "d_msm", "d_msm_leader", "NetVTable",
+           "msm_g2", "msm_g2_batched", "d_msm_g2", "d_msm_g2_leader", "g2_op", "g2_affine_to_jac", "G2_GENERATOR_AFFINE",
            "fr_pointwise", "fix_variable", "acc_product_tree", "d_acc_product", "sumcheck_rounds", "sumcheck_product",
            "c_sumcheck_product", "d_sumcheck_product", "sumcheck", "c_sumcheck", "d_sumcheck", "pss2ss", "degree_reduce", "PolynomialCommitment",
            "PackedProvingParameters", "HyperPlonkProof", "dhyperplonk", "dhyperplonk_data_parallel", "dpermcheck", "cpermcheck", "c_acc_product_and_share", "local_hyperplonk",

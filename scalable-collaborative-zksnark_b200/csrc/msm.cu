@@ -479,6 +479,32 @@ uint32_t msm_pick_window(size_t len) {
     return best;
 }
 
+// Steps 1-3 for a batch described by `d_segs` (device): histogram, exclusive scan, scatter.  Curve-independent (only the
+// scalars are read): the G2 path (msm_g2.cu) sorts with it too.  counts was zeroed by the caller; afterwards cursor[b] is the
+// END of bucket b in `sorted`, counts[b] its length.  tiles: ceil(buckets / SCAN_TILE) + 1 words of scratch.
+uint32_t msm_scan_tiles(uint64_t buckets) { return ceil_div_u32(buckets, SCAN_TILE); }
+int32_t msm_sort_entries(Ctx *ctx, const MsmSeg *d_segs, int K, uint32_t points, uint32_t buckets, uint32_t *counts,
+                         uint32_t *cursor, uint32_t *tile_scratch, uint2 *sorted) {
+    ProfScope ps(ctx, SCZ_K_MSM_SORT);
+    cudaStream_t st = ctx->stream;
+    const uint32_t tiles = msm_scan_tiles(buckets);
+    if (points) {
+        k_msm_recode<false><<<ceil_div_u32(points, CNT_THREADS), CNT_THREADS, 0, st>>>(d_segs, K, points, counts, nullptr, nullptr);
+        SCZ_LAUNCH_CHECK(ctx);
+    }
+    k_scan_tiles<<<tiles, SCAN_THREADS, 0, st>>>(counts, cursor, tile_scratch, buckets);
+    SCZ_LAUNCH_CHECK(ctx);
+    k_scan_tile_sums<<<1, 1024, 0, st>>>(tile_scratch, tiles);
+    SCZ_LAUNCH_CHECK(ctx);
+    k_scan_add<<<tiles, SCAN_THREADS, 0, st>>>(cursor, tile_scratch, buckets);
+    SCZ_LAUNCH_CHECK(ctx);
+    if (points) {
+        k_msm_recode<true><<<ceil_div_u32(points, CNT_THREADS), CNT_THREADS, 0, st>>>(d_segs, K, points, nullptr, cursor, sorted);
+        SCZ_LAUNCH_CHECK(ctx);
+    }
+    return SCZ_OK;
+}
+
 int32_t msm_g1_batched(Ctx *ctx, const void *const *d_bases, const void *const *d_scalars, const size_t *lens,
                        size_t batch, void *d_out, void *const *d_outs, const uint32_t *pre_c) {
     if (batch == 0) return SCZ_OK;
@@ -574,25 +600,7 @@ int32_t msm_g1_batched(Ctx *ctx, const void *const *d_bases, const void *const *
                                            (int)(FIN_THREADS * sizeof(G1Jac))));
         ctx->attr_msm = true;
     }
-    {
-        ProfScope ps(ctx, SCZ_K_MSM_SORT);
-        if (points) {
-            k_msm_recode<false><<<ceil_div_u32(points, CNT_THREADS), CNT_THREADS, 0, st>>>(
-                sp, K, (uint32_t)points, counts, nullptr, nullptr);
-            SCZ_LAUNCH_CHECK(ctx);
-        }
-        k_scan_tiles<<<tiles, SCAN_THREADS, 0, st>>>(counts, cursor, d_tiles.as<uint32_t>(), (uint32_t)buckets);
-        SCZ_LAUNCH_CHECK(ctx);
-        k_scan_tile_sums<<<1, 1024, 0, st>>>(d_tiles.as<uint32_t>(), tiles);
-        SCZ_LAUNCH_CHECK(ctx);
-        k_scan_add<<<tiles, SCAN_THREADS, 0, st>>>(cursor, d_tiles.as<uint32_t>(), (uint32_t)buckets);
-        SCZ_LAUNCH_CHECK(ctx);
-        if (points) {
-            k_msm_recode<true><<<ceil_div_u32(points, CNT_THREADS), CNT_THREADS, 0, st>>>(
-                sp, K, (uint32_t)points, nullptr, cursor, sorted);
-            SCZ_LAUNCH_CHECK(ctx);
-        }
-    }
+    SCZ_TRY(msm_sort_entries(ctx, sp, K, (uint32_t)points, (uint32_t)buckets, counts, cursor, d_tiles.as<uint32_t>(), sorted));
     if (points) {
         {
             // after the scatter cursor[last bucket] = entries really in the stream (the host only knows the

@@ -42,6 +42,12 @@ __device__ __forceinline__ int seg_by_bucket(const MsmSeg *segs, int K, uint32_t
 }
 #endif
 
+// The curve-independent front of the pipeline (msm.cu): histogram of the signed digits, exclusive scan, scatter of one
+// 8-byte entry (point | sign, bucket) per non-zero digit.  counts (zeroed by the caller) / cursor: one word per bucket.
+uint32_t msm_scan_tiles(uint64_t buckets);
+int32_t msm_sort_entries(Ctx *ctx, const MsmSeg *d_segs, int K, uint32_t points, uint32_t buckets, uint32_t *counts,
+                         uint32_t *cursor, uint32_t *tile_scratch, uint2 *sorted);
+
 // Batched-affine bucket accumulation (msm_affine.cu): replaces the k_msm_accumulate launch of a sequence.  Same
 // contract: whole buckets to `buckets` (XYZZ), pieces cut by the 2^logT-entry chunk boundaries to `parts`.
 // levels = affine tree levels (1 .. logT).  entries = host-side upper bound of the stream length, *E_ptr the real one.
