@@ -152,6 +152,19 @@ SCZ_HD uint32_t madc_hi(CF &c, uint32_t a, uint32_t b, uint32_t d) {
 struct FrP {
     static constexpr int N = 8;
     static constexpr uint32_t INV = 0xffffffffu;   // -r^{-1} mod 2^32
+    // The row multiplier m = e0 * INV mod 2^32 of a Montgomery step.  INV = -1 here, and when ptxas sees m = -e0 it
+    // splits every m * p_j of the row into IMAD.X (low half) + IMAD.HI.U32.X (high half) -- 176 multiply-pipe
+    // instructions per Fr product instead of the 128 IMAD.WIDE.U32(.X) it emits for Fq (seen in the SASS of every Fr
+    // kernel).  An opaque subtraction keeps the fused form.
+    SCZ_HD static uint32_t mont_m(uint32_t e0) {
+#ifdef __CUDA_ARCH__
+        uint32_t m;
+        asm volatile("sub.u32 %0, 0, %1;" : "=r"(m) : "r"(e0));
+        return m;
+#else
+        return e0 * INV;
+#endif
+    }
     SCZ_HD static constexpr uint32_t mod(int i) {
         constexpr uint32_t M[8] = {0x00000001u, 0xffffffffu, 0xfffe5bfeu, 0x53bda402u,
                                    0x09a1d805u, 0x3339d808u, 0x299d7d48u, 0x73eda753u};
@@ -172,6 +185,7 @@ struct FrP {
 struct FqP {
     static constexpr int N = 12;
     static constexpr uint32_t INV = 0xfffcfffdu;   // -p^{-1} mod 2^32
+    SCZ_HD static constexpr uint32_t mont_m(uint32_t e0) { return e0 * INV; }
     SCZ_HD static constexpr uint32_t mod(int i) {
         constexpr uint32_t M[12] = {0xffffaaabu, 0xb9feffffu, 0xb153ffffu, 0x1eabfffeu, 0xf6b0f624u, 0x6730d2a0u,
                                     0xf38512bfu, 0x64774b84u, 0x434bacd7u, 0x4b1ba7b6u, 0x397fe69au, 0x1a0111eau};
@@ -316,8 +330,13 @@ SCZ_HD void madc_n_rshift(CF &c, uint32_t *odd, const uint32_t *a, uint32_t bi) 
 template <class P, int off>
 SCZ_HD void cmad_mod(CF &c, uint32_t *acc, uint32_t mi) {
     constexpr int N = P::N;
-    acc[0] = mad_lo_cc(c, P::mod(off), mi, acc[0]);
-    acc[1] = madc_hi_cc(c, P::mod(off), mi, acc[1]);
+    if constexpr (P::mod(off) == 1u) {   // Fr: p_0 = 1, the product is mi itself (ptxas would still spend an IMAD.HI on its zero high half)
+        acc[0] = add_cc(c, acc[0], mi);
+        acc[1] = addc_cc(c, acc[1], 0);
+    } else {
+        acc[0] = mad_lo_cc(c, P::mod(off), mi, acc[0]);
+        acc[1] = madc_hi_cc(c, P::mod(off), mi, acc[1]);
+    }
 #pragma unroll
     for (int j = 2; j < N; j += 2) {
         acc[j] = madc_lo_cc(c, P::mod(j + off), mi, acc[j]);
@@ -337,7 +356,7 @@ SCZ_HD void mad_n_redc(uint32_t *even, uint32_t *odd, const uint32_t *a, uint32_
         cmad_n<N>(c, even, a, bi);
         odd[N - 1] = addc(c, odd[N - 1], 0);
     }
-    uint32_t mi = even[0] * P::INV;
+    uint32_t mi = P::mont_m(even[0]);
     cmad_mod<P, 1>(c, odd, mi);
     cmad_mod<P, 0>(c, even, mi);
     odd[N - 1] = addc(c, odd[N - 1], 0);
@@ -383,7 +402,7 @@ SCZ_HD void mad2_n_redc(uint32_t *even, uint32_t *odd, const uint32_t *a1, uint3
     cmad_n<N>(c, odd, a2 + 1, b2i);          // position 32N+32 and up stays empty: the sum is < 3p * 2^32 < 2^(32(N+1))
     cmad_n<N>(c, even, a2, b2i);
     odd[N - 1] = addc(c, odd[N - 1], 0);
-    uint32_t mi = even[0] * P::INV;
+    uint32_t mi = P::mont_m(even[0]);
     cmad_mod<P, 1>(c, odd, mi);
     cmad_mod<P, 0>(c, even, mi);
     odd[N - 1] = addc(c, odd[N - 1], 0);
@@ -497,7 +516,7 @@ SCZ_HD void redc_row(uint32_t *even, uint32_t *odd, bool first) {
         odd[N - 2] = addc(c, 0, 0);
         odd[N - 1] = 0;
     }
-    uint32_t mi = even[0] * P::INV;
+    uint32_t mi = P::mont_m(even[0]);
     cmad_mod<P, 1>(c, odd, mi);
     cmad_mod<P, 0>(c, even, mi);
     odd[N - 1] = addc(c, odd[N - 1], 0);
@@ -533,6 +552,98 @@ SCZ_HD Fp<P> fp_redc_wide(const uint32_t *t) {
     fp_final_sub(r);
     return r;
 }
+// ---------------------------------------------------------------- unreduced sums of products
+// A sum of Montgomery products sum_i a_i * b_i needs ONE Montgomery reduction, not one per term: the plain 2N-limb
+// integer products are added up in a (2N + 1)-limb accumulator (N^2 wide multiplies per term instead of 2 N^2) and the
+// accumulator is reduced once at the end.  Used by the product sumcheck rounds (poly.cu), whose three round sums are
+// exactly such sums (dsumcheck.rs:37-85).  Operands < p, at most 2^32 terms.
+namespace detail {
+// ev + (od << 32) = a * b: products a_j b_i with i + j even go to the `ev` columns, the others to `od` (od[k] sits at
+// limb k + 1), so that every mad.lo.cc / madc.hi.cc pair is one IMAD.WIDE on an aligned register pair (as in the CIOS rows)
+template <int N>
+SCZ_HD void mul_wide(uint32_t *ev, uint32_t *od, const uint32_t *a, const uint32_t *b) {
+    static_assert(N % 2 == 0, "even limb count");
+#pragma unroll
+    for (int k = 0; k < 2 * N; k++) ev[k] = od[k] = 0;
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+        {
+            CF c{0};
+            int top = 0;
+#pragma unroll
+            for (int j = (i & 1); j < N; j += 2) {
+                const int k = i + j;
+                ev[k] = j == (i & 1) ? mad_lo_cc(c, a[j], b[i], ev[k]) : madc_lo_cc(c, a[j], b[i], ev[k]);
+                ev[k + 1] = madc_hi_cc(c, a[j], b[i], ev[k + 1]);
+                top = k + 2;
+            }
+            if (top < 2 * N) ev[top] = addc(c, ev[top], 0);
+        }
+        {
+            CF c{0};
+            int top = 0;
+#pragma unroll
+            for (int j = 1 - (i & 1); j < N; j += 2) {
+                const int k = i + j - 1;
+                od[k] = j == 1 - (i & 1) ? mad_lo_cc(c, a[j], b[i], od[k]) : madc_lo_cc(c, a[j], b[i], od[k]);
+                od[k + 1] = madc_hi_cc(c, a[j], b[i], od[k + 1]);
+                top = k + 2;
+            }
+            if (top < 2 * N) od[top] = addc(c, od[top], 0);
+        }
+    }
+}
+}   // namespace detail
+// acc[0 .. 2N] += a * b
+template <class P>
+SCZ_HD void fp_mul_acc_wide(uint32_t *acc, const Fp<P> &a, const Fp<P> &b) {
+    constexpr int N = P::N;
+    uint32_t ev[2 * N], od[2 * N];
+    detail::mul_wide<N>(ev, od, a.l, b.l);
+    CF c{0};
+    acc[0] = add_cc(c, acc[0], ev[0]);
+#pragma unroll
+    for (int k = 1; k < 2 * N; k++) acc[k] = addc_cc(c, acc[k], ev[k]);
+    acc[2 * N] = addc(c, acc[2 * N], 0);
+    acc[1] = add_cc(c, acc[1], od[0]);
+#pragma unroll
+    for (int k = 1; k < 2 * N - 1; k++) acc[k + 1] = addc_cc(c, acc[k + 1], od[k]);   // od[2N - 1] is never written
+    acc[2 * N] = addc(c, acc[2 * N], 0);
+}
+// the accumulator as a field element: acc / 2^(32N) mod p (= the sum of the Montgomery products).  acc = H 2^(64N) + L:
+// the high half of L is brought below p by conditional subtractions (2^(32N) / p < 3 for Fr, < 10 for Fq) so that
+// fp_redc_wide applies; H 2^(64N) / 2^(32N) = H 2^(32N) = the Montgomery form of the integer H.
+template <class P>
+SCZ_HD Fp<P> fp_acc_wide_reduce(const uint32_t *acc) {
+    constexpr int N = P::N;
+    uint32_t t[2 * N];
+    Fp<P> hi;
+#pragma unroll
+    for (int k = 0; k < N; k++) {
+        t[k] = acc[k];
+        hi.l[k] = acc[N + k];
+    }
+    // hi < 2^(32N): floor(2^(32N) / p) conditional subtractions (full-width compare: hi may have its top bit set)
+    constexpr int REPS = (int)(0xffffffffu / P::mod(N - 1));
+#pragma unroll
+    for (int rep = 0; rep < REPS; rep++) {
+        CF c{0};
+        uint32_t d[N];
+        d[0] = sub_cc(c, hi.l[0], P::mod(0));
+#pragma unroll
+        for (int k = 1; k < N; k++) d[k] = subc_cc(c, hi.l[k], P::mod(k));
+        uint32_t borrow = borrow_mask(c);
+#pragma unroll
+        for (int k = 0; k < N; k++) hi.l[k] = borrow ? hi.l[k] : d[k];
+    }
+#pragma unroll
+    for (int k = 0; k < N; k++) t[N + k] = hi.l[k];
+    Fp<P> lo = fp_redc_wide<P>(t);
+    Fp<P> h = Fp<P>::zero();
+    h.l[0] = acc[2 * N];
+    return fp_add(lo, fp_mul(h, Fp<P>::rsquared()));
+}
+
 SCZ_HD Fp<FqP> fq_sqr_sos(const Fp<FqP> &a) {
     uint32_t t[24];
     detail::sqr_wide<12>(t, a.l);

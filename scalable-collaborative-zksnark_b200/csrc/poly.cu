@@ -71,11 +71,83 @@ __device__ __forceinline__ void product_pair(const Fr &f0, const Fr &f1, const F
     go = fp_add(g0, fp_mul(r, dg));
 }
 
-// One round over h pairs.  Every CTA leaves its partial triple in `partial`; the last CTA to finish (ticket)
-// adds them up and writes the round message.
-__global__ void __launch_bounds__(PL_THREADS) k_sumcheck_round(const void *f_in, const void *g_in, void *f_out,
-                                                                void *g_out, uint32_t h, const void *challenge,
-                                                                Fr3 *partial, uint32_t *ticket, Fr3 *out) {
+// One round over h pairs, big rounds.  The three round sums are sums of products: a thread adds the plain 512-bit
+// products of its pairs into three 17-limb accumulators and reduces each ONCE at the end (field.cuh fp_mul_acc_wide:
+// 64 instead of 128 wide multiplies per term -- 436 instead of 610 multiply-pipe instructions per pair with the two fold
+// products).  One CTA per SM, every thread strides over h with the next pair's four loads in flight while it works on
+// the current one (228 registers; measured against 2 x 256 and 3 x 128 threads per SM without the prefetch: 1.38 vs
+// 1.45 - 1.48 ms for all rounds of a 2^24-entry table).  Every CTA leaves its partial triple in `partial`; the last
+// CTA to finish (ticket) adds them up and writes the round message.
+constexpr int SC_THREADS = 256;
+__global__ void __launch_bounds__(SC_THREADS, 1) k_sumcheck_round(const void *f_in, const void *g_in, void *f_out, void *g_out,
+                                                                  uint32_t h, const void *challenge, Fr3 *partial,
+                                                                  uint32_t *ticket, Fr3 *out) {
+    constexpr int PL_THREADS = SC_THREADS;
+    __shared__ Fr sh[3 * PL_THREADS / 32];
+    __shared__ bool last;
+    const Fr r = fp_load<FrP>(challenge, 0);
+    uint32_t a0[17], a1[17], a2[17];
+#pragma unroll
+    for (int k = 0; k < 17; k++) a0[k] = a1[k] = a2[k] = 0;
+    const uint32_t stride = gridDim.x * PL_THREADS;
+    uint32_t i = blockIdx.x * PL_THREADS + threadIdx.x;
+    Fr nf0, nf1, ng0, ng1;
+    if (i < h) {
+        nf0 = fp_load_rw<FrP>(f_in, i), nf1 = fp_load_rw<FrP>(f_in, (size_t)h + i);
+        ng0 = fp_load_rw<FrP>(g_in, i), ng1 = fp_load_rw<FrP>(g_in, (size_t)h + i);
+    }
+    for (; i < h; i += stride) {
+        const Fr f0 = nf0, f1 = nf1, g0 = ng0, g1 = ng1;
+        const uint32_t n = i + stride < h ? i + stride : i;   // the next pair (the last iteration re-reads its own)
+        nf0 = fp_load_rw<FrP>(f_in, n), nf1 = fp_load_rw<FrP>(f_in, (size_t)h + n);
+        ng0 = fp_load_rw<FrP>(g_in, n), ng1 = fp_load_rw<FrP>(g_in, (size_t)h + n);
+        fp_mul_acc_wide<FrP>(a0, f0, g0);
+        fp_mul_acc_wide<FrP>(a1, f1, g1);
+        Fr df = fp_sub(f1, f0), dg = fp_sub(g1, g0);
+        fp_store<FrP>(f_out, i, fp_add(f0, fp_mul(r, df)));        // f0 (1 - r) + f1 r
+        fp_store<FrP>(g_out, i, fp_add(g0, fp_mul(r, dg)));
+        fp_mul_acc_wide<FrP>(a2, fp_add(f1, df), fp_add(g1, dg));   // (2 f1 - f0)(2 g1 - g0)
+    }
+    Fr s0 = fp_acc_wide_reduce<FrP>(a0), s1 = fp_acc_wide_reduce<FrP>(a1), s2 = fp_acc_wide_reduce<FrP>(a2);
+    block_sum3<PL_THREADS>(s0, s1, s2, sh);
+    if (threadIdx.x == 0) {
+        partial[blockIdx.x].a = s0;
+        partial[blockIdx.x].b = s1;
+        partial[blockIdx.x].c = s2;
+        __threadfence();
+        last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    s0 = Fr::zero(), s1 = Fr::zero(), s2 = Fr::zero();
+    for (uint32_t b = threadIdx.x; b < gridDim.x; b += PL_THREADS) {
+        const uint4 *p = reinterpret_cast<const uint4 *>(&partial[b]);   // written by other CTAs: read through L2
+        Fr3 t;
+        uint32_t *w = &t.a.l[0];
+#pragma unroll
+        for (int k = 0; k < 6; k++) {
+            uint4 v = __ldcg(p + k);
+            w[4 * k] = v.x, w[4 * k + 1] = v.y, w[4 * k + 2] = v.z, w[4 * k + 3] = v.w;
+        }
+        s0 = fp_add(s0, t.a);
+        s1 = fp_add(s1, t.b);
+        s2 = fp_add(s2, t.c);
+    }
+    block_sum3<PL_THREADS>(s0, s1, s2, sh);
+    if (threadIdx.x == 0) {
+        out->a = s0;
+        out->b = s1;
+        out->c = s2;
+        *ticket = 0;   // ready for the next round
+    }
+}
+
+// The same round with one Montgomery product per term (product_pair): for rounds with only a few pairs per thread,
+// where the three accumulator reductions at the end of the lazy kernel would cost more than they save.
+__global__ void __launch_bounds__(PL_THREADS) k_sumcheck_round_direct(const void *f_in, const void *g_in, void *f_out,
+                                                                       void *g_out, uint32_t h, const void *challenge,
+                                                                       Fr3 *partial, uint32_t *ticket, Fr3 *out) {
     __shared__ Fr sh[3 * PL_THREADS / 32];
     __shared__ bool last;
     const Fr r = fp_load<FrP>(challenge, 0);
@@ -118,7 +190,7 @@ __global__ void __launch_bounds__(PL_THREADS) k_sumcheck_round(const void *f_in,
         out->a = s0;
         out->b = s1;
         out->c = s2;
-        *ticket = 0;   // ready for the next round
+        *ticket = 0;
     }
 }
 
@@ -211,9 +283,10 @@ __global__ void __launch_bounds__(PL_THREADS) k_sum_round(const void *f_in, void
 // rounds as it folds them down.  Traffic per folded entry: 2^R * 32 B read + 32 B written instead of 96 B per pair per
 // round (R = 3: 288 B instead of 672 B), and a third of the launches -- this chain of halving passes is bandwidth- and
 // launch-bound, not compute-bound (one product per pair).
-template <int R>
-__global__ void __launch_bounds__(PL_THREADS) k_sum_rounds(const void *f_in, void *f_out, uint32_t w, const void *challenge,
-                                                            Fr *partial, uint32_t *ticket, Fr2 *out) {
+template <int R, int T, int MINB>
+__global__ void __launch_bounds__(T, MINB) k_sum_rounds(const void *f_in, void *f_out, uint32_t w, const void *challenge,
+                                                        Fr *partial, uint32_t *ticket, Fr2 *out) {
+    constexpr int PL_THREADS = T;
     constexpr int M = 1 << R, NV = 2 * R;
     __shared__ Fr sh[NV * PL_THREADS / 32];
     __shared__ bool last;
@@ -262,11 +335,11 @@ __global__ void __launch_bounds__(PL_THREADS) k_sum_rounds(const void *f_in, voi
     __syncthreads();
     if (!last) return;
     __threadfence();
-    // the last CTA adds the partials: warp k sums accumulator k
-    if (wid < NV) {
+    // the last CTA adds the partials: one warp per accumulator
+    for (int acc_k = wid; acc_k < NV; acc_k += PL_THREADS / 32) {
         Fr acc = Fr::zero();
         for (uint32_t b = lane; b < gridDim.x; b += 32) {
-            const uint4 *p = reinterpret_cast<const uint4 *>(reinterpret_cast<const char *>(partial) + ((size_t)b * NV + wid) * 32);
+            const uint4 *p = reinterpret_cast<const uint4 *>(reinterpret_cast<const char *>(partial) + ((size_t)b * NV + acc_k) * 32);
             Fr t;
 #pragma unroll
             for (int q = 0; q < 2; q++) {
@@ -279,7 +352,7 @@ __global__ void __launch_bounds__(PL_THREADS) k_sum_rounds(const void *f_in, voi
         for (int d = 16; d > 0; d >>= 1) acc = fp_add(acc, fr_shfl_down(acc, d));
         if (lane == 0) {
             Fr *o = reinterpret_cast<Fr *>(out);   // round t: (sum lo, sum hi) = accumulators 2t, 2t + 1
-            o[wid] = acc;
+            o[acc_k] = acc;
         }
     }
     if (threadIdx.x == 0) *ticket = 0;
@@ -434,9 +507,9 @@ __global__ void __launch_bounds__(DIV_THREADS) k_div_phase2(const void *num, con
     }
 }
 
-static uint32_t grid_for(Ctx *c, size_t items) {
-    size_t want = (items + PL_THREADS - 1) / PL_THREADS;
-    size_t cap = (size_t)c->sm_count * 8;   // a multiple of the SM count; grid-stride loops cover the rest
+static uint32_t grid_for(Ctx *c, size_t items, int threads = PL_THREADS, int ctas_per_sm = 8) {
+    size_t want = (items + threads - 1) / threads;
+    size_t cap = (size_t)c->sm_count * ctas_per_sm;   // a multiple of the SM count; grid-stride loops cover the rest
     return (uint32_t)(want < cap ? (want ? want : 1) : cap);
 }
 
@@ -469,16 +542,20 @@ int32_t sumcheck_product_rounds(Ctx *ctx, const void *d_f, const void *d_g, size
     DevTmp tf(ctx), tg(ctx), partial(ctx), ticket(ctx);
     SCZ_TRY(tf.alloc(h * 32));
     SCZ_TRY(tg.alloc(h * 32));
-    SCZ_TRY(partial.alloc((size_t)grid_for(ctx, h) * sizeof(Fr3)));
+    SCZ_TRY(partial.alloc((size_t)ctx->sm_count * 16 * sizeof(Fr3)));
     SCZ_TRY(ticket.alloc(4));
     SCZ_CUDA(ctx, cudaMemsetAsync(ticket.p, 0, 4, st));
     const void *fi = d_f, *gi = d_g;
     size_t round = 0;
+    // the lazy kernel from ~4 pairs per thread of its one-CTA-per-SM grid, the direct one below (measured on B200)
+    const size_t lazy_from = (size_t)4 * ctx->sm_count * SC_THREADS;
     while (h > TAIL_PAIRS) {
-        k_sumcheck_round<<<grid_for(ctx, h), PL_THREADS, 0, st>>>(fi, gi, tf.p, tg.p, (uint32_t)h,
-                                                                  (const char *)d_challenge + round * 32,
-                                                                  partial.as<Fr3>(), ticket.as<uint32_t>(),
-                                                                  reinterpret_cast<Fr3 *>(d_out) + round);
+        const void *ch = (const char *)d_challenge + round * 32;
+        Fr3 *o = reinterpret_cast<Fr3 *>(d_out) + round;
+        if (h >= lazy_from)
+            k_sumcheck_round<<<ctx->sm_count, SC_THREADS, 0, st>>>(fi, gi, tf.p, tg.p, (uint32_t)h, ch, partial.as<Fr3>(), ticket.as<uint32_t>(), o);
+        else
+            k_sumcheck_round_direct<<<grid_for(ctx, h), PL_THREADS, 0, st>>>(fi, gi, tf.p, tg.p, (uint32_t)h, ch, partial.as<Fr3>(), ticket.as<uint32_t>(), o);
         SCZ_LAUNCH_CHECK(ctx);
         fi = tf.p;
         gi = tg.p;
@@ -507,7 +584,8 @@ int32_t sumcheck_rounds(Ctx *ctx, const void *d_f, size_t len, const void *d_cha
     size_t h = len / 2, round = 0;
     DevTmp tf(ctx), partial(ctx), ticket(ctx);
     SCZ_TRY(tf.alloc((h > TAIL_PAIRS ? h : len) * 32));
-    SCZ_TRY(partial.alloc((size_t)grid_for(ctx, h) * 6 * sizeof(Fr)));
+    SCZ_TRY(partial.alloc((size_t)ctx->sm_count * 16 * 6 * sizeof(Fr)));
+
     SCZ_TRY(ticket.alloc(4));
     SCZ_CUDA(ctx, cudaMemsetAsync(ticket.p, 0, 4, st));
     const void *fi = d_f;
@@ -518,9 +596,13 @@ int32_t sumcheck_rounds(Ctx *ctx, const void *d_f, size_t len, const void *d_cha
         const uint32_t w = (uint32_t)((2 * h) >> R);
         const void *ch = (const char *)d_challenge + round * 32;
         Fr2 *o = reinterpret_cast<Fr2 *>(d_out) + round;
-        if (R == 3) k_sum_rounds<3><<<grid_for(ctx, w), PL_THREADS, 0, st>>>(fi, tf.p, w, ch, partial.as<Fr>(), ticket.as<uint32_t>(), o);
-        else if (R == 2) k_sum_rounds<2><<<grid_for(ctx, w), PL_THREADS, 0, st>>>(fi, tf.p, w, ch, partial.as<Fr>(), ticket.as<uint32_t>(), o);
-        else k_sum_round<<<grid_for(ctx, h), PL_THREADS, 0, st>>>(fi, tf.p, (uint32_t)h, ch, partial.as<Fr3>(), ticket.as<uint32_t>(), o);
+        Fr *pa = partial.as<Fr>();
+        uint32_t *tk = ticket.as<uint32_t>();
+        // R = 3 runs with 128-thread CTAs, three per SM (168 registers): 0.44 ms for a 2^24-entry table against 0.51 ms
+        // with one 256-thread CTA per SM
+        if (R == 3) k_sum_rounds<3, 128, 3><<<grid_for(ctx, w, 128, 3), 128, 0, st>>>(fi, tf.p, w, ch, pa, tk, o);
+        else if (R == 2) k_sum_rounds<2, 256, 2><<<grid_for(ctx, w, 256, 2), 256, 0, st>>>(fi, tf.p, w, ch, pa, tk, o);
+        else k_sum_round<<<grid_for(ctx, h), PL_THREADS, 0, st>>>(fi, tf.p, (uint32_t)h, ch, partial.as<Fr3>(), tk, o);
         SCZ_LAUNCH_CHECK(ctx);
         fi = tf.p;
         h >>= R;

@@ -52,6 +52,17 @@ extern "C" void emu_fq_sqr_sos(const uint32_t *a, uint32_t *r, size_t n) {
 extern "C" void emu_fq_dot2_sub(const uint32_t *a, const uint32_t *b, const uint32_t *c, const uint32_t *d, uint32_t *r, size_t n) {
     for (size_t i = 0; i < n; i++) st<FqP>(r, i, fp_dot2_sub(ld<FqP>(a, i), ld<FqP>(b, i), ld<FqP>(c, i), ld<FqP>(d, i)));
 }
+// sum_i a_i * b_i with ONE reduction (fp_mul_acc_wide / fp_acc_wide_reduce: the round sums of the product sumcheck)
+extern "C" void emu_fr_dot_wide(const uint32_t *a, const uint32_t *b, size_t n, uint32_t *r) {
+    uint32_t acc[17] = {0};
+    for (size_t i = 0; i < n; i++) fp_mul_acc_wide<FrP>(acc, ld<FrP>(a, i), ld<FrP>(b, i));
+    st<FrP>(r, 0, fp_acc_wide_reduce<FrP>(acc));
+}
+extern "C" void emu_fq_dot_wide(const uint32_t *a, const uint32_t *b, size_t n, uint32_t *r) {
+    uint32_t acc[25] = {0};
+    for (size_t i = 0; i < n; i++) fp_mul_acc_wide<FqP>(acc, ld<FqP>(a, i), ld<FqP>(b, i));
+    st<FqP>(r, 0, fp_acc_wide_reduce<FqP>(acc));
+}
 extern "C" void emu_fq_inv_bingcd(const uint32_t *a, uint32_t *r, size_t n) {
     for (size_t i = 0; i < n; i++) st<FqP>(r, i, fp_inv_bingcd(ld<FqP>(a, i)));
 }

@@ -46,6 +46,36 @@ def test_field_ops(orc, emu):
             assert np.array_equal(out, ref(a, b)), (name, op)
 
 
+def test_dot_wide(orc, emu):
+    """sum a_i b_i through the unreduced (2N + 1)-limb accumulator == the sum of the Montgomery products"""
+    rng = np.random.default_rng(105)
+    for name, mod, rnd, frm, omul, oadd in (
+        ("fr", tw.R_MOD, lambda n: orc.random_fr(rng, n), orc.fr_from_ints, orc.fr_mul, orc.fr_add),
+        ("fq", tw.P_MOD, lambda n: orc.fq_from_ints([int.from_bytes(rng.bytes(64), "little") for _ in range(n)]),
+         orc.fq_from_ints, orc.fq_mul, orc.fq_add),
+    ):
+        e = _edge(orc, mod, frm, 0)
+        top = frm([mod - 1])
+        cases = [
+            (rnd(1), rnd(1)), (rnd(700), rnd(700)), (np.repeat(e, len(e), axis=0), np.tile(e, (len(e), 1))),
+            (np.repeat(top, 5000, axis=0), np.repeat(top, 5000, axis=0)),   # the accumulator's 2N-th limb fills up
+            (np.concatenate([np.repeat(top, 3000, axis=0), rnd(500)]), np.concatenate([np.repeat(top, 3000, axis=0), rnd(500)])),
+        ]
+        for a, b in cases:
+            a, b = np.ascontiguousarray(a), np.ascontiguousarray(b)
+            out = np.zeros_like(a[:1])
+            getattr(emu, f"emu_{name}_dot_wide")(_p(a), _p(b), C.c_size_t(len(a)), _p(out))
+            prod = omul(a, b)
+            want = prod[:1]
+            # tree-sum with the oracle's vector add
+            acc = prod
+            while len(acc) > 1:
+                if len(acc) % 2:
+                    acc = np.concatenate([acc, np.zeros_like(acc[:1])])
+                acc = oadd(acc[0::2], acc[1::2])
+            assert np.array_equal(out, acc), (name, len(a))
+
+
 def test_fq_dot2_sub(orc, emu):
     """a*b - c*d with one shared Montgomery reduction (field.cuh fp_dot2_sub): the Y coordinate of every G1 formula"""
     rng = np.random.default_rng(102)

@@ -9,7 +9,7 @@ import torch  # noqa: E402
 import scz_b200 as scz  # noqa: E402
 
 ctx = scz.Context(device=0, n_parties=8)
-n = 1 << 22
+n = 1 << (int(sys.argv[1]) if len(sys.argv) > 1 else 22)
 g = torch.Generator(device=ctx.device).manual_seed(7)
 f = torch.randint(-2**63, 2**63 - 1, (n, 4), dtype=torch.int64, device=ctx.device, generator=g)
 f[:, 3] &= (1 << 62) - 1

@@ -22,10 +22,14 @@ for logn in (22, 24):
             fn()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize()
+        import time
+        t0 = time.perf_counter()
         a.record()
         for _ in range(5):
             fn()
         b.record()
+        t1 = time.perf_counter()
         torch.cuda.synchronize()
         ms = a.elapsed_time(b) / 5
-        print(f"2^{logn} {name:22s} {ms:8.4f} ms  {nbytes / ms / 1e6:8.1f} GB/s algorithmic", flush=True)
+        print(f"2^{logn} {name:22s} {ms:8.4f} ms  {nbytes / ms / 1e6:8.1f} GB/s algorithmic   (host enqueue {(t1 - t0) / 5 * 1e3:.4f} ms per call)",
+              flush=True)
