@@ -557,38 +557,47 @@ def run_own(args):
 
     # ---- end to end: the witness / selector / challenge tables start in pinned HOST memory every proof, the proof
     #      ends in host memory; the SRS (proving key, reused across proofs) stays resident.  Two resident table sets per
-    #      party: the host -> device copy of proof i+1 runs on a copy stream while proof i computes (both inside the
-    #      timed region), the device -> host read of proof i's result closes step i.
-    e2e_steps = max(2, min(args.steps, 4))
+    #      party: the host -> device copy of proof i+1 runs on a copy stream under the MSM phase of proof i (both inside
+    #      the timed region); the device -> host read of proof i is queued right behind it on a third stream and collected
+    #      by the host after proof i + 1 has been enqueued (scz.ProofReader), so the GPU queue never runs dry between
+    #      proofs.  Every step moves its own inputs in and its own proof out; the wall clock covers all of it, including
+    #      the first proof's cold start and the last proof's read-back.
+    e2e_steps = max(2, min(args.steps, 20))
     host_tabs, alt = [], []
     for ctx, pp, pk in parties:
         host_tabs.append({name: torch.empty(t.shape, dtype=torch.int64).pin_memory().copy_(t) for name, t in pk.t.items()})
         alt.append(scz.PackedProvingParameters(ctx, n, L_PACK, {k: v.clone() for k, v in pk.t.items()}, pk.c_commitment,
                                                pk.d_commitment))
     h2d = sum(t.numel() * 8 for t in host_tabs[0].values())
+    readers = [scz.ProofReader(ctx, depth=2) for ctx, _, _ in parties]
 
     def e2e_loop(p, steps):
         ctx, pp, pk = parties[p]
         sets = [pk, alt[p]]
         main, copy = torch.cuda.current_stream(), torch.cuda.Stream()
         up = [torch.cuda.Event(), torch.cuda.Event()]
-        done = [torch.cuda.Event(), torch.cuda.Event()]
         with torch.cuda.stream(copy):
             sets[0].upload(host_tabs[p])
             up[0].record(copy)
-        out = None
+        out, pending = None, None
         for i in range(steps):
             main.wait_event(up[i % 2])                       # this proof's inputs are in HBM
+            proof = scz.dhyperplonk(ctx, n, sets[i % 2], pp)
             if i + 1 < steps:
+                # the next proof's tables: behind the END OF THIS PROOF'S PROTOCOL PHASE, i.e. under its MSM phase.  (The
+                # other table set was last read by proof i - 1, which has finished by then.)  Started at a proof boundary the
+                # copy shares PCIe with the command fetches of ~1 100 short launches: +6 ms per proof, tools/e2e_probe.py
+                ctx.stream_wait_protocol_phase(copy)
                 with torch.cuda.stream(copy):
-                    if i >= 1:
-                        copy.wait_event(done[(i + 1) % 2])   # the proof that last read this table set has finished
                     sets[(i + 1) % 2].upload(host_tabs[p])
                     up[(i + 1) % 2].record(copy)
-            proof = scz.dhyperplonk(ctx, n, sets[i % 2], pp)
-            done[i % 2].record(main)
-            out = proof.to_host()                             # device -> host, synchronises: the step's result
-        return out
+            # device -> host: queued behind the proof on the reader's stream; the host collects proof i - 1 now, while
+            # proof i is already enqueued
+            ticket = proof.to_host_async(readers[p])
+            if pending is not None:
+                out = readers[p].collect(pending)
+            pending = ticket
+        return readers[p].collect(pending)
 
     def e2e_all(steps):
         if P == 1:
@@ -777,7 +786,8 @@ def run_own(args):
                 "d2h_bytes_per_step": d2h * parties_total, "steps": e2e_steps, "ms_per_step": e2e_s / e2e_steps * 1e3,
                 "single_proof_ms_no_overlap": single_s * 1e3,
                 "api": "PackedProvingParameters.upload (pinned host tables -> HBM, on a copy stream, double-buffered so that the "
-                       "copy of proof i+1 overlaps proof i) + scz_dhyperplonk_dev + proof -> host"},
+                       "copy of proof i+1 overlaps proof i) + scz_dhyperplonk_dev + proof -> pinned host buffers on a read-back stream "
+                       "(ProofReader: collected one proof behind, status bits with it); wall clock over all steps"},
         "gpu_launches": launches,
         "d_msm": {"metric": "d_msm G1-adds/sec", "unit": "G1 adds/s",
                   "value_all_msm_kernels": adds / (msm_ms * 1e-3) if msm_ms > 0 else None,

@@ -123,6 +123,16 @@ int32_t scz_ctx_get_comm(const scz_ctx *ctx, uint64_t *upload, uint64_t *downloa
  * and the Rust shim panics when it sees it. */
 #define SCZ_STATUS_DIV_BY_ZERO 1u
 int32_t scz_ctx_take_status(scz_ctx *ctx, uint32_t *bits);
+/* The same without synchronising: a copy of the bits (as of this point of the ctx stream) is written to the device word
+ * d_bits_out and the sticky word is cleared, both in stream order.  For hosts that read a proof back asynchronously
+ * (several proofs in flight): the snapshot travels with the proof's device -> host copy. */
+int32_t scz_ctx_status_snapshot_dev(scz_ctx *ctx, void *d_bits_out);
+/* Makes `stream` (a cudaStream_t of the host's) wait until the PROTOCOL PHASE of the prover call most recently enqueued on
+ * this ctx has executed -- the ~1 100 short launches of dhyperplonk.rs:196-554 before the MSM sequences and leader rounds
+ * take over (no-op before the first prover call).  A bulk host -> device copy (the next proof's tables) queued behind it
+ * runs under the MSM phase; started at a proof boundary it shares PCIe with the command fetches of those short launches
+ * and costs 6 ms per proof (measured, tools/e2e_probe.py). */
+int32_t scz_ctx_stream_wait_protocol_phase(scz_ctx *ctx, void *stream);
 
 /* ---- native data plane: NCCL over NVLink in place of the reference's TCP star (mpc-net/src/multi.rs:98-266) ----
  * One process per GPU ("rank"), `parties_per_rank` MPC parties hosted by each rank (1 on an 8-GPU box at l = 1; 8 l / W

@@ -31,6 +31,7 @@ from .api import (  # noqa: F401
     msm,
     PackedProvingParameters,
     HyperPlonkProof,
+    ProofReader,
     dhyperplonk,
     dhyperplonk_data_parallel,
     dpermcheck,

@@ -91,6 +91,11 @@ class Context:
     def sync(self):
         self.check(self.L.scz_ctx_sync(self.h))
 
+    def stream_wait_protocol_phase(self, stream):
+        """`stream` (torch.cuda.Stream) waits until the protocol phase of the prover call last enqueued on this ctx has
+        run (scz_ctx_stream_wait_protocol_phase): queue the next proof's host -> device copy behind it"""
+        self.check(self.L.scz_ctx_stream_wait_protocol_phase(self.h, C.c_void_p(stream.cuda_stream)))
+
     def take_status(self):
         """sticky SCZ_STATUS_* bits of the work executed so far (synchronises); bit 0: a division met a zero denominator"""
         bits = C.c_uint32()
@@ -847,6 +852,53 @@ def _fr_one(ctx):
     return ctx.to_device(one, 4)
 
 
+class ProofReader:
+    """Device -> host read-back of proofs without stalling the prover's stream: the copy of proof i runs on its own
+    stream behind an event, into pinned staging buffers, together with a snapshot of the ctx's status bits
+    (scz_ctx_status_snapshot_dev) taken in stream order right after the proof.  `depth` proofs may be outstanding."""
+
+    def __init__(self, ctx, depth=2):
+        self.ctx, self.depth = ctx, depth
+        with torch.cuda.device(ctx.device):
+            self.stream = torch.cuda.Stream()
+        self.slots = [None] * depth
+        self.next = 0
+
+    def submit(self, proof):
+        ctx = self.ctx
+        t, p, v = proof.used()
+        slot = self.next % self.depth
+        self.next += 1
+        views = (proof.triples[: 3 * t], proof.points[:p], proof.values[:v])
+        st = self.slots[slot]
+        if st is None or any(h.shape != d.shape for h, d in zip(st["host"], views)):
+            st = {"host": [torch.empty(d.shape, dtype=d.dtype).pin_memory() for d in views],
+                  "bits_host": torch.zeros(1, dtype=torch.int32).pin_memory(),
+                  "bits": torch.zeros(1, dtype=torch.int32, device=ctx.device),
+                  "ready": torch.cuda.Event(), "done": torch.cuda.Event()}
+            self.slots[slot] = st
+        ctx.check(ctx.L.scz_ctx_status_snapshot_dev(ctx.h, C.c_void_p(st["bits"].data_ptr())))
+        with torch.cuda.device(ctx.device):
+            main = torch.cuda.current_stream()
+            st["ready"].record(main)
+            with torch.cuda.stream(self.stream):
+                self.stream.wait_event(st["ready"])
+                for h, d in zip(st["host"], views):
+                    h.copy_(d, non_blocking=True)
+                st["bits_host"].copy_(st["bits"], non_blocking=True)
+                st["done"].record(self.stream)
+        st["keep"] = proof                      # the arenas stay alive until the copy has run
+        return slot
+
+    def collect(self, slot):
+        st = self.slots[slot]
+        st["done"].synchronize()
+        st["keep"] = None
+        if int(st["bits_host"][0]) & 1:
+            raise ZeroDivisionError("field division by zero (arkworks panics here: hyperplonk/src/dhyperplonk.rs:338-339)")
+        return tuple(h.numpy().view(np.uint64).copy() for h in st["host"])
+
+
 class HyperPlonkProof:
     """The return value of `dhyperplonk` (dhyperplonk.rs:567-570) on the device: three arenas + the item table.
     `nested()` rebuilds the reference's tuple
@@ -869,6 +921,12 @@ class HyperPlonkProof:
         t, p, v = self.used()
         self.ctx.raise_on_status()
         return (self.ctx.to_host(self.triples[: 3 * t]), self.ctx.to_host(self.points[:p]), self.ctx.to_host(self.values[:v]))
+
+    def to_host_async(self, reader):
+        """the same copy queued on `reader`'s stream without waiting for it: `reader.collect(ticket)` returns the three
+        arrays.  A host that keeps several proofs in flight reads proof i back while proof i + 1 is already enqueued
+        (bench.py's e2e leg)."""
+        return reader.submit(self)
 
     def nested(self):
         tri = self.ctx.to_host(self.triples).reshape(-1, 3, 4)

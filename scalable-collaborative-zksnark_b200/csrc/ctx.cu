@@ -256,6 +256,7 @@ void scz_ctx_destroy(scz_ctx *h) {
     c->prof_clear();
     for (cudaEvent_t e : c->prof_pool) cudaEventDestroy(e);
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+    if (c->phase_mark) cudaEventDestroy(c->phase_mark);
     if (c->msm_stream) {
         cudaStreamSynchronize(c->msm_stream);
         cudaStreamDestroy(c->msm_stream);
@@ -330,6 +331,21 @@ int32_t scz_ctx_take_status(scz_ctx *h, uint32_t *bits) {
     SCZ_CUDA(c, cudaMemsetAsync(c->d_status, 0, sizeof v, c->stream));
     SCZ_CUDA(c, cudaStreamSynchronize(c->stream));
     *bits = v;
+    return SCZ_OK;
+}
+int32_t scz_ctx_status_snapshot_dev(scz_ctx *h, void *d_bits_out) {
+    scz::DeviceGuard dg__(h);
+    if (!h || !d_bits_out) return SCZ_ERR_BAD_ARG;
+    Ctx *c = &h->c;
+    SCZ_CUDA(c, cudaMemcpyAsync(d_bits_out, c->d_status, sizeof(uint32_t), cudaMemcpyDeviceToDevice, c->stream));
+    SCZ_CUDA(c, cudaMemsetAsync(c->d_status, 0, sizeof(uint32_t), c->stream));
+    return SCZ_OK;
+}
+int32_t scz_ctx_stream_wait_protocol_phase(scz_ctx *h, void *stream) {
+    scz::DeviceGuard dg__(h);
+    if (!h) return SCZ_ERR_BAD_ARG;
+    Ctx *c = &h->c;
+    if (c->phase_mark) SCZ_CUDA(c, cudaStreamWaitEvent(reinterpret_cast<cudaStream_t>(stream), c->phase_mark, 0));
     return SCZ_OK;
 }
 int32_t scz_ctx_get_comm(const scz_ctx *h, uint64_t *up, uint64_t *down) {

@@ -21,6 +21,9 @@ struct Ctx {
     bool own_stream = false;
     cudaStream_t msm_stream = nullptr;         // optional lowest-priority stream of the MSM launch sequences (msm.cu, flush_msm)
     cudaEvent_t msm_fork = nullptr, msm_join = nullptr;
+    // recorded on `stream` where a prover's protocol phase ends and only its MSM sequences / leader rounds remain
+    // (Deferred::run); scz_ctx_stream_wait_protocol_phase lets a host copy stream wait for it
+    cudaEvent_t phase_mark = nullptr;
     int sm_count = 148;
     std::string err;
     // pinned host staging for small results

@@ -739,6 +739,10 @@ int32_t Deferred::flush_msm() {
     return rc;
 }
 int32_t Deferred::run() {
+    // the protocol phase (about a thousand short launches) ends here: what follows are the MSM launch sequences and the
+    // leader rounds.  Hosts queue their next bulk host -> device copy behind this mark (scz_ctx_stream_wait_protocol_phase)
+    if (!ctx->phase_mark) SCZ_CUDA(ctx, cudaEventCreateWithFlags(&ctx->phase_mark, cudaEventDisableTiming));
+    SCZ_CUDA(ctx, cudaEventRecord(ctx->phase_mark, ctx->stream));
     while (!lens.empty() || !after.empty() || !gathers.empty() || !after_gather.empty() || !pss_jobs.empty() ||
            !colsum_jobs.empty() || !scatters.empty() || !after2.empty()) {
         SCZ_TRY(flush_msm());

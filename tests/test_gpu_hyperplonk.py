@@ -352,3 +352,40 @@ np.savez(sys.argv[1], **out)
     for n in (6, 12, 16):   # and a proof repeats itself
         for kind in "tpv":
             assert np.array_equal(b[f"{kind}{n}_0"], b[f"{kind}{n}_1"]), (kind, n)
+
+
+def test_proof_reader_pipelined_readback(orc):
+    """ProofReader (api.py): proofs read back one behind the prover on a separate stream are the same proofs as the
+    synchronous `to_host()` gives (field elements byte for byte; points as group elements -- the Jacobian representative
+    depends on the order in which the counting sort's atomics lay out a bucket's entries), and the status snapshot travels with each proof (a division by zero in proof 1 is reported
+    for proof 1 only; arkworks panics there, dhyperplonk.rs:338-339)."""
+    import torch
+
+    import scz_b200 as scz
+    ctx = scz.Context(device=0, n_parties=8)
+    pp = scz.PackedSharingParams(ctx, 1)
+    n = 8
+    pks = [scz.PackedProvingParameters.new(ctx, n, 1, seed=11 + i) for i in range(3)]
+    want = [scz.dhyperplonk(ctx, n, pk, pp).to_host() for pk in pks]
+    reader = scz.ProofReader(ctx, depth=2)
+    got, pending = [], None
+    for pk in pks:
+        ticket = scz.dhyperplonk(ctx, n, pk, pp).to_host_async(reader)
+        if pending is not None:
+            got.append(reader.collect(pending))
+        pending = ticket
+    got.append(reader.collect(pending))
+    for a, b in zip(got, want):
+        assert a[0].shape == b[0].shape and np.array_equal(a[0], b[0])          # triples
+        assert a[1].shape == b[1].shape and orc.canon_g1(a[1]) == orc.canon_g1(b[1])   # points
+        assert a[2].shape == b[2].shape and np.array_equal(a[2], b[2])          # values
+    # a zero denominator in the middle proof: only that ticket raises
+    a = ctx.to_device(np.ones((4, 4), dtype=np.uint64), 4)
+    z = torch.zeros_like(a)
+    t0 = scz.dhyperplonk(ctx, n, pks[0], pp).to_host_async(reader)
+    scz.fr_pointwise(ctx, "div", a, z)                      # raises the sticky bit in stream order
+    t1 = scz.dhyperplonk(ctx, n, pks[1], pp).to_host_async(reader)
+    reader.collect(t0)
+    with pytest.raises(ZeroDivisionError):
+        reader.collect(t1)
+    assert ctx.take_status() == 0
