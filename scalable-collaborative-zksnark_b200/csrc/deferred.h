@@ -61,6 +61,7 @@ struct Deferred {
     std::vector<std::shared_ptr<DevTmp>> keep;         // temporaries that must stay alive until run() returns
 
     bool early_pending = false;                        // a sequence started by flush_early() has not been joined yet
+    size_t early_after = 0, early_after2 = 0;          // continuations registered before the last flush_early()
 
     explicit Deferred(Ctx *c) : ctx(c) {}
     ~Deferred();

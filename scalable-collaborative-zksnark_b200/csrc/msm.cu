@@ -727,6 +727,8 @@ int32_t Deferred::flush_msm_on_side(bool wait) {
 int32_t Deferred::flush_early() {
     if (!msm_side_stream() || lens.empty()) return SCZ_OK;
     SCZ_TRY(join_early());
+    early_after = after.size();      // every continuation registered so far has its MSMs in this sequence
+    early_after2 = after2.size();
     return flush_msm_on_side(false);
 }
 int32_t Deferred::flush_msm() {
@@ -743,21 +745,49 @@ int32_t Deferred::run() {
     // leader rounds.  Hosts queue their next bulk host -> device copy behind this mark (scz_ctx_stream_wait_protocol_phase)
     if (!ctx->phase_mark) SCZ_CUDA(ctx, cudaEventCreateWithFlags(&ctx->phase_mark, cudaEventDisableTiming));
     SCZ_CUDA(ctx, cudaEventRecord(ctx->phase_mark, ctx->stream));
-    while (!lens.empty() || !after.empty() || !gathers.empty() || !after_gather.empty() || !pss_jobs.empty() ||
-           !colsum_jobs.empty() || !scatters.empty() || !after2.empty()) {
-        SCZ_TRY(flush_msm());
-        std::vector<std::function<int32_t()>> now;
-        now.swap(after);
+    using Fn = std::function<int32_t()>;
+    // one leader stage over the first n1 continuations of `after` and the first n2 of `after2` (plus whatever the stage
+    // itself appends to after2); continuations appended to `after` wait for the next flush
+    auto stage = [&](size_t n1, size_t n2) -> int32_t {
+        std::vector<Fn> now(std::make_move_iterator(after.begin()), std::make_move_iterator(after.begin() + n1));
+        after.erase(after.begin(), after.begin() + n1);
+        std::vector<Fn> now2(std::make_move_iterator(after2.begin()), std::make_move_iterator(after2.begin() + n2));
+        after2.erase(after2.begin(), after2.begin() + n2);
+        const size_t base2 = after2.size();
         for (auto &f : now) SCZ_TRY(f());
         SCZ_TRY(do_gathers());
-        now.clear();
-        now.swap(after_gather);
-        for (auto &f : now) SCZ_TRY(f());
+        std::vector<Fn> g;
+        g.swap(after_gather);
+        for (auto &f : g) SCZ_TRY(f());
         SCZ_TRY(flush_closures());
         SCZ_TRY(do_scatters());
-        now.clear();
-        now.swap(after2);
-        for (auto &f : now) SCZ_TRY(f());
+        for (auto &f : now2) SCZ_TRY(f());
+        std::vector<Fn> appended(std::make_move_iterator(after2.begin() + base2), std::make_move_iterator(after2.end()));
+        after2.erase(after2.begin() + base2, after2.end());
+        for (auto &f : appended) SCZ_TRY(f());
+        return SCZ_OK;
+    };
+    // SCZ_MSM_OVERLAP_CLOSURES=1 (dev knob, off): with an early-started sequence (flush_early) and more MSMs queued after
+    // it, start the second sequence on the side stream BEFORE the leader rounds of the first one's results, so that their
+    // closures (two 255-doubling chains per round, latency-bound: ~3.7 ms per 2^20 proof) run under its bucket
+    // accumulation.  Bit-identical proofs (the continuations registered before the early start only read results of the
+    // first sequence; every party splits at the same place), but measured SLOWER on B200: 155.7 vs 153.2 ms per proof --
+    // the closures' 32-thread CTAs take 18 ms instead of 3.7 next to the bucket kernels and cost the second sequence
+    // more SM time than the 3 ms they hide.
+    static const bool overlap = [] { const char *e = getenv("SCZ_MSM_OVERLAP_CLOSURES"); return e && e[0] == '1'; }();
+    if (overlap && early_pending && early_after > 0 && !lens.empty() && early_after <= after.size() && early_after2 <= after2.size()) {
+        const size_t late1 = after.size() - early_after, late2 = after2.size() - early_after2;
+        SCZ_TRY(join_early());
+        SCZ_TRY(flush_msm_on_side(false));
+        SCZ_TRY(stage(early_after, early_after2));
+        SCZ_TRY(join_early());
+        SCZ_TRY(stage(late1, late2));
+    }
+    early_after = early_after2 = 0;
+    while (!lens.empty() || !after.empty() || !gathers.empty() || !after_gather.empty() || !pss_jobs.empty() ||
+           !colsum_jobs.empty() || !scatters.empty() || !after2.empty() || early_pending) {
+        SCZ_TRY(flush_msm());
+        SCZ_TRY(stage(after.size(), after2.size()));
     }
     return SCZ_OK;
 }
