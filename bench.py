@@ -574,7 +574,7 @@ def run_own(args):
     def e2e_loop(p, steps):
         ctx, pp, pk = parties[p]
         sets = [pk, alt[p]]
-        main, copy = torch.cuda.current_stream(), torch.cuda.Stream()
+        main, copy = ctx.stream, torch.cuda.Stream()
         up = [torch.cuda.Event(), torch.cuda.Event()]
         with torch.cuda.stream(copy):
             sets[0].upload(host_tabs[p])

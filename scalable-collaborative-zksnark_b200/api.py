@@ -70,8 +70,8 @@ class Context:
     def use_torch_stream(self):
         """run on torch's current stream so torch.cuda.Event timing and tensors order with our kernels"""
         with torch.cuda.device(self.device):
-            s = torch.cuda.current_stream().cuda_stream
-        self.check(self.L.scz_ctx_set_stream(self.h, C.c_void_p(s)))
+            self.stream = torch.cuda.current_stream()
+        self.check(self.L.scz_ctx_set_stream(self.h, C.c_void_p(self.stream.cuda_stream)))
 
     def check(self, rc):
         if rc != 0:
@@ -879,8 +879,7 @@ class ProofReader:
             self.slots[slot] = st
         ctx.check(ctx.L.scz_ctx_status_snapshot_dev(ctx.h, C.c_void_p(st["bits"].data_ptr())))
         with torch.cuda.device(ctx.device):
-            main = torch.cuda.current_stream()
-            st["ready"].record(main)
+            st["ready"].record(ctx.stream)           # the stream the proof was enqueued on, whatever the caller's current one
             with torch.cuda.stream(self.stream):
                 self.stream.wait_event(st["ready"])
                 for h, d in zip(st["host"], views):
