@@ -42,12 +42,16 @@ int32_t Ctx::h2d_staged(void *d_dst, const void *h_src, size_t bytes) {
         SCZ_CUDA(this, cudaStreamSynchronize(stream));
         return SCZ_OK;
     }
+    if (!stage[0].p) {   // all slots at once (see ctx.h)
+        char *block = nullptr;
+        SCZ_CUDA(this, cudaMallocHost(&block, STAGE_BYTES * STAGE_SLOTS));
+        for (int i = 0; i < STAGE_SLOTS; i++) {
+            stage[i].p = block + (size_t)i * STAGE_BYTES;
+            SCZ_CUDA(this, cudaEventCreateWithFlags(&stage[i].ev, cudaEventDisableTiming));
+        }
+    }
     Stage &s = stage[stage_next];
     stage_next = (stage_next + 1) % STAGE_SLOTS;
-    if (!s.p) {
-        SCZ_CUDA(this, cudaMallocHost(&s.p, STAGE_BYTES));
-        SCZ_CUDA(this, cudaEventCreateWithFlags(&s.ev, cudaEventDisableTiming));
-    }
     if (s.busy) SCZ_CUDA(this, cudaEventSynchronize(s.ev));
     memcpy(s.p, h_src, bytes);
     SCZ_CUDA(this, cudaMemcpyAsync(d_dst, s.p, bytes, cudaMemcpyHostToDevice, stream));
@@ -247,10 +251,9 @@ void scz_ctx_destroy(scz_ctx *h) {
     cudaStreamSynchronize(c->stream);
     if (c->pinned) cudaFreeHost(c->pinned);
     if (c->d_status) cudaFree(c->d_status);
-    for (auto &st : c->stage) {
-        if (st.p) cudaFreeHost(st.p);
+    if (c->stage[0].p) cudaFreeHost(c->stage[0].p);   // one block, sliced into the slots
+    for (auto &st : c->stage)
         if (st.ev) cudaEventDestroy(st.ev);
-    }
     c->msm_affine_ws.reset();
     if (c->device < 64) g_live_ctx[c->device]--;
     c->prof_clear();

@@ -64,7 +64,13 @@ struct Ctx {
     // Small host -> device tables (MSM segment tables, closure job lists) go through a ring of pinned slots so that
     // the copy is truly asynchronous and the host can run ahead of the GPU; a slot is reused only after the copy
     // that last used it has executed.
-    static constexpr int STAGE_SLOTS = 8;
+    // 32 slots: a 2^20 proof stages ~10 tables, and the one of its second MSM sequence sits behind ~115 ms of bucket
+    // kernels on the side stream -- with 8 slots the host met that copy's event again inside the same proof and stalled
+    // until the first sequence had finished (host enqueue 115 ms instead of 12 ms per proof).  The pinned memory of all
+    // slots is allocated in one piece on first use: cudaMallocHost synchronises the device, and slots allocated one by
+    // one as the ring advanced stalled the first three or four proofs of a process (432 ms for the first timed proof of a
+    // bench run with three warm-up proofs, 153 ms for the rest).
+    static constexpr int STAGE_SLOTS = 32;
     static constexpr size_t STAGE_BYTES = 1 << 20;
     struct Stage {
         char *p = nullptr;

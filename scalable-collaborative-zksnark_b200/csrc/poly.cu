@@ -290,6 +290,9 @@ __global__ void __launch_bounds__(T, MINB) k_sum_rounds(const void *f_in, void *
     constexpr int M = 1 << R, NV = 2 * R;
     __shared__ Fr sh[NV * PL_THREADS / 32];
     __shared__ bool last;
+    // (measured, not kept: the round sums as unreduced 9-limb integers reduced once per thread -- 9 add-with-carry
+    // instead of fp_add's 26 instructions per term, but 6 more registers at the 168-register cap: 0.199 / 0.466 ms
+    // instead of 0.179 / 0.440 ms for a whole call at 2^22 / 2^24 entries)
     Fr r[R], s[NV];
 #pragma unroll
     for (int t = 0; t < R; t++) r[t] = fp_load<FrP>(challenge, t);

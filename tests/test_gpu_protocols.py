@@ -45,7 +45,9 @@ def _levels(ctx, orc, rng, sizes):
 
 
 # ------------------------------------------------------------------------------------------- kernels
-@pytest.mark.parametrize("logn", [0, 1, 2, 5, 11, 12, 13, 15])
+# 19, 20: the first rounds run in the lazy kernel (unreduced 17-limb round sums, poly.cu k_sumcheck_round), which takes
+# over from ~4 pairs per thread of a one-CTA-per-SM grid; below that every round is k_sumcheck_round_direct
+@pytest.mark.parametrize("logn", [0, 1, 2, 5, 11, 12, 13, 15, 19, 20])
 def test_sumcheck_product_matches_oracle(orc, ctx, logn):
     import scz_b200 as scz
     rng = np.random.default_rng(400 + logn)
@@ -186,7 +188,7 @@ def test_d_sumcheck_product_leader_mode(orc, ctx, logn):
     assert np.array_equal(got, orc.d_sumcheck_product(orc.LEADER_SIM, 8, [f], [g], ch))
 
 
-@pytest.mark.parametrize("logn", [0, 1, 3, 8, 9, 13, 16])
+@pytest.mark.parametrize("logn", [0, 1, 3, 8, 9, 13, 16, 20])
 def test_single_mle_sumcheck_family(orc, ctx, logn):
     """sumcheck / c_sumcheck / d_sumcheck (dsumcheck.rs:6-26, 92-146, 287-357), leader mode, against the oracle"""
     import scz_b200 as scz
