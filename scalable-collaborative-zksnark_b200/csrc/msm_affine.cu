@@ -209,6 +209,9 @@ __device__ __forceinline__ void ba_phase2_cta(const MsmSeg *segs, int nseg, cons
     }
 }
 
+// (measured, not kept: level-0 phase 1 with two pairs per step -- one 16-byte load for the two adjacent entries of a pair,
+// the four x gathers of a step issued before the first product, 88 registers: 120.4 vs 119.8 ms of accumulation per 2^20
+// proof; the kernel's DRAM rate is set by the random 128-byte line fills, not by the loads in flight.)
 // (measured, not kept: level-0 phase 2 with its two gathered operands staged per thread in shared memory by cp.async,
 // two pairs deep, four CTAs per SM -- 121.0 instead of 119.5 ms of accumulation per 2^20 proof.  The level-0 kernels are
 // bound by the DRAM rate of random 96 B gathers (ncu: 2.6 - 3.9 TB/s of 128 B line fills), not by exposed latency.)
