@@ -197,8 +197,14 @@ __device__ __forceinline__ void ba_phase2_cta(const MsmSeg *segs, int nseg, cons
         Fq d = fp_sub(Q.x, P.x);
         G1Affine r;
         if (d.is_zero() || P.x.is_zero() || Q.x.is_zero()) {
-            d = ba_denominator_slow(P, Q);
-            ba_add_slow(P, Q, dinv, r);
+            // copies, so that only they have their address taken: with P, Q, dinv and r themselves passed by reference
+            // to the out-of-line slow path every pair stored ~250 B to the stack frame before this (rare) branch
+            const G1Affine Pc = P, Qc = Q;
+            const Fq dc = dinv;
+            G1Affine rc;
+            d = ba_denominator_slow(Pc, Qc);
+            ba_add_slow(Pc, Qc, dc, rc);
+            r = rc;
         } else {
             Fq lam = fp_mul(fp_sub(Q.y, P.y), dinv);
             r.x = fp_sub(fp_sub(fp_sqr(lam), P.x), Q.x);   // (a dedicated squaring, fq_sqr_sos, measured slower: +1.5 ms per proof)
