@@ -499,6 +499,9 @@ int32_t msm_sort_entries(Ctx *ctx, const MsmSeg *d_segs, int K, uint32_t points,
     k_scan_add<<<tiles, SCAN_THREADS, 0, st>>>(cursor, tile_scratch, buckets);
     SCZ_LAUNCH_CHECK(ctx);
     if (points) {
+        // (measured, not kept: a persisting L2 access-policy window over the cursor array during this pass, whose slot
+        // reservations hit it at random while GBs of 8-byte stores stream through L2 -- sort 12.1 / 17.8 ms per 2^20 proof
+        // with a 32 / 64 MiB set-aside against 10.5 ms without)
         k_msm_recode<true><<<ceil_div_u32(points, CNT_THREADS), CNT_THREADS, 0, st>>>(d_segs, K, points, nullptr, cursor, sorted);
         SCZ_LAUNCH_CHECK(ctx);
     }
