@@ -1,7 +1,8 @@
 // Device-wide batch inversion (Montgomery's trick as a product tree): inverses of n field elements for ONE field
 // inversion.  Used by the batched-affine bucket accumulation (msm_affine.cu, Fq: the denominators of a whole tree level)
 // and by the point-wise division h = num / den of dhyperplonk.rs:338-339 (poly.cu, Fr).
-//   up    thread g owns values [g F, (g + 1) F): inclusive prefix products inside the group, group total to the next level
+//   up    thread g owns values g, g + G, g + 2 G, ... (G groups of at most F values): inclusive prefix products inside the
+//         group, group total to the next level
 //   top   at most INV_TOP values: one thread, one inversion (binary extended Euclid, field.cuh fp_inv_bingcd)
 //   down  inverse of value e = (inverse of the group's prefix through e) * (prefix through e - 1), walking backwards
 // Values must be non-zero (callers substitute one where no inverse is needed).
@@ -15,16 +16,18 @@
 namespace scz {
 
 constexpr int INV_THREADS = 128;
-constexpr int INV_F = 32;     // fan-in (contiguous per thread)
+constexpr int INV_F = 32;     // fan-in (values per thread, strided by the number of groups)
 constexpr int INV_TOP = 32;   // the tree stops at <= this many values
 
+// Group g owns the values g, g + ngroups, g + 2 ngroups, ... (at most INV_F of them): consecutive lanes touch consecutive
+// elements in every step.  (With contiguous groups -- lane stride 32 elements -- every load of a warp touched 32 lines and the
+// two big levels of a tree ran at ~150 GB/s.)
 template <class P>
 __global__ void __launch_bounds__(INV_THREADS) k_inv_tree_up(const void *V, uint32_t n, void *pfx, void *tot, uint32_t ngroups) {
     uint32_t g = blockIdx.x * INV_THREADS + threadIdx.x;
     if (g >= ngroups) return;
-    uint32_t lo = g * INV_F, hi = min(n, lo + INV_F);
     Fp<P> run = Fp<P>::one();
-    for (uint32_t e = lo; e < hi; e++) {
+    for (uint32_t e = g; e < n; e += ngroups) {
         run = fp_mul(run, fp_load_rw<P>(V, e));
         fp_store<P>(pfx, e, run);
     }
@@ -50,13 +53,16 @@ template <class P>
 __global__ void __launch_bounds__(INV_THREADS) k_inv_tree_down(const void *V, uint32_t n, void *pfx, const void *inv_parent,
                                                                uint32_t ngroups) {
     uint32_t g = blockIdx.x * INV_THREADS + threadIdx.x;
-    if (g >= ngroups) return;
-    uint32_t lo = g * INV_F, hi = min(n, lo + INV_F);
+    if (g >= ngroups || g >= n) return;
     Fp<P> I = fp_load_rw<P>(inv_parent, g);
-    for (uint32_t e = hi; e-- > lo;) {
-        Fp<P> inv_e = e > lo ? fp_mul(I, fp_load_rw<P>(pfx, e - 1)) : I;
-        if (e > lo) I = fp_mul(I, fp_load_rw<P>(V, e));
+    uint32_t e = g + (n - 1 - g) / ngroups * ngroups;   // the group's last element
+    while (true) {
+        const bool first = e == g;
+        Fp<P> inv_e = first ? I : fp_mul(I, fp_load_rw<P>(pfx, e - ngroups));
+        if (!first) I = fp_mul(I, fp_load_rw<P>(V, e));
         fp_store<P>(pfx, e, inv_e);
+        if (first) break;
+        e -= ngroups;
     }
 }
 
