@@ -115,6 +115,9 @@ uint64_t scz_ctx_launch_count(const scz_ctx *ctx);
 #define SCZ_K_POINTWISE 9       /* element-wise Fr maps, batch inversion */
 int32_t scz_prof_enable(scz_ctx *ctx, int32_t on);
 int32_t scz_prof_read(scz_ctx *ctx, int32_t kernel_class, double *ms_total, uint64_t *brackets);
+/* Creates CUDA events ahead of time until the ctx's pool holds `events` of them (two per bracket): a measurement loop that
+ * profiles K calls back to back reserves 2 * K * brackets-per-call first, so that no event is created inside its timed region */
+int32_t scz_prof_reserve(scz_ctx *ctx, uint64_t events);
 /* MPCNet::get_comm (mpc-net/src/lib.rs:59): (upload, download) in the reference's serialised bytes */
 int32_t scz_ctx_get_comm(const scz_ctx *ctx, uint64_t *upload, uint64_t *download);
 /* Sticky status bits of work already EXECUTED on the ctx stream; synchronises the stream, returns and clears them.

@@ -118,6 +118,10 @@ class Context:
         """bracket every kernel class with CUDA events on the ctx stream (scz_prof_enable); clears old records"""
         self.check(self.L.scz_prof_enable(self.h, C.c_int32(1 if on else 0)))
 
+    def prof_reserve(self, events):
+        """create CUDA events ahead of time (scz_prof_reserve) so that a profiled, timed loop creates none"""
+        self.check(self.L.scz_prof_reserve(self.h, C.c_uint64(int(events))))
+
     def prof_read(self, kernel_class):
         """-> (summed device ms, number of brackets) of one kernel class since prof_enable"""
         ms, n = C.c_double(), C.c_uint64()

@@ -306,6 +306,18 @@ int32_t scz_prof_enable(scz_ctx *h, int32_t on) {
     h->c.prof = on != 0;
     return SCZ_OK;
 }
+int32_t scz_prof_reserve(scz_ctx *h, uint64_t events) {
+    scz::DeviceGuard dg__(h);
+    if (!h) return SCZ_ERR_BAD_ARG;
+    Ctx *c = &h->c;
+    if (events > (1u << 22)) return c->fail(SCZ_ERR_BAD_ARG, "prof_reserve: %llu events", (unsigned long long)events);
+    while (c->prof_pool.size() < events) {
+        cudaEvent_t e;
+        SCZ_CUDA(c, cudaEventCreate(&e));
+        c->prof_pool.push_back(e);
+    }
+    return SCZ_OK;
+}
 int32_t scz_prof_read(scz_ctx *h, int32_t kernel_class, double *ms_total, uint64_t *brackets) {
     scz::DeviceGuard dg__(h);
     if (!h) return SCZ_ERR_BAD_ARG;
