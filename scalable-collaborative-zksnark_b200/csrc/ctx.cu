@@ -226,6 +226,12 @@ int32_t scz_ctx_create(int32_t device, uint32_t party_id, uint32_t n_parties, co
         if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
             uint64_t thr = UINT64_MAX;
             cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+            // reuse decided by stream order and event dependencies only, never by what the GPU happens to have finished:
+            // with the opportunistic policy on, the pool kept growing into the 2nd and 3rd proof of a process depending on
+            // how far the host ran ahead (4480 -> 4736 -> 4992 MiB at 2^20, +7.6 ms on the proof that grew it); without it
+            // the pool is final after the first proof (4608 MiB) -- tools/pool_probe.py, profiles/r2_pool_probe.txt
+            int off = 0;
+            if (!getenv("SCZ_POOL_OPPORTUNISTIC")) cudaMemPoolSetAttribute(pool, cudaMemPoolReuseAllowOpportunistic, &off);
         }
     }
     if (net) {
