@@ -61,6 +61,19 @@ def hbm_peak():
     return HBM_FALLBACK_GBS, "fallback (B200_PROFILING.md)"
 
 
+def pool_reserved_mib(device_index):
+    """MiB the device's stream-ordered memory pool holds (host-side allocator state; None without cuda-python).  Read before
+    and after the timed region: a pool that still grows inside it costs ~0.1 ms of stalled stream per MiB (tools/pool_probe.py)"""
+    try:
+        from cuda.bindings import driver as cu
+        err, dev = cu.cuDeviceGet(device_index)
+        err, pool = cu.cuDeviceGetDefaultMemPool(dev)
+        err, v = cu.cuMemPoolGetAttribute(pool, cu.CUmemPool_attribute.CU_MEMPOOL_ATTR_RESERVED_MEM_CURRENT)
+        return int(v) >> 20 if int(err) == 0 else None
+    except Exception:
+        return None
+
+
 class ClockSampler:
     """SM clock + throttle reasons DURING the timed region.  In-process NVML (two light queries every 500 ms from a
     thread -- every query takes driver locks the launch path also needs, so the rate is kept low); `nvidia-smi --query-gpu ... -lms` is the fallback -- its full query holds driver locks long enough to slow
@@ -508,11 +521,13 @@ def run_own(args):
 
     run_steps(args.warmup)
     ctx0 = parties[0][0]
-    # every bracket event of the timed region exists before it starts (a proof records ~1 300 brackets; without this the
-    # host creates 2 600 events per proof from step `warmup` + 1 on, while the first proofs are still executing), and the
-    # cyclic GC stays out of it: a sporadic ~300 ms hole inside the FIRST timed step (1 run in 4, kernels themselves at
-    # normal speed) was never pinned down -- tools/first_step_probe.py does not reproduce it -- so the timed region is kept
-    # free of every host-side allocation we control
+    # every bracket event of the timed region exists (and has been recorded once) before it starts -- a proof records ~1 300
+    # brackets; without this the host creates 2 600 events per proof from step `warmup` + 1 on, while the first proofs are
+    # still executing -- and the cyclic GC stays out of it.  Background: with the profiled brackets on, the host runs only
+    # ~one proof ahead of the GPU (host_enqueue_ms_each_step_rank0), so a host stall longer than that leaves a hole in the
+    # timeline.  One run in four had a 300 - 400 ms hole in timed step 0 or 1; the one cause found is the device memory pool
+    # (a stream-ordered allocation that cannot reuse its block maps new memory at ~0.1 ms per MiB; the pool's
+    # timing-dependent reuse policy is now off, csrc/ctx.cu), its size is reported around the timed region
     per_proof = max(sum(ctx0.prof_read(k)[1] for k in ctx0.KERNEL_CLASSES) // max(1, args.warmup), 1)
     for ctx, _, _ in parties:
         ctx.prof_enable(True)          # clears the warm-up's records, keeps the event pool
@@ -521,6 +536,7 @@ def run_own(args):
     gc.collect()
     gc.disable()
     launches0 = sum(c.launches for c, _, _ in parties)
+    pool0 = pool_reserved_mib(local_rank)
     coll0 = dict(hub.calls) if hub else {}
     stats0 = ctx0.msm_cum_stats()
     comm0 = ctx0.get_comm()
@@ -529,6 +545,7 @@ def run_own(args):
         sampler.mark_begin()
     e0, e1, marks, host_enqueue_ms, proofs = run_steps(args.steps)
     gc.enable()
+    pool1 = pool_reserved_mib(local_rank)
     step_ms = [round((marks[i - 1] if i else e0).elapsed_time(marks[i]), 2) for i in range(len(marks))]
     if sampler:
         sampler.mark_end()
@@ -774,9 +791,12 @@ def run_own(args):
             "ms_each_step_rank0": step_ms,
             "ms_per_step_median_rank0": sorted(step_ms)[len(step_ms) // 2],
             "host_enqueue_ms_each_step_rank0": host_enqueue_ms,
-            "step_outliers_note": ("one step of this run took > 1.5x the median: a sporadic ~300 ms hole in the GPU timeline (the "
-                                   "kernels themselves at normal speed, the per-class sums unchanged) that hits one of the first steps "
-                                   "in roughly one run out of four and was not pinned down (DESIGN.md 6); `value` includes it"
+            "mem_pool_reserved_mib_before_after_rank0": [pool0, pool1],
+            "step_outliers_note": ("one step of this run took > 1.5x the median: a hole in the GPU timeline (the kernels themselves "
+                                   "at normal speed, the per-class sums unchanged) that hit one of the first two timed steps in roughly "
+                                   "one run out of four before the memory pool's opportunistic reuse was switched off (DESIGN.md 6: a "
+                                   "stream-ordered allocation that cannot reuse its block grows the pool at ~0.1 ms per MiB); `value` "
+                                   "includes it; compare host_enqueue_ms_each_step_rank0 and mem_pool_reserved_mib_before_after_rank0"
                                    if step_ms and max(step_ms) > 1.5 * sorted(step_ms)[len(step_ms) // 2] else None),
             "srs_fixed_base_tables": (not args.no_precompute) and "window multiples of every SRS level beside the points "
                                      "(csrc/srs.cu), 12.4 GB per party, built at set-up like the SRS itself",

@@ -317,11 +317,17 @@ int32_t scz_prof_reserve(scz_ctx *h, uint64_t events) {
     if (!h) return SCZ_ERR_BAD_ARG;
     Ctx *c = &h->c;
     if (events > (1u << 22)) return c->fail(SCZ_ERR_BAD_ARG, "prof_reserve: %llu events", (unsigned long long)events);
+    // every new event is also recorded once here: whatever the driver sets up lazily behind a timing event on its first
+    // record happens now, not inside the region the caller is about to time
+    bool fresh = false;
     while (c->prof_pool.size() < events) {
         cudaEvent_t e;
         SCZ_CUDA(c, cudaEventCreate(&e));
+        SCZ_CUDA(c, cudaEventRecord(e, c->stream));
         c->prof_pool.push_back(e);
+        fresh = true;
     }
+    if (fresh) SCZ_CUDA(c, cudaStreamSynchronize(c->stream));
     return SCZ_OK;
 }
 int32_t scz_prof_read(scz_ctx *h, int32_t kernel_class, double *ms_total, uint64_t *brackets) {
