@@ -875,6 +875,9 @@ class ProofReader:
         self.next += 1
         views = (proof.triples[: 3 * t], proof.points[:p], proof.values[:v])
         st = self.slots[slot]
+        if st is not None and st.get("keep") is not None:
+            raise RuntimeError(f"ProofReader: {self.depth} proofs already outstanding -- collect() the oldest ticket first "
+                               "(its staging buffers would be overwritten)")
         if st is None or any(h.shape != d.shape for h, d in zip(st["host"], views)):
             st = {"host": [torch.empty(d.shape, dtype=d.dtype).pin_memory() for d in views],
                   "bits_host": torch.zeros(1, dtype=torch.int32).pin_memory(),
@@ -895,6 +898,8 @@ class ProofReader:
 
     def collect(self, slot):
         st = self.slots[slot]
+        if st is None or st.get("keep") is None:
+            raise RuntimeError("ProofReader.collect: no outstanding proof behind this ticket (collected twice?)")
         st["done"].synchronize()
         st["keep"] = None
         if int(st["bits_host"][0]) & 1:
