@@ -1,4 +1,4 @@
-// TEST-ONLY host build of the device arithmetic headers (csrc/field.cuh, g1.cuh,
+// TEST-ONLY host build of the device arithmetic headers (csrc/field.cuh, g1.cuh, g2.cuh,
 // msm_digits.cuh).  The authoring container has no GPU, so the limb logic that the
 // CUDA kernels inline is compiled here with g++ (carry-chain primitives fall back
 // to their host emulation) and compared with the oracle by tests/test_emu_arith.py.
@@ -6,6 +6,7 @@
 #include <cstring>
 #include "../../scalable-collaborative-zksnark_b200/csrc/field.cuh"
 #include "../../scalable-collaborative-zksnark_b200/csrc/g1.cuh"
+#include "../../scalable-collaborative-zksnark_b200/csrc/g2.cuh"
 #include "../../tools/ubench/fq_f64.cuh"
 #include "../../scalable-collaborative-zksnark_b200/csrc/g1_batch_affine.cuh"
 #include <vector>
@@ -136,5 +137,59 @@ extern "C" void emu_g1_batch_affine_add(const uint32_t *p, const uint32_t *q, ui
     for (size_t i = 0; i < n; i++) {
         st<FqP>(out, 2 * i, R[i].x);
         st<FqP>(out, 2 * i + 1, R[i].y);
+    }
+}
+
+// ---- G2 (g2.cuh): Fq2 = c0 | c1 (24 words), Jacobian X | Y | Z (72 words), packed affine x | y (48 words, all-zero = identity)
+static Fq2 ld2(const uint32_t *p, size_t i) {
+    Fq2 r;
+    r.c0 = ld<FqP>(p, 2 * i);
+    r.c1 = ld<FqP>(p, 2 * i + 1);
+    return r;
+}
+static void st2(uint32_t *p, size_t i, const Fq2 &v) {
+    st<FqP>(p, 2 * i, v.c0);
+    st<FqP>(p, 2 * i + 1, v.c1);
+}
+static G2Jac ldj2(const uint32_t *p, size_t i) {
+    G2Jac r;
+    r.x = ld2(p, 3 * i);
+    r.y = ld2(p, 3 * i + 1);
+    r.z = ld2(p, 3 * i + 2);
+    return r;
+}
+static void stj2(uint32_t *p, size_t i, const G2Jac &v) {
+    st2(p, 3 * i, v.x);
+    st2(p, 3 * i + 1, v.y);
+    st2(p, 3 * i + 2, v.z);
+}
+extern "C" void emu_fq2_mul(const uint32_t *a, const uint32_t *b, uint32_t *r, size_t n) {
+    for (size_t i = 0; i < n; i++) st2(r, i, f2_mul(ld2(a, i), ld2(b, i)));
+}
+extern "C" void emu_fq2_sqr(const uint32_t *a, uint32_t *r, size_t n) {
+    for (size_t i = 0; i < n; i++) st2(r, i, f2_sqr(ld2(a, i)));
+}
+extern "C" void emu_g2_add(const uint32_t *a, const uint32_t *b, uint32_t *out, size_t n) {
+    for (size_t i = 0; i < n; i++) stj2(out, i, g2x_to_jac(g2x_add(g2x_from_jac(ldj2(a, i)), g2x_from_jac(ldj2(b, i)))));
+}
+extern "C" void emu_g2_double(const uint32_t *a, uint32_t *out, size_t n) {
+    for (size_t i = 0; i < n; i++) stj2(out, i, g2x_to_jac(g2x_double(g2x_from_jac(ldj2(a, i)))));
+}
+extern "C" void emu_g2_add_affine(const uint32_t *acc, const uint32_t *aff, const uint8_t *neg, uint32_t *out, size_t n) {
+    for (size_t i = 0; i < n; i++) {
+        G2X a = g2x_from_jac(ldj2(acc, i));
+        G2Affine p;
+        p.x = ld2(aff, 2 * i);
+        p.y = ld2(aff, 2 * i + 1);
+        g2x_add_affine(a, p, neg[i] != 0);
+        stj2(out, i, g2x_to_jac(a));
+    }
+}
+// k = canonical 256-bit scalars (8 words each)
+extern "C" void emu_g2_mul_bits(const uint32_t *a, const uint32_t *k, uint32_t *out, size_t n) {
+    for (size_t i = 0; i < n; i++) {
+        uint32_t kk[8];
+        memcpy(kk, k + 8 * i, sizeof kk);
+        stj2(out, i, g2x_to_jac(g2x_mul_bits(g2x_from_jac(ldj2(a, i)), kk)));
     }
 }

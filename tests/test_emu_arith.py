@@ -1,4 +1,4 @@
-"""Host build of the DEVICE arithmetic headers (csrc/field.cuh, g1.cuh, msm_digits.cuh)
+"""Host build of the DEVICE arithmetic headers (csrc/field.cuh, g1.cuh, g2.cuh, msm_digits.cuh)
 checked against the oracle.  This exercises the limb/carry logic the CUDA kernels inline;
 it is a CI aid for the GPU-less authoring box, not a product path (tests/emu/emu.cpp)."""
 import ctypes as C
@@ -257,3 +257,104 @@ def test_inverse_by_binary_gcd(orc, emu):
     out = np.zeros_like(fr)
     emu.emu_fr_inv_bingcd(_p(fr), _p(out), C.c_size_t(len(fr)))
     assert np.array_equal(out, orc.fr_inv(fr))
+
+
+# ---------------------------------------------------------------- G2 (csrc/g2.cuh) against the Python big-int twin
+def _f2_limbs(orc, vals):
+    """list of Fq2 (c0, c1) ints -> (n, 12) uint64 Montgomery limbs"""
+    flat = []
+    for a in vals:
+        flat += [a[0], a[1]]
+    return np.ascontiguousarray(orc.fq_from_ints(flat).reshape(len(vals), 12))
+
+
+def _f2_ints(orc, limbs):
+    v = orc.fq_to_ints(np.ascontiguousarray(limbs, dtype=np.uint64).reshape(-1, 6))
+    return [(v[2 * i], v[2 * i + 1]) for i in range(len(v) // 2)]
+
+
+def _g2_jac(orc, pts, z=None):
+    """affine twin points (None = identity) -> (n, 36) Jacobian limbs; `z`: per-point Fq2 to scale the representative with"""
+    rows = []
+    for i, p in enumerate(pts):
+        if p is None:
+            rows += [(1, 0), (1, 0), (0, 0)]
+            continue
+        zz = (1, 0) if z is None else z[i]
+        z2 = tw.f2_mul(zz, zz)
+        rows += [tw.f2_mul(p[0], z2), tw.f2_mul(p[1], tw.f2_mul(z2, zz)), zz]
+    return _f2_limbs(orc, rows).reshape(len(pts), 36)
+
+
+def _g2_canon(orc, jac):
+    out = []
+    for row in np.ascontiguousarray(jac, dtype=np.uint64).reshape(-1, 36):
+        X, Y, Z = _f2_ints(orc, row)
+        if Z == (0, 0):
+            out.append(None)
+            continue
+        zi = tw.f2_inv(Z)
+        zi2 = tw.f2_mul(zi, zi)
+        out.append((tw.f2_mul(X, zi2), tw.f2_mul(Y, tw.f2_mul(zi2, zi))))
+    return out
+
+
+def test_fq2_mul_sqr(orc, emu):
+    import random
+    r = random.Random(31)
+    P = tw.P_MOD
+    edge = [(0, 0), (1, 0), (0, 1), (P - 1, P - 1), (P - 1, 0), (0, P - 1), (1, 1), ((P - 1) // 2, 2)]
+    a = edge + [(r.randrange(P), r.randrange(P)) for _ in range(40)]
+    b = list(reversed(edge)) + [(r.randrange(P), r.randrange(P)) for _ in range(40)]
+    A, B = _f2_limbs(orc, a), _f2_limbs(orc, b)
+    out = np.zeros_like(A)
+    emu.emu_fq2_mul(_p(A), _p(B), _p(out), C.c_size_t(len(a)))
+    assert _f2_ints(orc, out) == [tw.f2_mul(x, y) for x, y in zip(a, b)]
+    out = np.zeros_like(A)
+    emu.emu_fq2_sqr(_p(A), _p(out), C.c_size_t(len(a)))
+    assert _f2_ints(orc, out) == [tw.f2_mul(x, x) for x in a]
+
+
+def test_g2_group_law(orc, emu):
+    """XYZZ addition / doubling / mixed addition / scalar multiplication of g2.cuh incl. every exceptional case (P + P, P - P,
+    identities on either side), on non-trivial Jacobian representatives"""
+    import random
+    r = random.Random(32)
+    G = (tw.G2_X, tw.G2_Y)
+    assert tw.g2_on_curve(G)
+    ks = [r.randrange(1, tw.R_MOD) for _ in range(6)]
+    pts = [tw.g2_mul(G, k) for k in ks]
+    zs = [(r.randrange(1, tw.P_MOD), r.randrange(tw.P_MOD)) for _ in pts]
+    neg = lambda p: (p[0], tw.f2_sub((0, 0), p[1]))   # noqa: E731
+    a_pts = pts + [pts[0], pts[0], None, pts[1], None]
+    b_pts = pts[1:] + pts[:1] + [pts[0], neg(pts[0]), pts[2], None, None]
+    za = zs + [zs[1], zs[2], None, zs[3], None]
+    zb = zs[1:] + zs[:1] + [zs[4], zs[5], zs[0], None, None]
+    A, B = _g2_jac(orc, a_pts, za), _g2_jac(orc, b_pts, zb)
+    out = np.zeros_like(A)
+    emu.emu_g2_add(_p(A), _p(B), _p(out), C.c_size_t(len(A)))
+    want = [tw.g2_add(p, q) for p, q in zip(a_pts, b_pts)]
+    assert _g2_canon(orc, out) == want
+    assert want[len(pts) + 1] is None and want[-1] is None and all(tw.g2_on_curve(p) for p in want)
+    out = np.zeros_like(A)
+    emu.emu_g2_double(_p(A), _p(out), C.c_size_t(len(A)))
+    assert _g2_canon(orc, out) == [tw.g2_add(p, p) for p in a_pts]
+    # mixed addition: acc (Jacobian) += affine, optionally negated; acc == P, acc == -P, acc identity, P identity
+    acc_pts = pts + [pts[0], pts[1], None, pts[2]]
+    aff_pts = pts[2:] + pts[:2] + [pts[0], pts[1], pts[3], None]
+    flags = np.zeros(len(acc_pts), dtype=np.uint8)
+    flags[1] = flags[len(pts) + 1] = 1
+    ACC = _g2_jac(orc, acc_pts, zs + [zs[3], zs[4], None, zs[5]])
+    AFF = _f2_limbs(orc, [c for p in aff_pts for c in (((0, 0), (0, 0)) if p is None else p)]).reshape(len(aff_pts), 24)
+    out = np.zeros_like(ACC)
+    emu.emu_g2_add_affine(_p(ACC), _p(AFF), _p(flags), _p(out), C.c_size_t(len(ACC)))
+    want = [tw.g2_add(p, (neg(q) if f and q is not None else q)) for p, q, f in zip(acc_pts, aff_pts, flags)]
+    assert _g2_canon(orc, out) == want
+    assert want[len(pts)] == tw.g2_add(pts[0], pts[0]) and want[len(pts) + 1] is None
+    # k * P, canonical scalars: 0, 1, r - 1, random
+    sc = [0, 1, tw.R_MOD - 1] + [r.randrange(tw.R_MOD) for _ in range(3)]
+    K = np.array([[(k >> (64 * j)) & ((1 << 64) - 1) for j in range(4)] for k in sc], dtype=np.uint64)
+    PJ = _g2_jac(orc, pts, zs)
+    out = np.zeros_like(PJ)
+    emu.emu_g2_mul_bits(_p(PJ), _p(K), _p(out), C.c_size_t(len(sc)))
+    assert _g2_canon(orc, out) == [tw.g2_mul(p, k) for p, k in zip(pts, sc)]
