@@ -91,6 +91,6 @@ pub async fn d_msm_g2<Net: GpuNet>(
     let lens: Vec<usize> = bases.iter().map(|b| b.len()).collect();
     let d_o = p.alloc(bases.len().max(1) * SCZ_G2_JAC_BYTES)?;
     crate::check(p, unsafe { scz_d_msm_g2_dev(p.ctx(), dpp, bp.as_ptr(), sp.as_ptr(), lens.as_ptr(), bases.len(), d_o.ptr) })?;
-    let raw = p.download::<[u64; 36]>(&d_o, bases.len())?;
-    Ok(raw.iter().map(|j| G2Projective::new_unchecked(fq2(&j[0..12]), fq2(&j[12..24]), fq2(&j[24..36]))).collect())
+    let raw = p.download::<u64>(&d_o, bases.len() * 36)?; // flat: `[u64; 36]` has no `Default` (arrays stop at 32)
+    Ok(raw.chunks_exact(36).map(|j| G2Projective::new_unchecked(fq2(&j[0..12]), fq2(&j[12..24]), fq2(&j[24..36]))).collect())
 }
